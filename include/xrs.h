@@ -1,0 +1,132 @@
+/*
+ * xrs.h -- C ABI of libxrs.so, the B200 (sm_100a) spatial-resampling kernels.
+ *
+ * This is the drop-in boundary below the Python entry points
+ * (resample_in_space / rectify_dataset / reproject_dataset /
+ * affine_transform_dataset).  The reference (xcube-dev/xcube-resampling
+ * v0.1.0) has no FFI of its own: its "native" layer is a set of numba-jitted
+ * functions and calls into scipy / numpy / PROJ.  Each entry point below
+ * replaces one of those and cites it (paths relative to the reference root).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host;
+ *  - the caller owns every buffer; functions never allocate device memory;
+ *  - work is enqueued on the caller's stream (a cudaStream_t passed as void*;
+ *    NULL = legacy default stream) and the call returns without synchronising
+ *    unless stated otherwise;
+ *  - return value 0 = ok, non-zero = error, message via xrs_last_error()
+ *    (thread-local);
+ *  - images are row-major, spatial dimensions last, pitches in ELEMENTS;
+ *  - one call touches exactly one device (the current one).
+ */
+#ifndef XRS_H_
+#define XRS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XRS_VERSION 100 /* 0.1.0 */
+
+/* element types of data variables */
+enum xrs_dtype {
+    XRS_F32 = 0, XRS_F64 = 1, XRS_U8 = 2, XRS_I8 = 3, XRS_U16 = 4,
+    XRS_I16 = 5, XRS_I32 = 6, XRS_U32 = 7, XRS_I64 = 8
+};
+
+/* interpolation methods (constants.py:66-70) */
+enum xrs_interp { XRS_NEAREST = 0, XRS_BILINEAR = 1, XRS_TRIANGULAR = 2 };
+
+/* aggregation methods (constants.py:34-65) */
+enum xrs_agg {
+    XRS_AGG_CENTER = 0, XRS_AGG_COUNT = 1, XRS_AGG_FIRST = 2, XRS_AGG_LAST = 3, XRS_AGG_MAX = 4,
+    XRS_AGG_MEAN = 5, XRS_AGG_MEDIAN = 6, XRS_AGG_MODE = 7, XRS_AGG_MIN = 8, XRS_AGG_PROD = 9,
+    XRS_AGG_STD = 10, XRS_AGG_SUM = 11, XRS_AGG_VAR = 12
+};
+
+/* map projections understood by the device code */
+enum xrs_proj_kind {
+    XRS_PROJ_GEOGRAPHIC = 0, /* lon/lat degrees (EPSG:4326 always_xy, OGC:CRS84) */
+    XRS_PROJ_TMERC = 1,      /* transverse Mercator / UTM, Krueger n-series to n^6 */
+    XRS_PROJ_WEBMERC = 2,    /* EPSG:3857 spherical Mercator */
+    XRS_PROJ_LAEA = 3        /* Lambert azimuthal equal-area, ellipsoidal (EPSG:3035) */
+};
+
+/* A projected or geographic CRS reduced to what the formulas need. */
+typedef struct xrs_proj {
+    int32_t kind;   /* enum xrs_proj_kind */
+    int32_t _pad;
+    double a;       /* semi-major axis [m] */
+    double inv_f;   /* inverse flattening (0 = sphere) */
+    double lon0;    /* central meridian [deg] */
+    double lat0;    /* latitude of origin [deg] */
+    double k0;      /* scale factor */
+    double fe;      /* false easting [m] */
+    double fn;      /* false northing [m] */
+} xrs_proj;
+
+int xrs_version(void);
+int xrs_device_count(void);
+const char *xrs_last_error(void);
+
+/* ------------------------------------------------------------------------
+ * Rectification (rectify.py)
+ * --------------------------------------------------------------------- */
+
+/* K0 -- per-target-tile source windows.
+ * Replaces GridMapping.ij_bboxes_from_xy_bboxes -> compute_ij_bboxes
+ * (gridmapping/base.py:565-629, gridmapping/bboxes.py:28-106) for the
+ * separable tile boxes of a regular target grid (gridmapping/base.py:521-533):
+ * tile (ty,tx) has the x-interval [x_lo[tx], x_hi[tx]] and the y-interval
+ * [y_lo[ty], y_hi[ty]], both ALREADY grown by xy_border by the caller (so the
+ * comparisons use the same doubles as bboxes.py:60-69).  Single O(S) pass.
+ * out_boxes: (nty*ntx, 4) int64 rows (i_min, j_min, i_max, j_max), -1 row if no
+ * source point falls into the tile; grown by ij_border and clipped to
+ * [0,w]x[0,h] (bboxes.py:90-106).
+ * workspace: xrs_tile_src_bboxes_workspace_bytes(ntx, nty) bytes. */
+int64_t xrs_tile_src_bboxes_workspace_bytes(int32_t ntx, int32_t nty);
+int xrs_tile_src_bboxes(const double *x, const double *y, int64_t src_h, int64_t src_w, int64_t src_pitch,
+                        const double *x_lo, const double *x_hi, int32_t ntx, const double *y_lo,
+                        const double *y_hi, int32_t nty, int32_t ij_border, int64_t *out_boxes, void *workspace,
+                        void *stream);
+
+/* K1 -- source-index (ij) image of a regular target grid.
+ * Replaces _compute_target_source_ij / _compute_target_source_ij_block /
+ * _compute_target_source_ij_sequential / _line (rectify.py:312-576) including
+ * _fdet/_fu/_fv/_fclamp (rectify.py:737-768).  Result is identical to the
+ * sequential first-writer-wins scatter: per target pixel the accepting source
+ * quad with the smallest row-major index inside the reference tile's source
+ * window wins (DESIGN.md "K1 equivalence").
+ *   x, y          source coordinate images (src_h, src_w), pitch src_pitch
+ *   tile_boxes    (nty*ntx, 4) int64 from xrs_tile_src_bboxes (row-major tiles)
+ *   ij            (2, dst_h, dst_w) float64, plane 0 = i (x index), 1 = j
+ *   tile_w/h      the reference tile size of the target grid mapping
+ *   x_min,y_min,y_max,x_res,y_res,is_j_axis_up  target grid (rectify.py:402-416)
+ *   uv_delta      barycentric tolerance (constants.py:80, 1e-3)
+ * workspace: xrs_rectify_ij_workspace_bytes(dst_h, dst_w, tile_h, tile_w) bytes. */
+int64_t xrs_rectify_ij_workspace_bytes(int64_t dst_h, int64_t dst_w, int32_t tile_h, int32_t tile_w);
+int xrs_rectify_ij(const double *x, const double *y, int64_t src_h, int64_t src_w, int64_t src_pitch,
+                   const int64_t *tile_boxes, double *ij, int64_t dst_h, int64_t dst_w, int32_t tile_h,
+                   int32_t tile_w, double x_min, double y_min, double y_max, double x_res, double y_res,
+                   int32_t is_j_axis_up, double uv_delta, void *workspace, void *stream);
+
+/* K2 -- gather of all bands through the ij image.
+ * Replaces _compute_var_image / _compute_var_image_block /
+ * _compute_var_image_sequential / _for_dest_line (rectify.py:579-734).
+ *   src_planes_host  HOST array of n_bands device pointers, each a
+ *                    (src_h, src_w) plane of `dtype`, pitch src_pitch
+ *   dst_planes_host  HOST array of n_bands device pointers, each a
+ *                    (dst_h, dst_w) plane of `dtype`, contiguous rows
+ *   ij               (2, dst_h, dst_w) float64 from xrs_rectify_ij
+ *   fill             value written where ij is NaN (cast to dtype with a C cast)
+ * Arithmetic is float64 without FMA contraction, one C cast to dtype at the end. */
+int xrs_gather_ij(const void *const *src_planes_host, void *const *dst_planes_host, int32_t n_bands,
+                  int32_t dtype, int64_t src_h, int64_t src_w, int64_t src_pitch, const double *ij,
+                  int64_t dst_h, int64_t dst_w, int32_t method, double fill, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XRS_H_ */

@@ -1,0 +1,253 @@
+"""GPU parity of the rectify path: libxrs.so (through the C ABI / ctypes) against
+the CPU oracle and the committed reference-kernel goldens.
+
+ij image: bit-exact expected (tolerance of the north star: 1e-6 px);
+nearest / bilinear / triangular gathers: bit-exact (same fp64 arithmetic, no FMA).
+"""
+
+import numpy as np
+import pytest
+
+from oracle import grid as ogrid
+from oracle import rectify as orect
+
+from .helpers import assert_same, covering_grid_args, grid_from_golden, load_golden, swath
+
+pytestmark = pytest.mark.gpu
+nan = np.nan
+
+
+@pytest.fixture(scope="module")
+def xrs():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import xcube_resampling_b200 as pkg
+    from xcube_resampling_b200 import _dev, rectify
+
+    pkg.dev = _dev
+    pkg.rect = rectify
+    return pkg
+
+
+def _gm(xrs, g: ogrid.RegularGrid):
+    return xrs.GridMapping.regular((g.width, g.height), (g.x_min, g.y_min), (g.x_res, g.y_res), "EPSG:4326",
+                                   tile_size=(g.tile_w, g.tile_h), is_j_axis_up=g.is_j_axis_up)
+
+
+def _device_rectify(xrs, x, y, gm):
+    xd = xrs.dev.to_device(x, dtype=np.float64)
+    yd = xrs.dev.to_device(y, dtype=np.float64)
+    windows = xrs.rect.tile_source_windows_dev(xd, yd, gm.xy_bboxes, xrs.rect._xy_border(gm), 1)
+    ij = xrs.rect.compute_target_source_ij(xd, yd, gm, tile_boxes=windows)
+    return xrs.dev.to_host(windows), ij
+
+
+def _golden_cases():
+    z = load_golden("rectify.npz")
+    return [str(c) for c in z["cases"]]
+
+
+@pytest.mark.parametrize("case", _golden_cases())
+def test_golden_windows_ij_and_gather(xrs, case):
+    z = load_golden("rectify.npz")
+    g = grid_from_golden(z[f"{case}/grid"])
+    gm = _gm(xrs, g)
+    # the golden grid was built from raw floats; make sure the GridMapping kept them
+    assert (gm.x_min, gm.y_min, gm.y_max, gm.x_res, gm.y_res) == (g.x_min, g.y_min, g.y_max, g.x_res, g.y_res)
+    windows, ij = _device_rectify(xrs, z[f"{case}/x"], z[f"{case}/y"], gm)
+    assert_same(windows, z[f"{case}/windows"], "K0 windows")
+    ij_host = xrs.dev.to_host(ij)
+    ref_ij = z[f"{case}/ij"]
+    assert np.array_equal(np.isnan(ij_host), np.isnan(ref_ij)), "NaN mask of the ij image differs"
+    assert np.nanmax(np.abs(ij_host - ref_ij), initial=0.0) <= 1e-6  # north-star tolerance
+    assert_same(ij_host, ref_ij, "K1 ij (bit-exact)")
+    for vname, fill in (("f32", nan), ("u8", 255), ("i16", -1), ("f64", nan)):
+        src = xrs.dev.to_device(z[f"{case}/src_{vname}"])
+        for method in ("nearest", "bilinear", "triangular"):
+            out = xrs.dev.to_host(xrs.rect.gather_ij(src, ij, method, fill))
+            assert_same(out, z[f"{case}/out_{vname}_{method}"], f"K2 {vname}/{method}")
+
+
+@pytest.mark.parametrize("shape,theta,tile", [
+    ((700, 520), 12.0, 512),       # several reference tiles, windows span many CTA tiles
+    ((1030, 333), -40.0, None),    # single reference tile, odd pitch (bulk-copy alignment shifts)
+    ((257, 900), 77.0, (100, 64)),  # strongly rotated, small ragged tiles
+    ((400, 300), 0.0, 2048),       # axis-aligned swath
+])
+def test_seeded_swaths_against_oracle(xrs, shape, theta, tile):
+    w, h = shape
+    x, y = swath(w, h, theta=theta, seed=w + h)
+    res = 0.0027
+    size, xy_min = covering_grid_args(x, y, res)
+    g = ogrid.regular_grid(size, xy_min, res, tile_size=tile)  # tile may exceed the image (as in the reference)
+    gm = _gm(xrs, g)
+    windows, ij = _device_rectify(xrs, x, y, gm)
+    assert_same(windows, orect.source_windows(x, y, g), "K0 windows")
+    ref_ij = orect.rectify_ij(x, y, g)
+    ij_host = xrs.dev.to_host(ij)
+    assert np.array_equal(np.isnan(ij_host), np.isnan(ref_ij))
+    assert_same(ij_host, ref_ij, "K1 ij")
+    rng = np.random.default_rng(1)
+    src = rng.random((5, h, w)).astype(np.float32)
+    src[1, rng.random((h, w)) < 0.01] = nan
+    sd = xrs.dev.to_device(src)
+    for method in ("nearest", "bilinear"):
+        out = xrs.dev.to_host(xrs.rect.gather_ij(sd, ij, method, nan))
+        assert_same(out, orect.gather(src, ij_host, method, nan), f"K2 {method}")
+
+
+def test_fine_target_large_quads(xrs):
+    """Target 6x finer than the source: every quad covers ~36 pixels."""
+    x, y = swath(60, 50, theta=20.0, seed=3)
+    res = 0.0027 / 6.3
+    size, xy_min = covering_grid_args(x, y, res)
+    g = ogrid.regular_grid(size, xy_min, res, tile_size=200)
+    gm = _gm(xrs, g)
+    _, ij = _device_rectify(xrs, x, y, gm)
+    assert_same(xrs.dev.to_host(ij), orect.rectify_ij(x, y, g), "ij")
+
+
+def test_coarse_target_many_quads_per_pixel(xrs):
+    """Target 5x coarser: many quads compete for each pixel -> first-writer rule decides."""
+    x, y = swath(500, 400, theta=-15.0, seed=5)
+    res = 0.0027 * 5.0
+    size, xy_min = covering_grid_args(x, y, res)
+    g = ogrid.regular_grid(size, xy_min, res, tile_size=64)
+    g = ogrid.RegularGrid(g.width, g.height, min(g.tile_w, g.width), min(g.tile_h, g.height), g.x_min, g.y_min,
+                          g.x_max, g.y_max, g.x_res, g.y_res, g.is_j_axis_up)
+    gm = _gm(xrs, g)
+    _, ij = _device_rectify(xrs, x, y, gm)
+    assert_same(xrs.dev.to_host(ij), orect.rectify_ij(x, y, g), "ij")
+
+
+def test_wide_window_forces_chunking(xrs):
+    """A source much wider than one CTA window chunk (K1_MAX_COLS) mapped onto few pixels."""
+    w, h = 3000, 40
+    x, y = swath(w, h, theta=0.0, seed=9)
+    res = 0.0027 * 40.0
+    size, xy_min = covering_grid_args(x, y, res)
+    g = ogrid.regular_grid(size, xy_min, res)
+    gm = _gm(xrs, g)
+    _, ij = _device_rectify(xrs, x, y, gm)
+    assert_same(xrs.dev.to_host(ij), orect.rectify_ij(x, y, g), "ij")
+
+
+# ---------------------------------------------------------------------------
+# entry point, mirroring the reference's tests/test_rectify.py
+# ---------------------------------------------------------------------------
+LON_2X2 = np.array([[1.0, 6.0], [0.0, 2.0]])
+LAT_2X2 = np.array([[56.0, 53.0], [52.0, 50.0]])
+RAD_2X2 = np.array([[1.0, 2.0], [3.0, 4.0]])
+
+
+def _ds_2x2(xrs, rad=RAD_2X2, lon=LON_2X2):
+    return xrs.Dataset(data_vars=dict(rad=(("y", "x"), rad)),
+                       coords=dict(lon=(("y", "x"), lon), lat=(("y", "x"), LAT_2X2)))
+
+
+def test_rectify_dataset_2x2_to_default(xrs):
+    # tests/test_rectify.py:42-61
+    gm = xrs.GridMapping.regular(size=(4, 4), xy_min=(-1, 49), xy_res=2, crs=xrs.CRS_WGS84)
+    out = xrs.rectify_dataset(_ds_2x2(xrs), target_gm=gm, interp_methods=0)
+    np.testing.assert_almost_equal(out["rad"].values, np.array([
+        [nan, nan, nan, nan], [nan, 1.0, 2.0, nan], [3.0, 3.0, 2.0, nan], [nan, 4.0, nan, nan]]))
+    assert out["rad"].dims == ("lat", "lon")
+    assert "spatial_ref" in out.coords
+
+
+def test_rectify_dataset_2x2_to_regular(xrs):
+    # tests/test_rectify.py:63-78: target derived with to_regular()
+    out = xrs.rectify_dataset(_ds_2x2(xrs), interp_methods=0)
+    np.testing.assert_almost_equal(out["rad"].values, np.array([
+        [nan, nan, nan, nan], [nan, nan, nan, nan], [nan, 2.0, nan, nan], [nan, nan, nan, nan]]))
+
+
+def test_rectify_dataset_3d_and_passthrough(xrs):
+    # tests/test_rectify.py:80-110
+    rad = np.stack([RAD_2X2, RAD_2X2])
+    ds = xrs.Dataset(data_vars=dict(rad=(("time", "y", "x"), rad), time_series=(("time",), np.array([1, 2]))),
+                     coords=dict(lon=(("y", "x"), LON_2X2), lat=(("y", "x"), LAT_2X2), time=np.array([0, 1])))
+    gm = xrs.GridMapping.regular(size=(4, 4), xy_min=(-1, 49), xy_res=2, crs=xrs.CRS_WGS84)
+    out = xrs.rectify_dataset(ds, target_gm=gm, interp_methods=0)
+    exp = np.array([[nan, nan, nan, nan], [nan, 1.0, 2.0, nan], [3.0, 3.0, 2.0, nan], [nan, 4.0, nan, nan]])
+    np.testing.assert_almost_equal(out["rad"].values, np.stack([exp, exp]))
+    assert out["rad"].dims == ("time", "lat", "lon")
+    np.testing.assert_array_equal(out["time_series"].values, [1, 2])
+
+
+@pytest.mark.parametrize("tile_size", [None, 7, 5, (3, 13), (13, 3)])
+@pytest.mark.parametrize("j_up", [False, True])
+def test_rectify_dataset_2x2_to_13x13(xrs, tile_size, j_up):
+    # tests/test_rectify.py:261-387
+    from .test_oracle_golden import EXPECTED_RAD_13X13
+
+    gm = xrs.GridMapping.regular(size=(13, 13), xy_min=(-0.25, 49.75), xy_res=0.5, crs=xrs.CRS_WGS84,
+                                 tile_size=tile_size, is_j_axis_up=j_up)
+    out = xrs.rectify_dataset(_ds_2x2(xrs), target_gm=gm, interp_methods=0)
+    np.testing.assert_almost_equal(out["lon"].values, np.arange(0, 6.1, 0.5))
+    exp_lat = np.arange(50, 56.1, 0.5) if j_up else np.arange(56, 49.9, -0.5)
+    np.testing.assert_almost_equal(out["lat"].values, exp_lat)
+    np.testing.assert_almost_equal(out["rad"].values, EXPECTED_RAD_13X13[::-1] if j_up else EXPECTED_RAD_13X13)
+
+
+def test_rectify_dataset_antimeridian(xrs):
+    # tests/test_rectify.py:389-424
+    from .test_oracle_golden import EXPECTED_RAD_13X13
+
+    lon = np.array([[+179.0, -176.0], [+178.0, +180.0]])
+    gm = xrs.GridMapping.regular(size=(13, 13), xy_min=(177.75, 49.75), xy_res=0.5, crs=xrs.CRS_WGS84)
+    assert gm.is_lon_360 is True
+    out = xrs.rectify_dataset(_ds_2x2(xrs, lon=lon), target_gm=gm, interp_methods=0)
+    np.testing.assert_almost_equal(out["lon"].values, np.array(
+        [178.0, 178.5, 179.0, 179.5, 180.0, -179.5, -179.0, -178.5, -178.0, -177.5, -177.0, -176.5, -176.0]))
+    np.testing.assert_almost_equal(out["rad"].values, EXPECTED_RAD_13X13)
+
+
+@pytest.mark.parametrize("method,decimal,expected", [
+    ("triangular", 3, [
+        [nan, 1.000, nan, nan, nan, nan, nan],
+        [nan, 1.478, 1.391, nan, nan, nan, nan],
+        [nan, 1.957, 1.870, 1.784, 1.697, nan, nan],
+        [nan, 2.435, 2.348, 2.261, 2.174, 2.087, 2.000],
+        [3.000, 3.000, 3.000, 3.000, 3.000, nan, nan],
+        [nan, 4.000, 4.000, 4.000, nan, nan, nan],
+        [nan, nan, 5.000, nan, nan, nan, nan]]),
+    ("bilinear", 3, [
+        [nan, 1.000, nan, nan, nan, nan, nan],
+        [nan, 1.488, 1.410, nan, nan, nan, nan],
+        [nan, 1.994, 1.949, 1.858, 1.722, nan, nan],
+        [nan, 2.520, 2.506, 2.448, 2.344, 2.195, 2.000],
+        [3.000, 3.112, 3.163, 3.153, 3.082, nan, nan],
+        [nan, 4.000, 4.041, 4.020, nan, nan, nan],
+        [nan, nan, 5.000, nan, nan, nan, nan]]),
+])
+def test_rectify_dataset_7x7_interpolation(xrs, method, decimal, expected):
+    # tests/test_rectify.py:146-218
+    rad = RAD_2X2 + np.array([[0.0, 0.0], [0.0, 1.0]])
+    gm = xrs.GridMapping.regular(size=(7, 7), xy_min=(-0.5, 49.5), xy_res=1.0, crs=xrs.CRS_WGS84)
+    out = xrs.rectify_dataset(_ds_2x2(xrs, rad=rad), target_gm=gm, interp_methods=method)
+    np.testing.assert_almost_equal(out["rad"].values, np.array(expected), decimal=decimal)
+
+
+def test_rectify_dataset_invalid_method(xrs):
+    # tests/test_rectify.py:220-228
+    gm = xrs.GridMapping.regular(size=(7, 7), xy_min=(-0.5, 49.5), xy_res=1.0, crs=xrs.CRS_WGS84)
+    with pytest.raises(NotImplementedError):
+        xrs.rectify_dataset(_ds_2x2(xrs), target_gm=gm, interp_methods="cubic")
+
+
+@pytest.mark.parametrize("xy_min", [(10.0, 50.0), (-10.0, 50.0), (0.0, 58.0), (0.0, 42.0)])
+def test_rectify_dataset_no_overlap(xrs, xy_min):
+    # tests/test_rectify.py:426-459
+    gm = xrs.GridMapping.regular(size=(13, 13), xy_min=xy_min, xy_res=0.5, crs=xrs.CRS_WGS84)
+    out = xrs.rectify_dataset(_ds_2x2(xrs), target_gm=gm, interp_methods=0)
+    assert np.isnan(out["rad"].values).all()
+
+
+def test_c_abi_rejects_bad_arguments(xrs):
+    from xcube_resampling_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.xrs_gather_ij(None, None, 1, 0, 4, 4, 4, None, 4, 4, 0, 0.0, None) != 0
+    assert b"null" in lib.xrs_last_error()

@@ -1,0 +1,83 @@
+"""Device-buffer plumbing: torch tensors as HBM buffers, nothing else.
+
+torch is used for allocation, host<->device copies (pinned staging) and stream
+handles; every computation happens in libxrs.so.
+"""
+
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from ._lib import XrsError
+
+_TORCH_DTYPES = {
+    np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64, np.dtype(np.uint8): torch.uint8,
+    np.dtype(np.int8): torch.int8, np.dtype(np.int16): torch.int16, np.dtype(np.int32): torch.int32,
+    np.dtype(np.int64): torch.int64, np.dtype(np.uint16): torch.uint16, np.dtype(np.uint32): torch.uint32,
+}
+
+
+def require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise XrsError("no CUDA device available: xcube_resampling_b200 has no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def torch_dtype(np_dtype) -> torch.dtype:
+    dt = np.dtype(np_dtype)
+    if dt not in _TORCH_DTYPES:
+        raise TypeError(f"unsupported data type {dt}")
+    return _TORCH_DTYPES[dt]
+
+
+def to_device(array, device=None, dtype=None) -> torch.Tensor:
+    """numpy (or torch) array -> contiguous device tensor (H2D through pinned memory)."""
+    dev = require_cuda(device)
+    if isinstance(array, torch.Tensor):
+        t = array
+        if dtype is not None:
+            t = t.to(torch_dtype(dtype))
+        return t.to(dev, non_blocking=True).contiguous()
+    a = np.ascontiguousarray(array if dtype is None else np.asarray(array, dtype=dtype))
+    t = torch.from_numpy(a)
+    if a.nbytes >= (1 << 20):
+        t = t.pin_memory()
+    return t.to(dev, non_blocking=True)
+
+
+def to_host(t: torch.Tensor) -> np.ndarray:
+    """device tensor -> numpy via a pinned host buffer."""
+    if t.device.type != "cuda":
+        return t.numpy()
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=t.numel() * t.element_size() >= (1 << 20))
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host.numpy()
+
+
+def empty(shape, np_dtype, device=None) -> torch.Tensor:
+    return torch.empty(tuple(int(s) for s in shape), dtype=torch_dtype(np_dtype), device=require_cuda(device))
+
+
+def workspace(n_bytes: int, device=None) -> torch.Tensor:
+    return torch.empty(max(int(n_bytes), 16), dtype=torch.uint8, device=require_cuda(device))
+
+
+def ptr(t: torch.Tensor) -> ctypes.c_void_p:
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr_array(tensors) -> ctypes.Array:
+    arr = (ctypes.c_void_p * len(tensors))()
+    for k, t in enumerate(tensors):
+        arr[k] = t.data_ptr()
+    return arr

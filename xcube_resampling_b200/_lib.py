@@ -1,0 +1,80 @@
+"""ctypes binding of ``libxrs.so`` (the C ABI declared in ``include/xrs.h``).
+
+There is no CPU fallback: if the shared library is missing or cannot be loaded
+the first call raises.  Build it with ``python -m xcube_resampling_b200.build``.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxrs.so")
+
+c_int = ctypes.c_int
+c_i32 = ctypes.c_int32
+c_i64 = ctypes.c_int64
+c_f64 = ctypes.c_double
+c_p = ctypes.c_void_p
+
+
+class XrsError(RuntimeError):
+    """A libxrs call returned a non-zero status."""
+
+
+class XrsProj(ctypes.Structure):
+    """``struct xrs_proj`` of include/xrs.h."""
+
+    _fields_ = [("kind", c_i32), ("_pad", c_i32), ("a", c_f64), ("inv_f", c_f64), ("lon0", c_f64),
+                ("lat0", c_f64), ("k0", c_f64), ("fe", c_f64), ("fn", c_f64)]
+
+    @classmethod
+    def from_crs(cls, crs) -> "XrsProj":
+        kind, a, inv_f, lon0, lat0, k0, fe, fn = crs.proj_params()
+        return cls(kind, 0, a, inv_f, lon0, lat0, k0, fe, fn)
+
+
+# name -> (restype, argtypes); must list every symbol of include/xrs.h
+SIGNATURES = {
+    "xrs_version": (c_int, []),
+    "xrs_device_count": (c_int, []),
+    "xrs_last_error": (ctypes.c_char_p, []),
+    "xrs_tile_src_bboxes_workspace_bytes": (c_i64, [c_i32, c_i32]),
+    "xrs_tile_src_bboxes": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_i32, c_p, c_p, c_i32, c_i32, c_p,
+                                    c_p, c_p]),
+    "xrs_rectify_ij_workspace_bytes": (c_i64, [c_i64, c_i64, c_i32, c_i32]),
+    "xrs_rectify_ij": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_i64, c_i64, c_i32, c_i32, c_f64, c_f64,
+                               c_f64, c_f64, c_f64, c_i32, c_f64, c_p, c_p]),
+    "xrs_gather_ij": (c_int, [c_p, c_p, c_i32, c_i32, c_i64, c_i64, c_i64, c_p, c_i64, c_i64, c_i32, c_f64, c_p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load libxrs.so (once) and type every entry point.  Fails loudly."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise XrsError(
+                f"{LIB_PATH} not found: the CUDA extension is not built. Run "
+                "`python -m xcube_resampling_b200.build` (needs nvcc); there is no CPU fallback."
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is missing
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str = "libxrs call"):
+    if rc != 0:
+        msg = load().xrs_last_error().decode("utf-8", "replace")
+        raise XrsError(f"{what} failed (status {rc}): {msg}")
