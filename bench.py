@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the rectify hot path on B200 (BASELINE.json configs[1], "C2").
+
+Workload: Sentinel-3 OLCI-shaped swath (4865 x 4091 lon/lat float64, 21 float32 bands) rectified to
+a regular 0.0027 deg (~300 m) EPSG:4326 grid with nearest AND bilinear interpolation.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One *step* on N GPUs rectifies N scenes; every scene is cut into N target row bands and rank r
+computes band r of every scene (no collective; weak scaling: one scene-equivalent per GPU and step).
+A scene pass = rectify(nearest) + rectify(bilinear), each a complete K0 (tile windows) + K1 (ij
+image) + K2 (gather of all 21 bands).  ``value`` is output Mpix*band/s with the inputs resident in
+HBM; ``e2e`` is the same metric through ``rectify_dataset`` with host (pinned) inputs and host
+outputs, copies inside the timed region.  Rank 0 prints ONE JSON line.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "output Mpix*band/s"
+UNIT = "Mpix*band/s"
+TILE = 512
+METHODS = ("nearest", "bilinear")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the scene (debugging only; 1.0 = BASELINE config)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (debugging only)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (debugging only)")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------
+def make_scene(scale=1.0, seed=0, n_bands=None):
+    from xcube_resampling_b200 import synthetic as syn
+
+    w = max(64, int(round(syn.OLCI_WIDTH * scale)))
+    h = max(64, int(round(syn.OLCI_HEIGHT * scale)))
+    nb = syn.OLCI_BANDS if n_bands is None else n_bands
+    lon, lat = syn.swath(w, h, res=syn.OLCI_RES_DEG, theta=12.0, seed=seed)
+    size, xy_min = syn.covering_grid_args(lon, lat, syn.OLCI_RES_DEG)
+    bands = syn.band_stack(nb, h, w, seed=seed)
+    return lon, lat, bands, size, xy_min, syn.OLCI_RES_DEG
+
+
+def workload_config(w, h, nb, size, n_gpus):
+    return {
+        "workload": "rectify_dataset: OLCI-shaped swath -> regular 300 m EPSG:4326 grid, nearest + bilinear",
+        "source": f"{w}x{h} lon/lat float64, {nb} float32 bands",
+        "target": f"{size[0]}x{size[1]} @0.0027deg, reference tile_size {TILE}",
+        "scene_pass": "rectify(nearest)+rectify(bilinear); each = K0 tile windows + K1 ij image + K2 gather",
+        "scenes_per_step": n_gpus,
+        "partition": "target row bands, rank r = band r of every scene, no collective",
+        "l2": "inputs (2.0 GB) and outputs (3.3 GB per method) exceed the 126 MB L2; no explicit flush",
+    }
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's kernels on the host cores
+# ---------------------------------------------------------------------------
+def cpu_scene_pass(orect, ogrid, lon, lat, bands, size, xy_min, res):
+    """One scene pass with the C restatement of the reference kernels (all OpenMP threads)."""
+    g = ogrid.regular_grid(size, xy_min, res, tile_size=TILE)
+    n = 0
+    for method in METHODS:
+        windows = orect.source_windows(lon, lat, g)
+        ij = orect.rectify_ij(lon, lat, g, windows=windows)
+        out = orect.gather(bands, ij, method, np.nan)
+        n += out.size
+    return n
+
+
+def run_cpu(steps, warmup, scale):
+    import oracle
+    from oracle import grid as ogrid
+    from oracle import rectify as orect
+
+    oracle.build()
+    lon, lat, bands, size, xy_min, res = make_scene(scale=scale)
+    cores = oracle.lib().xrso_num_threads()
+    for _ in range(warmup):
+        cpu_scene_pass(orect, ogrid, lon, lat, bands, size, xy_min, res)
+    t0 = time.perf_counter()
+    units = 0
+    for _ in range(steps):
+        units += cpu_scene_pass(orect, ogrid, lon, lat, bands, size, xy_min, res)
+    dt = time.perf_counter() - t0
+    h, w = lon.shape
+    sample = (f"{steps} scene pass(es) of a {w}x{h} swath ({scale:g}x linear scale of the workload), "
+              f"{bands.shape[0]} bands, -> {size[0]}x{size[1]}, nearest+bilinear, {dt:.1f} s")
+    return units / dt / 1e6, cores, sample, dt / steps * 1e3, (w, h, bands.shape[0], size)
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU algorithm (oracle port, kind 'port') on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scale = 0.5 * args.scale
+    value, cores, sample, ms, _sample_dims = run_cpu(args.steps, args.warmup, scale)
+    # describe the full workload (same strings as the GPU arm); the sample is named separately
+    from xcube_resampling_b200 import synthetic as syn
+
+    w, h = max(64, int(round(syn.OLCI_WIDTH * args.scale))), max(64, int(round(syn.OLCI_HEIGHT * args.scale)))
+    lon, lat = syn.swath(w, h, res=syn.OLCI_RES_DEG, theta=12.0, seed=0)
+    size, _ = syn.covering_grid_args(lon, lat, syn.OLCI_RES_DEG)
+    nb = syn.OLCI_BANDS
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(w, h, nb, size, 1) | {"bounded_sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import xcube_resampling_b200 as xrs
+    from xcube_resampling_b200 import _dev, _lib, bands as xbands, rectify as xrect
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- scene + geometry (every rank builds the same synthetic scene) ----------------
+    lon, lat, bands, size, xy_min, res = make_scene(scale=args.scale)
+    nb, h, w = bands.shape
+    target_gm = xrs.GridMapping.regular(size, xy_min, res, "EPSG:4326", tile_size=TILE)
+    source_gm = xrs.GridMapping.from_coords(lon, lat, "EPSG:4326", xy_res=res, xy_dim_names=("x", "y"))
+    W_t, H_t = target_gm.size
+    rows = xbands.row_bands(H_t, world, align=32)[rank]
+    band_px = (rows[1] - rows[0]) * W_t
+
+    # ---- device residency: full coordinates + the band's source footprint of all bands ----
+    x_dev = _dev.to_device(lon)
+    y_dev = _dev.to_device(lat)
+    plan = xrect.RectifyPlan(target_gm, dev, rows=rows)
+    boxes_host = _dev.to_host(plan.windows(x_dev, y_dev))
+    fp = xbands.rectify_band_footprint(boxes_host, target_gm, rows, (w, h)) or (0, 0, w, min(h, 2))
+    fi0, fj0, fi1, fj1 = 0, fp[1], w, fp[3]  # full-width rows of the footprint
+    src_dev = _dev.to_device(bands[:, fj0:fj1, :])
+    outs = {m: torch.empty((nb, rows[1] - rows[0], W_t), dtype=torch.float32, device=dev) for m in METHODS}
+    torch.cuda.synchronize()
+
+    phase_ms = {"k0": 0.0, "k1": 0.0, "k2_nearest": 0.0, "k2_bilinear": 0.0}
+    pending = []
+
+    def scene_pass(record):
+        for m in METHODS:
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
+            if record:
+                evs[0].record()
+            boxes = plan.windows(x_dev, y_dev)
+            if record:
+                evs[1].record()
+            ij = plan.ij(x_dev, y_dev, boxes)
+            if record:
+                evs[2].record()
+            xrect.gather_ij(src_dev, ij, m, np.nan, out=outs[m], window_origin=(fi0, fj0), full_size=(w, h))
+            if record:
+                evs[3].record()
+                pending.append((m, evs))
+
+    def step(record=False):
+        for _scene in range(world):
+            scene_pass(record)
+
+    # ---- device-resident timing ------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.xrs_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(record=True)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = lib.xrs_launch_count() - launches0
+    my_ms = e0.elapsed_time(e1)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = max_over_ranks(my_ms)
+    units_rank = args.steps * world * len(METHODS) * nb * band_px
+    units = sum_over_ranks(float(units_rank))
+    value = units / (total_ms * 1e-3) / 1e6
+    for m, evs in pending:
+        phase_ms["k0"] += evs[0].elapsed_time(evs[1])
+        phase_ms["k1"] += evs[1].elapsed_time(evs[2])
+        phase_ms["k2_" + m] += evs[2].elapsed_time(evs[3])
+    n_pass = args.steps * world
+    phase_ms = {k: v / n_pass / (len(METHODS) if k in ("k0", "k1") else 1) for k, v in phase_ms.items()}
+
+    # ---- roofline of the dominant kernel: K2 bilinear gather of all bands -------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    s_used = (fj1 - fj0) * w  # source pixels resident for this band
+    k2_bytes = 16.0 * band_px + 4.0 * nb * s_used + 4.0 * nb * band_px
+    k2_ms = phase_ms["k2_bilinear"]
+    achieved = k2_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
+    roofline = {
+        "bound": "hbm", "kernel": "k2_gather<float, bilinear> (21 bands fused)", "achieved": achieved, "peak": peak,
+        "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "algorithmic_bytes_per_launch": k2_bytes,
+        "bytes_model": "16*T (ij) + 4*B*S_used (source once) + 4*B*T (output once)", "ms_per_launch": k2_ms,
+        "phase_ms_per_rectify": phase_ms,
+    }
+
+    # ---- end to end through the public API with host buffers --------------------------
+    e2e = None
+    if not args.no_e2e:
+        # page-locked host inputs; this rank's band of the target grid as its own GridMapping
+        lon_p, lat_p = _dev.pinned_empty(lon.shape, np.float64), _dev.pinned_empty(lat.shape, np.float64)
+        lon_p[...] = lon
+        lat_p[...] = lat
+        bands_p = _dev.pinned_empty((nb, fj1 - fj0, w), np.float32)
+        bands_p[...] = bands[:, fj0:fj1, :]
+        e2e_steps = max(1, min(args.steps, 3))
+
+        ds = xrs.Dataset(data_vars=dict(bands=(("band", "y", "x"), bands_p)),
+                         coords=dict(lon=(("y", "x"), lon_p), lat=(("y", "x"), lat_p)))
+
+        def e2e_step():
+            n = 0
+            for _scene in range(world):
+                for m in METHODS:
+                    if world == 1:  # the call a user makes
+                        out = xrs.rectify_dataset(ds, target_gm=target_gm, source_gm=source_gm,
+                                                  interp_methods=m)["bands"].values
+                    else:           # the same device pipeline on this rank's row band
+                        out = xrect.rectify_band_host(lon_p, lat_p, bands_p, (fi0, fj0), (w, h), target_gm, rows,
+                                                      m, np.nan)
+                    n += out.size
+            return n
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_units = 0
+        for _ in range(e2e_steps):
+            n_units += e2e_step()
+        torch.cuda.synchronize()
+        dt_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        n_units = sum_over_ranks(float(n_units))
+        h2d = world * len(METHODS) * (lon_p.nbytes + lat_p.nbytes + bands_p.nbytes)
+        d2h = world * len(METHODS) * nb * band_px * 4
+        e2e = {"value": n_units / (dt_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": dt_ms / e2e_steps,
+               "api": ("rectify_dataset(ds, target_gm, source_gm, interp_methods)" if world == 1 else
+                       "rectify_band_host (rectify_dataset's device pipeline on this rank's row band)")
+                      + ": pinned host arrays in, pinned host arrays out, host clock around synchronised calls"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, cores, sample, _ms, _ = run_cpu(steps=2, warmup=1, scale=0.5 * args.scale)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(w, h, nb, size, world), "clocks": clocks, "e2e": e2e,
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

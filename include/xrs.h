@@ -70,6 +70,8 @@ typedef struct xrs_proj {
 int xrs_version(void);
 int xrs_device_count(void);
 const char *xrs_last_error(void);
+/* number of kernels this library has launched in the calling process (all threads) */
+uint64_t xrs_launch_count(void);
 
 /* ------------------------------------------------------------------------
  * Rectification (rectify.py)
@@ -105,26 +107,33 @@ int xrs_tile_src_bboxes(const double *x, const double *y, int64_t src_h, int64_t
  *   tile_w/h      the reference tile size of the target grid mapping
  *   x_min,y_min,y_max,x_res,y_res,is_j_axis_up  target grid (rectify.py:402-416)
  *   uv_delta      barycentric tolerance (constants.py:80, 1e-3)
+ *   row_begin/end only target rows [row_begin, row_end) are computed (multi-GPU row
+ *                 bands); ij then is (2, row_end-row_begin, dst_w).  Results do not
+ *                 depend on the band split.
  * workspace: xrs_rectify_ij_workspace_bytes(dst_h, dst_w, tile_h, tile_w) bytes. */
 int64_t xrs_rectify_ij_workspace_bytes(int64_t dst_h, int64_t dst_w, int32_t tile_h, int32_t tile_w);
 int xrs_rectify_ij(const double *x, const double *y, int64_t src_h, int64_t src_w, int64_t src_pitch,
                    const int64_t *tile_boxes, double *ij, int64_t dst_h, int64_t dst_w, int32_t tile_h,
                    int32_t tile_w, double x_min, double y_min, double y_max, double x_res, double y_res,
-                   int32_t is_j_axis_up, double uv_delta, void *workspace, void *stream);
+                   int32_t is_j_axis_up, double uv_delta, int64_t row_begin, int64_t row_end, void *workspace,
+                   void *stream);
 
 /* K2 -- gather of all bands through the ij image.
  * Replaces _compute_var_image / _compute_var_image_block /
  * _compute_var_image_sequential / _for_dest_line (rectify.py:579-734).
- *   src_planes_host  HOST array of n_bands device pointers, each a
- *                    (src_h, src_w) plane of `dtype`, pitch src_pitch
+ *   src_planes_host  HOST array of n_bands device pointers, each pointing at element
+ *                    (win_j0, win_i0) of a (src_h, src_w) plane of `dtype`, row pitch
+ *                    src_pitch: only the window the ij values reach has to be resident
+ *                    (row-band footprints); src_h/src_w stay the full image size
+ *                    because neighbour taps clamp at the true image edge
  *   dst_planes_host  HOST array of n_bands device pointers, each a
  *                    (dst_h, dst_w) plane of `dtype`, contiguous rows
  *   ij               (2, dst_h, dst_w) float64 from xrs_rectify_ij
  *   fill             value written where ij is NaN (cast to dtype with a C cast)
  * Arithmetic is float64 without FMA contraction, one C cast to dtype at the end. */
 int xrs_gather_ij(const void *const *src_planes_host, void *const *dst_planes_host, int32_t n_bands,
-                  int32_t dtype, int64_t src_h, int64_t src_w, int64_t src_pitch, const double *ij,
-                  int64_t dst_h, int64_t dst_w, int32_t method, double fill, void *stream);
+                  int32_t dtype, int64_t src_h, int64_t src_w, int64_t src_pitch, int64_t win_i0, int64_t win_j0,
+                  const double *ij, int64_t dst_h, int64_t dst_w, int32_t method, double fill, void *stream);
 
 #ifdef __cplusplus
 }

@@ -19,26 +19,7 @@ def grid_from_golden(vec) -> ogrid.RegularGrid:
                              float(y_max), float(x_res), float(y_res), bool(j_up))
 
 
-def swath(width, height, res=0.0027, theta=12.0, seed=0, lon0=10.0, lat0=45.0):
-    """OLCI-like rotated swath with a smooth sub-pixel perturbation."""
-    i = np.arange(width, dtype=np.float64)[None, :]
-    j = np.arange(height, dtype=np.float64)[:, None]
-    a = (i - width / 2) * res
-    b = (height / 2 - j) * res
-    th = np.deg2rad(theta)
-    lat = lat0 + a * np.sin(th) + b * np.cos(th)
-    lon = lon0 + (a * np.cos(th) - b * np.sin(th)) / np.cos(np.deg2rad(lat))
-    lon = lon + 0.1 * res * np.sin(i / 37.0 + seed) * np.cos(j / 29.0)
-    lat = lat + 0.1 * res * np.cos(i / 31.0) * np.sin(j / 41.0 + seed)
-    return lon, lat
-
-
-def covering_grid_args(x, y, res):
-    """(size, xy_min) of a regular grid at *res* covering finite coordinates x, y."""
-    xf, yf = x[np.isfinite(x)], y[np.isfinite(y)]
-    w = int(np.ceil((xf.max() - xf.min()) / res)) + 1
-    h = int(np.ceil((yf.max() - yf.min()) / res)) + 1
-    return (w, h), (float(xf.min()) - res / 2, float(yf.min()) - res / 2)
+from xcube_resampling_b200.synthetic import covering_grid_args, swath  # noqa: E402,F401
 
 
 def assert_same(a, b, what=""):

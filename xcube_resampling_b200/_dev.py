@@ -44,10 +44,11 @@ def to_device(array, device=None, dtype=None) -> torch.Tensor:
             t = t.to(torch_dtype(dtype))
         return t.to(dev, non_blocking=True).contiguous()
     a = np.ascontiguousarray(array if dtype is None else np.asarray(array, dtype=dtype))
-    t = torch.from_numpy(a)
-    if a.nbytes >= (1 << 20):
-        t = t.pin_memory()
-    return t.to(dev, non_blocking=True)
+    if not a.flags.writeable:
+        a = a.copy()
+    # Pinned inputs (see pinned_empty) go over DMA asynchronously; pageable ones are staged by the
+    # driver.  No extra host-side staging copy is made here.
+    return torch.from_numpy(a).to(dev, non_blocking=True)
 
 
 def to_host(t: torch.Tensor) -> np.ndarray:
@@ -58,6 +59,12 @@ def to_host(t: torch.Tensor) -> np.ndarray:
     host.copy_(t, non_blocking=True)
     torch.cuda.current_stream(t.device).synchronize()
     return host.numpy()
+
+
+def pinned_empty(shape, np_dtype) -> np.ndarray:
+    """Page-locked host array (numpy view of a pinned torch tensor) for fast H2D/D2H."""
+    t = torch.empty(tuple(int(s) for s in shape), dtype=torch_dtype(np_dtype), pin_memory=torch.cuda.is_available())
+    return t.numpy()
 
 
 def empty(shape, np_dtype, device=None) -> torch.Tensor:

@@ -41,13 +41,15 @@ SIGNATURES = {
     "xrs_version": (c_int, []),
     "xrs_device_count": (c_int, []),
     "xrs_last_error": (ctypes.c_char_p, []),
+    "xrs_launch_count": (ctypes.c_uint64, []),
     "xrs_tile_src_bboxes_workspace_bytes": (c_i64, [c_i32, c_i32]),
     "xrs_tile_src_bboxes": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_i32, c_p, c_p, c_i32, c_i32, c_p,
                                     c_p, c_p]),
     "xrs_rectify_ij_workspace_bytes": (c_i64, [c_i64, c_i64, c_i32, c_i32]),
     "xrs_rectify_ij": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_i64, c_i64, c_i32, c_i32, c_f64, c_f64,
-                               c_f64, c_f64, c_f64, c_i32, c_f64, c_p, c_p]),
-    "xrs_gather_ij": (c_int, [c_p, c_p, c_i32, c_i32, c_i64, c_i64, c_i64, c_p, c_i64, c_i64, c_i32, c_f64, c_p]),
+                               c_f64, c_f64, c_f64, c_i32, c_f64, c_i64, c_i64, c_p, c_p]),
+    "xrs_gather_ij": (c_int, [c_p, c_p, c_i32, c_i32, c_i64, c_i64, c_i64, c_i64, c_i64, c_p, c_i64, c_i64, c_i32,
+                              c_f64, c_p]),
 }
 
 _lock = threading.Lock()

@@ -1,9 +1,14 @@
 // capi.cu -- library-level entry points and error plumbing of libxrs.so.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace xrs {
 
 static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const std::string &msg) { g_last_error = msg; }
 
@@ -34,5 +39,7 @@ int xrs_device_count(void) {
 }
 
 const char *xrs_last_error(void) { return xrs::g_last_error.c_str(); }
+
+uint64_t xrs_launch_count(void) { return xrs::g_launches.load(std::memory_order_relaxed); }
 
 }  // extern "C"

@@ -22,7 +22,13 @@ int check_cuda(cudaError_t e, const char *what);
         if (_rc) return _rc;                             \
     } while (0)
 
-#define XRS_LAUNCH_CHECK(name) XRS_CUDA((cudaGetLastError()))
+void count_launch();
+
+#define XRS_LAUNCH_CHECK(name)            \
+    do {                                  \
+        ::xrs::count_launch();            \
+        XRS_CUDA((cudaGetLastError()));   \
+    } while (0)
 
 __host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

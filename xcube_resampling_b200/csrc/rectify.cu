@@ -177,6 +177,8 @@ struct RectGeom {
     int j_up;
     double uv_delta;
     int4 *cta_win;  // per CTA tile: quad-index bounds (i_lo, j_lo, i_hi, j_hi), inclusive
+    int64_t row_begin, row_end;  // target rows computed by this call; ij holds exactly these rows
+    int cy_begin, cy_end;        // CTA tile rows intersecting [row_begin, row_end)
 };
 
 __device__ __forceinline__ double tri_det(double ax, double ay, double bx, double by, double cx, double cy) {
@@ -259,8 +261,9 @@ __global__ void __launch_bounds__(256) k1_bin_quads(RectGeom g) {
         const int gy0 = static_cast<int>(floor(fmax(lo_y, 0.0))), gy1 = static_cast<int>(floor(fmin(hi_y, H - 1.0)));
         cxa = cta_index_of_px(gx0, g.tile_w, g.ncx_per_tile, K1_CW);
         cxb = cta_index_of_px(gx1, g.tile_w, g.ncx_per_tile, K1_CW);
-        cya = cta_index_of_px(gy0, g.tile_h, g.ncy_per_tile, K1_CH);
-        cyb = cta_index_of_px(gy1, g.tile_h, g.ncy_per_tile, K1_CH);
+        cya = max(cta_index_of_px(gy0, g.tile_h, g.ncy_per_tile, K1_CH), g.cy_begin);
+        cyb = min(cta_index_of_px(gy1, g.tile_h, g.ncy_per_tile, K1_CH), g.cy_end - 1);
+        valid = cya <= cyb;
     }
     // warp aggregation: lanes with the same CTA range share one set of atomics
     const unsigned m = __ballot_sync(0xffffffffu, valid);
@@ -322,19 +325,23 @@ __global__ void __launch_bounds__(K1_THREADS) k1_rectify_ij(RectGeom g) {
     K1Smem &s = *reinterpret_cast<K1Smem *>(k1_smem_raw);
     const int tid = threadIdx.x;
 
-    const int cta = blockIdx.x;
-    const int cy = cta / g.ncx_total, cx = cta - cy * g.ncx_total;
+    const int cy = g.cy_begin + blockIdx.x / g.ncx_total, cx = blockIdx.x % g.ncx_total;
+    const int cta = cy * g.ncx_total + cx;
     const int ty = cy / g.ncy_per_tile, sy = cy - ty * g.ncy_per_tile;
     const int tx = cx / g.ncx_per_tile, sx = cx - tx * g.ncx_per_tile;
     const int64_t r0 = static_cast<int64_t>(ty) * g.tile_h, c0 = static_cast<int64_t>(tx) * g.tile_w;
     const int th = static_cast<int>(min(static_cast<int64_t>(g.tile_h), g.dst_h - r0));
     const int tw = static_cast<int>(min(static_cast<int64_t>(g.tile_w), g.dst_w - c0));
-    const int lx0 = sx * K1_CW, ly0 = sy * K1_CH;  // CTA origin, tile-local px
-    const int lw = min(K1_CW, tw - lx0), lh = min(K1_CH, th - ly0);
-    if (lw <= 0 || lh <= 0) return;  // sub-tile beyond a clipped edge tile
+    const int lx0 = sx * K1_CW;  // CTA origin, tile-local px
+    const int lw = min(K1_CW, tw - lx0);
+    // rows of this CTA tile, clipped to the tile and to the requested row range
+    const int ly0 = static_cast<int>(max(static_cast<int64_t>(sy) * K1_CH, g.row_begin - r0));
+    const int ly1 = static_cast<int>(min(static_cast<int64_t>(min((sy + 1) * K1_CH, th)), g.row_end - r0));
+    const int lh = ly1 - ly0;
+    if (lw <= 0 || lh <= 0) return;  // sub-tile beyond a clipped edge tile or outside the row range
 
-    const int64_t plane = g.dst_h * g.dst_w;
-    double *out_i = g.ij + (r0 + ly0) * g.dst_w + c0 + lx0;
+    const int64_t plane = (g.row_end - g.row_begin) * g.dst_w;
+    double *out_i = g.ij + (r0 + ly0 - g.row_begin) * g.dst_w + c0 + lx0;
     double *out_j = out_i + plane;
 
     // reference tile window (rectify.py:393-399) intersected with this CTA's quad window
@@ -525,8 +532,8 @@ __device__ __forceinline__ double ld_f64(const T *p) { return static_cast<double
 
 template <typename T, int METHOD>
 __global__ void __launch_bounds__(K2_BX *K2_BY)
-k2_gather(PlaneTable<T> planes, int n_bands, int64_t src_h, int64_t src_w, int64_t src_pitch,
-          const double *__restrict__ ij, int64_t dst_h, int64_t dst_w, T fill) {
+k2_gather(PlaneTable<T> planes, int n_bands, int64_t src_h, int64_t src_w, int64_t src_pitch, int64_t win_i0,
+          int64_t win_j0, const double *__restrict__ ij, int64_t dst_h, int64_t dst_w, T fill) {
     const int64_t c = static_cast<int64_t>(blockIdx.x) * K2_BX + threadIdx.x;
     const int64_t r = static_cast<int64_t>(blockIdx.y) * K2_BY + threadIdx.y;
     if (c >= dst_w || r >= dst_h) return;
@@ -542,14 +549,14 @@ k2_gather(PlaneTable<T> planes, int n_bands, int64_t src_h, int64_t src_w, int64
     if (METHOD == XRS_NEAREST) {
         if (u > 0.5) i0 = min(max(i0 + 1, int64_t(0)), src_w - 1);
         if (v > 0.5) j0 = min(max(j0 + 1, int64_t(0)), src_h - 1);
-        const int64_t so = j0 * src_pitch + i0;
+        const int64_t so = (j0 - win_j0) * src_pitch + (i0 - win_i0);
 #pragma unroll 4
         for (int b = 0; b < n_bands; ++b) st_stream(planes.dst[b] + o, __ldg(planes.src[b] + so));
         return;
     }
     const int64_t i1 = min(max(i0 + 1, int64_t(0)), src_w - 1), j1 = min(max(j0 + 1, int64_t(0)), src_h - 1);
-    const int64_t o00 = j0 * src_pitch + i0, o01 = j0 * src_pitch + i1;
-    const int64_t o10 = j1 * src_pitch + i0, o11 = j1 * src_pitch + i1;
+    const int64_t o00 = (j0 - win_j0) * src_pitch + (i0 - win_i0), o01 = (j0 - win_j0) * src_pitch + (i1 - win_i0);
+    const int64_t o10 = (j1 - win_j0) * src_pitch + (i0 - win_i0), o11 = (j1 - win_j0) * src_pitch + (i1 - win_i0);
     if (METHOD == XRS_BILINEAR) {
 #pragma unroll 4
         for (int b = 0; b < n_bands; ++b) {
@@ -581,8 +588,8 @@ k2_gather(PlaneTable<T> planes, int n_bands, int64_t src_h, int64_t src_w, int64
 
 template <typename T>
 static int launch_gather(const void *const *src_planes, void *const *dst_planes, int n_bands, int64_t src_h,
-                         int64_t src_w, int64_t src_pitch, const double *ij, int64_t dst_h, int64_t dst_w,
-                         int method, double fill, cudaStream_t st) {
+                         int64_t src_w, int64_t src_pitch, int64_t win_i0, int64_t win_j0, const double *ij,
+                         int64_t dst_h, int64_t dst_w, int method, double fill, cudaStream_t st) {
     const dim3 block(K2_BX, K2_BY);
     const dim3 grid(static_cast<unsigned>(ceil_div(dst_w, K2_BX)), static_cast<unsigned>(ceil_div(dst_h, K2_BY)));
     T fill_t;
@@ -597,13 +604,13 @@ static int launch_gather(const void *const *src_planes, void *const *dst_planes,
         }
         switch (method) {
         case XRS_NEAREST:
-            k2_gather<T, XRS_NEAREST><<<grid, block, 0, st>>>(pt, nb, src_h, src_w, src_pitch, ij, dst_h, dst_w, fill_t);
+            k2_gather<T, XRS_NEAREST><<<grid, block, 0, st>>>(pt, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fill_t);
             break;
         case XRS_BILINEAR:
-            k2_gather<T, XRS_BILINEAR><<<grid, block, 0, st>>>(pt, nb, src_h, src_w, src_pitch, ij, dst_h, dst_w, fill_t);
+            k2_gather<T, XRS_BILINEAR><<<grid, block, 0, st>>>(pt, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fill_t);
             break;
         default:
-            k2_gather<T, XRS_TRIANGULAR><<<grid, block, 0, st>>>(pt, nb, src_h, src_w, src_pitch, ij, dst_h, dst_w, fill_t);
+            k2_gather<T, XRS_TRIANGULAR><<<grid, block, 0, st>>>(pt, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fill_t);
             break;
         }
         XRS_LAUNCH_CHECK("k2_gather");
@@ -674,8 +681,10 @@ int64_t xrs_rectify_ij_workspace_bytes(int64_t dst_h, int64_t dst_w, int32_t til
 int xrs_rectify_ij(const double *x, const double *y, int64_t src_h, int64_t src_w, int64_t src_pitch,
                    const int64_t *tile_boxes, double *ij, int64_t dst_h, int64_t dst_w, int32_t tile_h,
                    int32_t tile_w, double x_min, double y_min, double y_max, double x_res, double y_res,
-                   int32_t is_j_axis_up, double uv_delta, void *workspace, void *stream) {
+                   int32_t is_j_axis_up, double uv_delta, int64_t row_begin, int64_t row_end, void *workspace,
+                   void *stream) {
     if (!x || !y || !tile_boxes || !ij || !workspace) return fail("xrs_rectify_ij: null pointer");
+    if (row_begin < 0 || row_end > dst_h || row_begin >= row_end) return fail("xrs_rectify_ij: bad row range");
     if (src_h < 2 || src_w < 2 || src_pitch < src_w) return fail("xrs_rectify_ij: source must be at least 2x2");
     if (dst_h < 1 || dst_w < 1 || tile_h < 1 || tile_w < 1) return fail("xrs_rectify_ij: bad target shape");
     if (dst_h > (1 << 30) || dst_w > (1 << 30) || src_w > (1 << 30) || src_h > (1 << 30)) return fail("xrs_rectify_ij: image too large");
@@ -694,6 +703,10 @@ int xrs_rectify_ij(const double *x, const double *y, int64_t src_h, int64_t src_
     g.j_up = is_j_axis_up ? 1 : 0; g.uv_delta = uv_delta;
     g.cta_win = static_cast<int4 *>(workspace);
     const int64_t n_cta = static_cast<int64_t>(g.ncx_total) * g.ncy_total;
+    g.row_begin = row_begin; g.row_end = row_end;
+    g.cy_begin = static_cast<int>(row_begin / g.tile_h) * g.ncy_per_tile + static_cast<int>(row_begin % g.tile_h) / K1_CH;
+    g.cy_end = static_cast<int>((row_end - 1) / g.tile_h) * g.ncy_per_tile + static_cast<int>((row_end - 1) % g.tile_h) / K1_CH + 1;
+    const int64_t n_launch = static_cast<int64_t>(g.ncx_total) * (g.cy_end - g.cy_begin);
     if ((src_h - 1) * (src_w - 1) >= 0xffffffffLL) return fail("xrs_rectify_ij: source has too many quads");
 
     k1_init_windows<<<static_cast<unsigned>(ceil_div(n_cta, 256)), 256, 0, st>>>(g.cta_win, static_cast<int>(n_cta));
@@ -702,24 +715,25 @@ int xrs_rectify_ij(const double *x, const double *y, int64_t src_h, int64_t src_
     k1_bin_quads<<<bgrid, 256, 0, st>>>(g);
     XRS_LAUNCH_CHECK("k1_bin_quads");
     XRS_CUDA(cudaFuncSetAttribute(k1_rectify_ij, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Smem))));
-    k1_rectify_ij<<<static_cast<unsigned>(n_cta), K1_THREADS, sizeof(K1Smem), st>>>(g);
+    k1_rectify_ij<<<static_cast<unsigned>(n_launch), K1_THREADS, sizeof(K1Smem), st>>>(g);
     XRS_LAUNCH_CHECK("k1_rectify_ij");
     return 0;
 }
 
 int xrs_gather_ij(const void *const *src_planes_host, void *const *dst_planes_host, int32_t n_bands,
-                  int32_t dtype, int64_t src_h, int64_t src_w, int64_t src_pitch, const double *ij,
-                  int64_t dst_h, int64_t dst_w, int32_t method, double fill, void *stream) {
+                  int32_t dtype, int64_t src_h, int64_t src_w, int64_t src_pitch, int64_t win_i0, int64_t win_j0,
+                  const double *ij, int64_t dst_h, int64_t dst_w, int32_t method, double fill, void *stream) {
     if (!src_planes_host || !dst_planes_host || !ij) return fail("xrs_gather_ij: null pointer");
     if (n_bands < 1) return fail("xrs_gather_ij: n_bands must be >= 1");
     if (method != XRS_NEAREST && method != XRS_BILINEAR && method != XRS_TRIANGULAR)
         return fail("interp_methods must be one of 0, 1, 'nearest', 'bilinear', 'triangular'");
-    if (src_h < 1 || src_w < 1 || src_pitch < src_w || dst_h < 1 || dst_w < 1) return fail("xrs_gather_ij: bad shape");
+    if (src_h < 1 || src_w < 1 || src_pitch < 1 || dst_h < 1 || dst_w < 1) return fail("xrs_gather_ij: bad shape");
+    if (win_i0 < 0 || win_j0 < 0 || win_i0 >= src_w || win_j0 >= src_h) return fail("xrs_gather_ij: bad source window origin");
     if (ceil_div(dst_h, K2_BY) > 65535) return fail("xrs_gather_ij: target too tall for one launch");
     for (int b = 0; b < n_bands; ++b)
         if (!src_planes_host[b] || !dst_planes_host[b]) return fail("xrs_gather_ij: null plane pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    XRS_DISPATCH_DTYPE(dtype, T, return launch_gather<T>(src_planes_host, dst_planes_host, n_bands, src_h, src_w, src_pitch, ij, dst_h, dst_w, method, fill, st));
+    XRS_DISPATCH_DTYPE(dtype, T, return launch_gather<T>(src_planes_host, dst_planes_host, n_bands, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, method, fill, st));
     return 0;
 }
 

@@ -70,10 +70,72 @@ def _separable_axes(xy_bboxes: np.ndarray, xy_border: float):
     return x_lo, x_hi, y_lo, y_hi, ntx, nty
 
 
+class RectifyPlan:
+    """Device-resident constants and scratch buffers of one (source shape, target grid) pair.
+
+    Building the plan uploads the tile axis tables once and allocates the K0/K1 workspaces and
+    the ij buffer; afterwards :meth:`windows` and :meth:`ij` only enqueue kernels (no allocation,
+    no host<->device traffic, no synchronisation), which is what the steady state of a
+    scene-after-scene service looks like.
+    """
+
+    def __init__(self, target_gm: GridMapping, device=None, rows: tuple[int, int] | None = None,
+                 uv_delta: float = UV_DELTA, ij_border: int = 1):
+        lib = load()
+        self.lib = lib
+        self.gm = target_gm
+        self.device = _dev.require_cuda(device)
+        self.uv_delta = float(uv_delta)
+        self.ij_border = int(ij_border)
+        H, W = target_gm.height, target_gm.width
+        self.rows = (0, H) if rows is None else (int(rows[0]), int(rows[1]))
+        x_lo, x_hi, y_lo, y_hi, self.ntx, self.nty = _separable_axes(target_gm.xy_bboxes, _xy_border(target_gm))
+        self._axes = _dev.to_device(np.concatenate([x_lo, x_hi, y_lo, y_hi]), self.device)
+        self.tile_boxes = _dev.empty((self.ntx * self.nty, 4), np.int64, self.device)
+        self._ws0 = _dev.workspace(lib.xrs_tile_src_bboxes_workspace_bytes(self.ntx, self.nty), self.device)
+        self._ws1 = _dev.workspace(
+            lib.xrs_rectify_ij_workspace_bytes(H, W, target_gm.tile_height, target_gm.tile_width), self.device)
+        self.ij_buf = _dev.empty((2, self.rows[1] - self.rows[0], W), np.float64, self.device)
+
+    def windows(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """K0: per-reference-tile source windows, (n_tiles, 4) int64 on the device."""
+        _check_coords(x, y)
+        h, w = x.shape
+        base, ntx, nty = self._axes.data_ptr(), self.ntx, self.nty
+        check(self.lib.xrs_tile_src_bboxes(
+            _dev.ptr(x), _dev.ptr(y), h, w, x.stride(0), base, base + 8 * ntx, ntx, base + 16 * ntx,
+            base + 16 * ntx + 8 * nty, nty, self.ij_border, _dev.ptr(self.tile_boxes), _dev.ptr(self._ws0),
+            _dev.stream_ptr(self.device)), "xrs_tile_src_bboxes")
+        return self.tile_boxes
+
+    def ij(self, x: torch.Tensor, y: torch.Tensor, tile_boxes: torch.Tensor | None = None) -> torch.Tensor:
+        """K0 (unless ``tile_boxes`` is given) + K1: the source-index image of ``rows``."""
+        _check_coords(x, y)
+        if tile_boxes is None:
+            tile_boxes = self.windows(x, y)
+        gm = self.gm
+        x_min, y_min, x_max, y_max = gm.xy_bbox
+        h, w = x.shape
+        check(self.lib.xrs_rectify_ij(
+            _dev.ptr(x), _dev.ptr(y), h, w, x.stride(0), _dev.ptr(tile_boxes), _dev.ptr(self.ij_buf), gm.height,
+            gm.width, gm.tile_height, gm.tile_width, float(x_min), float(y_min), float(y_max), float(gm.x_res),
+            float(gm.y_res), int(bool(gm.is_j_axis_up)), self.uv_delta, self.rows[0], self.rows[1],
+            _dev.ptr(self._ws1), _dev.stream_ptr(self.device)), "xrs_rectify_ij")
+        return self.ij_buf
+
+
+def _check_coords(x: torch.Tensor, y: torch.Tensor):
+    if x.dtype != torch.float64 or y.dtype != torch.float64:
+        raise TypeError("source coordinates must be float64 device tensors")
+    if x.dim() != 2 or x.shape != y.shape or x.stride() != y.stride() or x.stride(1) != 1:
+        raise ValueError("x and y must be 2-D with the same shape and row-major layout")
+
+
 def tile_source_windows_dev(x: torch.Tensor, y: torch.Tensor, xy_bboxes: np.ndarray, xy_border: float,
                             ij_border: int) -> torch.Tensor:
-    """K0 on device coordinates; returns (n_tiles, 4) int64 on the device."""
+    """K0 on device coordinates for arbitrary separable boxes; (n_tiles, 4) int64 on the device."""
     lib = load()
+    _check_coords(x, y)
     x_lo, x_hi, y_lo, y_hi, ntx, nty = _separable_axes(xy_bboxes, xy_border)
     dev = x.device
     axes = _dev.to_device(np.concatenate([x_lo, x_hi, y_lo, y_hi]), dev)
@@ -98,38 +160,25 @@ def tile_source_windows_for_boxes(source_gm: GridMapping, xy_bboxes: np.ndarray,
 
 
 def compute_target_source_ij(x: torch.Tensor, y: torch.Tensor, target_gm: GridMapping,
-                             uv_delta: float = UV_DELTA, tile_boxes: torch.Tensor | None = None) -> torch.Tensor:
+                             uv_delta: float = UV_DELTA, tile_boxes: torch.Tensor | None = None,
+                             rows: tuple[int, int] | None = None) -> torch.Tensor:
     """``_compute_target_source_ij`` (rectify.py:312-370) on device buffers.
 
     x, y: (h, w) float64 device tensors with the source coordinates in the target
-    CRS.  Returns the (2, H, W) float64 source-index image on the device.
+    CRS.  Returns the (2, H, W) float64 source-index image on the device, or only
+    its target rows ``rows=(begin, end)`` (one row band of a multi-GPU split).
     """
-    lib = load()
-    if x.dtype != torch.float64 or y.dtype != torch.float64:
-        raise TypeError("source coordinates must be float64 device tensors")
-    if x.shape != y.shape or x.stride() != y.stride() or x.stride(1) != 1:
-        raise ValueError("x and y must have the same shape and row-major layout")
-    dev = x.device
-    if tile_boxes is None:
-        tile_boxes = tile_source_windows_dev(x, y, target_gm.xy_bboxes, _xy_border(target_gm), 1)
-    H, W = target_gm.height, target_gm.width
-    ij = _dev.empty((2, H, W), np.float64, dev)
-    ws = _dev.workspace(lib.xrs_rectify_ij_workspace_bytes(H, W, target_gm.tile_height, target_gm.tile_width), dev)
-    x_min, y_min, x_max, y_max = target_gm.xy_bbox
-    h, w = x.shape
-    check(lib.xrs_rectify_ij(
-        _dev.ptr(x), _dev.ptr(y), h, w, x.stride(0), _dev.ptr(tile_boxes), _dev.ptr(ij), H, W,
-        target_gm.tile_height, target_gm.tile_width, float(x_min), float(y_min), float(y_max),
-        float(target_gm.x_res), float(target_gm.y_res), int(bool(target_gm.is_j_axis_up)), float(uv_delta),
-        _dev.ptr(ws), _dev.stream_ptr(dev)), "xrs_rectify_ij")
-    return ij
+    return RectifyPlan(target_gm, x.device, rows=rows, uv_delta=uv_delta).ij(x, y, tile_boxes)
 
 
 def gather_ij(src: torch.Tensor, ij: torch.Tensor, interp_method: str, fill_value,
-              out: torch.Tensor | None = None) -> torch.Tensor:
+              out: torch.Tensor | None = None, window_origin: tuple[int, int] = (0, 0),
+              full_size: tuple[int, int] | None = None) -> torch.Tensor:
     """``_compute_var_image`` (rectify.py:579-734) on device buffers.
 
-    src: (bands, h, w) or (h, w) device tensor; ij: (2, H, W) float64.
+    src: (bands, h, w) or (h, w) device tensor; ij: (2, H, W) float64.  When only a
+    window of the source is resident (row-band footprint) ``window_origin=(i0, j0)``
+    is its position in the full image of size ``full_size=(width, height)``.
     """
     lib = load()
     if interp_method not in INTERP_CODES:
@@ -143,6 +192,8 @@ def gather_ij(src: torch.Tensor, ij: torch.Tensor, interp_method: str, fill_valu
         src3 = src3.contiguous()
     np_dtype = np.dtype(str(src3.dtype).replace("torch.", ""))
     bands, h, w = src3.shape
+    if full_size is not None:
+        w, h = int(full_size[0]), int(full_size[1])
     _, H, W = ij.shape
     if out is None:
         out = torch.empty((bands, H, W), dtype=src3.dtype, device=src3.device)
@@ -150,9 +201,31 @@ def gather_ij(src: torch.Tensor, ij: torch.Tensor, interp_method: str, fill_valu
     dst_planes = _dev.ptr_array([out[b] for b in range(bands)])
     fill = float(fill_value)
     check(lib.xrs_gather_ij(src_planes, dst_planes, bands, DTYPE_CODES[np_dtype], h, w, src3.stride(1),
-                            _dev.ptr(ij), H, W, INTERP_CODES[interp_method], fill, _dev.stream_ptr(src3.device)),
+                            int(window_origin[0]), int(window_origin[1]), _dev.ptr(ij), H, W,
+                            INTERP_CODES[interp_method], fill, _dev.stream_ptr(src3.device)),
           "xrs_gather_ij")
     return out[0] if squeeze else out
+
+
+def rectify_band_host(x: np.ndarray, y: np.ndarray, src_window: np.ndarray, window_origin: tuple[int, int],
+                      full_size: tuple[int, int], target_gm: GridMapping, rows: tuple[int, int], interp_method: str,
+                      fill_value, device=None) -> np.ndarray:
+    """Rectify one target row band from host buffers to a host buffer (multi-GPU building block).
+
+    x, y: full (h, w) source coordinates (needed to find the band's source windows);
+    src_window: (bands, wh, ww) window of the data variable whose element (0, 0, 0) is pixel
+    ``window_origin=(i0, j0)`` of the full ``full_size=(width, height)`` image and which covers
+    :func:`xcube_resampling_b200.bands.rectify_band_footprint` of ``rows``.
+    Returns (bands, rows[1]-rows[0], target width) in (pinned) host memory.
+    """
+    dev = _dev.require_cuda(device)
+    x_dev = _dev.to_device(x, dev, dtype=np.float64)
+    y_dev = _dev.to_device(y, dev, dtype=np.float64)
+    src_dev = _dev.to_device(src_window, dev)
+    plan = RectifyPlan(target_gm, dev, rows=rows)
+    ij = plan.ij(x_dev, y_dev)
+    out = gather_ij(src_dev, ij, interp_method, fill_value, window_origin=window_origin, full_size=full_size)
+    return _dev.to_host(out)
 
 
 # ---------------------------------------------------------------------------
