@@ -240,7 +240,7 @@ def ours(args):
     boxes_host = _dev.to_host(plan.windows(x_dev, y_dev))
     fp = xbands.rectify_band_footprint(boxes_host, target_gm, rows, (w, h)) or (0, 0, w, min(h, 2))
     fi0, fj0, fi1, fj1 = 0, fp[1], w, fp[3]  # full-width rows of the footprint
-    src_dev = _dev.to_device(bands[:, fj0:fj1, :])
+    src_dev = _dev.to_device_pitched(bands[:, fj0:fj1, :])  # 128-byte row pitch -> TMA-staged gather
     outs = {m: torch.empty((nb, rows[1] - rows[0], W_t), dtype=torch.float32, device=dev) for m in METHODS}
     torch.cuda.synchronize()
 

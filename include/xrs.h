@@ -110,8 +110,9 @@ int xrs_tile_src_bboxes(const double *x, const double *y, int64_t src_h, int64_t
  *   row_begin/end only target rows [row_begin, row_end) are computed (multi-GPU row
  *                 bands); ij then is (2, row_end-row_begin, dst_w).  Results do not
  *                 depend on the band split.
- * workspace: xrs_rectify_ij_workspace_bytes(dst_h, dst_w, tile_h, tile_w) bytes. */
-int64_t xrs_rectify_ij_workspace_bytes(int64_t dst_h, int64_t dst_w, int32_t tile_h, int32_t tile_w);
+ * workspace: xrs_rectify_ij_workspace_bytes(src_h, src_w, row_end - row_begin, dst_w) bytes,
+ *            16-byte aligned. */
+int64_t xrs_rectify_ij_workspace_bytes(int64_t src_h, int64_t src_w, int64_t dst_rows, int64_t dst_w);
 int xrs_rectify_ij(const double *x, const double *y, int64_t src_h, int64_t src_w, int64_t src_pitch,
                    const int64_t *tile_boxes, double *ij, int64_t dst_h, int64_t dst_w, int32_t tile_h,
                    int32_t tile_w, double x_min, double y_min, double y_max, double x_res, double y_res,
@@ -123,9 +124,11 @@ int xrs_rectify_ij(const double *x, const double *y, int64_t src_h, int64_t src_
  * _compute_var_image_sequential / _for_dest_line (rectify.py:579-734).
  *   src_planes_host  HOST array of n_bands device pointers, each pointing at element
  *                    (win_j0, win_i0) of a (src_h, src_w) plane of `dtype`, row pitch
- *                    src_pitch: only the window the ij values reach has to be resident
- *                    (row-band footprints); src_h/src_w stay the full image size
- *                    because neighbour taps clamp at the true image edge
+ *                    src_pitch: only the (win_h, win_w) window the ij values reach has
+ *                    to be resident (row-band footprints); src_h/src_w stay the full
+ *                    image size because neighbour taps clamp at the true image edge.
+ *                    A pitch that is a multiple of 16 bytes (and 16-byte aligned planes)
+ *                    enables the TMA-staged kernel; anything else runs the direct one.
  *   dst_planes_host  HOST array of n_bands device pointers, each a
  *                    (dst_h, dst_w) plane of `dtype`, contiguous rows
  *   ij               (2, dst_h, dst_w) float64 from xrs_rectify_ij
@@ -133,7 +136,8 @@ int xrs_rectify_ij(const double *x, const double *y, int64_t src_h, int64_t src_
  * Arithmetic is float64 without FMA contraction, one C cast to dtype at the end. */
 int xrs_gather_ij(const void *const *src_planes_host, void *const *dst_planes_host, int32_t n_bands,
                   int32_t dtype, int64_t src_h, int64_t src_w, int64_t src_pitch, int64_t win_i0, int64_t win_j0,
-                  const double *ij, int64_t dst_h, int64_t dst_w, int32_t method, double fill, void *stream);
+                  int64_t win_w, int64_t win_h, const double *ij, int64_t dst_h, int64_t dst_w, int32_t method,
+                  double fill, void *stream);
 
 #ifdef __cplusplus
 }

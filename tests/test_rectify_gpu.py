@@ -249,5 +249,5 @@ def test_c_abi_rejects_bad_arguments(xrs):
     from xcube_resampling_b200 import _lib
 
     lib = _lib.load()
-    assert lib.xrs_gather_ij(None, None, 1, 0, 4, 4, 4, 0, 0, None, 4, 4, 0, 0.0, None) != 0
+    assert lib.xrs_gather_ij(None, None, 1, 0, 4, 4, 4, 0, 0, 4, 4, None, 4, 4, 0, 0.0, None) != 0
     assert b"null" in lib.xrs_last_error()

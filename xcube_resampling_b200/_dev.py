@@ -51,6 +51,27 @@ def to_device(array, device=None, dtype=None) -> torch.Tensor:
     return torch.from_numpy(a).to(dev, non_blocking=True)
 
 
+def to_device_pitched(array, device=None, multiple_bytes: int = 128) -> torch.Tensor:
+    """Upload an (.., h, w) array into a device buffer whose row pitch is a multiple of
+    ``multiple_bytes`` and return the (.., h, w) view.  A 16-byte aligned pitch is what lets the
+    gather kernel stage source boxes with TMA tensor copies (include/xrs.h, xrs_gather_ij)."""
+    dev = require_cuda(device)
+    if isinstance(array, torch.Tensor):
+        src = array
+    else:
+        a = np.ascontiguousarray(array)
+        if not a.flags.writeable:
+            a = a.copy()
+        src = torch.from_numpy(a)
+    w = src.shape[-1]
+    per = max(1, multiple_bytes // src.element_size())
+    wp = -(-w // per) * per
+    buf = torch.empty(tuple(src.shape[:-1]) + (wp,), dtype=src.dtype, device=dev)
+    view = buf[..., :w]
+    view.copy_(src, non_blocking=True)
+    return view
+
+
 def to_host(t: torch.Tensor) -> np.ndarray:
     """device tensor -> numpy via a pinned host buffer."""
     if t.device.type != "cuda":

@@ -45,11 +45,11 @@ SIGNATURES = {
     "xrs_tile_src_bboxes_workspace_bytes": (c_i64, [c_i32, c_i32]),
     "xrs_tile_src_bboxes": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_i32, c_p, c_p, c_i32, c_i32, c_p,
                                     c_p, c_p]),
-    "xrs_rectify_ij_workspace_bytes": (c_i64, [c_i64, c_i64, c_i32, c_i32]),
+    "xrs_rectify_ij_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64, c_i64]),
     "xrs_rectify_ij": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_i64, c_i64, c_i32, c_i32, c_f64, c_f64,
                                c_f64, c_f64, c_f64, c_i32, c_f64, c_i64, c_i64, c_p, c_p]),
-    "xrs_gather_ij": (c_int, [c_p, c_p, c_i32, c_i32, c_i64, c_i64, c_i64, c_i64, c_i64, c_p, c_i64, c_i64, c_i32,
-                              c_f64, c_p]),
+    "xrs_gather_ij": (c_int, [c_p, c_p, c_i32, c_i32, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_p, c_i64,
+                              c_i64, c_i32, c_f64, c_p]),
 }
 
 _lock = threading.Lock()

@@ -28,6 +28,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
 SOURCES = {
     "capi.cu": [],
     "rectify.cu": ["-fmad=false"],
+    "rectify_ij.cu": ["-fmad=false"],
+    "gather.cu": ["-fmad=false"],
     "resample.cu": ["-fmad=false"],
     "reproject.cu": ["-fmad=false"],
 }

@@ -51,8 +51,11 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+// Make freshly initialised mbarriers visible to other threads AND to the async proxy (the TMA
+// engine completes transactions on them; without the proxy fence it faults on sm_100).
 __device__ __forceinline__ void mbar_fence_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -78,7 +81,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();
+        if (++spins > (1u << 26)) {
+            printf("xrs: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+            __trap();
+        }
     }
 }
 // global -> shared bulk copy; dst, src 16-byte aligned, bytes a multiple of 16.

@@ -1,0 +1,500 @@
+// rectify_ij.cu -- K1: the source-index (ij) image of a regular target grid.
+//
+//   xrs_rectify_ij   rectify.py:312-576 (_compute_target_source_ij*), 737-768 (_fdet/_fu/_fv/_fclamp)
+//
+// The reference scatters every source quad's two triangles onto the target tile sequentially and
+// lets the FIRST writer win.  Whether a quad accepts a pixel never depends on earlier writes, so
+// the result equals "per pixel, the accepting quad with the smallest row-major index wins".  That
+// form is order-free and runs as two kernels:
+//
+//   k1_scatter  one lane per source quad.  A warp marches down a strip of 31 quad columns, keeping
+//               the previous vertex row in registers (every coordinate is loaded once, coalesced).
+//               The quad's pixel box is scanned with division-free half-plane tests and each
+//               accepted pixel receives atomicMin(claim, quad index).
+//   k1_resolve  one thread per target pixel: the winning quad recomputes its barycentric
+//               coordinates with the reference's exact expressions and writes (i, j).
+//
+// All parity-critical arithmetic uses round-to-nearest intrinsics in the reference's expression
+// order (no FMA contraction) and the reference TILE-LOCAL offsets (rectify.py:402-416), so the ij
+// image is bit-identical to the numba kernel's for any reference tile size.
+//
+// (A first version gathered per target tile with the source window staged in shared memory by
+// bulk copies; it measured 3.0 ms on the OLCI scene against the scatter form's fraction of that,
+// because window over-fetch, two passes over the quads and divergent pixel loops cost ~100
+// warp-instructions per quad.  See DESIGN.md.)
+#include "common.cuh"
+
+namespace xrs {
+
+constexpr uint32_t K1_NOCLAIM = 0xffffffffu;
+constexpr int K1_SENTINEL = INT32_MIN;  // stands for np.int64 min (non-finite vertex)
+constexpr int K1S_ROWS = 64;            // quad rows marched by one warp
+constexpr int K1S_WARPS = 8;
+constexpr int K1R_THREADS = 256;
+
+struct IjGeom {
+    const double *x, *y;
+    int64_t src_h, src_w, src_pitch;
+    const int64_t *tile_boxes;
+    double *ij;
+    uint32_t *claims;  // (row_end - row_begin, dst_w): smallest accepting quad index per pixel
+    int64_t dst_h, dst_w;
+    int tile_h, tile_w, ntx, nty;
+    double x_min, y_min, y_max, x_res, y_res;
+    int j_up;
+    double uv_delta;
+    int64_t row_begin, row_end;  // target rows computed by this call
+    uint32_t *slow_list;         // quads that need the generic (multi-tile) treatment
+    unsigned int *slow_count;
+};
+
+__device__ __forceinline__ double tri_det(double ax, double ay, double bx, double by, double cx, double cy) {
+    return dsub(dmul(dsub(ax, bx), dsub(ay, cy)), dmul(dsub(ax, cx), dsub(ay, by)));
+}
+__device__ __forceinline__ double tri_u(double px, double py, double ax, double ay, double cx, double cy) {
+    return dsub(dmul(dsub(ax, px), dsub(ay, cy)), dmul(dsub(ay, py), dsub(ax, cx)));
+}
+__device__ __forceinline__ double tri_v(double px, double py, double ax, double ay, double bx, double by) {
+    return dsub(dmul(dsub(ay, py), dsub(ax, bx)), dmul(dsub(ax, px), dsub(ay, by)));
+}
+__device__ __forceinline__ double clamp01(double t) { return t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t); }
+
+// np.floor(v).astype(np.int64) reduced to int32: non-finite / out-of-range -> sentinel
+// (x86 gives INT64_MIN for those), everything else clamped to +-2^30, which preserves
+// every comparison against pixel ranges.
+__device__ __forceinline__ int floor_px(double v) {
+    const double f = floor(v);
+    if (!(f >= -9223372036854775808.0 && f < 9223372036854775808.0)) return K1_SENTINEL;
+    return static_cast<int>(fmin(fmax(f, -1073741824.0), 1073741824.0));
+}
+
+// floor_px(num / den) where the quotient is first approximated by num * fl(1/den) (error
+// < 4e-16 relative): only when that lands within 1e-9 (relative) of an integer can the floor
+// differ from the exactly rounded quotient's, and only then is the division carried out.
+__device__ __forceinline__ int floor_px_div(double num, double den, double inv_den) {
+    double q = num * inv_den;
+    if (fabs(q - rint(q)) <= 1e-9 * fmax(1.0, fabs(q))) q = ddiv(num, den);
+    return floor_px(q);
+}
+
+// rectify.py:558-573 acceptance of one triangle, exact form.
+__device__ __forceinline__ bool tri_accepts_exact(double nu, double nv, double det, double lo, double hi) {
+    const double u = ddiv(nu, det), v = ddiv(nv, det);
+    return u >= lo && v >= lo && dadd(u, v) <= hi;
+}
+
+// The same decision without divisions.  With s = sign(det), ad = |det| the three conditions
+// u >= lo, v >= lo, u + v <= hi become half-plane tests s*nu >= lo*ad, s*nv >= lo*ad,
+// s*(nu+nv) <= hi*ad.  The rounded quotients the reference compares differ from the real ones
+// by < 1e-15 (relative to ad) whenever the outcome is not already decided by another condition,
+// so outside a band of 1e-12*ad around the thresholds the decision is certain; inside the band
+// (and for NaN / infinite operands, where every comparison below is false) the exact form runs.
+struct TriTest {
+    double det, sgn, t_lo_m, t_lo_p, t_hi_m, t_hi_p;
+    bool live;
+};
+__device__ __forceinline__ TriTest make_tri_test(double det, double lo, double hi) {
+    TriTest t;
+    t.det = det;
+    t.live = det != 0.0;
+    t.sgn = det < 0.0 ? -1.0 : 1.0;
+    const double ad = fabs(det), m = 1e-12 * ad;
+    t.t_lo_m = lo * ad - m; t.t_lo_p = lo * ad + m;
+    t.t_hi_m = hi * ad - m; t.t_hi_p = hi * ad + m;
+    return t;
+}
+__device__ __forceinline__ bool tri_accepts(const TriTest &t, double nu, double nv, double lo, double hi) {
+    if (!t.live) return false;
+    const double a = t.sgn * nu, b = t.sgn * nv, c = a + b;
+    if (a < t.t_lo_m || b < t.t_lo_m || c > t.t_hi_p) return false;
+    if (a > t.t_lo_p && b > t.t_lo_p && c < t.t_hi_m) return true;
+    return tri_accepts_exact(nu, nv, t.det, lo, hi);
+}
+
+// floor(g / d) for 0 <= g < 2^30, 1 <= d < 2^30 via a float estimate and one correction step
+__device__ __forceinline__ int fast_div(int g, int d, float inv_d) {
+    int t = static_cast<int>(static_cast<float>(g) * inv_d);
+    const long long p = static_cast<long long>(t) * d;
+    if (p > g) --t;
+    else if (p + d <= g) ++t;
+    return t;
+}
+
+// reference tile geometry a lane keeps cached while its quads stay in the same tile
+struct TileCtx {
+    int id;                    // ty * ntx + tx, -1 = nothing cached
+    int r0, c0, th, tw;        // tile origin and clipped size
+    int dj_lo, dj_hi;          // tile-local rows inside [row_begin, row_end)
+    int qi_lo, qi_hi, qj_lo, qj_hi;  // quads inside the tile's source window (rectify.py:397-399)
+    double x_off, y_off;
+    bool has_window;
+};
+
+__device__ __forceinline__ void load_tile_ctx(const IjGeom &g, int ty, int tx, TileCtx &t) {
+    t.id = ty * g.ntx + tx;
+    t.r0 = ty * g.tile_h; t.c0 = tx * g.tile_w;
+    t.th = static_cast<int>(min(static_cast<int64_t>(g.tile_h), g.dst_h - t.r0));
+    t.tw = static_cast<int>(min(static_cast<int64_t>(g.tile_w), g.dst_w - t.c0));
+    t.dj_lo = static_cast<int>(max(int64_t(0), g.row_begin - t.r0));
+    t.dj_hi = static_cast<int>(min(static_cast<int64_t>(t.th), g.row_end - t.r0)) - 1;
+    const int64_t *bb = g.tile_boxes + 4 * static_cast<int64_t>(t.id);
+    const int64_t b0 = __ldg(bb), b1 = __ldg(bb + 1), b2 = __ldg(bb + 2), b3 = __ldg(bb + 3);
+    t.has_window = b0 != -1;
+    t.qi_lo = static_cast<int>(b0); t.qj_lo = static_cast<int>(b1);
+    t.qi_hi = static_cast<int>(min(b2 + 1, g.src_w)) - 2;  // vertex slice [b0, min(b2+1, w)) -> last quad column
+    t.qj_hi = static_cast<int>(min(b3 + 1, g.src_h)) - 2;
+    // rectify.py:402-406
+    t.x_off = dadd(g.x_min, dmul(static_cast<double>(t.c0), g.x_res));
+    t.y_off = g.j_up ? dadd(g.y_min, dmul(static_cast<double>(t.r0), g.y_res))
+                     : dsub(g.y_max, dmul(static_cast<double>(t.r0), g.y_res));
+}
+
+__global__ void k1_init_claims(uint4 *claims, int64_t n_vec, unsigned int *slow_count) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n_vec) claims[i] = make_uint4(K1_NOCLAIM, K1_NOCLAIM, K1_NOCLAIM, K1_NOCLAIM);
+    if (i == 0) *slow_count = 0u;
+}
+
+// ---------------------------------------------------------------------------
+// k1_scatter
+// ---------------------------------------------------------------------------
+struct ScatterConst {
+    double x_scale, y_scale, inv_xs, inv_ys, uv_lo, uv_hi;
+};
+
+// rectify.py:516-576 for one quad inside one reference tile, given the quad's tile-local pixel
+// box [i_lo, i_hi] x [j_lo, j_hi] (already clipped to the tile and to the requested rows).
+__device__ __forceinline__ void claim_pixels(const IjGeom &g, const TileCtx &tc, const ScatterConst &k, double x0,
+                                             double y0, double x1, double y1, double x2, double y2, double x3,
+                                             double y3, int i_lo, int i_hi, int j_lo, int j_hi, uint32_t qkey) {
+    // rectify.py:528-542
+    double det_a = tri_det(x0, y0, x1, y1, x2, y2);
+    if (det_a != det_a) det_a = 0.0;
+    double det_b = tri_det(x3, y3, x2, y2, x1, y1);
+    if (det_b != det_b) det_b = 0.0;
+    if (det_a == 0.0 && det_b == 0.0) return;
+    const TriTest ta = make_tri_test(det_a, k.uv_lo, k.uv_hi), tb = make_tri_test(det_b, k.uv_lo, k.uv_hi);
+    uint32_t *claim_row = g.claims + (static_cast<int64_t>(tc.r0) + j_lo - g.row_begin) * g.dst_w + tc.c0;
+    for (int dj = j_lo; dj <= j_hi; ++dj, claim_row += g.dst_w) {
+        const double py = dadd(tc.y_off, dmul(dadd(static_cast<double>(dj), 0.5), k.y_scale));
+        for (int di = i_lo; di <= i_hi; ++di) {
+            const double px = dadd(tc.x_off, dmul(dadd(static_cast<double>(di), 0.5), k.x_scale));
+            bool acc = tri_accepts(ta, tri_u(px, py, x0, y0, x2, y2), tri_v(px, py, x0, y0, x1, y1), k.uv_lo, k.uv_hi);
+            if (!acc) acc = tri_accepts(tb, tri_u(px, py, x3, y3, x1, y1), tri_v(px, py, x3, y3, x2, y2), k.uv_lo, k.uv_hi);
+            if (acc) atomicMin(claim_row + di, qkey);
+        }
+    }
+}
+
+// Quads near a reference-tile border, with non-finite vertices or reaching outside the target:
+// visit every tile a conservative pixel box touches and redo the tile-local arithmetic there.
+__device__ __forceinline__ void scatter_quad_generic(const IjGeom &g, const ScatterConst &k, double x0, double y0,
+                                                  double x1, double y1, double x2, double y2, double x3, double y3,
+                                                  int qi, int qj, uint32_t qkey) {
+    const double inv_xr = 1.0 / g.x_res, inv_yr = 1.0 / g.y_res;
+    const double W = static_cast<double>(g.dst_w);
+    const double R0 = static_cast<double>(g.row_begin), R1 = static_cast<double>(g.row_end);
+    const double fx0 = (x0 - g.x_min) * inv_xr, fx1 = (x1 - g.x_min) * inv_xr;
+    const double fx2 = (x2 - g.x_min) * inv_xr, fx3 = (x3 - g.x_min) * inv_xr;
+    const double fy0 = g.j_up ? (y0 - g.y_min) * inv_yr : (g.y_max - y0) * inv_yr;
+    const double fy1 = g.j_up ? (y1 - g.y_min) * inv_yr : (g.y_max - y1) * inv_yr;
+    const double fy2 = g.j_up ? (y2 - g.y_min) * inv_yr : (g.y_max - y2) * inv_yr;
+    const double fy3 = g.j_up ? (y3 - g.y_min) * inv_yr : (g.y_max - y3) * inv_yr;
+    const bool f0 = isfinite(fx0) && isfinite(fy0), f1 = isfinite(fx1) && isfinite(fy1);
+    const bool f2 = isfinite(fx2) && isfinite(fy2), f3 = isfinite(fx3) && isfinite(fy3);
+    double lo_x = INFINITY, hi_x = -INFINITY, lo_y = INFINITY, hi_y = -INFINITY;
+    if (f0 && f1 && f2 && f3) {
+        // the reference scans [min floor(p), max floor(p)] (rectify.py:500-526); +-1 px absorbs the
+        // difference between this global and the tile-local pixel arithmetic
+        lo_x = fmin(fmin(fx0, fx1), fmin(fx2, fx3)) - 1.0; hi_x = fmax(fmax(fx0, fx1), fmax(fx2, fx3)) + 1.0;
+        lo_y = fmin(fmin(fy0, fy1), fmin(fy2, fy3)) - 1.0; hi_y = fmax(fmax(fy0, fy1), fmax(fy2, fy3)) + 1.0;
+    } else {
+        // A triangle with a non-finite vertex never accepts a pixel (its u or v is NaN): only
+        // all-finite triangles count; their acceptance region is the triangle grown by the uv
+        // tolerance, bounded by a few % of its extent + 1 px.
+        if (f0 && f1 && f2) {
+            lo_x = fmin(fx0, fmin(fx1, fx2)); hi_x = fmax(fx0, fmax(fx1, fx2));
+            lo_y = fmin(fy0, fmin(fy1, fy2)); hi_y = fmax(fy0, fmax(fy1, fy2));
+        }
+        if (f3 && f2 && f1) {
+            lo_x = fmin(lo_x, fmin(fx3, fmin(fx1, fx2))); hi_x = fmax(hi_x, fmax(fx3, fmax(fx1, fx2)));
+            lo_y = fmin(lo_y, fmin(fy3, fmin(fy1, fy2))); hi_y = fmax(hi_y, fmax(fy3, fmax(fy1, fy2)));
+        }
+        const double margin_k = 0.01 + 4.0 * g.uv_delta;
+        const double mx = margin_k * (hi_x - lo_x) + 1.0, my = margin_k * (hi_y - lo_y) + 1.0;
+        lo_x -= mx; hi_x += mx; lo_y -= my; hi_y += my;
+    }
+    if (!(lo_x <= hi_x) || hi_x < 0.0 || hi_y < R0 || lo_x >= W || lo_y >= R1) return;
+    const int gx0 = static_cast<int>(fmax(lo_x, 0.0)), gx1 = static_cast<int>(fmin(hi_x, W - 1.0));
+    const int gy0 = static_cast<int>(fmax(lo_y, R0)), gy1 = static_cast<int>(fmin(hi_y, R1 - 1.0));
+    const int tx_a = gx0 / g.tile_w, tx_b = gx1 / g.tile_w, ty_a = gy0 / g.tile_h, ty_b = gy1 / g.tile_h;
+    TileCtx tc;
+    for (int ty = ty_a; ty <= ty_b; ++ty)
+        for (int tx = tx_a; tx <= tx_b; ++tx) {
+            load_tile_ctx(g, ty, tx, tc);
+            if (!tc.has_window || qi < tc.qi_lo || qi > tc.qi_hi || qj < tc.qj_lo || qj > tc.qj_hi) continue;
+            // rectify.py:500-526: tile-local pixel box of the quad
+            const int pi0 = floor_px_div(dsub(x0, tc.x_off), k.x_scale, k.inv_xs);
+            const int pi1 = floor_px_div(dsub(x1, tc.x_off), k.x_scale, k.inv_xs);
+            const int pi2 = floor_px_div(dsub(x2, tc.x_off), k.x_scale, k.inv_xs);
+            const int pi3 = floor_px_div(dsub(x3, tc.x_off), k.x_scale, k.inv_xs);
+            const int pj0 = floor_px_div(dsub(y0, tc.y_off), k.y_scale, k.inv_ys);
+            const int pj1 = floor_px_div(dsub(y1, tc.y_off), k.y_scale, k.inv_ys);
+            const int pj2 = floor_px_div(dsub(y2, tc.y_off), k.y_scale, k.inv_ys);
+            const int pj3 = floor_px_div(dsub(y3, tc.y_off), k.y_scale, k.inv_ys);
+            int i_lo = min(min(pi0, pi1), min(pi2, pi3)), i_hi = max(max(pi0, pi1), max(pi2, pi3));
+            int j_lo = min(min(pj0, pj1), min(pj2, pj3)), j_hi = max(max(pj0, pj1), max(pj2, pj3));
+            if (i_hi < 0 || j_hi < 0 || i_lo >= tc.tw || j_lo >= tc.th) continue;
+            i_lo = max(i_lo, 0); i_hi = min(i_hi, tc.tw - 1);
+            j_lo = max(j_lo, tc.dj_lo); j_hi = min(j_hi, tc.dj_hi);  // tile clip + requested rows
+            if (j_lo > j_hi) continue;
+            claim_pixels(g, tc, k, x0, y0, x1, y1, x2, y2, x3, y3, i_lo, i_hi, j_lo, j_hi, qkey);
+        }
+}
+
+// A vertex's pixel index in the reference tile that (approximately) contains it.  For a vertex that
+// is non-finite or outside the target image, tile = -(1 + outcode): bit 0 left, 1 right, 2 above,
+// 3 below the image by more than 2 px, bit 4 non-finite.
+struct VertexPx {
+    int pi, pj, tile;
+};
+
+__device__ __forceinline__ VertexPx vertex_px(const IjGeom &g, const ScatterConst &k, double vx, double vy,
+                                              double inv_xr, double inv_yr, float inv_tw, float inv_th, TileCtx &tc) {
+    VertexPx v;
+    v.pi = v.pj = 0;
+    v.tile = -1;
+    const double fx = (vx - g.x_min) * inv_xr;
+    const double fy = g.j_up ? (vy - g.y_min) * inv_yr : (g.y_max - vy) * inv_yr;
+    const double W = static_cast<double>(g.dst_w), H = static_cast<double>(g.dst_h);
+    if (!(fx >= 0.0 && fx < W && fy >= 0.0 && fy < H)) {
+        int code = (isfinite(fx) && isfinite(fy)) ? 0 : 16;
+        if (fx < -2.0) code |= 1;
+        if (fx >= W + 2.0) code |= 2;
+        if (fy < -2.0) code |= 4;
+        if (fy >= H + 2.0) code |= 8;
+        v.tile = -(1 + code);
+        return v;
+    }
+    const int tx = fast_div(static_cast<int>(fx), g.tile_w, inv_tw), ty = fast_div(static_cast<int>(fy), g.tile_h, inv_th);
+    if (tc.id != ty * g.ntx + tx) load_tile_ctx(g, ty, tx, tc);
+    v.tile = tc.id;
+    v.pi = floor_px_div(dsub(vx, tc.x_off), k.x_scale, k.inv_xs);
+    v.pj = floor_px_div(dsub(vy, tc.y_off), k.y_scale, k.inv_ys);
+    return v;
+}
+
+__global__ void __launch_bounds__(K1S_WARPS * 32) k1_scatter(IjGeom g) {
+    const int64_t nqi = g.src_w - 1, nqj = g.src_h - 1;
+    const int lane = threadIdx.x & 31;
+    const int64_t strip = static_cast<int64_t>(blockIdx.x) * K1S_WARPS + (threadIdx.x >> 5);
+    if (strip * 31 >= nqi) return;  // whole warp out of range
+    const int64_t col = strip * 31 + lane;  // vertex column of this lane
+    const int64_t j_begin = static_cast<int64_t>(blockIdx.y) * K1S_ROWS;
+    const int64_t j_end = min(j_begin + K1S_ROWS, nqj);  // quad rows [j_begin, j_end)
+    const bool col_ok = col < g.src_w;
+    const bool quad_lane = lane < 31 && col < nqi;
+
+    ScatterConst k;
+    k.x_scale = g.x_res; k.y_scale = g.j_up ? g.y_res : -g.y_res;
+    k.inv_xs = 1.0 / k.x_scale; k.inv_ys = 1.0 / k.y_scale;
+    k.uv_lo = -g.uv_delta; k.uv_hi = dadd(1.0, dmul(2.0, g.uv_delta));
+    const double inv_xr = 1.0 / g.x_res, inv_yr = 1.0 / g.y_res;
+    const float inv_tw = 1.0f / static_cast<float>(g.tile_w), inv_th = 1.0f / static_cast<float>(g.tile_h);
+    const int qi = static_cast<int>(col);
+
+    TileCtx tc;
+    tc.id = -1;
+    // previous vertex row: this lane's vertex (x0, y0, v0) and its right neighbour (x1, y1, v1)
+    double x0 = col_ok ? __ldg(g.x + j_begin * g.src_pitch + col) : NAN;
+    double y0 = col_ok ? __ldg(g.y + j_begin * g.src_pitch + col) : NAN;
+    VertexPx v0 = vertex_px(g, k, x0, y0, inv_xr, inv_yr, inv_tw, inv_th, tc);
+    double x1 = __shfl_down_sync(0xffffffffu, x0, 1), y1 = __shfl_down_sync(0xffffffffu, y0, 1);
+    VertexPx v1;
+    v1.pi = __shfl_down_sync(0xffffffffu, v0.pi, 1);
+    v1.pj = __shfl_down_sync(0xffffffffu, v0.pj, 1);
+    v1.tile = __shfl_down_sync(0xffffffffu, v0.tile, 1);
+
+    for (int64_t j = j_begin; j < j_end; ++j) {
+        const double x2 = col_ok ? __ldg(g.x + (j + 1) * g.src_pitch + col) : NAN;
+        const double y2 = col_ok ? __ldg(g.y + (j + 1) * g.src_pitch + col) : NAN;
+        const VertexPx v2 = vertex_px(g, k, x2, y2, inv_xr, inv_yr, inv_tw, inv_th, tc);
+        const double x3 = __shfl_down_sync(0xffffffffu, x2, 1), y3 = __shfl_down_sync(0xffffffffu, y2, 1);
+        VertexPx v3;
+        v3.pi = __shfl_down_sync(0xffffffffu, v2.pi, 1);
+        v3.pj = __shfl_down_sync(0xffffffffu, v2.pj, 1);
+        v3.tile = __shfl_down_sync(0xffffffffu, v2.tile, 1);
+        bool slow = quad_lane;
+        if (quad_lane) {
+            const uint32_t qkey = static_cast<uint32_t>(j * nqi + col);
+            const int qj = static_cast<int>(j);
+            const int i_lo = min(min(v0.pi, v1.pi), min(v2.pi, v3.pi)), i_hi = max(max(v0.pi, v1.pi), max(v2.pi, v3.pi));
+            const int j_lo = min(min(v0.pj, v1.pj), min(v2.pj, v3.pj)), j_hi = max(max(v0.pj, v1.pj), max(v2.pj, v3.pj));
+            // Fast path: all four vertices were indexed in the lane's cached tile and the pixel box stays
+            // at least one pixel inside it, so no other tile can see the quad (tile-local and neighbouring
+            // tile arithmetic differ by less than one pixel) and the box needs no tile clipping.
+            const bool same_tile = v2.tile >= 0 && v2.tile == tc.id && v0.tile == v2.tile && v1.tile == v2.tile &&
+                                   v3.tile == v2.tile;
+            if (same_tile && i_lo >= 1 && j_lo >= 1 && i_hi <= tc.tw - 2 && j_hi <= tc.th - 2) {
+                if (tc.has_window && qi >= tc.qi_lo && qi <= tc.qi_hi && qj >= tc.qj_lo && qj <= tc.qj_hi) {
+                    const int jl = max(j_lo, tc.dj_lo), jh = min(j_hi, tc.dj_hi);  // requested rows
+                    if (jl <= jh) claim_pixels(g, tc, k, x0, y0, x1, y1, x2, y2, x3, y3, i_lo, i_hi, jl, jh, qkey);
+                }
+                slow = false;
+            } else if (v0.tile < 0 && v1.tile < 0 && v2.tile < 0 && v3.tile < 0) {
+                // all four vertices outside the target: if they are finite and share an outside
+                // half-plane (with 2 px to spare) the quad cannot reach any target pixel
+                const int c0 = -v0.tile - 1, c1 = -v1.tile - 1, c2 = -v2.tile - 1, c3 = -v3.tile - 1;
+                if (((c0 | c1 | c2 | c3) & 16) == 0 && (c0 & c1 & c2 & c3 & 15) != 0) slow = false;
+            }
+        }
+        // quads for the generic path are queued (warp-aggregated append) and handled by k1_scatter_slow,
+        // one quad per thread, instead of stalling the 30 other lanes of this warp
+        const unsigned slow_mask = __ballot_sync(0xffffffffu, slow);
+        if (slow_mask) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(g.slow_count, __popc(slow_mask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (slow) g.slow_list[base + __popc(slow_mask & ((1u << lane) - 1u))] = static_cast<uint32_t>(j * nqi + col);
+        }
+        x0 = x2; y0 = y2; x1 = x3; y1 = y3;
+        v0 = v2; v1 = v3;
+    }
+}
+
+// The queued quads, one per thread (grid-stride over the queue).
+__global__ void __launch_bounds__(256) k1_scatter_slow(IjGeom g) {
+    ScatterConst k;
+    k.x_scale = g.x_res; k.y_scale = g.j_up ? g.y_res : -g.y_res;
+    k.inv_xs = 1.0 / k.x_scale; k.inv_ys = 1.0 / k.y_scale;
+    k.uv_lo = -g.uv_delta; k.uv_hi = dadd(1.0, dmul(2.0, g.uv_delta));
+    const unsigned n = *g.slow_count;
+    const int64_t nqi = g.src_w - 1;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const uint32_t qkey = g.slow_list[e];
+        const int64_t j0 = qkey / nqi, i0 = qkey - j0 * nqi;
+        const int64_t s0 = j0 * g.src_pitch + i0, s2 = s0 + g.src_pitch;
+        scatter_quad_generic(g, k, __ldg(g.x + s0), __ldg(g.y + s0), __ldg(g.x + s0 + 1), __ldg(g.y + s0 + 1),
+                             __ldg(g.x + s2), __ldg(g.y + s2), __ldg(g.x + s2 + 1), __ldg(g.y + s2 + 1),
+                             static_cast<int>(i0), static_cast<int>(j0), qkey);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k1_resolve
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(K1R_THREADS) k1_resolve(IjGeom g) {
+    const int64_t c = static_cast<int64_t>(blockIdx.x) * K1R_THREADS + threadIdx.x;
+    const int64_t r = g.row_begin + blockIdx.y;
+    if (c >= g.dst_w) return;
+    const int64_t n_rows = g.row_end - g.row_begin;
+    const int64_t o = static_cast<int64_t>(blockIdx.y) * g.dst_w + c;
+    const uint32_t qkey = __ldcs(g.claims + o);
+    double oi = NAN, oj = NAN;
+    if (qkey != K1_NOCLAIM) {
+        const int64_t nqi = g.src_w - 1;
+        const int64_t j0 = qkey / nqi, i0 = qkey - j0 * nqi;
+        const int ty = static_cast<int>(r) / g.tile_h, tx = static_cast<int>(c) / g.tile_w;
+        const int64_t r0 = static_cast<int64_t>(ty) * g.tile_h, c0 = static_cast<int64_t>(tx) * g.tile_w;
+        const int64_t *bb = g.tile_boxes + 4 * (static_cast<int64_t>(ty) * g.ntx + tx);
+        const int64_t bb0 = __ldg(bb), bb1 = __ldg(bb + 1);
+        const double x_off = dadd(g.x_min, dmul(static_cast<double>(c0), g.x_res));
+        const double y_off = g.j_up ? dadd(g.y_min, dmul(static_cast<double>(r0), g.y_res))
+                                    : dsub(g.y_max, dmul(static_cast<double>(r0), g.y_res));
+        const double x_scale = g.x_res, y_scale = g.j_up ? g.y_res : -g.y_res;
+        const double uv_lo = -g.uv_delta, uv_hi = dadd(1.0, dmul(2.0, g.uv_delta));
+        const double px = dadd(x_off, dmul(dadd(static_cast<double>(c - c0), 0.5), x_scale));
+        const double py = dadd(y_off, dmul(dadd(static_cast<double>(r - r0), 0.5), y_scale));
+        const int64_t s0 = j0 * g.src_pitch + i0, s2 = s0 + g.src_pitch;
+        const double x0 = __ldg(g.x + s0), x1 = __ldg(g.x + s0 + 1), x2 = __ldg(g.x + s2), x3 = __ldg(g.x + s2 + 1);
+        const double y0 = __ldg(g.y + s0), y1 = __ldg(g.y + s0 + 1), y2 = __ldg(g.y + s2), y3 = __ldg(g.y + s2 + 1);
+        double det_a = tri_det(x0, y0, x1, y1, x2, y2);
+        if (det_a != det_a) det_a = 0.0;
+        const double nu_a = tri_u(px, py, x0, y0, x2, y2), nv_a = tri_v(px, py, x0, y0, x1, y1);
+        double u, v;
+        bool tri_b = true;
+        if (tri_accepts(make_tri_test(det_a, uv_lo, uv_hi), nu_a, nv_a, uv_lo, uv_hi)) {
+            u = ddiv(nu_a, det_a); v = ddiv(nv_a, det_a);
+            tri_b = false;
+        } else {  // the claim guarantees that triangle B accepts
+            const double det_b = tri_det(x3, y3, x2, y2, x1, y1);
+            u = ddiv(tri_u(px, py, x3, y3, x1, y1), det_b);
+            v = ddiv(tri_v(px, py, x3, y3, x2, y2), det_b);
+        }
+        const double fi = clamp01(u), fj = clamp01(v);
+        // rectify.py:564-576: window-local index + fraction, then + window origin
+        const double li = tri_b ? dsub(static_cast<double>(i0 + 1 - bb0), fi) : dadd(static_cast<double>(i0 - bb0), fi);
+        const double lj = tri_b ? dsub(static_cast<double>(j0 + 1 - bb1), fj) : dadd(static_cast<double>(j0 - bb1), fj);
+        oi = dadd(static_cast<double>(bb0), li);
+        oj = dadd(static_cast<double>(bb1), lj);
+    }
+    st_stream(g.ij + o, oi);
+    st_stream(g.ij + n_rows * g.dst_w + o, oj);
+}
+
+}  // namespace xrs
+
+using namespace xrs;
+
+extern "C" {
+
+static int64_t claims_bytes(int64_t rows, int64_t dst_w) {
+    return (rows * dst_w * static_cast<int64_t>(sizeof(uint32_t)) + 15) / 16 * 16;
+}
+
+// layout: [claims: 4 B per target pixel of the row band][slow-quad queue: 4 B per source quad][counter]
+int64_t xrs_rectify_ij_workspace_bytes(int64_t src_h, int64_t src_w, int64_t dst_rows, int64_t dst_w) {
+    if (src_h < 2 || src_w < 2 || dst_rows < 1 || dst_w < 1) return 0;
+    return claims_bytes(dst_rows, dst_w) + (src_h - 1) * (src_w - 1) * static_cast<int64_t>(sizeof(uint32_t)) + 16;
+}
+
+int xrs_rectify_ij(const double *x, const double *y, int64_t src_h, int64_t src_w, int64_t src_pitch,
+                   const int64_t *tile_boxes, double *ij, int64_t dst_h, int64_t dst_w, int32_t tile_h,
+                   int32_t tile_w, double x_min, double y_min, double y_max, double x_res, double y_res,
+                   int32_t is_j_axis_up, double uv_delta, int64_t row_begin, int64_t row_end, void *workspace,
+                   void *stream) {
+    if (!x || !y || !tile_boxes || !ij || !workspace) return fail("xrs_rectify_ij: null pointer");
+    if (row_begin < 0 || row_end > dst_h || row_begin >= row_end) return fail("xrs_rectify_ij: bad row range");
+    if (src_h < 2 || src_w < 2 || src_pitch < src_w) return fail("xrs_rectify_ij: source must be at least 2x2");
+    if (dst_h < 1 || dst_w < 1 || tile_h < 1 || tile_w < 1) return fail("xrs_rectify_ij: bad target shape");
+    if (dst_h > (1 << 30) || dst_w > (1 << 30) || src_w > (1 << 30) || src_h > (1 << 30)) return fail("xrs_rectify_ij: image too large");
+    if (!(x_res > 0.0) || !(y_res > 0.0)) return fail("xrs_rectify_ij: resolution must be positive");
+    if ((src_h - 1) * (src_w - 1) >= 0xffffffffLL) return fail("xrs_rectify_ij: source has too many quads");
+    if (reinterpret_cast<uintptr_t>(workspace) & 15) return fail("xrs_rectify_ij: workspace must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    IjGeom g;
+    g.x = x; g.y = y; g.src_h = src_h; g.src_w = src_w; g.src_pitch = src_pitch;
+    g.tile_boxes = tile_boxes; g.ij = ij; g.claims = static_cast<uint32_t *>(workspace);
+    g.dst_h = dst_h; g.dst_w = dst_w;
+    g.tile_h = static_cast<int>(std::min<int64_t>(tile_h, dst_h));
+    g.tile_w = static_cast<int>(std::min<int64_t>(tile_w, dst_w));
+    g.ntx = static_cast<int>(ceil_div(dst_w, g.tile_w));
+    g.nty = static_cast<int>(ceil_div(dst_h, g.tile_h));
+    g.x_min = x_min; g.y_min = y_min; g.y_max = y_max; g.x_res = x_res; g.y_res = y_res;
+    g.j_up = is_j_axis_up ? 1 : 0; g.uv_delta = uv_delta;
+    g.row_begin = row_begin; g.row_end = row_end;
+    const int64_t n_rows = row_end - row_begin;
+    g.slow_list = reinterpret_cast<uint32_t *>(static_cast<char *>(workspace) + claims_bytes(n_rows, dst_w));
+    g.slow_count = reinterpret_cast<unsigned int *>(g.slow_list + (src_h - 1) * (src_w - 1));
+
+    const int64_t n_vec = ceil_div(n_rows * dst_w, 4);
+    k1_init_claims<<<static_cast<unsigned>(ceil_div(n_vec, 256)), 256, 0, st>>>(reinterpret_cast<uint4 *>(g.claims), n_vec, g.slow_count);
+    XRS_LAUNCH_CHECK("k1_init_claims");
+    const dim3 sgrid(static_cast<unsigned>(ceil_div(ceil_div(src_w - 1, 31), K1S_WARPS)),
+                     static_cast<unsigned>(ceil_div(src_h - 1, K1S_ROWS)));
+    if (sgrid.y > 65535) return fail("xrs_rectify_ij: source too tall");
+    k1_scatter<<<sgrid, K1S_WARPS * 32, 0, st>>>(g);
+    XRS_LAUNCH_CHECK("k1_scatter");
+    int dev = 0, sms = 0;
+    XRS_CUDA(cudaGetDevice(&dev));
+    XRS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    k1_scatter_slow<<<static_cast<unsigned>(sms * 4), 256, 0, st>>>(g);
+    XRS_LAUNCH_CHECK("k1_scatter_slow");
+    if (n_rows > 65535) return fail("xrs_rectify_ij: more than 65535 target rows per call");
+    const dim3 rgrid(static_cast<unsigned>(ceil_div(dst_w, K1R_THREADS)), static_cast<unsigned>(n_rows));
+    k1_resolve<<<rgrid, K1R_THREADS, 0, st>>>(g);
+    XRS_LAUNCH_CHECK("k1_resolve");
+    return 0;
+}
+
+}  // extern "C"

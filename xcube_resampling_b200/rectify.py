@@ -93,8 +93,7 @@ class RectifyPlan:
         self._axes = _dev.to_device(np.concatenate([x_lo, x_hi, y_lo, y_hi]), self.device)
         self.tile_boxes = _dev.empty((self.ntx * self.nty, 4), np.int64, self.device)
         self._ws0 = _dev.workspace(lib.xrs_tile_src_bboxes_workspace_bytes(self.ntx, self.nty), self.device)
-        self._ws1 = _dev.workspace(
-            lib.xrs_rectify_ij_workspace_bytes(H, W, target_gm.tile_height, target_gm.tile_width), self.device)
+        self._ws1 = None  # K1 workspace, sized on first use (depends on the source shape)
         self.ij_buf = _dev.empty((2, self.rows[1] - self.rows[0], W), np.float64, self.device)
 
     def windows(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
@@ -116,6 +115,9 @@ class RectifyPlan:
         gm = self.gm
         x_min, y_min, x_max, y_max = gm.xy_bbox
         h, w = x.shape
+        need = self.lib.xrs_rectify_ij_workspace_bytes(h, w, self.rows[1] - self.rows[0], gm.width)
+        if self._ws1 is None or self._ws1.numel() < need:
+            self._ws1 = _dev.workspace(need, self.device)
         check(self.lib.xrs_rectify_ij(
             _dev.ptr(x), _dev.ptr(y), h, w, x.stride(0), _dev.ptr(tile_boxes), _dev.ptr(self.ij_buf), gm.height,
             gm.width, gm.tile_height, gm.tile_width, float(x_min), float(y_min), float(y_max), float(gm.x_res),
@@ -188,12 +190,11 @@ def gather_ij(src: torch.Tensor, ij: torch.Tensor, interp_method: str, fill_valu
         )
     squeeze = src.dim() == 2
     src3 = src.unsqueeze(0) if squeeze else src
-    if src3.stride(2) != 1:
+    if src3.stride(2) != 1 or (src3.shape[0] > 1 and src3.stride(0) < src3.stride(1) * src3.shape[1]):
         src3 = src3.contiguous()
     np_dtype = np.dtype(str(src3.dtype).replace("torch.", ""))
-    bands, h, w = src3.shape
-    if full_size is not None:
-        w, h = int(full_size[0]), int(full_size[1])
+    bands, win_h, win_w = src3.shape
+    w, h = (win_w, win_h) if full_size is None else (int(full_size[0]), int(full_size[1]))
     _, H, W = ij.shape
     if out is None:
         out = torch.empty((bands, H, W), dtype=src3.dtype, device=src3.device)
@@ -201,7 +202,7 @@ def gather_ij(src: torch.Tensor, ij: torch.Tensor, interp_method: str, fill_valu
     dst_planes = _dev.ptr_array([out[b] for b in range(bands)])
     fill = float(fill_value)
     check(lib.xrs_gather_ij(src_planes, dst_planes, bands, DTYPE_CODES[np_dtype], h, w, src3.stride(1),
-                            int(window_origin[0]), int(window_origin[1]), _dev.ptr(ij), H, W,
+                            int(window_origin[0]), int(window_origin[1]), win_w, win_h, _dev.ptr(ij), H, W,
                             INTERP_CODES[interp_method], fill, _dev.stream_ptr(src3.device)),
           "xrs_gather_ij")
     return out[0] if squeeze else out
@@ -221,7 +222,7 @@ def rectify_band_host(x: np.ndarray, y: np.ndarray, src_window: np.ndarray, wind
     dev = _dev.require_cuda(device)
     x_dev = _dev.to_device(x, dev, dtype=np.float64)
     y_dev = _dev.to_device(y, dev, dtype=np.float64)
-    src_dev = _dev.to_device(src_window, dev)
+    src_dev = _dev.to_device_pitched(src_window, dev)
     plan = RectifyPlan(target_gm, dev, rows=rows)
     ij = plan.ij(x_dev, y_dev)
     out = gather_ij(src_dev, ij, interp_method, fill_value, window_origin=window_origin, full_size=full_size)
@@ -303,7 +304,7 @@ def rectify_dataset(
                     f"interp_methods must be one of 0, 1, 'nearest', 'bilinear', "
                     f"'triangular', was '{interp_method}'."
                 )
-            src = _dev.to_device(var.values)
+            src = _dev.to_device_pitched(var.values)
             out = _dev.to_host(gather_ij(src, ij, interp_method, fill_value))
             dims = t_dims if len(var.dims) == 2 else (var.dims[0],) + t_dims
             target_ds[var_name] = DataArray(out, dims=dims, attrs=var.attrs, name=var_name)
