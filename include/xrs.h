@@ -139,6 +139,35 @@ int xrs_gather_ij(const void *const *src_planes_host, void *const *dst_planes_ho
                   int64_t win_w, int64_t win_h, const double *ij, int64_t dst_h, int64_t dst_w, int32_t method,
                   double fill, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Affine resampling and block aggregation (affine.py, coarsen.py)
+ * --------------------------------------------------------------------- */
+
+/* K4+K5 -- affine resampling (scale + offset per axis, order 0 or 1) with optional fused block
+ * aggregation.  Replaces _resample_array / _downscale / _upscale (affine.py:243-362), i.e.
+ * dask_image.ndinterp.affine_transform -> scipy.ndimage.affine_transform(matrix=diag(1.., j_scale,
+ * i_scale), offset=(0.., j_off, i_off), order, mode="constant", cval) followed by
+ * dask.array.coarsen(agg, {y: f_j, x: f_i}) with the reducers of coarsen.py:50-155 and
+ * constants.py:51-65.
+ *   src        (n_slices, src_h, src_w) of `dtype`, row pitch src_pitch, slice stride src_slice_stride
+ *   dst        (n_slices, dst_h, dst_w) contiguous; element type is `dtype`, except int64 for
+ *              agg = mode / count and for sum / prod of integer data (what numpy returns)
+ *   j/i_scale, j/i_off  source index = intermediate index * scale + off; the intermediate image is
+ *              (dst_h * f_j, dst_w * f_i) (affine.py:287-297 has already divided the scale by f)
+ *   order      0 nearest, 1 linear; anything else fails like affine.py:329-335
+ *   agg, f_j, f_i  reducer (enum xrs_agg) over f_j x f_i intermediate samples; f_j = f_i = 1: none
+ *   slice_blend  1 reproduces scipy's zero-weight read of the neighbouring slice for 3-D float
+ *              arrays with order 1 (non-finite values there make the sample NaN)  */
+int xrs_affine(const void *src, void *dst, int32_t dtype, int64_t n_slices, int64_t src_h, int64_t src_w,
+               int64_t src_pitch, int64_t src_slice_stride, int64_t dst_h, int64_t dst_w, double j_scale, double j_off,
+               double i_scale, double i_off, int32_t order, double cval, int32_t agg, int32_t f_j, int32_t f_i,
+               int32_t slice_blend, void *stream);
+
+/* K5 alone -- dask.array.coarsen(agg, array, {y: f_j, x: f_i}) with the same reducers
+ * (coarsen.py:50-155); f_j, f_i must divide src_h, src_w.  dst as for xrs_affine. */
+int xrs_coarsen(const void *src, void *dst, int32_t dtype, int64_t n_slices, int64_t src_h, int64_t src_w,
+                int64_t src_pitch, int64_t src_slice_stride, int32_t agg, int32_t f_j, int32_t f_i, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

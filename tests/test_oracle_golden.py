@@ -177,3 +177,101 @@ def test_ref_compute_ij_bboxes():
     assert orect.ij_bboxes(lon, lat, box, 1.0, 0).tolist() == [[2, 1, 4, 3]]
     assert orect.ij_bboxes(lon, lat, box, 2.0, 0).tolist() == [[1, 0, 5, 4]]
     assert orect.ij_bboxes(lon, lat, box, 2.0, 2).tolist() == [[0, 0, 7, 6]]
+
+
+# ---------------------------------------------------------------------------
+# affine / coarsen
+# ---------------------------------------------------------------------------
+from oracle import resample as ores  # noqa: E402
+
+
+def _coarsen_cases():
+    z = load_golden("coarsen.npz")
+    return z, [str(c) for c in z["cases"]]
+
+
+@pytest.mark.parametrize("case", _coarsen_cases()[1])
+def test_coarsen_reducers_match_reference(case):
+    # outputs of the reference's AGG_METHODS table (constants.py:51-65, coarsen.py:50-155)
+    z, _ = _coarsen_cases()
+    a = z[f"{case}/input"]
+    f_j, f_i = (int(v) for v in z[f"{case}/factors"])
+    for agg in ores.AGG_NAMES:
+        key = f"{case}/{agg}"
+        if key not in z:
+            continue
+        got = np.asarray(ores.coarsen(a, f_j, f_i, agg))
+        ref = z[key]
+        assert got.dtype == ref.dtype and np.array_equal(got, ref, equal_nan=got.dtype.kind == "f"), f"{case}/{agg}"
+
+
+def test_ref_coarsen_unit_test_values():
+    # tests/test_coarsen.py:35-61
+    arr_float = np.array([[1.0, 2.0], [3.0, 4.0]])
+    arr_int = np.array([[1, 2], [3, 4]])
+    arr_mode = np.array([[1, 2, 2], [3, 2, 2]])
+    assert ores.coarsen(arr_float, 2, 2, "first") == 1.0
+    assert ores.coarsen(arr_float, 2, 2, "last") == 4.0
+    assert ores.coarsen(arr_float, 2, 2, "center") == 4.0
+    assert ores.coarsen(arr_float, 2, 2, "mean") == 2.5
+    assert ores.coarsen(arr_int, 2, 2, "mean") == 2
+    assert ores.coarsen(arr_float, 2, 2, "median") == 2.5
+    np.testing.assert_almost_equal(ores.coarsen(arr_float, 2, 2, "std"), np.std(arr_float))
+    assert ores.coarsen(arr_int, 2, 2, "sum") == 10
+    np.testing.assert_almost_equal(ores.coarsen(arr_float, 2, 2, "var"), np.var(arr_float))
+    assert ores.coarsen(arr_mode, 2, 3, "mode") == 2
+
+
+REFL_8X6 = np.array([[0, 1, 0, 2, 0, 3, 0, 4], [2, 0, 3, 0, 4, 0, 1, 0], [0, 4, 0, nan, 0, 2, 0, 3],
+                     [1, 0, 2, 0, 3, 0, 4, 0], [0, 3, 0, 4, 0, 1, 0, 2], [4, 0, 1, 0, 2, 0, 3, 0]], dtype=np.float64)
+
+
+def _affine(size, xy_min, res, **kw):
+    src = ogrid.regular_grid((8, 6), (50, 10), 0.1)  # what GridMapping.from_dataset derives for the 8x6 sample
+    tgt = ogrid.regular_grid(size, xy_min, res)
+    return ores.affine_transform(REFL_8X6, src, tgt, interp=1, **kw)
+
+
+def test_ref_affine_subset_and_recover_nans():
+    # tests/test_affine.py:46-140
+    np.testing.assert_almost_equal(_affine((3, 3), (50.0, 10.0), 0.1), [[1, 0, 2], [0, 3, 0], [4, 0, 1]])
+    np.testing.assert_almost_equal(_affine((3, 3), (50.1, 10.1), 0.1), [[4, nan, nan], [0, 2, 0], [3, 0, 4]])
+    np.testing.assert_almost_equal(_affine((3, 3), (50.05, 10.05), 0.1),
+                                   [[1.25, 1.5, nan], [1.0, 1.25, 1.5], [1.75, 1.0, 1.25]])
+    np.testing.assert_almost_equal(_affine((3, 3), (50.05, 10.05), 0.1, recover_nan=True),
+                                   [[1.25, 1.5, 0.6666667], [1.0, 1.25, 1.5], [1.75, 1.0, 1.25]])
+
+
+def test_ref_affine_downscale_upscale_shift():
+    # tests/test_affine.py:295-478 (incl. the zero-weight NaN contamination value 1.0 at [3, 1])
+    np.testing.assert_almost_equal(_affine((8, 6), (50, 10), 0.2), [
+        [nan] * 8, [nan] * 8, [nan] * 8, [0.75, 1.0, 1.75, 1.25, nan, nan, nan, nan],
+        [1.25, 1.0, 1.25, 1.75, nan, nan, nan, nan], [1.75, 1.25, 0.75, 1.25, nan, nan, nan, nan]])
+    np.testing.assert_almost_equal(_affine((8, 6), (49.8, 9.8), 0.2), [
+        [nan] * 8, [nan] * 8, [nan, 0.75, 1.0, 1.75, 1.25, nan, nan, nan], [nan, 1.25, 1.0, 1.25, 1.75, nan, nan, nan],
+        [nan, 1.75, 1.25, 0.75, 1.25, nan, nan, nan], [nan] * 8])
+    np.testing.assert_almost_equal(_affine((8, 6), (50, 10), 0.05), [
+        [1.0, 0.5, 0.0, 1.0, 2.0, 1.0, 0.0, 1.5], [0.5, 1.0, 1.5, 1.25, 1.0, 1.5, 2.0, 1.75],
+        [0.0, 1.5, 3.0, 1.5, 0.0, 2.0, 4.0, 2.0], [2.0, 1.75, 1.5, 1.0, 0.5, 1.25, 2.0, 1.5],
+        [4.0, 2.0, 0.0, 0.5, 1.0, 0.5, 0.0, 1.0], [nan] * 8])
+    np.testing.assert_almost_equal(_affine((8, 6), (50.2, 10.1), 0.1), [
+        [nan] * 8, [0.0, 2.0, 0.0, 3.0, 0.0, 4.0, nan, nan], [nan, nan, 4.0, 0.0, 1.0, 0.0, nan, nan],
+        [nan, nan, 0.0, 2.0, 0.0, 3.0, nan, nan], [2.0, 0.0, 3.0, 0.0, 4.0, 0.0, nan, nan],
+        [0.0, 4.0, 0.0, 1.0, 0.0, 2.0, nan, nan]])
+    np.testing.assert_almost_equal(_affine((8, 6), (49.8, 9.9), 0.1), [
+        [nan, nan, 2.0, 0.0, nan, nan, 4.0, 0.0], [nan, nan, 0.0, 4.0, nan, nan, 0.0, 2.0],
+        [nan, nan, 1.0, 0.0, 2.0, 0.0, 3.0, 0.0], [nan, nan, 0.0, 3.0, 0.0, 4.0, 0.0, 1.0],
+        [nan, nan, 4.0, 0.0, 1.0, 0.0, 2.0, 0.0], [nan] * 8])
+
+
+def test_ref_affine_order_above_one():
+    # tests/test_affine.py:480-497
+    with pytest.raises(ValueError):
+        ores.upscale(REFL_8X6, ((1.0, 0, 0), (0, 1.0, 0)), (6, 8), 3, False, nan)
+
+
+def test_ref_affine_matrix_algebra():
+    # gridmapping/base.py:436-478 with the affine package's algebra: exact offsets the goldens need
+    src = ogrid.regular_grid((8, 6), (50, 10), 0.1)
+    assert ogrid.ij_transform_to(ogrid.regular_grid((3, 3), (50.0, 10.0), 0.1), src) == ((1.0, 0.0, 0.0), (0.0, 1.0, 3.0))
+    assert ogrid.ij_transform_to(ogrid.regular_grid((8, 6), (50, 10), 0.2), src) == ((2.0, 0.0, 0.0), (0.0, 2.0, -6.0))

@@ -6,7 +6,9 @@
 
 #include <cmath>
 #include <cstdio>
+#include <limits>
 #include <string>
+#include <type_traits>
 
 #include "xrs.h"
 
