@@ -24,7 +24,7 @@ def make_coarsen():
             a[rng.random((h, w)) < 0.06] = np.nan
             a[:f_j, :f_i] = np.nan
         else:
-            coarse = rng.integers(0, 12, (4, 5))
+            coarse = rng.integers(0, 12, (-(-h // 7), -(-w // 7)))
             a = np.repeat(np.repeat(coarse, 7, axis=0), 7, axis=1)[:h, :w].astype(dtype)
             a[rng.random((h, w)) < 0.15] = 5
         block = a.reshape(h // f_j, f_j, w // f_i, f_i)
