@@ -140,6 +140,51 @@ int xrs_gather_ij(const void *const *src_planes_host, void *const *dst_planes_ho
                   double fill, void *stream);
 
 /* ------------------------------------------------------------------------
+ * Reprojection (reproject.py) and CRS point transforms
+ * --------------------------------------------------------------------- */
+
+/* K3a -- CRS transform of n points, always_xy axis order.
+ * Replaces pyproj.Transformer.from_crs(from_crs, to_crs, always_xy=True).transform(x, y) at
+ * reproject.py:483 (_transform_gridpoints), rectify.py:196-204 (_transform_coords) and, with the
+ * densified tile edges built by the host, transform_bounds (reproject.py:347,398).  Points that a
+ * projection cannot represent come back as NaN (PROJ reports inf).  x_out / y_out may alias the
+ * inputs. */
+int xrs_transform_points(const xrs_proj *from_crs, const xrs_proj *to_crs, const double *x_in, const double *y_in,
+                         double *x_out, double *y_out, int64_t n, void *stream);
+
+/* K3 -- target-pixel CRS transform fused with the gather of all bands.
+ * Replaces _transform_gridpoints (reproject.py:472-496) + _reproject_block (reproject.py:268-335);
+ * the padded, re-tiled source copy of _reorganize_data_array_slice (reproject.py:499-530) is never
+ * materialised -- taps outside the source read `fill`, as da.pad(constant_values=fill) provides.
+ *   src_planes_host  HOST array of n_bands device pointers, each at element (win_j0, win_i0) of a
+ *                    (src_h, src_w) plane of `dtype`, row pitch src_pitch: only the resident
+ *                    (win_h, win_w) window has to be valid memory (row-band footprints)
+ *   dst_planes_host  HOST array of n_bands device pointers to (row_end-row_begin, dst_w) planes of
+ *                    `out_dtype`: `dtype` for nearest and triangular; for bilinear float64 (what
+ *                    numpy's promotion yields in the reference) or `dtype` (value cast once)
+ *   src_crs/dst_crs  source and target CRS; points go dst_crs -> src_crs (reproject.py:124-126)
+ *   dst_x, dst_y     pixel-centre coordinates of the target grid, (dst_w,) and (dst_h,) float64
+ *                    (GridMapping.x_coords / y_coords, regular.py:44-63)
+ *   tile_h/w         reference tile size of the target grid mapping; tile t = ty * ntx + tx
+ *   tile_x0/y0       per tile: coordinate of window element 0 -- the FLOAT32 value the reference
+ *                    stores (reproject.py:427-450) widened to float64
+ *   tile_i0/j0       per tile: source index of window element 0 (before padding, may be negative)
+ *   tile_win_w/h     common window size of all tiles (reproject.py:407-423); window indices follow
+ *                    numpy (negative counts from the end); indices still outside give `fill`
+ *                    where the reference raises IndexError
+ *   src_x_res/y_res  source resolution (positive); fractional index = (X - x0) / x_res,
+ *                    (Y - y0) / -y_res (reproject.py:278-279)
+ *   row_begin/end    target rows computed by this call
+ * A target pixel whose transform is not finite gets `fill` (the reference indexes garbage). */
+int xrs_reproject(const void *const *src_planes_host, void *const *dst_planes_host, int32_t n_bands, int32_t dtype,
+                  int32_t out_dtype, int64_t src_h, int64_t src_w, int64_t src_pitch, int64_t win_i0, int64_t win_j0,
+                  int64_t win_w, int64_t win_h, const xrs_proj *src_crs, const xrs_proj *dst_crs, const double *dst_x,
+                  const double *dst_y, int64_t dst_h, int64_t dst_w, int32_t tile_h, int32_t tile_w,
+                  const double *tile_x0, const double *tile_y0, const int32_t *tile_i0, const int32_t *tile_j0,
+                  int32_t tile_win_w, int32_t tile_win_h, double src_x_res, double src_y_res, int32_t method,
+                  double fill, int64_t row_begin, int64_t row_end, void *stream);
+
+/* ------------------------------------------------------------------------
  * Affine resampling and block aggregation (affine.py, coarsen.py)
  * --------------------------------------------------------------------- */
 

@@ -157,3 +157,34 @@ def xy_to_ij(g: RegularGrid):
 def ij_transform_to(g: RegularGrid, other: RegularGrid):
     """gridmapping/base.py:461-478: image coords of *g* -> image coords of *other*."""
     return affine_mul(xy_to_ij(other), ij_to_xy(g))
+
+
+# --- resolution a 1-D coordinate axis is given by the reference -----------------------------
+def round_to_fraction(value: float, digits: int = 2, resolution: float = 1.0):
+    """gridmapping/helpers.py:192-239: keep ``digits`` significant digits and round the remainder
+    to a multiple of ``resolution`` (0.1, 0.2, 0.25, 0.5 or 1) of the last kept digit; exact
+    rational arithmetic, returned as ``Fraction``."""
+    from fractions import Fraction
+
+    if value == 0:
+        return Fraction(0)
+    sign = -1 if value < 0 else 1
+    value = abs(value)
+    # the step expressed as an integer number of units one (or, for quarters, two) decimal
+    # places below the last kept digit -- the same table as helpers.py:192-198
+    unit, shift = {10: (1, 0), 20: (2, 0), 25: (25, 1), 50: (5, 0), 100: (1, -1)}[round(100 * resolution)]
+    exponent = math.floor(math.log10(value)) - digits - shift
+    magnitude = Fraction(10) ** exponent
+    return sign * (unit * round(value / magnitude / unit)) * magnitude
+
+
+def axis_resolution(coords, tolerance=1e-5) -> float:
+    """gridmapping/coords.py:143-164: resolution the reference derives from a 1-D axis."""
+    d = np.abs(np.diff(np.asarray(coords, dtype=np.float64)))
+    d = np.where(d == 0, np.nan, d)
+    r = d[0]
+    if np.allclose(d, r, atol=tolerance):
+        r = round_to_fraction(float(r), 5, 0.25)
+    else:
+        r = round_to_fraction(float(np.nanmedian(d)), 2, 0.5)
+    return to_int_or_float(r)

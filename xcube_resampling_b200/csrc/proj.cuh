@@ -1,0 +1,218 @@
+// proj.cuh -- fp64 map-projection math for the reprojection kernels (sm_100a).
+//
+// The reference hands every CRS transform to pyproj.Transformer -> the PROJ C library
+// (reproject.py:124,347,398,483; rectify.py:196-204; gridmapping/transform.py:77-91).  PROJ is not
+// part of this build; the four projection families the path needs are evaluated here from their
+// published closed forms, always in always_xy axis order:
+//
+//   geographic    degrees, identity
+//   tmerc / UTM   Krueger n-series to n^6 (Karney 2011 eqs. 7-12, 35-36) -- the algorithm behind
+//                 PROJ's default tmerc; series summed with Clenshaw recurrences
+//   web Mercator  spherical formulas on the semi-major axis (EPSG:3857)
+//   LAEA          Snyder (1987) pp. 187-190, ellipsoidal oblique / equatorial aspect (EPSG:3035)
+//
+// The auxiliary-latitude conversions (geodetic <-> conformal, authalic -> geodetic) are 6-term
+// trigonometric series whose coefficients are NOT typed in from tables: make_proj_consts() derives
+// them on the host from the exact closed forms by a discrete sine transform in long double, so
+// they are exact to double rounding for any ellipsoid.
+//
+// Host side: make_proj_consts(xrs_proj) -> ProjC (plain struct passed to kernels by value).
+// Device side: proj_inverse(ProjC, x, y) -> (lam, phi) radians; proj_forward(ProjC, lam, phi).
+#pragma once
+
+#include "common.cuh"
+
+namespace xrs {
+
+constexpr int PROJ_TERMS = 6;
+constexpr double PROJ_PI = 3.14159265358979323846;
+constexpr double PROJ_DEG2RAD = PROJ_PI / 180.0;
+constexpr double PROJ_RAD2DEG = 180.0 / PROJ_PI;
+constexpr double TMERC_ETA_MAX = 2.623395162778;  // PROJ's domain limit (|lon - lon0| ~ 90 deg)
+
+struct ProjC {
+    int kind;
+    double a, e, es, one_es;
+    double lon0;  // radians
+    double fe, fn;
+    // transverse Mercator
+    double Qn;               // k0 * a * (A / a)
+    double xi0;              // xi of the latitude of origin
+    double alpha[PROJ_TERMS];  // Gaussian sphere -> projected plane
+    double beta[PROJ_TERMS];   // projected plane -> Gaussian sphere
+    double cbg[PROJ_TERMS];    // geodetic -> conformal latitude
+    double cgb[PROJ_TERMS];    // conformal -> geodetic latitude
+    // Lambert azimuthal equal-area
+    double qp, rq, dd, sinb1, cosb1, lat0;
+    double apa[PROJ_TERMS];    // authalic -> geodetic latitude
+};
+
+int make_proj_consts(const xrs_proj *p, ProjC *out);  // reproject.cu (host)
+
+// ---------------------------------------------------------------------------
+// device math
+// ---------------------------------------------------------------------------
+// sum_{k=1..6} c[k-1] * sin(2 k t), given s2 = sin 2t, c2 = cos 2t (Clenshaw)
+__device__ __forceinline__ double clenshaw_sin(const double *c, double s2, double c2) {
+    const double r = 2.0 * c2;
+    double h1 = c[PROJ_TERMS - 1], h2 = 0.0;
+#pragma unroll
+    for (int k = PROJ_TERMS - 2; k >= 0; --k) {
+        const double h = r * h1 - h2 + c[k];
+        h2 = h1;
+        h1 = h;
+    }
+    return s2 * h1;
+}
+
+// sum_k c[k-1] * sin(2 k (xi + i eta)) -> (d_xi, d_eta), complex Clenshaw
+__device__ __forceinline__ void clenshaw_complex(const double *c, double sin2xi, double cos2xi, double sinh2eta,
+                                                 double cosh2eta, double &d_xi, double &d_eta) {
+    const double r = 2.0 * cos2xi * cosh2eta, i = -2.0 * sin2xi * sinh2eta;
+    double hr1 = c[PROJ_TERMS - 1], hi1 = 0.0, hr2 = 0.0, hi2 = 0.0;
+#pragma unroll
+    for (int k = PROJ_TERMS - 2; k >= 0; --k) {
+        const double hr = -hr2 + r * hr1 - i * hi1 + c[k];
+        const double hi = -hi2 + i * hr1 + r * hi1;
+        hr2 = hr1; hi2 = hi1;
+        hr1 = hr; hi1 = hi;
+    }
+    const double sr = sin2xi * cosh2eta, si = cos2xi * sinh2eta;
+    d_xi = sr * hr1 - si * hi1;
+    d_eta = sr * hi1 + si * hr1;
+}
+
+__device__ __forceinline__ double wrap_pi(double lam) {
+    if (fabs(lam) > PROJ_PI) lam -= 2.0 * PROJ_PI * rint(lam / (2.0 * PROJ_PI));
+    return lam;
+}
+
+__device__ __forceinline__ double laea_q(const ProjC &P, double sinphi) {
+    const double es_ = P.e * sinphi;
+    return P.one_es * (sinphi / (1.0 - es_ * es_) - (0.5 / P.e) * log((1.0 - es_) / (1.0 + es_)));
+}
+
+// CRS coordinates -> geographic (lam, phi) in radians.  false = outside the projection's domain.
+__device__ __forceinline__ bool proj_inverse(const ProjC &P, double x, double y, double &lam, double &phi) {
+    switch (P.kind) {
+    case XRS_PROJ_GEOGRAPHIC:
+        lam = x * PROJ_DEG2RAD;
+        phi = y * PROJ_DEG2RAD;
+        return true;
+    case XRS_PROJ_WEBMERC:
+        lam = wrap_pi(P.lon0 + (x - P.fe) / P.a);
+        phi = atan(sinh((y - P.fn) / P.a));
+        return true;
+    case XRS_PROJ_TMERC: {
+        const double xi = (y - P.fn) / P.Qn + P.xi0, eta = (x - P.fe) / P.Qn;
+        if (!(fabs(eta) <= TMERC_ETA_MAX)) return false;
+        double s2, c2;
+        sincos(2.0 * xi, &s2, &c2);
+        const double e2 = exp(2.0 * eta), ie2 = 1.0 / e2;
+        double dxi, deta;
+        clenshaw_complex(P.beta, s2, c2, 0.5 * (e2 - ie2), 0.5 * (e2 + ie2), dxi, deta);
+        const double xip = xi - dxi, etap = eta - deta;
+        double sx, cx;
+        sincos(xip, &sx, &cx);
+        const double sh = sinh(etap);
+        lam = wrap_pi(P.lon0 + atan2(sh, cx));
+        const double hyp = sqrt(sh * sh + cx * cx);  // cos(chi) * cosh(eta')
+        const double chi = atan2(sx, hyp);
+        const double inv = 1.0 / (sx * sx + hyp * hyp);
+        phi = chi + clenshaw_sin(P.cgb, 2.0 * sx * hyp * inv, (hyp * hyp - sx * sx) * inv);
+        return true;
+    }
+    case XRS_PROJ_LAEA: {
+        const double xx = (x - P.fe) / P.dd, yy = (y - P.fn) * P.dd;
+        const double rho = sqrt(xx * xx + yy * yy);
+        if (rho < 1e-10) {
+            lam = P.lon0;
+            phi = P.lat0;
+            return true;
+        }
+        const double sce = rho / (2.0 * P.rq);
+        if (!(sce <= 1.0)) return false;
+        const double sin_ce = 2.0 * sce * sqrt(1.0 - sce * sce), cos_ce = 1.0 - 2.0 * sce * sce;
+        double sinb = cos_ce * P.sinb1 + yy * sin_ce * P.cosb1 / rho;
+        sinb = fmin(1.0, fmax(-1.0, sinb));
+        lam = wrap_pi(P.lon0 + atan2(xx * sin_ce, rho * P.cosb1 * cos_ce - yy * P.sinb1 * sin_ce));
+        const double cosb = sqrt(1.0 - sinb * sinb);
+        phi = asin(sinb) + clenshaw_sin(P.apa, 2.0 * sinb * cosb, 1.0 - 2.0 * sinb * sinb);
+        return true;
+    }
+    }
+    return false;
+}
+
+// geographic (lam, phi) radians -> CRS coordinates
+__device__ __forceinline__ bool proj_forward(const ProjC &P, double lam, double phi, double &x, double &y) {
+    switch (P.kind) {
+    case XRS_PROJ_GEOGRAPHIC:
+        x = lam * PROJ_RAD2DEG;
+        y = phi * PROJ_RAD2DEG;
+        return true;
+    case XRS_PROJ_WEBMERC: {
+        if (!(fabs(phi) < 0.5 * PROJ_PI)) return false;
+        x = P.fe + P.a * wrap_pi(lam - P.lon0);
+        y = P.fn + P.a * asinh(tan(phi));
+        return true;
+    }
+    case XRS_PROJ_TMERC: {
+        if (!(fabs(phi) <= 0.5 * PROJ_PI)) return false;
+        const double dl = wrap_pi(lam - P.lon0);
+        double s2, c2;
+        sincos(2.0 * phi, &s2, &c2);
+        const double chi = phi + clenshaw_sin(P.cbg, s2, c2);
+        double sc, cc, sl, cl;
+        sincos(chi, &sc, &cc);
+        sincos(dl, &sl, &cl);
+        const double ccl = cc * cl;
+        const double xip = atan2(sc, ccl);
+        const double inv = 1.0 / sqrt(sc * sc + ccl * ccl);  // cosh(eta')
+        const double tan_ce = sl * cc * inv;                  // sinh(eta')
+        const double etap = asinh(tan_ce);
+        if (!(fabs(etap) <= TMERC_ETA_MAX)) return false;
+        const double two_inv = 2.0 * inv, two_inv_sq = two_inv * inv, tmp = ccl * two_inv_sq;
+        double dxi, deta;
+        clenshaw_complex(P.alpha, sc * tmp, ccl * tmp - 1.0, tan_ce * two_inv, two_inv_sq - 1.0, dxi, deta);
+        x = P.fe + P.Qn * (etap + deta);
+        y = P.fn + P.Qn * (xip + dxi - P.xi0);
+        return true;
+    }
+    case XRS_PROJ_LAEA: {
+        if (!(fabs(phi) <= 0.5 * PROJ_PI)) return false;
+        const double dl = wrap_pi(lam - P.lon0);
+        double sl, cl;
+        sincos(dl, &sl, &cl);
+        double sinb = laea_q(P, sin(phi)) / P.qp;
+        sinb = fmin(1.0, fmax(-1.0, sinb));
+        const double cosb = sqrt(1.0 - sinb * sinb);
+        double b = 1.0 + P.sinb1 * sinb + P.cosb1 * cosb * cl;
+        if (!(b > 1e-10)) return false;  // antipode of the projection centre
+        b = P.rq * sqrt(2.0 / b);
+        x = P.fe + b * P.dd * cosb * sl;
+        y = P.fn + (b / P.dd) * (P.cosb1 * sinb - P.sinb1 * cosb * cl);
+        return true;
+    }
+    }
+    return false;
+}
+
+// pyproj.Transformer.from_crs(from, to, always_xy=True).transform(x, y); NaN when not transformable
+// (PROJ reports inf there).  Two geographic CRSs pass the coordinates through untouched (the datum
+// shift WGS84 <-> ETRS89 is PROJ's "ballpark" identity).
+__device__ __forceinline__ void proj_transform(const ProjC &from, const ProjC &to, double x, double y, double &ox,
+                                               double &oy) {
+    if (from.kind == XRS_PROJ_GEOGRAPHIC && to.kind == XRS_PROJ_GEOGRAPHIC) {
+        ox = x;
+        oy = y;
+        return;
+    }
+    double lam, phi;
+    bool ok = proj_inverse(from, x, y, lam, phi);
+    if (ok && from.kind == XRS_PROJ_GEOGRAPHIC && !(fabs(y) <= 90.0)) ok = false;
+    ok = ok && proj_forward(to, lam, phi, ox, oy);
+    if (!ok) ox = oy = NAN;
+}
+
+}  // namespace xrs

@@ -1,0 +1,417 @@
+// reproject.cu -- K3: CRS transform of target pixel centres fused with the gather of all bands.
+//
+//   xrs_transform_points   pyproj.Transformer.transform call sites: reproject.py:472-496
+//                          (_transform_gridpoints), rectify.py:182-231 (_transform_coords),
+//                          and, through the host, transform_bounds (reproject.py:347,398)
+//   xrs_reproject          reproject.py:472-496 + 268-335 (_transform_gridpoints + _reproject_block)
+//                          reading the source in place of the padded / re-tiled copy of
+//                          reproject.py:499-530 (_reorganize_data_array_slice)
+//
+// The projection math (proj.cuh) is compiled with FMA contraction; everything the reference
+// computes with numpy after the transform -- fractional index, rounding, tap differences in the
+// source dtype, the lerps in float64 -- uses explicit round-to-nearest intrinsics in the
+// reference's operation order.
+#include <cmath>
+
+#include "proj.cuh"
+
+namespace xrs {
+
+// ---------------------------------------------------------------------------
+// host: projection constants
+// ---------------------------------------------------------------------------
+namespace {
+
+typedef long double ld;
+const ld LD_PI = 3.14159265358979323846264338327950288L;
+
+ld taup_ld(ld tau, ld e) {
+    const ld s1 = sqrtl(1 + tau * tau);
+    const ld sigma = sinhl(e * atanhl(e * tau / s1));
+    return tau * sqrtl(1 + sigma * sigma) - sigma * s1;
+}
+
+// geodetic tangent from conformal tangent (Karney 2011 eqs. 19-21)
+ld tau_from_taup_ld(ld taup, ld e) {
+    const ld e2m = 1 - e * e;
+    ld tau = taup / e2m;
+    for (int it = 0; it < 16; ++it) {
+        const ld tp = taup_ld(tau, e);
+        tau += (taup - tp) / sqrtl(1 + tp * tp) * (1 + e2m * tau * tau) / (e2m * sqrtl(1 + tau * tau));
+    }
+    return tau;
+}
+
+ld q_ld(ld s, ld e) {
+    const ld es = e * s;
+    return (1 - e * e) * (s / (1 - es * es) - (0.5L / e) * logl((1 - es) / (1 + es)));
+}
+
+// geodetic latitude from authalic latitude: Newton on q(phi) (Snyder eq. 3-16)
+ld phi_from_beta_ld(ld beta, ld e) {
+    const ld q = q_ld(1, e) * sinl(beta);
+    ld phi = asinl(q / 2);
+    for (int it = 0; it < 40; ++it) {
+        const ld s = sinl(phi), c = cosl(phi), es = e * s;
+        phi += (1 - es * es) * (1 - es * es) / (2 * c) *
+               (q / (1 - e * e) - s / (1 - es * es) + (0.5L / e) * logl((1 - es) / (1 + es)));
+    }
+    return phi;
+}
+
+// Sine-series coefficients c_k, k = 1..6, of the odd pi-periodic function g(t) = f(t) - t:
+// midpoint rule on (0, pi/2), exact up to rounding because the series decays like n^k.
+template <typename F>
+void sine_series(F f, double *out) {
+    const int M = 64;
+    ld acc[PROJ_TERMS] = {0, 0, 0, 0, 0, 0};
+    for (int m = 0; m < M; ++m) {
+        const ld t = (LD_PI / 2) * (m + 0.5L) / M;
+        const ld g = f(t) - t;
+        for (int k = 1; k <= PROJ_TERMS; ++k) acc[k - 1] += g * sinl(2 * k * t);
+    }
+    for (int k = 0; k < PROJ_TERMS; ++k) out[k] = static_cast<double>(acc[k] * 2 / M);
+}
+
+}  // namespace
+
+int make_proj_consts(const xrs_proj *p, ProjC *c) {
+    if (!p) return fail("projection descriptor is null");
+    ProjC z = {};
+    *c = z;
+    c->kind = p->kind;
+    if (p->kind < XRS_PROJ_GEOGRAPHIC || p->kind > XRS_PROJ_LAEA)
+        return fail("unknown projection kind " + std::to_string(p->kind));
+    if (!(p->a > 0.0)) return fail("projection: semi-major axis must be positive");
+    const double f = p->inv_f != 0.0 ? 1.0 / p->inv_f : 0.0;
+    c->a = p->a;
+    c->es = f * (2.0 - f);
+    c->e = std::sqrt(c->es);
+    c->one_es = 1.0 - c->es;
+    c->lon0 = p->lon0 * PROJ_DEG2RAD;
+    c->lat0 = p->lat0 * PROJ_DEG2RAD;
+    c->fe = p->fe;
+    c->fn = p->fn;
+    if (p->kind == XRS_PROJ_GEOGRAPHIC || p->kind == XRS_PROJ_WEBMERC) return 0;
+    if (f == 0.0) return fail("spherical tmerc / laea are not supported (inverse flattening must be non-zero)");
+    const ld e = sqrtl(static_cast<ld>(f) * (2 - static_cast<ld>(f)));
+    if (p->kind == XRS_PROJ_TMERC) {
+        const double n = f / (2.0 - f), n2 = n * n, n3 = n2 * n, n4 = n3 * n, n5 = n4 * n, n6 = n5 * n;
+        // Karney (2011) eqs. 35, 36
+        const double al[PROJ_TERMS] = {
+            n / 2 - 2 * n2 / 3 + 5 * n3 / 16 + 41 * n4 / 180 - 127 * n5 / 288 + 7891 * n6 / 37800,
+            13 * n2 / 48 - 3 * n3 / 5 + 557 * n4 / 1440 + 281 * n5 / 630 - 1983433 * n6 / 1935360,
+            61 * n3 / 240 - 103 * n4 / 140 + 15061 * n5 / 26880 + 167603 * n6 / 181440,
+            49561 * n4 / 161280 - 179 * n5 / 168 + 6601661 * n6 / 7257600,
+            34729 * n5 / 80640 - 3418889 * n6 / 1995840,
+            212378941 * n6 / 319334400};
+        const double be[PROJ_TERMS] = {
+            n / 2 - 2 * n2 / 3 + 37 * n3 / 96 - n4 / 360 - 81 * n5 / 512 + 96199 * n6 / 604800,
+            n2 / 48 + n3 / 15 - 437 * n4 / 1440 + 46 * n5 / 105 - 1118711 * n6 / 3870720,
+            17 * n3 / 480 - 37 * n4 / 840 - 209 * n5 / 4480 + 5569 * n6 / 90720,
+            4397 * n4 / 161280 - 11 * n5 / 504 - 830251 * n6 / 7257600,
+            4583 * n5 / 161280 - 108847 * n6 / 3991680,
+            20648693 * n6 / 638668800};
+        for (int k = 0; k < PROJ_TERMS; ++k) {
+            c->alpha[k] = al[k];
+            c->beta[k] = be[k];
+        }
+        c->Qn = p->k0 * p->a * (1 + n2 / 4 + n4 / 64 + n6 / 256) / (1 + n);
+        sine_series([e](ld t) { return atanl(taup_ld(tanl(t), e)); }, c->cbg);
+        sine_series([e](ld t) { return atanl(tau_from_taup_ld(tanl(t), e)); }, c->cgb);
+        c->xi0 = 0.0;
+        if (p->lat0 != 0.0) {
+            const ld xip = atanl(taup_ld(tanl(static_cast<ld>(p->lat0) * LD_PI / 180), e));
+            ld xi = xip;
+            for (int k = 1; k <= PROJ_TERMS; ++k) xi += al[k - 1] * sinl(2 * k * xip);
+            c->xi0 = static_cast<double>(xi);
+        }
+        return 0;
+    }
+    // LAEA, oblique or equatorial aspect
+    if (std::fabs(std::fabs(p->lat0) - 90.0) < 1e-9) return fail("polar LAEA is not supported");
+    const ld phi1 = static_cast<ld>(p->lat0) * LD_PI / 180;
+    const ld qp = q_ld(1, e), q1 = q_ld(sinl(phi1), e);
+    const ld sinb1 = q1 / qp, cosb1 = sqrtl(1 - sinb1 * sinb1);
+    const ld rq = p->a * sqrtl(qp / 2);
+    const ld m1 = cosl(phi1) / sqrtl(1 - e * e * sinl(phi1) * sinl(phi1));
+    c->qp = static_cast<double>(qp);
+    c->rq = static_cast<double>(rq);
+    c->dd = static_cast<double>(p->a * m1 / (rq * cosb1));
+    c->sinb1 = static_cast<double>(sinb1);
+    c->cosb1 = static_cast<double>(cosb1);
+    sine_series([e](ld t) { return phi_from_beta_ld(t, e); }, c->apa);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// K3a: point transform
+// ---------------------------------------------------------------------------
+__device__ __noinline__ void transform_point(const ProjC &from, const ProjC &to, double x, double y, double &ox,
+                                             double &oy) {
+    proj_transform(from, to, x, y, ox, oy);
+}
+
+__global__ void __launch_bounds__(256)
+k3_transform_points(const __grid_constant__ ProjC from, const __grid_constant__ ProjC to, const double *__restrict__ x,
+                    const double *__restrict__ y, double *__restrict__ ox, double *__restrict__ oy, int64_t n) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        double tx, ty;
+        transform_point(from, to, x[i], y[i], tx, ty);
+        ox[i] = tx;
+        oy[i] = ty;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K3: fused transform + gather
+// ---------------------------------------------------------------------------
+constexpr int K3_MAX_BANDS = 24;
+constexpr int K3_BX = 32, K3_BY = 8;
+
+template <typename T, typename OUT>
+struct K3Planes {
+    const T *src[K3_MAX_BANDS];
+    OUT *dst[K3_MAX_BANDS];
+};
+
+struct K3Geom {
+    ProjC from, to;  // target CRS -> source CRS
+    const double *dst_x, *dst_y;
+    int64_t dst_h, dst_w, row_begin, row_end;
+    int tile_h, tile_w, ntx;
+    const double *tile_x0, *tile_y0;  // float32 window origins (widened), reproject.py:427-450
+    const int32_t *tile_i0, *tile_j0; // window start in source index space (may be negative)
+    int tile_win_w, tile_win_h;
+    double x_res, y_res;              // source resolution
+    int64_t src_h, src_w, src_pitch, win_i0, win_j0, win_w, win_h;
+};
+
+// numpy index semantics inside the reference window: negative indices count from the end
+// (reproject.py:284,295-298,321-324).  Anything still outside raises IndexError there; here it
+// reads as "no data".
+__device__ __forceinline__ bool window_index(int64_t &k, int n) {
+    if (k < 0) k += n;
+    return k >= 0 && k < n;
+}
+
+// a - b in the array's own dtype (numpy: value_01 - value_00 before the float64 promotion)
+template <typename T>
+__device__ __forceinline__ double diff_as_f64(T a, T b) {
+    if constexpr (std::is_same<T, float>::value) {
+        return static_cast<double>(__fsub_rn(a, b));
+    } else if constexpr (std::is_same<T, double>::value) {
+        return dsub(a, b);
+    } else if constexpr (sizeof(T) == 8) {
+        return static_cast<double>(static_cast<T>(static_cast<uint64_t>(a) - static_cast<uint64_t>(b)));
+    } else {
+        return static_cast<double>(static_cast<T>(static_cast<uint32_t>(a) - static_cast<uint32_t>(b)));
+    }
+}
+
+// float64 -> integer the way numpy's astype does it on x86-64 (reproject.py:299-300 assigns float64
+// results into an array of the source dtype): types up to 32 bits go through a 32-bit cvttsd2si
+// (uint32 through the 64-bit one), whose out-of-range / NaN result is the "integer indefinite"
+// value 0x80000000 (0x8000000000000000), and are then truncated to the destination width.
+template <typename OUT>
+__device__ __forceinline__ OUT cast_like_numpy(double v) {
+    if constexpr (std::is_floating_point<OUT>::value) {
+        return static_cast<OUT>(v);
+    } else if constexpr (sizeof(OUT) == 8 || std::is_same<OUT, uint32_t>::value) {
+        const bool ok = v > -9223372036854775809.0 && v < 9223372036854775808.0;
+        const long long w = ok ? static_cast<long long>(v) : static_cast<long long>(0x8000000000000000ull);
+        return static_cast<OUT>(w);
+    } else {
+        const bool ok = v > -2147483649.0 && v < 2147483648.0;
+        const int w = ok ? static_cast<int>(v) : static_cast<int>(0x80000000u);
+        return static_cast<OUT>(w);
+    }
+}
+
+template <typename T, typename OUT>
+__device__ __forceinline__ OUT k3_store_cast(double v) {
+    if constexpr (std::is_same<OUT, double>::value) return v;
+    else return cast_like_numpy<OUT>(v);
+}
+
+template <typename T, typename OUT, int METHOD>
+__global__ void __launch_bounds__(K3_BX *K3_BY)
+k3_reproject(const __grid_constant__ K3Geom g, const __grid_constant__ K3Planes<T, OUT> planes, int n_bands, T fill) {
+    const int64_t c = static_cast<int64_t>(blockIdx.x) * K3_BX + threadIdx.x;
+    const int64_t r = g.row_begin + static_cast<int64_t>(blockIdx.y) * K3_BY + threadIdx.y;
+    if (c >= g.dst_w || r >= g.row_end) return;
+    const int64_t o = (r - g.row_begin) * g.dst_w + c;
+    double sx, sy;
+    transform_point(g.from, g.to, __ldg(g.dst_x + c), __ldg(g.dst_y + r), sx, sy);
+    const int t = static_cast<int>(r / g.tile_h) * g.ntx + static_cast<int>(c / g.tile_w);
+    // reproject.py:278-279
+    const double fx = ddiv(dsub(sx, __ldg(g.tile_x0 + t)), g.x_res);
+    const double fy = ddiv(dsub(sy, __ldg(g.tile_y0 + t)), -g.y_res);
+    const int64_t i_base = __ldg(g.tile_i0 + t), j_base = __ldg(g.tile_j0 + t);
+    const OUT fill_out = static_cast<OUT>(fill);
+    const bool finite = fabs(fx) < 1e15 && fabs(fy) < 1e15;  // false for NaN / inf too
+
+    // source offset of window index (wy, wx), or -1 for the constant padding
+    // (reproject.py:507 da.pad(..., constant_values=fill_value))
+    auto tap = [&](int64_t wy, int64_t wx, bool &ok) -> int64_t {
+        ok = ok && window_index(wx, g.tile_win_w) && window_index(wy, g.tile_win_h);
+        const int64_t si = i_base + wx, sj = j_base + wy;
+        if (si < 0 || sj < 0 || si >= g.src_w || sj >= g.src_h) return -1;
+        const int64_t li = si - g.win_i0, lj = sj - g.win_j0;
+        if (li < 0 || lj < 0 || li >= g.win_w || lj >= g.win_h) return -1;  // not resident (host bug)
+        return lj * g.src_pitch + li;
+    };
+
+    if (METHOD == XRS_NEAREST) {
+        bool ok = finite;
+        int64_t off = -1;
+        if (finite) off = tap(static_cast<int64_t>(rint(fy)), static_cast<int64_t>(rint(fx)), ok);
+        if (!ok) off = -1;
+#pragma unroll 4
+        for (int b = 0; b < n_bands; ++b) {
+            const T v = off >= 0 ? __ldg(planes.src[b] + off) : fill;
+            st_stream(planes.dst[b] + o, static_cast<OUT>(v));
+        }
+        return;
+    }
+    if (!finite) {
+        for (int b = 0; b < n_bands; ++b) st_stream(planes.dst[b] + o, fill_out);
+        return;
+    }
+    const double fx0 = floor(fx), fy0 = floor(fy);
+    const double u = dsub(fx, fx0), v = dsub(fy, fy0);
+    const int64_t ix0 = static_cast<int64_t>(fx0), ix1 = static_cast<int64_t>(ceil(fx));
+    const int64_t iy0 = static_cast<int64_t>(fy0), iy1 = static_cast<int64_t>(ceil(fy));
+    bool ok = true;
+    const int64_t o00 = tap(iy0, ix0, ok), o01 = tap(iy0, ix1, ok), o10 = tap(iy1, ix0, ok), o11 = tap(iy1, ix1, ok);
+    if (!ok) {
+        for (int b = 0; b < n_bands; ++b) st_stream(planes.dst[b] + o, fill_out);
+        return;
+    }
+    const bool lower = dadd(u, v) < 1.0;                 // reproject.py:301
+    const double u1 = dsub(1.0, u), v1 = dsub(1.0, v);
+#pragma unroll 2
+    for (int b = 0; b < n_bands; ++b) {
+        const T *sp = planes.src[b];
+        const T v00 = o00 >= 0 ? __ldg(sp + o00) : fill, v01 = o01 >= 0 ? __ldg(sp + o01) : fill;
+        const T v10 = o10 >= 0 ? __ldg(sp + o10) : fill, v11 = o11 >= 0 ? __ldg(sp + o11) : fill;
+        double val;
+        if (METHOD == XRS_BILINEAR) {  // reproject.py:325-327
+            const double a = dadd(static_cast<double>(v00), dmul(u, diff_as_f64(v01, v00)));
+            const double bb = dadd(static_cast<double>(v10), dmul(u, diff_as_f64(v11, v10)));
+            val = dadd(a, dmul(v, dsub(bb, a)));
+        } else if (lower) {            // reproject.py:303-307
+            val = dadd(dadd(static_cast<double>(v00), dmul(u, diff_as_f64(v01, v00))), dmul(v, diff_as_f64(v10, v00)));
+        } else {                       // reproject.py:309-313
+            val = dadd(dadd(static_cast<double>(v11), dmul(u1, diff_as_f64(v10, v11))), dmul(v1, diff_as_f64(v01, v11)));
+        }
+        st_stream(planes.dst[b] + o, k3_store_cast<T, OUT>(val));
+    }
+}
+
+template <typename T, typename OUT, int METHOD>
+int launch_reproject(const K3Geom &g, const void *const *src_planes, void *const *dst_planes, int n_bands, double fill,
+                     cudaStream_t st) {
+    const int64_t rows = g.row_end - g.row_begin;
+    const dim3 grid(static_cast<unsigned>(ceil_div(g.dst_w, K3_BX)), static_cast<unsigned>(ceil_div(rows, K3_BY)));
+    if (grid.y > 65535) return fail("xrs_reproject: more than 524280 target rows per call");
+    T fill_t;
+    if constexpr (std::is_floating_point<T>::value) fill_t = static_cast<T>(fill);
+    else fill_t = static_cast<T>(static_cast<long long>(fill));
+    for (int b0 = 0; b0 < n_bands; b0 += K3_MAX_BANDS) {
+        const int nb = std::min(K3_MAX_BANDS, n_bands - b0);
+        K3Planes<T, OUT> planes = {};
+        for (int b = 0; b < nb; ++b) {
+            planes.src[b] = static_cast<const T *>(src_planes[b0 + b]);
+            planes.dst[b] = static_cast<OUT *>(dst_planes[b0 + b]);
+        }
+        k3_reproject<T, OUT, METHOD><<<grid, dim3(K3_BX, K3_BY), 0, st>>>(g, planes, nb, fill_t);
+        XRS_LAUNCH_CHECK("k3_reproject");
+    }
+    return 0;
+}
+
+template <typename T>
+int dispatch_reproject(const K3Geom &g, const void *const *src_planes, void *const *dst_planes, int n_bands,
+                       int out_is_f64, int method, double fill, cudaStream_t st) {
+    constexpr bool t_is_f64 = std::is_same<T, double>::value;
+    switch (method) {
+    case XRS_NEAREST:
+        if (out_is_f64 && !t_is_f64) return fail("xrs_reproject: nearest writes the source dtype");
+        return launch_reproject<T, T, XRS_NEAREST>(g, src_planes, dst_planes, n_bands, fill, st);
+    case XRS_TRIANGULAR:
+        if (out_is_f64 && !t_is_f64) return fail("xrs_reproject: triangular writes the source dtype");
+        return launch_reproject<T, T, XRS_TRIANGULAR>(g, src_planes, dst_planes, n_bands, fill, st);
+    case XRS_BILINEAR:
+        if (out_is_f64 && !t_is_f64)
+            return launch_reproject<T, double, XRS_BILINEAR>(g, src_planes, dst_planes, n_bands, fill, st);
+        return launch_reproject<T, T, XRS_BILINEAR>(g, src_planes, dst_planes, n_bands, fill, st);
+    default:
+        return fail("interp_methods must be one of 0, 1, 'nearest', 'bilinear', 'triangular', was code " +
+                    std::to_string(method));
+    }
+}
+
+}  // namespace xrs
+
+using namespace xrs;
+
+extern "C" {
+
+int xrs_transform_points(const xrs_proj *from_crs, const xrs_proj *to_crs, const double *x_in, const double *y_in,
+                         double *x_out, double *y_out, int64_t n, void *stream) {
+    if (n < 0) return fail("xrs_transform_points: negative count");
+    if (n == 0) return 0;
+    if (!x_in || !y_in || !x_out || !y_out) return fail("xrs_transform_points: null pointer");
+    ProjC from, to;
+    if (int rc = make_proj_consts(from_crs, &from)) return rc;
+    if (int rc = make_proj_consts(to_crs, &to)) return rc;
+    const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(ceil_div(n, 256), 148 * 16));
+    k3_transform_points<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(from, to, x_in, y_in, x_out, y_out, n);
+    XRS_LAUNCH_CHECK("k3_transform_points");
+    return 0;
+}
+
+int xrs_reproject(const void *const *src_planes_host, void *const *dst_planes_host, int32_t n_bands, int32_t dtype,
+                  int32_t out_dtype, int64_t src_h, int64_t src_w, int64_t src_pitch, int64_t win_i0, int64_t win_j0,
+                  int64_t win_w, int64_t win_h, const xrs_proj *src_crs, const xrs_proj *dst_crs, const double *dst_x,
+                  const double *dst_y, int64_t dst_h, int64_t dst_w, int32_t tile_h, int32_t tile_w,
+                  const double *tile_x0, const double *tile_y0, const int32_t *tile_i0, const int32_t *tile_j0,
+                  int32_t tile_win_w, int32_t tile_win_h, double src_x_res, double src_y_res, int32_t method,
+                  double fill, int64_t row_begin, int64_t row_end, void *stream) {
+    if (!src_planes_host || !dst_planes_host || !dst_x || !dst_y || !tile_x0 || !tile_y0 || !tile_i0 || !tile_j0)
+        return fail("xrs_reproject: null pointer");
+    if (n_bands < 1) return fail("xrs_reproject: n_bands must be >= 1");
+    if (src_h < 1 || src_w < 1 || src_pitch < win_w || dst_h < 1 || dst_w < 1 || tile_h < 1 || tile_w < 1)
+        return fail("xrs_reproject: bad image shape");
+    if (win_i0 < 0 || win_j0 < 0 || win_w < 1 || win_h < 1 || win_i0 + win_w > src_w || win_j0 + win_h > src_h)
+        return fail("xrs_reproject: resident window outside the source image");
+    if (row_begin < 0 || row_end > dst_h || row_begin >= row_end) return fail("xrs_reproject: bad row range");
+    if (tile_win_w < 1 || tile_win_h < 1) return fail("xrs_reproject: bad tile window size");
+    if (!(src_x_res > 0.0) || !(src_y_res > 0.0)) return fail("xrs_reproject: resolution must be positive");
+    if (out_dtype != dtype && out_dtype != XRS_F64) return fail("xrs_reproject: out_dtype must be dtype or float64");
+    for (int b = 0; b < n_bands; ++b)
+        if (!src_planes_host[b] || !dst_planes_host[b]) return fail("xrs_reproject: null plane pointer");
+    K3Geom g;
+    if (int rc = make_proj_consts(dst_crs, &g.from)) return rc;
+    if (int rc = make_proj_consts(src_crs, &g.to)) return rc;
+    g.dst_x = dst_x; g.dst_y = dst_y; g.dst_h = dst_h; g.dst_w = dst_w;
+    g.row_begin = row_begin; g.row_end = row_end;
+    g.tile_h = static_cast<int>(std::min<int64_t>(tile_h, dst_h));
+    g.tile_w = static_cast<int>(std::min<int64_t>(tile_w, dst_w));
+    g.ntx = static_cast<int>(ceil_div(dst_w, g.tile_w));
+    g.tile_x0 = tile_x0; g.tile_y0 = tile_y0; g.tile_i0 = tile_i0; g.tile_j0 = tile_j0;
+    g.tile_win_w = tile_win_w; g.tile_win_h = tile_win_h;
+    g.x_res = src_x_res; g.y_res = src_y_res;
+    g.src_h = src_h; g.src_w = src_w; g.src_pitch = src_pitch;
+    g.win_i0 = win_i0; g.win_j0 = win_j0; g.win_w = win_w; g.win_h = win_h;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int out_is_f64 = out_dtype == XRS_F64;
+    XRS_DISPATCH_DTYPE(dtype, T,
+                       return dispatch_reproject<T>(g, src_planes_host, dst_planes_host, n_bands, out_is_f64, method,
+                                                    fill, st));
+    return 0;
+}
+
+}  // extern "C"
