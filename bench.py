@@ -163,7 +163,7 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    scale = 0.5 * args.scale
+    scale = args.scale
     value, cores, sample, ms, _sample_dims = run_cpu(args.steps, args.warmup, scale)
     # describe the full workload (same strings as the GPU arm); the sample is named separately
     from xcube_resampling_b200 import synthetic as syn
@@ -275,12 +275,16 @@ def ours(args):
     if rank == 0:
         sampler.start()
     launches0 = lib.xrs_launch_count()
+    _lib.profile_collect()
+    _lib.profile_enable(True)  # per-kernel CUDA events inside libxrs, on the launching stream
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step(record=True)
     e1.record()
     torch.cuda.synchronize()
+    _lib.profile_enable(False)
+    kernel_times = _lib.profile_collect()
     launches = lib.xrs_launch_count() - launches0
     my_ms = e0.elapsed_time(e1)
     barrier()
@@ -296,7 +300,7 @@ def ours(args):
     n_pass = args.steps * world
     phase_ms = {k: v / n_pass / (len(METHODS) if k in ("k0", "k1") else 1) for k, v in phase_ms.items()}
 
-    # ---- roofline of the dominant kernel: K2 bilinear gather of all bands -------------
+    # ---- roofline of the dominant kernel (largest share of the timed region) ------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -304,16 +308,45 @@ def ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    s_used = (fj1 - fj0) * w  # source pixels resident for this band
-    k2_bytes = 16.0 * band_px + 4.0 * nb * s_used + 4.0 * nb * band_px
-    k2_ms = phase_ms["k2_bilinear"]
-    achieved = k2_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
+    S = float(h * w)                      # source pixels (coordinates are resident in full)
+    s_used = float((fj1 - fj0) * w)       # source pixels of the data bands resident for this row band
+    T = float(band_px)
+    # algorithmic (compulsory) bytes per launch, DESIGN.md "Kernels"
+    models = {
+        "k0_tile_windows": (16.0 * S, "16*S (lon+lat fp64 read once)"),
+        "k1_init_claims": (4.0 * T, "4*T (claim word per target pixel)"),
+        "k1_scatter": (16.0 * S + 4.0 * T, "16*S (lon+lat fp64 read once) + 4*T (claim word per target pixel)"),
+        "k1_scatter_slow": (0.0, "queue of border quads, no compulsory traffic of its own"),
+        "k1_resolve": (4.0 * T + 16.0 * T + 16.0 * S, "4*T (claims) + 16*T (ij fp64 out) + 16*S (winning quads' vertices)"),
+        "k2_gather_staged<nearest>": (16.0 * T + 4.0 * nb * s_used + 4.0 * nb * T,
+                                      "16*T (ij) + 4*B*S_used (source once) + 4*B*T (output once)"),
+        "k2_gather_staged<bilinear>": (16.0 * T + 4.0 * nb * s_used + 4.0 * nb * T,
+                                       "16*T (ij) + 4*B*S_used (source once) + 4*B*T (output once)"),
+    }
+    total_kernel_ms = sum(v[0] for v in kernel_times.values()) or 1.0
+    kernels = []
+    for name, (ms_total, n_launch) in sorted(kernel_times.items(), key=lambda kv: -kv[1][0]):
+        ms_launch = ms_total / max(n_launch, 1)
+        nbytes, model = models.get(name, (0.0, "n/a"))
+        gbs = nbytes / (ms_launch * 1e-3) / 1e9 if ms_launch > 0 else 0.0
+        kernels.append({"kernel": name, "launches": int(n_launch), "ms_per_launch": ms_launch,
+                        "share_of_kernel_time": ms_total / total_kernel_ms, "algorithmic_bytes_per_launch": nbytes,
+                        "achieved_gbs": gbs, "frac": gbs / peak, "bytes_model": model})
+    top = kernels[0] if kernels else {"kernel": "none", "ms_per_launch": 0.0, "achieved_gbs": 0.0, "frac": 0.0,
+                                      "algorithmic_bytes_per_launch": 0.0, "bytes_model": "n/a",
+                                      "share_of_kernel_time": 0.0}
+    traffic = {"k1_scatter": 533.7e6, "k2_gather_staged<bilinear>": 5672.8e6, "k2_gather_staged<nearest>": 5695.0e6,
+               "k1_resolve": 1063.0e6}.get(top["kernel"]) if (world == 1 and args.scale == 1.0) else None
     roofline = {
-        "bound": "hbm", "kernel": "k2_gather<float, bilinear> (21 bands fused)", "achieved": achieved, "peak": peak,
-        "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-        "algorithmic_bytes_per_launch": k2_bytes,
-        "bytes_model": "16*T (ij) + 4*B*S_used (source once) + 4*B*T (output once)", "ms_per_launch": k2_ms,
-        "phase_ms_per_rectify": phase_ms,
+        "bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_gbs"], "peak": peak,
+        "peak_kind": peak_kind, "unit": "GB/s", "frac": top["frac"],
+        "traffic": traffic,
+        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of this "
+                          "workload (profiles/r01_*_ncu_full.txt)" if traffic else None,
+        "algorithmic_bytes_per_launch": top["algorithmic_bytes_per_launch"], "bytes_model": top["bytes_model"],
+        "ms_per_launch": top["ms_per_launch"], "share_of_kernel_time": top["share_of_kernel_time"],
+        "timing": "CUDA events recorded by libxrs around every launch on the launching stream, timed region only",
+        "kernels": kernels, "phase_ms_per_rectify": phase_ms,
     }
 
     # ---- end to end through the public API with host buffers --------------------------
@@ -363,7 +396,7 @@ def ours(args):
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, cores, sample, _ms, _ = run_cpu(steps=2, warmup=1, scale=0.5 * args.scale)
+        v, cores, sample, _ms, _ = run_cpu(steps=5, warmup=1, scale=args.scale)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:

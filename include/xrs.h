@@ -73,6 +73,14 @@ const char *xrs_last_error(void);
 /* number of kernels this library has launched in the calling process (all threads) */
 uint64_t xrs_launch_count(void);
 
+/* Per-kernel timing for bench.py and profiling runs (off by default, no cost when off).  While on,
+ * every kernel launch is bracketed by CUDA events on the stream it is launched on.
+ * xrs_profile_collect waits for the recorded events, sums them per kernel name and clears the
+ * records: names come back newline-separated in `names`, total milliseconds and launch counts in
+ * the parallel arrays; returns the number of entries written (<= max_entries). */
+int xrs_profile_enable(int32_t on);
+int32_t xrs_profile_collect(char *names, int64_t names_len, double *total_ms, int64_t *launches, int32_t max_entries);
+
 /* ------------------------------------------------------------------------
  * Rectification (rectify.py)
  * --------------------------------------------------------------------- */

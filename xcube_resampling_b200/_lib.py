@@ -42,6 +42,8 @@ SIGNATURES = {
     "xrs_device_count": (c_int, []),
     "xrs_last_error": (ctypes.c_char_p, []),
     "xrs_launch_count": (ctypes.c_uint64, []),
+    "xrs_profile_enable": (c_int, [c_i32]),
+    "xrs_profile_collect": (c_i32, [c_p, c_i64, c_p, c_p, c_i32]),
     "xrs_tile_src_bboxes_workspace_bytes": (c_i64, [c_i32, c_i32]),
     "xrs_tile_src_bboxes": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_i32, c_p, c_p, c_i32, c_i32, c_p,
                                     c_p, c_p]),
@@ -87,3 +89,20 @@ def check(rc: int, what: str = "libxrs call"):
     if rc != 0:
         msg = load().xrs_last_error().decode("utf-8", "replace")
         raise XrsError(f"{what} failed (status {rc}): {msg}")
+
+
+def profile_enable(on: bool):
+    """Switch per-kernel event timing of libxrs on or off (include/xrs.h: xrs_profile_enable)."""
+    load().xrs_profile_enable(1 if on else 0)
+
+
+def profile_collect() -> dict:
+    """{kernel name: (total ms, launches)} since the last collect; waits for the kernels."""
+    lib = load()
+    n_max = 64
+    names = ctypes.create_string_buffer(4096)
+    ms = (ctypes.c_double * n_max)()
+    cnt = (ctypes.c_int64 * n_max)()
+    n = lib.xrs_profile_collect(ctypes.cast(names, c_p), 4096, ctypes.cast(ms, c_p), ctypes.cast(cnt, c_p), n_max)
+    keys = names.value.decode().split("\n")[:n]
+    return {k: (ms[i], cnt[i]) for i, k in enumerate(keys)}

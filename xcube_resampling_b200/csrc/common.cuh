@@ -32,6 +32,20 @@ void count_launch();
         XRS_CUDA((cudaGetLastError()));   \
     } while (0)
 
+// Optional per-kernel timing (xrs_profile_enable): brackets one launch with CUDA events on its stream.
+void profile_begin(const char *name, cudaStream_t st);
+void profile_end(cudaStream_t st);
+struct ProfileScope {
+    cudaStream_t st;
+    ProfileScope(const char *name, cudaStream_t s) : st(s) { profile_begin(name, s); }
+    ~ProfileScope() { profile_end(st); }
+};
+#define XRS_TIMED(name, st, ...)                  \
+    do {                                          \
+        ::xrs::ProfileScope _xrs_ps((name), (st)); \
+        __VA_ARGS__;                              \
+    } while (0)
+
 __host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------------------

@@ -326,8 +326,8 @@ static int launch_staged(const StagedParams<T> &sp, int nb, int64_t src_h, int64
     XRS_CUDA(cudaFuncSetAttribute(k2_gather_staged<T, METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
     const dim3 grid(static_cast<unsigned>(ceil_div(dst_w, K2S_TW)), static_cast<unsigned>(ceil_div(dst_h, K2S_TH)));
-    k2_gather_staged<T, METHOD><<<grid, K2S_THREADS, smem, st>>>(sp, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij,
-                                                                 dst_h, dst_w, fill);
+    XRS_TIMED(METHOD == XRS_NEAREST ? "k2_gather_staged<nearest>" : METHOD == XRS_BILINEAR ? "k2_gather_staged<bilinear>" : "k2_gather_staged<triangular>", st, k2_gather_staged<T, METHOD><<<grid, K2S_THREADS, smem, st>>>(sp, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij,
+                                                                 dst_h, dst_w, fill));
     XRS_LAUNCH_CHECK("k2_gather_staged");
     return 0;
 }
@@ -394,13 +394,13 @@ static int launch_gather(const void *const *src_planes, void *const *dst_planes,
         const dim3 grid(static_cast<unsigned>(ceil_div(dst_w, K2_BX)), static_cast<unsigned>(ceil_div(dst_h, K2_BY)));
         switch (method) {
         case XRS_NEAREST:
-            k2_gather_direct<T, XRS_NEAREST><<<grid, block, 0, st>>>(pt, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fill_t);
+            XRS_TIMED("k2_gather_direct", st, k2_gather_direct<T, XRS_NEAREST><<<grid, block, 0, st>>>(pt, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fill_t));
             break;
         case XRS_BILINEAR:
-            k2_gather_direct<T, XRS_BILINEAR><<<grid, block, 0, st>>>(pt, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fill_t);
+            XRS_TIMED("k2_gather_direct", st, k2_gather_direct<T, XRS_BILINEAR><<<grid, block, 0, st>>>(pt, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fill_t));
             break;
         default:
-            k2_gather_direct<T, XRS_TRIANGULAR><<<grid, block, 0, st>>>(pt, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fill_t);
+            XRS_TIMED("k2_gather_direct", st, k2_gather_direct<T, XRS_TRIANGULAR><<<grid, block, 0, st>>>(pt, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fill_t));
             break;
         }
         XRS_LAUNCH_CHECK("k2_gather_direct");

@@ -200,7 +200,7 @@ int xrs_tile_src_bboxes(const double *x, const double *y, int64_t src_h, int64_t
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int n_tiles = ntx * nty;
     int4 *table = static_cast<int4 *>(workspace);
-    k0_init_table<<<static_cast<unsigned>(ceil_div(n_tiles, 256)), 256, 0, st>>>(table, n_tiles);
+    XRS_TIMED("k0_init_table", st, k0_init_table<<<static_cast<unsigned>(ceil_div(n_tiles, 256)), 256, 0, st>>>(table, n_tiles));
     XRS_LAUNCH_CHECK("k0_init_table");
 
     const int64_t n_blocks = ceil_div(src_w, K0_THREADS) * ceil_div(src_h, K0_ROWS);
@@ -210,14 +210,14 @@ int xrs_tile_src_bboxes(const double *x, const double *y, int64_t src_h, int64_t
     if (n_tiles <= K0_SMEM_TILES) {
         const size_t smem = axis_bytes + static_cast<size_t>(n_tiles) * sizeof(int4);
         XRS_CUDA(cudaFuncSetAttribute(k0_tile_windows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        k0_tile_windows<true><<<grid, K0_THREADS, smem, st>>>(x, y, src_h, src_w, src_pitch, x_lo, x_hi, ntx, y_lo, y_hi, nty, table);
+        XRS_TIMED("k0_tile_windows", st, k0_tile_windows<true><<<grid, K0_THREADS, smem, st>>>(x, y, src_h, src_w, src_pitch, x_lo, x_hi, ntx, y_lo, y_hi, nty, table));
     } else {
         if (axis_bytes > 200 * 1024) return fail("xrs_tile_src_bboxes: too many tile rows/columns");
         XRS_CUDA(cudaFuncSetAttribute(k0_tile_windows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(axis_bytes)));
-        k0_tile_windows<false><<<grid, K0_THREADS, axis_bytes, st>>>(x, y, src_h, src_w, src_pitch, x_lo, x_hi, ntx, y_lo, y_hi, nty, table);
+        XRS_TIMED("k0_tile_windows", st, k0_tile_windows<false><<<grid, K0_THREADS, axis_bytes, st>>>(x, y, src_h, src_w, src_pitch, x_lo, x_hi, ntx, y_lo, y_hi, nty, table));
     }
     XRS_LAUNCH_CHECK("k0_tile_windows");
-    k0_finalize<<<static_cast<unsigned>(ceil_div(n_tiles, 256)), 256, 0, st>>>(table, n_tiles, ij_border, src_w, src_h, out_boxes);
+    XRS_TIMED("k0_finalize", st, k0_finalize<<<static_cast<unsigned>(ceil_div(n_tiles, 256)), 256, 0, st>>>(table, n_tiles, ij_border, src_w, src_h, out_boxes));
     XRS_LAUNCH_CHECK("k0_finalize");
     return 0;
 }

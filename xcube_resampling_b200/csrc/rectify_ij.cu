@@ -478,21 +478,21 @@ int xrs_rectify_ij(const double *x, const double *y, int64_t src_h, int64_t src_
     g.slow_count = reinterpret_cast<unsigned int *>(g.slow_list + (src_h - 1) * (src_w - 1));
 
     const int64_t n_vec = ceil_div(n_rows * dst_w, 4);
-    k1_init_claims<<<static_cast<unsigned>(ceil_div(n_vec, 256)), 256, 0, st>>>(reinterpret_cast<uint4 *>(g.claims), n_vec, g.slow_count);
+    XRS_TIMED("k1_init_claims", st, k1_init_claims<<<static_cast<unsigned>(ceil_div(n_vec, 256)), 256, 0, st>>>(reinterpret_cast<uint4 *>(g.claims), n_vec, g.slow_count));
     XRS_LAUNCH_CHECK("k1_init_claims");
     const dim3 sgrid(static_cast<unsigned>(ceil_div(ceil_div(src_w - 1, 31), K1S_WARPS)),
                      static_cast<unsigned>(ceil_div(src_h - 1, K1S_ROWS)));
     if (sgrid.y > 65535) return fail("xrs_rectify_ij: source too tall");
-    k1_scatter<<<sgrid, K1S_WARPS * 32, 0, st>>>(g);
+    XRS_TIMED("k1_scatter", st, k1_scatter<<<sgrid, K1S_WARPS * 32, 0, st>>>(g));
     XRS_LAUNCH_CHECK("k1_scatter");
     int dev = 0, sms = 0;
     XRS_CUDA(cudaGetDevice(&dev));
     XRS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    k1_scatter_slow<<<static_cast<unsigned>(sms * 4), 256, 0, st>>>(g);
+    XRS_TIMED("k1_scatter_slow", st, k1_scatter_slow<<<static_cast<unsigned>(sms * 4), 256, 0, st>>>(g));
     XRS_LAUNCH_CHECK("k1_scatter_slow");
     if (n_rows > 65535) return fail("xrs_rectify_ij: more than 65535 target rows per call");
     const dim3 rgrid(static_cast<unsigned>(ceil_div(dst_w, K1R_THREADS)), static_cast<unsigned>(n_rows));
-    k1_resolve<<<rgrid, K1R_THREADS, 0, st>>>(g);
+    XRS_TIMED("k1_resolve", st, k1_resolve<<<rgrid, K1R_THREADS, 0, st>>>(g));
     XRS_LAUNCH_CHECK("k1_resolve");
     return 0;
 }

@@ -326,7 +326,7 @@ int launch_reproject(const K3Geom &g, const void *const *src_planes, void *const
             planes.src[b] = static_cast<const T *>(src_planes[b0 + b]);
             planes.dst[b] = static_cast<OUT *>(dst_planes[b0 + b]);
         }
-        k3_reproject<T, OUT, METHOD><<<grid, dim3(K3_BX, K3_BY), 0, st>>>(g, planes, nb, fill_t);
+        XRS_TIMED(METHOD == XRS_NEAREST ? "k3_reproject<nearest>" : METHOD == XRS_BILINEAR ? "k3_reproject<bilinear>" : "k3_reproject<triangular>", st, k3_reproject<T, OUT, METHOD><<<grid, dim3(K3_BX, K3_BY), 0, st>>>(g, planes, nb, fill_t));
         XRS_LAUNCH_CHECK("k3_reproject");
     }
     return 0;
@@ -368,7 +368,7 @@ int xrs_transform_points(const xrs_proj *from_crs, const xrs_proj *to_crs, const
     if (int rc = make_proj_consts(from_crs, &from)) return rc;
     if (int rc = make_proj_consts(to_crs, &to)) return rc;
     const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(ceil_div(n, 256), 148 * 16));
-    k3_transform_points<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(from, to, x_in, y_in, x_out, y_out, n);
+    XRS_TIMED("k3_transform_points", static_cast<cudaStream_t>(stream), k3_transform_points<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(from, to, x_in, y_in, x_out, y_out, n));
     XRS_LAUNCH_CHECK("k3_transform_points");
     return 0;
 }

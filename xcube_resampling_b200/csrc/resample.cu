@@ -319,9 +319,9 @@ static int launch_affine(const void *src, void *dst, const AffineGeom &g, cudaSt
     const dim3 grid(static_cast<unsigned>(ceil_div(g.dst_w, 32)), static_cast<unsigned>(ceil_div(g.dst_h, 8)),
                     static_cast<unsigned>(g.n_slices));
     if (i64)
-        k4_affine_generic<T, int64_t><<<grid, block, 0, st>>>(static_cast<const T *>(src), static_cast<int64_t *>(dst), g);
+        XRS_TIMED("k4_affine_generic", st, k4_affine_generic<T, int64_t><<<grid, block, 0, st>>>(static_cast<const T *>(src), static_cast<int64_t *>(dst), g));
     else
-        k4_affine_generic<T, T><<<grid, block, 0, st>>>(static_cast<const T *>(src), static_cast<T *>(dst), g);
+        XRS_TIMED("k4_affine_generic", st, k4_affine_generic<T, T><<<grid, block, 0, st>>>(static_cast<const T *>(src), static_cast<T *>(dst), g));
     XRS_LAUNCH_CHECK("k4_affine_generic");
     return 0;
 }
