@@ -211,18 +211,10 @@ def ours(args):
         torch.cuda.synchronize()
 
     def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return xbands.max_over_ranks(ms, dev)
 
     def sum_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return xbands.sum_over_ranks(v, dev)
 
     # ---- scene + geometry (every rank builds the same synthetic scene) ----------------
     lon, lat, bands, size, xy_min, res = make_scene(scale=args.scale)

@@ -1,0 +1,122 @@
+"""Multi-GPU host logic on CPU: target row-band partition, per-band source footprints and the
+cross-rank bookkeeping, exercised by two ``gloo`` processes (the N>1 path has no data-path
+collective -- each rank computes its own band from its own footprint).
+
+The kernels are stood in for by the oracle here (CPU); what is under test is the sharding: a band
+computed from ONLY its footprint of the source must equal the same rows of the whole-image result.
+"""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import grid as ogrid
+from oracle import proj as oproj
+from oracle import rectify as orect
+from oracle import reproject as orep
+from xcube_resampling_b200 import GridMapping
+from xcube_resampling_b200 import bands as xbands
+from xcube_resampling_b200.synthetic import covering_grid_args, swath
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_row_bands_partition():
+    for height, n, align in ((5013, 8, 32), (100, 3, 32), (31, 4, 32), (4500 * 8, 8, 4500)):
+        bands = xbands.row_bands(height, n, align)
+        assert len(bands) == n and bands[0][0] == 0 and bands[-1][1] == height
+        for (a0, a1), (b0, b1) in zip(bands, bands[1:]):
+            assert a1 == b0 and a0 <= a1
+        assert all(a0 % align == 0 for a0, _ in bands)
+    with pytest.raises(ValueError):
+        xbands.row_bands(10, 0)
+
+
+def _rectify_worker(rank, world, port, result_dir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        w, h, res, tile = 160, 120, 0.0027, 64
+        lon, lat = swath(w, h, res=res, theta=12.0, seed=2)
+        size, xy_min = covering_grid_args(lon, lat, res)
+        gm = GridMapping.regular(size, xy_min, res, "EPSG:4326", tile_size=tile)
+        g = ogrid.regular_grid(size, xy_min, res, tile_size=tile)
+        data = np.random.default_rng(0).random((3, h, w)).astype(np.float32)
+        rows = xbands.row_bands(gm.height, world, align=32)[rank]
+        boxes = orect.source_windows(lon, lat, g)
+        fp = xbands.rectify_band_footprint(boxes, gm, rows, (w, h))
+        assert fp is not None
+        i0, j0, i1, j1 = fp
+        # the band's ij values (whole-image oracle, band rows) must stay inside the footprint
+        ij = orect.rectify_ij(lon, lat, g, windows=boxes)[:, rows[0]:rows[1]]
+        ok = np.isfinite(ij[0])
+        assert ok.any()
+        assert int(ij[0][ok].min()) >= i0 and min(int(ij[0][ok].max()) + 1, w - 1) <= i1 - 1
+        assert int(ij[1][ok].min()) >= j0 and min(int(ij[1][ok].max()) + 1, h - 1) <= j1 - 1
+        # gather from ONLY the footprint window, with shifted indices and true-edge clamping
+        masked = np.full_like(data, np.nan)
+        masked[:, j0:j1, i0:i1] = data[:, j0:j1, i0:i1]
+        for method in ("nearest", "bilinear"):
+            part = orect.gather(masked, ij, method, np.nan)
+            full = orect.gather(data, orect.rectify_ij(lon, lat, g, windows=boxes), method, np.nan)
+            assert np.array_equal(part, full[:, rows[0]:rows[1]], equal_nan=True), (rank, method)
+        # bookkeeping: per-rank unit counts sum, timings max
+        units = xbands.sum_over_ranks(float((rows[1] - rows[0]) * gm.width))
+        assert units == float(gm.height * gm.width)
+        assert xbands.max_over_ranks(float(rank + 1)) == float(world)
+        # every rank's rows gathered -> exact cover of the image
+        got = [None] * world
+        dist.all_gather_object(got, rows)
+        assert got[0][0] == 0 and got[-1][1] == gm.height and all(a[1] == b[0] for a, b in zip(got, got[1:]))
+        open(os.path.join(result_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def _reproject_worker(rank, world, port, result_dir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        utm, geo = oproj.from_epsg(32632), oproj.from_epsg(4326)
+        tgt_gm = GridMapping.regular((96, 128), (399960.0, 990240.0), 10.0, "EPSG:32632", tile_size=32)
+        g = ogrid.regular_grid((96, 128), (399960.0, 990240.0), 10.0, tile_size=32)
+        box = oproj.transform_bounds(utm, geo, *tgt_gm.xy_bbox)
+        res = 0.0001
+        x_min, y_min = np.floor(box[0] / res) * res - 4 * res, np.floor(box[1] / res) * res - 4 * res
+        w = int(np.ceil((box[2] - x_min) / res)) + 4
+        h = int(np.ceil((box[3] - y_min) / res)) + 4
+        sg = ogrid.regular_grid((w, h), (x_min, y_min), res)
+        xs, ys = ogrid.x_centres(sg), ogrid.y_centres(sg)
+        data = np.random.default_rng(1).random((2, h, w)).astype(np.float32)
+        args = (float(xs[0]), float(ys[0]), res, res, float(ys[1] - ys[0]))
+        win = orep.source_windows(*args, w, h, g, utm, geo)
+        rows = xbands.row_bands(tgt_gm.height, world, align=32)[rank]
+        fp = xbands.reproject_band_footprint(win["i0"], win["j0"], win["win_w"], win["win_h"], tgt_gm, rows, (w, h))
+        assert fp is not None
+        i0, j0, i1, j1 = fp
+        assert (i1 - i0) * (j1 - j0) < w * h  # a band needs less than the whole source
+        masked = np.full_like(data, -777.0)   # anything outside the footprint must never be read
+        masked[:, j0:j1, i0:i1] = data[:, j0:j1, i0:i1]
+        for method in ("nearest", "bilinear"):
+            full = orep.reproject(data, *args, g, utm, geo, method, np.nan)
+            part = orep.reproject(masked, *args, g, utm, geo, method, np.nan)
+            assert np.array_equal(part[:, rows[0]:rows[1]], full[:, rows[0]:rows[1]], equal_nan=True), (rank, method)
+        open(os.path.join(result_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("worker", [_rectify_worker, _reproject_worker])
+def test_two_rank_row_bands_gloo(worker, tmp_path):
+    world = 2
+    mp.spawn(worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]

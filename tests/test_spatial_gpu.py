@@ -1,0 +1,123 @@
+"""The reference's tests/test_spatial.py and the CRS-changing rectify cases
+(tests/test_rectify.py:461-500) through the B200 entry points: dispatch rules, rectify with a
+forward coordinate transform on the device (rectify.py:182-231) and the rectify pre-downscale
+(rectify.py:234-260)."""
+
+import logging
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+nan = np.nan
+
+
+@pytest.fixture(scope="module")
+def xrs():
+    import torch
+
+    assert torch.cuda.is_available()
+    import xcube_resampling_b200 as pkg
+
+    return pkg
+
+
+def _irregular_4x4(xrs):
+    """tests/sampledata.py:175-211."""
+    lon = np.array([[1.0, 2.0, 3.0, 4.0], [0.0, 1.0, 2.0, 3.0], [-1.0, 0.0, 1.0, 2.0], [-2.0, -1.0, 0.0, 1.0]])
+    lat = np.array([[56.0, 55.0, 54.0, 53.0], [55.0, 54.0, 53.0, 52.0], [54.0, 53.0, 52.0, 51.0],
+                    [53.0, 52.0, 51.0, 50.0]])
+    rad = np.arange(1.0, 17.0).reshape(4, 4)
+    return xrs.Dataset(data_vars=dict(rad=(("y", "x"), rad)),
+                       coords=dict(lon=(("y", "x"), lon), lat=(("y", "x"), lat)))
+
+
+def _irregular_2x2(xrs):
+    """tests/sampledata.py:29-39."""
+    return xrs.Dataset(data_vars=dict(rad=(("y", "x"), np.array([[1.0, 2.0], [3.0, 4.0]]))),
+                       coords=dict(lon=(("y", "x"), np.array([[1.0, 6.0], [0.0, 2.0]])),
+                                   lat=(("y", "x"), np.array([[56.0, 53.0], [52.0, 50.0]]))))
+
+
+def _regular_8x6(xrs):
+    """tests/sampledata.py:60-83."""
+    res = 0.1
+    refl = np.array([[0, 1, 0, 2, 0, 3, 0, 4], [2, 0, 3, 0, 4, 0, 1, 0], [0, 4, 0, nan, 0, 2, 0, 3],
+                     [1, 0, 2, 0, 3, 0, 4, 0], [0, 3, 0, 4, 0, 1, 0, 2], [4, 0, 1, 0, 2, 0, 3, 0]], dtype=np.float64)
+    return xrs.Dataset(data_vars=dict(refl=(("lat", "lon"), refl)),
+                       coords=dict(lon=("lon", 50.0 + res * np.arange(0, 8) + 0.5 * res),
+                                   lat=("lat", 10.6 - res * np.arange(0, 6) - 0.5 * res)))
+
+
+def _utm_5x5(xrs):
+    """tests/sampledata.py:95-109."""
+    return xrs.Dataset(
+        data_vars=dict(band_1=xrs.DataArray(np.arange(25).reshape(5, 5), dims=("y", "x"),
+                                            attrs=dict(grid_mapping="spatial_ref"))),
+        coords=dict(x=("x", np.arange(565300.0, 565800.0, 100.0)), y=("y", np.arange(5934300.0, 5933800.0, -100.0)),
+                    spatial_ref=xrs.DataArray(np.array(0), dims=(), attrs=xrs.CRS.from_epsg(32632).to_cf())))
+
+
+def test_ref_rectify_different_crs(xrs):
+    """tests/test_rectify.py:461-479: geographic 2-D coordinates, LAEA target."""
+    tgt = xrs.GridMapping.regular(size=(3, 3), xy_min=(3600000, 3200000), xy_res=100000, crs="epsg:3035")
+    out = xrs.rectify_dataset(_irregular_4x4(xrs), target_gm=tgt, interp_methods=0)
+    np.testing.assert_almost_equal(out.x.values, [3650000.0, 3750000.0, 3850000.0])
+    np.testing.assert_almost_equal(out.y.values, [3450000.0, 3350000.0, 3250000.0])
+    np.testing.assert_almost_equal(out.rad.values, [[10.0, 6.0, 3.0], [10.0, 7.0, 3.0], [11.0, 11.0, 8.0]])
+
+
+def test_ref_spatial_affine(xrs):
+    """tests/test_spatial.py:25-49."""
+    ds = _regular_8x6(xrs)
+    gm = xrs.GridMapping.from_dataset(ds)
+    tgt = xrs.GridMapping.regular((3, 3), (50.0, 10.0), 0.1, gm.crs)
+    out = xrs.resample_in_space(ds, tgt, interp_methods=1)
+    assert out.refl.shape == (3, 3)
+    np.testing.assert_almost_equal(out.refl.values, [[1, 0, 2], [0, 3, 0], [4, 0, 1]])
+
+
+def test_ref_spatial_rectify_and_downscale(xrs):
+    """tests/test_spatial.py:51-77."""
+    tgt = xrs.GridMapping.regular(size=(2, 2), xy_min=(-1, 51), xy_res=2, crs=xrs.CRS_WGS84)
+    out = xrs.resample_in_space(_irregular_4x4(xrs), target_gm=tgt, interp_methods=0)
+    np.testing.assert_almost_equal(out.rad.values, [[5, 2], [14, 8]])
+    out = xrs.resample_in_space(_irregular_4x4(xrs), target_gm=tgt, interp_methods=1)
+    np.testing.assert_almost_equal(out.rad.values, [[7.5, 4.5], [12.5, 9.5]])
+
+
+def test_ref_spatial_rectify_and_upscale(xrs):
+    """tests/test_spatial.py:79-96."""
+    tgt = xrs.GridMapping.regular(size=(4, 4), xy_min=(-1, 49), xy_res=2, crs=xrs.CRS_WGS84)
+    out = xrs.resample_in_space(_irregular_2x2(xrs), target_gm=tgt, interp_methods=0)
+    np.testing.assert_almost_equal(out.rad.values, [[nan, nan, nan, nan], [nan, 1.0, 2.0, nan], [3.0, 3.0, 2.0, nan],
+                                                    [nan, 4.0, nan, nan]])
+
+
+def test_ref_spatial_reproject(xrs):
+    """tests/test_spatial.py:98-177."""
+    cases = [
+        (dict(size=(5, 5), xy_min=(4320080, 3382480), xy_res=80, crs="epsg:3035"),
+         [[1, 1, 2, 3, 4], [6, 6, 7, 8, 9], [11, 12, 12, 13, 14], [16, 17, 17, 18, 19], [21, 17, 17, 18, 19]]),
+        (dict(size=(5, 5), xy_min=(4320080, 3382480), xy_res=20, crs="epsg:3035"),
+         [[15, 16, 16, 16, 16], [15, 16, 16, 16, 16], [15, 16, 16, 16, 16], [20, 21, 21, 21, 21], [20, 21, 21, 21, 21]]),
+        (dict(size=(5, 5), xy_min=(9.9886, 53.5499), xy_res=0.0006, crs=xrs.CRS_WGS84),
+         [[7, 8, 8, 8, 9], [12, 13, 13, 13, 14], [12, 13, 13, 13, 14], [17, 18, 18, 18, 19], [22, 23, 23, 23, 24]]),
+        (dict(size=(5, 5), xy_min=(9.9886, 53.5499), xy_res=0.0003, crs=xrs.CRS_WGS84),
+         [[12, 12, 12, 13, 13], [17, 17, 17, 18, 18], [17, 17, 17, 18, 18], [22, 17, 17, 18, 18], [22, 22, 22, 23, 23]]),
+    ]
+    for kw, expected in cases:
+        out = xrs.resample_in_space(_utm_5x5(xrs), target_gm=xrs.GridMapping.regular(**kw), interp_methods=0)
+        np.testing.assert_array_equal(out.band_1.values, expected)
+
+
+def test_ref_spatial_logs_and_passthrough(xrs, caplog):
+    """tests/test_spatial.py:179-193."""
+    ds = _utm_5x5(xrs)
+    with caplog.at_level(logging.WARNING, logger="xcube.resampling"):
+        out = xrs.resample_in_space(ds)
+    assert out is ds
+    assert any("If source grid mapping is regular `target_gm` must be given. Source dataset is returned." in m
+               for m in caplog.messages)
+    out = xrs.resample_in_space(ds, target_gm=xrs.GridMapping.from_dataset(ds))
+    assert out is ds

@@ -50,3 +50,44 @@ def rectify_band_footprint(tile_boxes: np.ndarray, target_gm: GridMapping, rows:
     i1 = min(int(boxes[:, 2].max()) + 2, src_w)
     j1 = min(int(boxes[:, 3].max()) + 2, src_h)
     return i0, j0, i1, j1
+
+
+def reproject_band_footprint(win_i0: np.ndarray, win_j0: np.ndarray, win_w: int, win_h: int, target_gm: GridMapping,
+                             rows: tuple[int, int], src_size: tuple[int, int]) -> tuple[int, int, int, int] | None:
+    """Source window (i0, j0, i1, j1), end-exclusive and clipped to the source, that a reproject
+    row band can read: the union of the reference tiles' source windows (``reproject.py:385-469``)
+    over the tile rows intersecting the band.  ``None`` if it lies entirely outside the source."""
+    src_w, src_h = src_size
+    ty0, ty1 = band_tile_rows(target_gm, rows)
+    i0, j0 = np.asarray(win_i0)[ty0:ty1], np.asarray(win_j0)[ty0:ty1]
+    i_lo, j_lo = max(int(i0.min()), 0), max(int(j0.min()), 0)
+    i_hi, j_hi = min(int(i0.max()) + int(win_w), src_w), min(int(j0.max()) + int(win_h), src_h)
+    if i_lo >= i_hi or j_lo >= j_hi:
+        return None
+    return i_lo, j_lo, i_hi, j_hi
+
+
+# ---------------------------------------------------------------------------
+# cross-rank bookkeeping (torch.distributed; NCCL on GPUs, gloo in the CPU tests).
+# The data path has no collective: these only aggregate timings and unit counts.
+# ---------------------------------------------------------------------------
+def max_over_ranks(value: float, device=None) -> float:
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, device=None) -> float:
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())

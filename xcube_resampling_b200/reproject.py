@@ -173,15 +173,11 @@ class ReprojectPlan:
     def footprint(self) -> tuple[int, int, int, int] | None:
         """Source window (i0, j0, i1, j1), end-exclusive and clipped to the source, that the tiles
         intersecting ``rows`` can read; ``None`` if they lie entirely outside the source."""
-        gm, w = self.target_gm, self.windows
-        ty0, ty1 = self.rows[0] // gm.tile_height, -(-self.rows[1] // gm.tile_height)
-        i_lo, j_lo = int(w.i0[ty0:ty1].min()), int(w.j0[ty0:ty1].min())
-        i_hi, j_hi = int(w.i0[ty0:ty1].max()) + w.win_w, int(w.j0[ty0:ty1].max()) + w.win_h
-        i_lo, j_lo = max(i_lo, 0), max(j_lo, 0)
-        i_hi, j_hi = min(i_hi, self.source_gm.width), min(j_hi, self.source_gm.height)
-        if i_lo >= i_hi or j_lo >= j_hi:
-            return None
-        return i_lo, j_lo, i_hi, j_hi
+        from .bands import reproject_band_footprint
+
+        w = self.windows
+        return reproject_band_footprint(w.i0, w.j0, w.win_w, w.win_h, self.target_gm, self.rows,
+                                        (self.source_gm.width, self.source_gm.height))
 
     def run(self, src: torch.Tensor, interp_method: str, fill_value, out: torch.Tensor | None = None,
             out_dtype=None, window_origin: tuple[int, int] = (0, 0)) -> torch.Tensor:
