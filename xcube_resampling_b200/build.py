@@ -31,6 +31,7 @@ SOURCES = {
     "rectify_ij.cu": ["-fmad=false"],
     "gather.cu": ["-fmad=false"],
     "resample.cu": ["-fmad=false"],
+    "resample_fast.cu": ["-fmad=false"],
     "reproject.cu": [],  # projection math may contract; the numpy-parity part uses _rn intrinsics
 }
 

@@ -20,67 +20,9 @@
 //     floor(t + 0.5) clipped at 0, both saturating.
 // Reducer semantics restated from numpy (nan-reducers for floats, float32 accumulation in numpy's
 // pairwise-by-row order so that means are bit-identical for the usual factors).
-#include "common.cuh"
+#include "resample_common.cuh"
 
 namespace xrs {
-
-constexpr int RS_MAX_WINDOW = 256;  // f_j * f_i samples buffered per output pixel (generic kernel)
-
-struct AffineGeom {
-    int64_t n_slices, src_h, src_w, src_pitch, src_slice_stride;
-    int64_t dst_h, dst_w;
-    double j_scale, j_off, i_scale, i_off;
-    double cval;
-    int order, agg, f_j, f_i, slice_blend;
-};
-
-// ---------------------------------------------------------------------------
-// scipy output conversion (CASE_INTERP_OUT*)
-// ---------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ T scipy_cast(double t) {
-    if constexpr (std::is_floating_point<T>::value) {
-        return static_cast<T>(t);
-    } else if constexpr (std::is_unsigned<T>::value) {
-        t = t > 0 ? t + 0.5 : 0.0;
-        const double mx = static_cast<double>(std::numeric_limits<T>::max());
-        t = t > mx ? mx : t;
-        t = t < 0 ? 0.0 : t;
-        return static_cast<T>(static_cast<unsigned long long>(t));
-    } else {
-        t = t > 0 ? t + 0.5 : t - 0.5;
-        const double mx = static_cast<double>(std::numeric_limits<T>::max());
-        const double mn = static_cast<double>(std::numeric_limits<T>::min());
-        t = t > mx ? mx : t;
-        t = t < mn ? mn : t;
-        return static_cast<T>(static_cast<long long>(t));
-    }
-}
-
-template <typename T>
-__device__ __forceinline__ bool non_finite(T v) {
-    if constexpr (std::is_floating_point<T>::value) return !isfinite(static_cast<double>(v));
-    return false;
-}
-
-// one axis of the order-1 filter: taps and weights, or outside
-struct Axis1 {
-    int64_t k0, k1;
-    double w0, w1;
-    bool inside;
-};
-__device__ __forceinline__ Axis1 axis_order1(double c, int64_t len) {
-    Axis1 a;
-    a.inside = !(c < 0.0 || c > static_cast<double>(len - 1));  // NaN coordinate -> treated as inside by scipy; cannot occur
-    const double f = floor(c);
-    a.k0 = static_cast<int64_t>(f);
-    a.k1 = a.k0 + 1;
-    if (a.k1 >= len) a.k1 = len > 2 ? len - 2 : 0;  // mirror (ni_interpolation.c edge handling)
-    const double t = dsub(c, f);
-    a.w0 = dsub(1.0, t);
-    a.w1 = dsub(1.0, a.w0);
-    return a;
-}
 
 // One intermediate sample of slice `sl` at intermediate index (J, I); `nx` = slice whose taps
 // contaminate with weight zero (nullptr: none).
@@ -110,46 +52,6 @@ __device__ __forceinline__ T affine_sample(const T *__restrict__ sl, const T *__
             t = NAN;
     }
     return scipy_cast<T>(t);
-}
-
-// ---------------------------------------------------------------------------
-// reducers over a window w[0 .. f_j*f_i) stored row-major
-// ---------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ bool is_nan(T v) {
-    if constexpr (std::is_floating_point<T>::value) return v != v;
-    return false;
-}
-
-// numpy's pairwise_sum for one contiguous run of n <= 128 elements (umath loops, used for the
-// innermost reduction axis); `get(k)` yields element k with NaN already replaced.
-template <typename A, typename Get>
-__device__ __forceinline__ A numpy_row_sum(int n, Get get) {
-    if (n < 8) {
-        A res = A(0);
-        for (int k = 0; k < n; ++k) res = res + get(k);
-        return res;
-    }
-    A r[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) r[k] = get(k);
-    int i = 8;
-    for (; i < n - (n % 8); i += 8) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = r[k] + get(i + k);
-    }
-    A res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-    for (; i < n; ++i) res = res + get(i);
-    return res;
-}
-
-// np.sum over the two window axes of the (h, f_j, w, f_i) view: innermost axis pairwise, rows
-// accumulated sequentially into the output element (starting from the identity 0).
-template <typename A, typename Get>
-__device__ __forceinline__ A numpy_window_sum(int f_j, int f_i, Get get) {
-    A s = A(0);
-    for (int a = 0; a < f_j; ++a) s = s + numpy_row_sum<A>(f_i, [&](int k) { return get(a * f_i + k); });
-    return s;
 }
 
 template <typename T>
@@ -356,6 +258,11 @@ int xrs_affine(const void *src, void *dst, int32_t dtype, int64_t n_slices, int6
     g.j_scale = j_scale; g.j_off = j_off; g.i_scale = i_scale; g.i_off = i_off; g.cval = cval;
     g.order = order; g.agg = agg; g.f_j = f_j; g.f_i = f_i; g.slice_blend = slice_blend;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (f_j * f_i > 1) {  // aligned integer-factor windows: streaming kernels (resample_fast.cu)
+        bool handled = false;
+        const int rc = launch_affine_fast(src, dst, dtype, g, st, &handled);
+        if (rc || handled) return rc;
+    }
     XRS_DISPATCH_DTYPE(dtype, T, return launch_affine<T>(src, dst, g, st));
     return 0;
 }
