@@ -198,6 +198,157 @@ __device__ __forceinline__ bool proj_forward(const ProjC &P, double lam, double 
     return false;
 }
 
+// ---------------------------------------------------------------------------
+// Separable forms for REGULAR grids.  On a regular grid in a transverse-Mercator CRS xi depends on
+// the row only and eta on the column only; on a geographic or web-Mercator grid longitude and
+// latitude themselves are separable.  The reprojection kernel evaluates the row-only and
+// column-only transcendental functions once per tile row / column ("terms") and finishes each
+// pixel with the "tail" below -- the same formulas as proj_inverse / proj_forward, regrouped.
+// ---------------------------------------------------------------------------
+struct Terms4 {
+    double a, b, c, d;
+};
+
+// sin / cos and sinh / cosh of a small argument (|x| <= 0.1): Taylor series, truncation < 1e-22
+__device__ __forceinline__ void sincos_small(double x, double &s, double &c) {
+    const double z = x * x;
+    s = x * (1.0 + z * (-1.0 / 6 + z * (1.0 / 120 + z * (-1.0 / 5040 + z * (1.0 / 362880 + z * (-1.0 / 39916800))))));
+    c = 1.0 + z * (-0.5 + z * (1.0 / 24 + z * (-1.0 / 720 + z * (1.0 / 40320 + z * (-1.0 / 3628800 + z * (1.0 / 479001600))))));
+}
+__device__ __forceinline__ void sinhcosh_small(double x, double &s, double &c) {
+    const double z = x * x;
+    s = x * (1.0 + z * (1.0 / 6 + z * (1.0 / 120 + z * (1.0 / 5040 + z * (1.0 / 362880 + z * (1.0 / 39916800))))));
+    c = 1.0 + z * (0.5 + z * (1.0 / 24 + z * (1.0 / 720 + z * (1.0 / 40320 + z * (1.0 / 3628800 + z * (1.0 / 479001600))))));
+}
+
+// transverse Mercator inverse: row terms (sin 2xi, cos 2xi, sin xi, cos xi) from y
+__device__ __forceinline__ Terms4 tmerc_inv_row_terms(const ProjC &P, double y) {
+    const double xi = (y - P.fn) / P.Qn + P.xi0;
+    Terms4 t;
+    sincos(xi, &t.c, &t.d);
+    t.a = 2.0 * t.c * t.d;
+    t.b = 1.0 - 2.0 * t.c * t.c;
+    return t;
+}
+// column terms (sinh 2eta, cosh 2eta, sinh eta, cosh eta) from x; NaN outside the domain
+__device__ __forceinline__ Terms4 tmerc_inv_col_terms(const ProjC &P, double x) {
+    const double eta = (x - P.fe) / P.Qn;
+    Terms4 t;
+    if (!(fabs(eta) <= TMERC_ETA_MAX)) {
+        t.a = t.b = t.c = t.d = NAN;
+        return t;
+    }
+    const double e1 = exp(eta), i1 = 1.0 / e1;
+    t.c = fabs(eta) < 1e-3 ? eta * (1.0 + eta * eta * (1.0 / 6)) : 0.5 * (e1 - i1);
+    t.d = 0.5 * (e1 + i1);
+    t.a = 2.0 * t.c * t.d;
+    t.b = 1.0 + 2.0 * t.c * t.c;
+    return t;
+}
+// per pixel: (lam, phi) from the terms.  false = corrections too large for the small-angle forms
+// (far outside any sensible zone): the caller evaluates proj_inverse instead.
+__device__ __forceinline__ bool tmerc_inv_tail(const ProjC &P, const Terms4 &r, const Terms4 &c, double &lam,
+                                               double &phi) {
+    double dxi, deta;
+    clenshaw_complex(P.beta, r.a, r.b, c.a, c.b, dxi, deta);
+    if (c.a != c.a) {  // column outside the projection's domain
+        lam = phi = NAN;
+        return true;
+    }
+    if (!(fabs(dxi) <= 0.1 && fabs(deta) <= 0.1)) return false;
+    double sd, cd, shd, chd;
+    sincos_small(dxi, sd, cd);
+    sinhcosh_small(deta, shd, chd);
+    const double sx = r.c * cd - r.d * sd, cx = r.d * cd + r.c * sd;  // sin, cos of xi' = xi - dxi
+    const double sh = c.c * chd - c.d * shd;                          // sinh of eta' = eta - deta
+    if (!(cx > 1e-9)) return false;  // at or beyond a pole: exact path
+    lam = wrap_pi(P.lon0 + atan(sh / cx));
+    const double hyp = sqrt(sh * sh + cx * cx);
+    const double chi = atan(sx / hyp);
+    const double inv = 1.0 / (sx * sx + hyp * hyp);
+    phi = chi + clenshaw_sin(P.cgb, 2.0 * sx * hyp * inv, (hyp * hyp - sx * sx) * inv);
+    return true;
+}
+
+// forward projections from separable geographic coordinates: row terms from phi, column terms
+// from lam, per-pixel tail.  kind GEOGRAPHIC / WEBMERC are fully separable (a = coordinate).
+__device__ __forceinline__ Terms4 fwd_row_terms(const ProjC &P, double phi, bool ok) {
+    Terms4 t;
+    t.a = t.b = t.c = t.d = NAN;
+    if (!ok || !(fabs(phi) <= 0.5 * PROJ_PI)) return t;
+    switch (P.kind) {
+    case XRS_PROJ_GEOGRAPHIC: t.a = phi * PROJ_RAD2DEG; break;
+    case XRS_PROJ_WEBMERC:
+        if (fabs(phi) < 0.5 * PROJ_PI) t.a = P.fn + P.a * asinh(tan(phi));
+        break;
+    case XRS_PROJ_TMERC: {
+        double s2, c2;
+        sincos(2.0 * phi, &s2, &c2);
+        sincos(phi + clenshaw_sin(P.cbg, s2, c2), &t.a, &t.b);  // sin, cos of the conformal latitude
+        break;
+    }
+    case XRS_PROJ_LAEA: {
+        double sinb = laea_q(P, sin(phi)) / P.qp;
+        sinb = fmin(1.0, fmax(-1.0, sinb));
+        t.a = sinb;
+        t.b = sqrt(1.0 - sinb * sinb);
+        break;
+    }
+    }
+    return t;
+}
+__device__ __forceinline__ Terms4 fwd_col_terms(const ProjC &P, double lam) {
+    Terms4 t;
+    t.a = t.b = t.c = t.d = NAN;
+    switch (P.kind) {
+    case XRS_PROJ_GEOGRAPHIC: t.a = lam * PROJ_RAD2DEG; break;
+    case XRS_PROJ_WEBMERC: t.a = P.fe + P.a * wrap_pi(lam - P.lon0); break;
+    case XRS_PROJ_TMERC:
+    case XRS_PROJ_LAEA: sincos(wrap_pi(lam - P.lon0), &t.a, &t.b); break;
+    }
+    return t;
+}
+__device__ __forceinline__ void fwd_tail(const ProjC &P, const Terms4 &r, const Terms4 &c, double &x, double &y) {
+    switch (P.kind) {
+    case XRS_PROJ_GEOGRAPHIC:
+    case XRS_PROJ_WEBMERC:
+        x = c.a;
+        y = r.a;
+        return;
+    case XRS_PROJ_TMERC: {
+        const double sc = r.a, cc = r.b, sl = c.a, cl = c.b;
+        const double ccl = cc * cl;
+        const double xip = atan2(sc, ccl);
+        const double inv = 1.0 / sqrt(sc * sc + ccl * ccl);
+        const double tan_ce = sl * cc * inv;
+        const double etap = asinh(tan_ce);
+        if (!(fabs(etap) <= TMERC_ETA_MAX)) {
+            x = y = NAN;
+            return;
+        }
+        const double two_inv = 2.0 * inv, two_inv_sq = two_inv * inv, tmp = ccl * two_inv_sq;
+        double dxi, deta;
+        clenshaw_complex(P.alpha, sc * tmp, ccl * tmp - 1.0, tan_ce * two_inv, two_inv_sq - 1.0, dxi, deta);
+        x = P.fe + P.Qn * (etap + deta);
+        y = P.fn + P.Qn * (xip + dxi - P.xi0);
+        return;
+    }
+    case XRS_PROJ_LAEA: {
+        const double sinb = r.a, cosb = r.b, sl = c.a, cl = c.b;
+        double b = 1.0 + P.sinb1 * sinb + P.cosb1 * cosb * cl;
+        if (!(b > 1e-10)) {
+            x = y = NAN;
+            return;
+        }
+        b = P.rq * sqrt(2.0 / b);
+        x = P.fe + b * P.dd * cosb * sl;
+        y = P.fn + (b / P.dd) * (P.cosb1 * sinb - P.sinb1 * cosb * cl);
+        return;
+    }
+    }
+    x = y = NAN;
+}
+
 // pyproj.Transformer.from_crs(from, to, always_xy=True).transform(x, y); NaN when not transformable
 // (PROJ reports inf there).  Two geographic CRSs pass the coordinates through untouched (the datum
 // shift WGS84 <-> ETRS89 is PROJ's "ballpark" identity).

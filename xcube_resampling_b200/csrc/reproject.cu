@@ -168,7 +168,6 @@ k3_transform_points(const __grid_constant__ ProjC from, const __grid_constant__ 
 // K3: fused transform + gather
 // ---------------------------------------------------------------------------
 constexpr int K3_MAX_BANDS = 24;
-constexpr int K3_BX = 32, K3_BY = 8;
 
 template <typename T, typename OUT>
 struct K3Planes {
@@ -235,67 +234,65 @@ __device__ __forceinline__ OUT k3_store_cast(double v) {
     else return cast_like_numpy<OUT>(v);
 }
 
+// ---- per-pixel gather (reproject.py:268-335) given the source-CRS coordinates (sx, sy) --------
+constexpr int K3_CHUNK = 4;  // bands whose taps are loaded before any of them is consumed
+
 template <typename T, typename OUT, int METHOD>
-__global__ void __launch_bounds__(K3_BX *K3_BY)
-k3_reproject(const __grid_constant__ K3Geom g, const __grid_constant__ K3Planes<T, OUT> planes, int n_bands, T fill) {
-    const int64_t c = static_cast<int64_t>(blockIdx.x) * K3_BX + threadIdx.x;
-    const int64_t r = g.row_begin + static_cast<int64_t>(blockIdx.y) * K3_BY + threadIdx.y;
-    if (c >= g.dst_w || r >= g.row_end) return;
-    const int64_t o = (r - g.row_begin) * g.dst_w + c;
-    double sx, sy;
-    transform_point(g.from, g.to, __ldg(g.dst_x + c), __ldg(g.dst_y + r), sx, sy);
-    const int t = static_cast<int>(r / g.tile_h) * g.ntx + static_cast<int>(c / g.tile_w);
+__device__ __forceinline__ void k3_gather_pixel(const K3Geom &g, const K3Planes<T, OUT> &planes, int n_bands, T fill,
+                                                int64_t o, int t, double sx, double sy) {
     // reproject.py:278-279
     const double fx = ddiv(dsub(sx, __ldg(g.tile_x0 + t)), g.x_res);
     const double fy = ddiv(dsub(sy, __ldg(g.tile_y0 + t)), -g.y_res);
-    const int64_t i_base = __ldg(g.tile_i0 + t), j_base = __ldg(g.tile_j0 + t);
+    const int i_base = __ldg(g.tile_i0 + t), j_base = __ldg(g.tile_j0 + t);
     const OUT fill_out = static_cast<OUT>(fill);
-    const bool finite = fabs(fx) < 1e15 && fabs(fy) < 1e15;  // false for NaN / inf too
+    if (!(fabs(fx) < 1e9 && fabs(fy) < 1e9)) {  // NaN / inf / absurdly far: no data
+        for (int b = 0; b < n_bands; ++b) st_stream(planes.dst[b] + o, fill_out);
+        return;
+    }
+    const int ww = g.tile_win_w, wh = g.tile_win_h;
+    // resident window expressed in source indices
+    const int res_i0 = static_cast<int>(g.win_i0), res_j0 = static_cast<int>(g.win_j0);
+    const int res_i1 = res_i0 + static_cast<int>(g.win_w), res_j1 = res_j0 + static_cast<int>(g.win_h);
+    const int pitch = static_cast<int>(g.src_pitch);
 
-    // source offset of window index (wy, wx), or -1 for the constant padding
-    // (reproject.py:507 da.pad(..., constant_values=fill_value))
-    auto tap = [&](int64_t wy, int64_t wx, bool &ok) -> int64_t {
-        ok = ok && window_index(wx, g.tile_win_w) && window_index(wy, g.tile_win_h);
-        const int64_t si = i_base + wx, sj = j_base + wy;
-        if (si < 0 || sj < 0 || si >= g.src_w || sj >= g.src_h) return -1;
-        const int64_t li = si - g.win_i0, lj = sj - g.win_j0;
-        if (li < 0 || lj < 0 || li >= g.win_w || lj >= g.win_h) return -1;  // not resident (host bug)
-        return lj * g.src_pitch + li;
+    // element offset of window index (wy, wx) inside a resident plane, or -1 for the constant
+    // padding (reproject.py:507 da.pad(..., constant_values=fill_value)); `ok` turns false where
+    // numpy would raise IndexError.  Negative window indices count from the end, as in numpy.
+    auto tap = [&](int wy, int wx, bool &ok) -> int {
+        if (wx < 0) wx += ww;
+        if (wy < 0) wy += wh;
+        ok = ok && wx >= 0 && wx < ww && wy >= 0 && wy < wh;
+        const int si = i_base + wx, sj = j_base + wy;
+        if (si < res_i0 || sj < res_j0 || si >= res_i1 || sj >= res_j1) return -1;  // padding (or not resident)
+        return (sj - res_j0) * pitch + (si - res_i0);
     };
 
     if (METHOD == XRS_NEAREST) {
-        bool ok = finite;
-        int64_t off = -1;
-        if (finite) off = tap(static_cast<int64_t>(rint(fy)), static_cast<int64_t>(rint(fx)), ok);
+        bool ok = true;
+        int off = tap(__double2int_rn(fy), __double2int_rn(fx), ok);
         if (!ok) off = -1;
-#pragma unroll 4
-        for (int b = 0; b < n_bands; ++b) {
-            const T v = off >= 0 ? __ldg(planes.src[b] + off) : fill;
-            st_stream(planes.dst[b] + o, static_cast<OUT>(v));
+        if (off >= 0) {
+            int b = 0;
+            for (; b + K3_CHUNK <= n_bands; b += K3_CHUNK) {
+                T v[K3_CHUNK];
+#pragma unroll
+                for (int q = 0; q < K3_CHUNK; ++q) v[q] = __ldg(planes.src[b + q] + off);
+#pragma unroll
+                for (int q = 0; q < K3_CHUNK; ++q) st_stream(planes.dst[b + q] + o, static_cast<OUT>(v[q]));
+            }
+            for (; b < n_bands; ++b) st_stream(planes.dst[b] + o, static_cast<OUT>(__ldg(planes.src[b] + off)));
+        } else {
+            for (int b = 0; b < n_bands; ++b) st_stream(planes.dst[b] + o, fill_out);
         }
-        return;
-    }
-    if (!finite) {
-        for (int b = 0; b < n_bands; ++b) st_stream(planes.dst[b] + o, fill_out);
         return;
     }
     const double fx0 = floor(fx), fy0 = floor(fy);
     const double u = dsub(fx, fx0), v = dsub(fy, fy0);
-    const int64_t ix0 = static_cast<int64_t>(fx0), ix1 = static_cast<int64_t>(ceil(fx));
-    const int64_t iy0 = static_cast<int64_t>(fy0), iy1 = static_cast<int64_t>(ceil(fy));
-    bool ok = true;
-    const int64_t o00 = tap(iy0, ix0, ok), o01 = tap(iy0, ix1, ok), o10 = tap(iy1, ix0, ok), o11 = tap(iy1, ix1, ok);
-    if (!ok) {
-        for (int b = 0; b < n_bands; ++b) st_stream(planes.dst[b] + o, fill_out);
-        return;
-    }
+    const int ix0 = __double2int_rd(fx), ix1 = __double2int_ru(fx);
+    const int iy0 = __double2int_rd(fy), iy1 = __double2int_ru(fy);
     const bool lower = dadd(u, v) < 1.0;                 // reproject.py:301
     const double u1 = dsub(1.0, u), v1 = dsub(1.0, v);
-#pragma unroll 2
-    for (int b = 0; b < n_bands; ++b) {
-        const T *sp = planes.src[b];
-        const T v00 = o00 >= 0 ? __ldg(sp + o00) : fill, v01 = o01 >= 0 ? __ldg(sp + o01) : fill;
-        const T v10 = o10 >= 0 ? __ldg(sp + o10) : fill, v11 = o11 >= 0 ? __ldg(sp + o11) : fill;
+    auto blend = [&](T v00, T v01, T v10, T v11) -> OUT {
         double val;
         if (METHOD == XRS_BILINEAR) {  // reproject.py:325-327
             const double a = dadd(static_cast<double>(v00), dmul(u, diff_as_f64(v01, v00)));
@@ -306,19 +303,171 @@ k3_reproject(const __grid_constant__ K3Geom g, const __grid_constant__ K3Planes<
         } else {                       // reproject.py:309-313
             val = dadd(dadd(static_cast<double>(v11), dmul(u1, diff_as_f64(v10, v11))), dmul(v1, diff_as_f64(v01, v11)));
         }
-        st_stream(planes.dst[b] + o, k3_store_cast<T, OUT>(val));
+        return k3_store_cast<T, OUT>(val);
+    };
+    // common case: the 2 x 2 taps lie inside the tile window and inside the resident source
+    const int si0 = i_base + ix0, sj0 = j_base + iy0, si1 = i_base + ix1, sj1 = j_base + iy1;
+    if (ix0 >= 0 && iy0 >= 0 && ix1 < ww && iy1 < wh && si0 >= res_i0 && sj0 >= res_j0 && si1 < res_i1 && sj1 < res_j1) {
+        const int o00 = (sj0 - res_j0) * pitch + (si0 - res_i0);
+        const int d01 = ix1 - ix0, d10 = (iy1 - iy0) * pitch, d11 = d10 + d01;
+        int b = 0;
+        for (; b + K3_CHUNK <= n_bands; b += K3_CHUNK) {
+            T w[K3_CHUNK][4];
+#pragma unroll
+            for (int q = 0; q < K3_CHUNK; ++q) {
+                const T *sp = planes.src[b + q] + o00;
+                w[q][0] = __ldg(sp); w[q][1] = __ldg(sp + d01); w[q][2] = __ldg(sp + d10); w[q][3] = __ldg(sp + d11);
+            }
+#pragma unroll
+            for (int q = 0; q < K3_CHUNK; ++q) st_stream(planes.dst[b + q] + o, blend(w[q][0], w[q][1], w[q][2], w[q][3]));
+        }
+        for (; b < n_bands; ++b) {
+            const T *sp = planes.src[b] + o00;
+            st_stream(planes.dst[b] + o, blend(__ldg(sp), __ldg(sp + d01), __ldg(sp + d10), __ldg(sp + d11)));
+        }
+        return;
     }
+    bool ok = true;
+    const int o00 = tap(iy0, ix0, ok), o01 = tap(iy0, ix1, ok), o10 = tap(iy1, ix0, ok), o11 = tap(iy1, ix1, ok);
+    if (!ok) {
+        for (int b = 0; b < n_bands; ++b) st_stream(planes.dst[b] + o, fill_out);
+        return;
+    }
+    for (int b = 0; b < n_bands; ++b) {
+        const T *sp = planes.src[b];
+        const T v00 = o00 >= 0 ? __ldg(sp + o00) : fill, v01 = o01 >= 0 ? __ldg(sp + o01) : fill;
+        const T v10 = o10 >= 0 ? __ldg(sp + o10) : fill, v11 = o11 >= 0 ? __ldg(sp + o11) : fill;
+        st_stream(planes.dst[b] + o, blend(v00, v01, v10, v11));
+    }
+}
+
+// ---- how the target -> source transform of a tile is evaluated --------------------------------
+enum K3Plan {
+    K3_PLAN_GENERIC = 0,    // per pixel, full formulas (target CRS = LAEA)
+    K3_PLAN_IDENTITY = 1,   // both CRSs geographic: coordinates pass through untouched
+    K3_PLAN_SEPARABLE = 2,  // target CRS geographic / web Mercator: lon by column, lat by row
+    K3_PLAN_TMERC_INV = 3   // target CRS transverse Mercator: xi by row, eta by column
+};
+
+__device__ __noinline__ void forward_point(const ProjC &to, double lam, double phi, double &ox, double &oy) {
+    if (!proj_forward(to, lam, phi, ox, oy)) ox = oy = NAN;
+}
+
+constexpr int K3T_COLS = 64, K3T_ROWS = 32, K3T_THREADS = 256;
+constexpr int K3T_RPT = K3T_ROWS / (K3T_THREADS / 32 / (K3T_COLS / 32));  // rows per thread (8)
+
+// One CTA per 64 x 32 target tile.  Phase 1: 32 + 64 threads evaluate the row-only and column-only
+// parts of the transform (one sincos / exp each instead of one per pixel) into shared memory.
+// Phase 2: a warp owns 32 columns x 8 rows; each lane keeps its column terms in registers,
+// finishes the transform per pixel and gathers all bands.
+template <typename T, typename OUT, int METHOD>
+__global__ void __launch_bounds__(K3T_THREADS)
+k3_reproject(const __grid_constant__ K3Geom g, const __grid_constant__ K3Planes<T, OUT> planes, int n_bands, T fill,
+             int plan) {
+    __shared__ Terms4 s_row[K3T_ROWS];
+    __shared__ Terms4 s_col[K3T_COLS];
+    __shared__ int s_ty[K3T_ROWS];
+    __shared__ int s_tx[K3T_COLS];
+    const int tid = threadIdx.x;
+    const int64_t c0 = static_cast<int64_t>(blockIdx.x) * K3T_COLS;
+    const int64_t r0 = g.row_begin + static_cast<int64_t>(blockIdx.y) * K3T_ROWS;
+    if (tid < K3T_ROWS) {
+        const int64_t r = r0 + tid;
+        if (r < g.row_end) {
+            const double y = __ldg(g.dst_y + r);
+            Terms4 t;
+            t.a = y; t.b = t.c = t.d = 0.0;
+            if (plan == K3_PLAN_TMERC_INV) {
+                t = tmerc_inv_row_terms(g.from, y);
+            } else if (plan == K3_PLAN_SEPARABLE) {
+                double phi;
+                bool ok = true;
+                if (g.from.kind == XRS_PROJ_GEOGRAPHIC) {
+                    phi = y * PROJ_DEG2RAD;
+                    ok = fabs(y) <= 90.0;
+                } else {
+                    phi = atan(sinh((y - g.from.fn) / g.from.a));
+                }
+                t = fwd_row_terms(g.to, phi, ok);
+            }
+            s_row[tid] = t;
+            s_ty[tid] = static_cast<int>(r / g.tile_h);
+        }
+    } else if (tid < K3T_ROWS + K3T_COLS) {
+        const int k = tid - K3T_ROWS;
+        const int64_t c = c0 + k;
+        if (c < g.dst_w) {
+            const double x = __ldg(g.dst_x + c);
+            Terms4 t;
+            t.a = x; t.b = t.c = t.d = 0.0;
+            if (plan == K3_PLAN_TMERC_INV) {
+                t = tmerc_inv_col_terms(g.from, x);
+            } else if (plan == K3_PLAN_SEPARABLE) {
+                const double lam = g.from.kind == XRS_PROJ_GEOGRAPHIC ? x * PROJ_DEG2RAD
+                                                                       : wrap_pi(g.from.lon0 + (x - g.from.fe) / g.from.a);
+                t = fwd_col_terms(g.to, lam);
+            }
+            s_col[k] = t;
+            s_tx[k] = static_cast<int>(c / g.tile_w);
+        }
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    const int col_l = (warp % (K3T_COLS / 32)) * 32 + lane;
+    const int row_l0 = (warp / (K3T_COLS / 32)) * K3T_RPT;
+    const int64_t c = c0 + col_l;
+    if (c >= g.dst_w) return;
+    const Terms4 ct = s_col[col_l];
+    const int tx = s_tx[col_l];
+#pragma unroll 1
+    for (int k = 0; k < K3T_RPT; ++k) {
+        const int rl = row_l0 + k;
+        const int64_t r = r0 + rl;
+        if (r >= g.row_end) break;
+        const Terms4 rt = s_row[rl];
+        double sx, sy;
+        if (plan == K3_PLAN_TMERC_INV) {
+            double lam, phi;
+            if (tmerc_inv_tail(g.from, rt, ct, lam, phi)) {
+                if (g.to.kind == XRS_PROJ_GEOGRAPHIC) {
+                    sx = lam * PROJ_RAD2DEG;
+                    sy = phi * PROJ_RAD2DEG;
+                } else {
+                    forward_point(g.to, lam, phi, sx, sy);
+                }
+            } else {
+                transform_point(g.from, g.to, __ldg(g.dst_x + c), __ldg(g.dst_y + r), sx, sy);
+            }
+        } else if (plan == K3_PLAN_SEPARABLE) {
+            fwd_tail(g.to, rt, ct, sx, sy);
+        } else if (plan == K3_PLAN_IDENTITY) {
+            sx = ct.a;
+            sy = rt.a;
+        } else {
+            transform_point(g.from, g.to, ct.a, rt.a, sx, sy);
+        }
+        k3_gather_pixel<T, OUT, METHOD>(g, planes, n_bands, fill, (r - g.row_begin) * g.dst_w + c,
+                                        s_ty[rl] * g.ntx + tx, sx, sy);
+    }
+}
+
+static int choose_plan(const ProjC &from, const ProjC &to) {
+    if (from.kind == XRS_PROJ_GEOGRAPHIC && to.kind == XRS_PROJ_GEOGRAPHIC) return K3_PLAN_IDENTITY;
+    if (from.kind == XRS_PROJ_GEOGRAPHIC || from.kind == XRS_PROJ_WEBMERC) return K3_PLAN_SEPARABLE;
+    if (from.kind == XRS_PROJ_TMERC) return K3_PLAN_TMERC_INV;
+    return K3_PLAN_GENERIC;
 }
 
 template <typename T, typename OUT, int METHOD>
 int launch_reproject(const K3Geom &g, const void *const *src_planes, void *const *dst_planes, int n_bands, double fill,
                      cudaStream_t st) {
     const int64_t rows = g.row_end - g.row_begin;
-    const dim3 grid(static_cast<unsigned>(ceil_div(g.dst_w, K3_BX)), static_cast<unsigned>(ceil_div(rows, K3_BY)));
-    if (grid.y > 65535) return fail("xrs_reproject: more than 524280 target rows per call");
+    const dim3 grid(static_cast<unsigned>(ceil_div(g.dst_w, K3T_COLS)), static_cast<unsigned>(ceil_div(rows, K3T_ROWS)));
+    if (grid.y > 65535) return fail("xrs_reproject: more than 2097120 target rows per call");
     T fill_t;
     if constexpr (std::is_floating_point<T>::value) fill_t = static_cast<T>(fill);
     else fill_t = static_cast<T>(static_cast<long long>(fill));
+    const int plan = choose_plan(g.from, g.to);
     for (int b0 = 0; b0 < n_bands; b0 += K3_MAX_BANDS) {
         const int nb = std::min(K3_MAX_BANDS, n_bands - b0);
         K3Planes<T, OUT> planes = {};
@@ -326,7 +475,7 @@ int launch_reproject(const K3Geom &g, const void *const *src_planes, void *const
             planes.src[b] = static_cast<const T *>(src_planes[b0 + b]);
             planes.dst[b] = static_cast<OUT *>(dst_planes[b0 + b]);
         }
-        XRS_TIMED(METHOD == XRS_NEAREST ? "k3_reproject<nearest>" : METHOD == XRS_BILINEAR ? "k3_reproject<bilinear>" : "k3_reproject<triangular>", st, k3_reproject<T, OUT, METHOD><<<grid, dim3(K3_BX, K3_BY), 0, st>>>(g, planes, nb, fill_t));
+        XRS_TIMED(METHOD == XRS_NEAREST ? "k3_reproject<nearest>" : METHOD == XRS_BILINEAR ? "k3_reproject<bilinear>" : "k3_reproject<triangular>", st, k3_reproject<T, OUT, METHOD><<<grid, K3T_THREADS, 0, st>>>(g, planes, nb, fill_t, plan));
         XRS_LAUNCH_CHECK("k3_reproject");
     }
     return 0;
@@ -389,6 +538,9 @@ int xrs_reproject(const void *const *src_planes_host, void *const *dst_planes_ho
         return fail("xrs_reproject: resident window outside the source image");
     if (row_begin < 0 || row_end > dst_h || row_begin >= row_end) return fail("xrs_reproject: bad row range");
     if (tile_win_w < 1 || tile_win_h < 1) return fail("xrs_reproject: bad tile window size");
+    if (win_h * src_pitch >= (int64_t(1) << 31) || src_w >= (int64_t(1) << 30) || src_h >= (int64_t(1) << 30))
+        return fail("xrs_reproject: resident source window has 2^31 or more elements per band; split the target "
+                    "into row bands");
     if (!(src_x_res > 0.0) || !(src_y_res > 0.0)) return fail("xrs_reproject: resolution must be positive");
     if (out_dtype != dtype && out_dtype != XRS_F64) return fail("xrs_reproject: out_dtype must be dtype or float64");
     for (int b = 0; b < n_bands; ++b)
