@@ -209,16 +209,23 @@ struct Terms4 {
     double a, b, c, d;
 };
 
-// sin / cos and sinh / cosh of a small argument (|x| <= 0.1): Taylor series, truncation < 1e-22
+// sin / cos and sinh / cosh of a small argument (|x| <= 0.1): Taylor series, truncation < 1e-22.
+// The coefficients live in constant memory so that they are read as instruction operands instead
+// of being rebuilt from immediates in every loop iteration.
+static __constant__ double PROJ_INV_FACT[13] = {
+    1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
+    1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600};
 __device__ __forceinline__ void sincos_small(double x, double &s, double &c) {
-    const double z = x * x;
-    s = x * (1.0 + z * (-1.0 / 6 + z * (1.0 / 120 + z * (-1.0 / 5040 + z * (1.0 / 362880 + z * (-1.0 / 39916800))))));
-    c = 1.0 + z * (-0.5 + z * (1.0 / 24 + z * (-1.0 / 720 + z * (1.0 / 40320 + z * (-1.0 / 3628800 + z * (1.0 / 479001600))))));
+    const double z = -(x * x);
+    const double *f = PROJ_INV_FACT;
+    s = x * (1.0 + z * (f[3] + z * (f[5] + z * (f[7] + z * (f[9] + z * f[11])))));
+    c = 1.0 + z * (f[2] + z * (f[4] + z * (f[6] + z * (f[8] + z * (f[10] + z * f[12])))));
 }
 __device__ __forceinline__ void sinhcosh_small(double x, double &s, double &c) {
     const double z = x * x;
-    s = x * (1.0 + z * (1.0 / 6 + z * (1.0 / 120 + z * (1.0 / 5040 + z * (1.0 / 362880 + z * (1.0 / 39916800))))));
-    c = 1.0 + z * (0.5 + z * (1.0 / 24 + z * (1.0 / 720 + z * (1.0 / 40320 + z * (1.0 / 3628800 + z * (1.0 / 479001600))))));
+    const double *f = PROJ_INV_FACT;
+    s = x * (1.0 + z * (f[3] + z * (f[5] + z * (f[7] + z * (f[9] + z * f[11])))));
+    c = 1.0 + z * (f[2] + z * (f[4] + z * (f[6] + z * (f[8] + z * (f[10] + z * f[12])))));
 }
 
 // transverse Mercator inverse: row terms (sin 2xi, cos 2xi, sin xi, cos xi) from y

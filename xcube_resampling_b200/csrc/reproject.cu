@@ -310,18 +310,29 @@ __device__ __forceinline__ void k3_gather_pixel(const K3Geom &g, const K3Planes<
     if (ix0 >= 0 && iy0 >= 0 && ix1 < ww && iy1 < wh && si0 >= res_i0 && sj0 >= res_j0 && si1 < res_i1 && sj1 < res_j1) {
         const int o00 = (sj0 - res_j0) * pitch + (si0 - res_i0);
         const int d01 = ix1 - ix0, d10 = (iy1 - iy0) * pitch, d11 = d10 + d01;
-        int b = 0;
-        for (; b + K3_CHUNK <= n_bands; b += K3_CHUNK) {
-            T w[K3_CHUNK][4];
+        if (d01 == 1 && iy1 != iy0) {
+            // generic position: the right-hand taps are the next element, so they are addressed with an
+            // immediate offset from the two row pointers (2 address computations per band instead of 4)
+            int b = 0;
+            for (; b + K3_CHUNK <= n_bands; b += K3_CHUNK) {
+                T w[K3_CHUNK][4];
 #pragma unroll
-            for (int q = 0; q < K3_CHUNK; ++q) {
-                const T *sp = planes.src[b + q] + o00;
-                w[q][0] = __ldg(sp); w[q][1] = __ldg(sp + d01); w[q][2] = __ldg(sp + d10); w[q][3] = __ldg(sp + d11);
+                for (int q = 0; q < K3_CHUNK; ++q) {
+                    const T *p0 = planes.src[b + q] + o00;
+                    const T *p1 = p0 + pitch;
+                    w[q][0] = __ldg(p0); w[q][1] = __ldg(p0 + 1); w[q][2] = __ldg(p1); w[q][3] = __ldg(p1 + 1);
+                }
+#pragma unroll
+                for (int q = 0; q < K3_CHUNK; ++q) st_stream(planes.dst[b + q] + o, blend(w[q][0], w[q][1], w[q][2], w[q][3]));
             }
-#pragma unroll
-            for (int q = 0; q < K3_CHUNK; ++q) st_stream(planes.dst[b + q] + o, blend(w[q][0], w[q][1], w[q][2], w[q][3]));
+            for (; b < n_bands; ++b) {
+                const T *p0 = planes.src[b] + o00;
+                const T *p1 = p0 + pitch;
+                st_stream(planes.dst[b] + o, blend(__ldg(p0), __ldg(p0 + 1), __ldg(p1), __ldg(p1 + 1)));
+            }
+            return;
         }
-        for (; b < n_bands; ++b) {
+        for (int b = 0; b < n_bands; ++b) {  // a coordinate exactly on a pixel centre: ceil == floor
             const T *sp = planes.src[b] + o00;
             st_stream(planes.dst[b] + o, blend(__ldg(sp), __ldg(sp + d01), __ldg(sp + d10), __ldg(sp + d11)));
         }
