@@ -251,3 +251,25 @@ def test_c_abi_rejects_bad_arguments(xrs):
     lib = _lib.load()
     assert lib.xrs_gather_ij(None, None, 1, 0, 4, 4, 4, 0, 0, 4, 4, None, 4, 4, 0, 0.0, None) != 0
     assert b"null" in lib.xrs_last_error()
+
+
+def test_band_pipeline_equals_plain_path(xrs, monkeypatch):
+    """Chunked upload / gather / download overlap (BandPipeline) gives the same bytes."""
+    from xcube_resampling_b200 import rectify as xrect
+
+    w, h = 300, 220
+    x, y = swath(w, h, theta=20.0, seed=4)
+    res = 0.0027
+    size, xy_min = covering_grid_args(x, y, res)
+    rng = np.random.default_rng(4)
+    bands = rng.random((11, h, w)).astype(np.float32)  # 11 = 2 full chunks of 4 + a ragged one
+    ds = xrs.Dataset(data_vars=dict(bands=(("band", "y", "x"), bands)),
+                     coords=dict(lon=(("y", "x"), x), lat=(("y", "x"), y)))
+    source_gm = xrs.GridMapping.from_coords(x, y, "EPSG:4326", xy_res=res, xy_dim_names=("x", "y"))
+    target_gm = xrs.GridMapping.regular(size, xy_min, res, "EPSG:4326", tile_size=128)
+    for method in ("nearest", "bilinear"):
+        plain = xrs.rectify_dataset(ds, target_gm=target_gm, source_gm=source_gm, interp_methods=method)["bands"].values
+        monkeypatch.setattr(xrect, "_PIPELINE_MIN_BYTES", 0)
+        piped = xrs.rectify_dataset(ds, target_gm=target_gm, source_gm=source_gm, interp_methods=method)["bands"].values
+        monkeypatch.undo()
+        assert_same(piped, plain, method)

@@ -109,3 +109,63 @@ def ptr_array(tensors) -> ctypes.Array:
     for k, t in enumerate(tensors):
         arr[k] = t.data_ptr()
     return arr
+
+
+class BandPipeline:
+    """Host -> device -> host streaming of a (bands, h, w) variable in band chunks.
+
+    Three streams: uploads (H2D) of chunk k+1, the kernels of chunk k on the caller's current stream
+    and the download (D2H) of chunk k-1 run concurrently, so a PCIe-bound call costs
+    max(H2D, D2H) instead of their sum.  Two device slots per direction (double buffering); the
+    source slots are row-pitched to 128 bytes (TMA-addressable, see :func:`to_device_pitched`).
+    ``process(src_chunk, out_chunk)`` must only enqueue work on the current stream.
+    """
+
+    def __init__(self, values: np.ndarray, out_shape_hw, out_dtype, device=None, chunk_bands: int = 4,
+                 pitch_bytes: int = 128):
+        self.dev = require_cuda(device)
+        v = np.ascontiguousarray(values)
+        if not v.flags.writeable:
+            v = v.copy()
+        self.src_host = torch.from_numpy(v)
+        self.bands, self.h, self.w = v.shape
+        self.chunk = max(1, min(int(chunk_bands), self.bands))
+        per = max(1, pitch_bytes // self.src_host.element_size())
+        wp = -(-self.w // per) * per
+        self.in_slots = [torch.empty((self.chunk, self.h, wp), dtype=self.src_host.dtype, device=self.dev)
+                         for _ in range(2)]
+        H, W = int(out_shape_hw[0]), int(out_shape_hw[1])
+        self.out_slots = [torch.empty((self.chunk, H, W), dtype=torch_dtype(out_dtype), device=self.dev)
+                          for _ in range(2)]
+        self.out_host = pinned_empty((self.bands, H, W), out_dtype)
+        self._out_host_t = torch.from_numpy(self.out_host)
+
+    def run(self, process) -> np.ndarray:
+        main = torch.cuda.current_stream(self.dev)
+        s_in, s_out = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+        in_ready = [torch.cuda.Event() for _ in range(2)]
+        in_free = [torch.cuda.Event() for _ in range(2)]
+        out_ready = [torch.cuda.Event() for _ in range(2)]
+        out_free = [torch.cuda.Event() for _ in range(2)]
+        for e in in_free + out_free:
+            e.record(main)
+        for k, b0 in enumerate(range(0, self.bands, self.chunk)):
+            slot, nb = k % 2, min(self.chunk, self.bands - b0)
+            src_view = self.in_slots[slot][:nb, :, : self.w]
+            out_view = self.out_slots[slot][:nb]
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(in_free[slot])
+                src_view.copy_(self.src_host[b0:b0 + nb], non_blocking=True)
+                in_ready[slot].record(s_in)
+            main.wait_event(in_ready[slot])
+            main.wait_event(out_free[slot])
+            process(src_view, out_view)
+            in_free[slot].record(main)
+            out_ready[slot].record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(out_ready[slot])
+                self._out_host_t[b0:b0 + nb].copy_(out_view, non_blocking=True)
+                out_free[slot].record(s_out)
+        s_out.synchronize()
+        main.synchronize()
+        return self.out_host

@@ -222,11 +222,9 @@ def rectify_band_host(x: np.ndarray, y: np.ndarray, src_window: np.ndarray, wind
     dev = _dev.require_cuda(device)
     x_dev = _dev.to_device(x, dev, dtype=np.float64)
     y_dev = _dev.to_device(y, dev, dtype=np.float64)
-    src_dev = _dev.to_device_pitched(src_window, dev)
     plan = RectifyPlan(target_gm, dev, rows=rows)
     ij = plan.ij(x_dev, y_dev)
-    out = gather_ij(src_dev, ij, interp_method, fill_value, window_origin=window_origin, full_size=full_size)
-    return _dev.to_host(out)
+    return _gather_from_host(np.asarray(src_window), ij, interp_method, fill_value, window_origin, full_size)
 
 
 # ---------------------------------------------------------------------------
@@ -304,13 +302,29 @@ def rectify_dataset(
                     f"interp_methods must be one of 0, 1, 'nearest', 'bilinear', "
                     f"'triangular', was '{interp_method}'."
                 )
-            src = _dev.to_device_pitched(var.values)
-            out = _dev.to_host(gather_ij(src, ij, interp_method, fill_value))
+            out = _gather_from_host(var.values, ij, interp_method, fill_value)
             dims = t_dims if len(var.dims) == 2 else (var.dims[0],) + t_dims
             target_ds[var_name] = DataArray(out, dims=dims, attrs=var.attrs, name=var_name)
         elif yx_dims[0] not in var.dims and yx_dims[1] not in var.dims:
             target_ds[var_name] = var
     return to_like(target_ds, user_ds)
+
+
+# a variable at least this large is streamed through the device in band chunks (upload, kernels
+# and download overlapped); smaller ones take the plain upload / gather / download sequence
+_PIPELINE_MIN_BYTES = 64 << 20
+
+
+def _gather_from_host(values: np.ndarray, ij: torch.Tensor, interp_method: str, fill_value,
+                      window_origin: tuple[int, int] = (0, 0), full_size: tuple[int, int] | None = None) -> np.ndarray:
+    """K2 for one host variable ((y, x) or (bands, y, x)), result in (pinned) host memory."""
+    if values.ndim == 3 and values.shape[0] > 1 and values.nbytes >= _PIPELINE_MIN_BYTES:
+        pipe = _dev.BandPipeline(values, ij.shape[1:], values.dtype, ij.device)
+        return pipe.run(lambda src, out: gather_ij(src, ij, interp_method, fill_value, out=out,
+                                                   window_origin=window_origin, full_size=full_size))
+    src = _dev.to_device_pitched(values, ij.device)
+    return _dev.to_host(gather_ij(src, ij, interp_method, fill_value, window_origin=window_origin,
+                                  full_size=full_size))
 
 
 def _gm_from_transformed(source_gm: GridMapping, target_gm: GridMapping, x_dev, y_dev) -> GridMapping:
