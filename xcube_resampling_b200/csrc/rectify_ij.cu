@@ -186,6 +186,92 @@ __device__ __forceinline__ void claim_pixels(const IjGeom &g, const TileCtx &tc,
     }
 }
 
+// The same scan for quads whose vertices are all finite (the fast path of k1_scatter), with the
+// three acceptance conditions of each triangle kept as affine "edge functions" of the pixel index:
+//   e1 = s*nu - lo*|det| >= 0,  e2 = s*nv - lo*|det| >= 0,  e3 = hi*|det| - s*(nu + nv) >= 0.
+// They are evaluated once at the box corner (from the reference's own expressions) and then stepped
+// by constant increments -- 3 additions per triangle and pixel instead of two 7-operation
+// determinants.  A pixel is decided by the edge functions only when all of them clear a margin
+// that bounds (a) the rounding drift of the stepping and (b) the difference between the stepped
+// pixel centre and the reference's rounded x_off + (i + 0.5) * x_scale; anything closer to an edge
+// is decided by the reference's exact divided form, so the claims are identical.
+struct EdgeFn {
+    double e1, e2, e3;     // values at the current pixel, margin already subtracted
+    double dx1, dx2, dx3;  // step per pixel column
+    double dy1, dy2, dy3;  // step per pixel row
+    double two_m;          // twice the margin
+    bool live;
+};
+
+__device__ __forceinline__ EdgeFn make_edge_fn(double det, double nu, double nv, double gu_x, double gu_y, double gv_x,
+                                               double gv_y, double lo, double hi, double x_scale, double y_scale,
+                                               double px_abs, double py_abs) {
+    EdgeFn f;
+    f.live = det != 0.0;
+    const double s = det < 0.0 ? -1.0 : 1.0, ad = fabs(det);
+    f.dx1 = s * gu_x * x_scale; f.dy1 = s * gu_y * y_scale;
+    f.dx2 = s * gv_x * x_scale; f.dy2 = s * gv_y * y_scale;
+    f.dx3 = -(f.dx1 + f.dx2);   f.dy3 = -(f.dy1 + f.dy2);
+    const double gx = fabs(gu_x) + fabs(gv_x), gy = fabs(gu_y) + fabs(gv_y);
+    const double m = 1e-11 * ad + 4e-15 * (px_abs * gx + py_abs * gy);
+    f.e1 = s * nu - lo * ad - m;
+    f.e2 = s * nv - lo * ad - m;
+    f.e3 = hi * ad - s * (nu + nv) - m;
+    f.two_m = 2.0 * m;
+    return f;
+}
+
+__device__ __forceinline__ void claim_pixels_fast(const IjGeom &g, const TileCtx &tc, const ScatterConst &k, double x0,
+                                                  double y0, double x1, double y1, double x2, double y2, double x3,
+                                                  double y3, int i_lo, int i_hi, int j_lo, int j_hi, uint32_t qkey) {
+    // rectify.py:528-542
+    const double det_a = tri_det(x0, y0, x1, y1, x2, y2);
+    const double det_b = tri_det(x3, y3, x2, y2, x1, y1);
+    if (det_a == 0.0 && det_b == 0.0) return;
+    // pixel centre of the box corner, the reference's expression (rectify.py:545,554)
+    const double px0 = dadd(tc.x_off, dmul(dadd(static_cast<double>(i_lo), 0.5), k.x_scale));
+    const double py0 = dadd(tc.y_off, dmul(dadd(static_cast<double>(j_lo), 0.5), k.y_scale));
+    const double px_abs = fmax(fabs(px0), fabs(px0 + (i_hi - i_lo) * k.x_scale));
+    const double py_abs = fmax(fabs(py0), fabs(py0 + (j_hi - j_lo) * k.y_scale));
+    // gradients of nu, nv with respect to the pixel centre (from _fu / _fv, rectify.py:744-757)
+    const EdgeFn fa = make_edge_fn(det_a, tri_u(px0, py0, x0, y0, x2, y2), tri_v(px0, py0, x0, y0, x1, y1),
+                                   -(y0 - y2), (x0 - x2), (y0 - y1), -(x0 - x1), k.uv_lo, k.uv_hi, k.x_scale, k.y_scale,
+                                   px_abs, py_abs);
+    const EdgeFn fb = make_edge_fn(det_b, tri_u(px0, py0, x3, y3, x1, y1), tri_v(px0, py0, x3, y3, x2, y2),
+                                   -(y3 - y1), (x3 - x1), (y3 - y2), -(x3 - x2), k.uv_lo, k.uv_hi, k.x_scale, k.y_scale,
+                                   px_abs, py_abs);
+    uint32_t *claim_row = g.claims + (static_cast<int64_t>(tc.r0) + j_lo - g.row_begin) * g.dst_w + tc.c0;
+    for (int dj = j_lo; dj <= j_hi; ++dj, claim_row += g.dst_w) {
+        const double rj = static_cast<double>(dj - j_lo);
+        double a1 = fa.e1 + rj * fa.dy1, a2 = fa.e2 + rj * fa.dy2, a3 = fa.e3 + rj * fa.dy3;
+        double b1 = fb.e1 + rj * fb.dy1, b2 = fb.e2 + rj * fb.dy2, b3 = fb.e3 + rj * fb.dy3;
+        for (int di = i_lo; di <= i_hi; ++di) {
+            bool acc = fa.live && a1 > 0.0 && a2 > 0.0 && a3 > 0.0;
+            bool exact = false;
+            if (!acc) {
+                const bool rej_a = !fa.live || a1 < -fa.two_m || a2 < -fa.two_m || a3 < -fa.two_m;
+                acc = fb.live && b1 > 0.0 && b2 > 0.0 && b3 > 0.0 && rej_a;
+                if (!acc) {
+                    const bool rej_b = !fb.live || b1 < -fb.two_m || b2 < -fb.two_m || b3 < -fb.two_m;
+                    exact = !(rej_a && rej_b);
+                }
+            }
+            if (exact) {  // within the margin of an edge: the reference's own arithmetic decides
+                const double px = dadd(tc.x_off, dmul(dadd(static_cast<double>(di), 0.5), k.x_scale));
+                const double py = dadd(tc.y_off, dmul(dadd(static_cast<double>(dj), 0.5), k.y_scale));
+                acc = fa.live && tri_accepts_exact(tri_u(px, py, x0, y0, x2, y2), tri_v(px, py, x0, y0, x1, y1), det_a,
+                                                   k.uv_lo, k.uv_hi);
+                if (!acc)
+                    acc = fb.live && tri_accepts_exact(tri_u(px, py, x3, y3, x1, y1), tri_v(px, py, x3, y3, x2, y2),
+                                                       det_b, k.uv_lo, k.uv_hi);
+            }
+            if (acc) atomicMin(claim_row + di, qkey);
+            a1 += fa.dx1; a2 += fa.dx2; a3 += fa.dx3;
+            b1 += fb.dx1; b2 += fb.dx2; b3 += fb.dx3;
+        }
+    }
+}
+
 // Quads near a reference-tile border, with non-finite vertices or reaching outside the target:
 // visit every tile a conservative pixel box touches and redo the tile-local arithmetic there.
 __device__ __forceinline__ void scatter_quad_generic(const IjGeom &g, const ScatterConst &k, double x0, double y0,
@@ -284,7 +370,7 @@ __device__ __forceinline__ VertexPx vertex_px(const IjGeom &g, const ScatterCons
     return v;
 }
 
-__global__ void __launch_bounds__(K1S_WARPS * 32) k1_scatter(IjGeom g) {
+__global__ void __launch_bounds__(K1S_WARPS * 32, 2) k1_scatter(IjGeom g) {
     const int64_t nqi = g.src_w - 1, nqj = g.src_h - 1;
     const int lane = threadIdx.x & 31;
     const int64_t strip = static_cast<int64_t>(blockIdx.x) * K1S_WARPS + (threadIdx.x >> 5);
@@ -315,9 +401,16 @@ __global__ void __launch_bounds__(K1S_WARPS * 32) k1_scatter(IjGeom g) {
     v1.pj = __shfl_down_sync(0xffffffffu, v0.pj, 1);
     v1.tile = __shfl_down_sync(0xffffffffu, v0.tile, 1);
 
+    // the next vertex row is fetched one iteration ahead so that its latency hides behind the
+    // pixel scans of the current row
+    double xn = (col_ok && j_begin < j_end) ? __ldg(g.x + (j_begin + 1) * g.src_pitch + col) : NAN;
+    double yn = (col_ok && j_begin < j_end) ? __ldg(g.y + (j_begin + 1) * g.src_pitch + col) : NAN;
     for (int64_t j = j_begin; j < j_end; ++j) {
-        const double x2 = col_ok ? __ldg(g.x + (j + 1) * g.src_pitch + col) : NAN;
-        const double y2 = col_ok ? __ldg(g.y + (j + 1) * g.src_pitch + col) : NAN;
+        const double x2 = xn, y2 = yn;
+        if (j + 1 < j_end) {
+            xn = col_ok ? __ldg(g.x + (j + 2) * g.src_pitch + col) : NAN;
+            yn = col_ok ? __ldg(g.y + (j + 2) * g.src_pitch + col) : NAN;
+        }
         const VertexPx v2 = vertex_px(g, k, x2, y2, inv_xr, inv_yr, inv_tw, inv_th, tc);
         const double x3 = __shfl_down_sync(0xffffffffu, x2, 1), y3 = __shfl_down_sync(0xffffffffu, y2, 1);
         VertexPx v3;
@@ -338,7 +431,7 @@ __global__ void __launch_bounds__(K1S_WARPS * 32) k1_scatter(IjGeom g) {
             if (same_tile && i_lo >= 1 && j_lo >= 1 && i_hi <= tc.tw - 2 && j_hi <= tc.th - 2) {
                 if (tc.has_window && qi >= tc.qi_lo && qi <= tc.qi_hi && qj >= tc.qj_lo && qj <= tc.qj_hi) {
                     const int jl = max(j_lo, tc.dj_lo), jh = min(j_hi, tc.dj_hi);  // requested rows
-                    if (jl <= jh) claim_pixels(g, tc, k, x0, y0, x1, y1, x2, y2, x3, y3, i_lo, i_hi, jl, jh, qkey);
+                    if (jl <= jh) claim_pixels_fast(g, tc, k, x0, y0, x1, y1, x2, y2, x3, y3, i_lo, i_hi, jl, jh, qkey);
                 }
                 slow = false;
             } else if (v0.tile < 0 && v1.tile < 0 && v2.tile < 0 && v3.tile < 0) {
