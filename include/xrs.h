@@ -216,6 +216,19 @@ int xrs_affine(const void *src, void *dst, int32_t dtype, int64_t n_slices, int6
                double i_scale, double i_off, int32_t order, double cval, int32_t agg, int32_t f_j, int32_t f_i,
                int32_t slice_blend, void *stream);
 
+/* NaN recovery for order-1 resampling of floating-point data (affine.py:344-360, recover_nans=True):
+ * the zero-filled image and the validity mask pass through the same filter and are divided, so a
+ * sample next to a NaN keeps the weighted mean of its valid neighbours instead of becoming NaN.
+ * The reference takes this branch only if the array holds a NaN at all (xrs_has_nan).  dst is
+ * float64 (numpy divides the filtered image by the float64 filtered mask); aggregation as for
+ * xrs_affine, carried out on those float64 samples. */
+int xrs_has_nan(const void *src, int32_t dtype, int64_t n_slices, int64_t src_h, int64_t src_w, int64_t src_pitch,
+                int64_t src_slice_stride, int32_t *flag, void *stream);
+int xrs_affine_recover(const void *src, double *dst, int32_t dtype, int64_t n_slices, int64_t src_h, int64_t src_w,
+                       int64_t src_pitch, int64_t src_slice_stride, int64_t dst_h, int64_t dst_w, double j_scale,
+                       double j_off, double i_scale, double i_off, double cval, int32_t agg, int32_t f_j, int32_t f_i,
+                       int32_t slice_blend, void *stream);
+
 /* K5 alone -- dask.array.coarsen(agg, array, {y: f_j, x: f_i}) with the same reducers
  * (coarsen.py:50-155); f_j, f_i must divide src_h, src_w.  dst as for xrs_affine. */
 int xrs_coarsen(const void *src, void *dst, int32_t dtype, int64_t n_slices, int64_t src_h, int64_t src_w,

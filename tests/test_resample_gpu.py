@@ -223,3 +223,51 @@ def test_config1_bilinear_downsample_4096(xrs):
                      coords=dict(lon=source_gm.x_coords.values, lat=source_gm.y_coords.values))
     out = xrs.affine_transform_dataset(ds, target_gm, source_gm=source_gm, interp_methods=1)
     assert_same(out["refl"].values, ref, "C1")
+
+
+# ---------------------------------------------------------------------------
+# recover_nans (affine.py:344-360)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("matrix,shape", [
+    (((0.5, 0.0, 0.25), (0.0, 0.5, -0.25)), (14, 18)),   # upscale
+    (((1.0, 0.0, 0.5), (0.0, 1.0, 0.5)), (6, 8)),        # half-pixel shift
+    (((2.0, 0.0, 0.0), (0.0, 2.0, 0.0)), (3, 4)),        # aligned downscale -> aggregation
+    (((2.5, 0.0, 1.0), (0.0, 2.5, -1.0)), (3, 3)),       # fractional downscale -> divisor 3
+])
+def test_recover_nans_matches_oracle(xrs, dtype, matrix, shape):
+    rng = np.random.default_rng(23)
+    a = rng.random((7, 9)).astype(dtype)
+    a[2, 3] = nan
+    a[5, 0] = nan
+    a[0, 8] = np.inf
+    for agg in ("mean", "max"):
+        ref = np.asarray(ores.resample_array(a, matrix, shape, 1, agg, True, nan))
+        got = _gpu_resample_recover(xrs, a, matrix, shape, agg)
+        assert got.dtype == ref.dtype == np.float64
+        assert_same(got, ref, f"{np.dtype(dtype).name} {agg} {matrix}")
+    # no NaN in the array: the ordinary path runs and the dtype stays (affine.py:349)
+    b = np.nan_to_num(a, nan=0.5, posinf=1.0)
+    got = _gpu_resample_recover(xrs, b, matrix, shape, "mean")
+    assert got.dtype == np.dtype(dtype)
+    assert_same(got, np.asarray(ores.resample_array(b, matrix, shape, 1, "mean", True, nan)).astype(dtype), "no-nan")
+
+
+def _gpu_resample_recover(xrs, arr, matrix, out_shape, agg):
+    out = xrs.aff._resample_array_dev(xrs.dev.to_device(arr), matrix, out_shape[-2:], 1, agg, True, nan)
+    return xrs.dev.to_host(out)
+
+
+def test_recover_nans_3d_and_reference_expectation(xrs):
+    """tests/test_affine.py:118-140: the NaN neighbour is recovered as 0.6666667."""
+    rng = np.random.default_rng(29)
+    a = rng.random((3, 6, 7))
+    a[1, 2, 2] = nan
+    matrix = ((0.7, 0.0, 0.3), (0.0, 0.7, 0.1))
+    ref = np.asarray(ores.resample_array(a, matrix, (3, 8, 9), 1, "mean", True, nan))
+    got = xrs.dev.to_host(xrs.aff._resample_array_dev(xrs.dev.to_device(a), matrix, (8, 9), 1, "mean", True, nan))
+    assert_same(got, ref, "3-D recover")
+    ds = _source_ds(xrs)
+    target_gm = xrs.GridMapping.regular((3, 3), (50.05, 10.05), 0.1, "EPSG:4326")
+    out = xrs.affine_transform_dataset(ds, target_gm, interp_methods=1, recover_nans=True)
+    np.testing.assert_almost_equal(out["refl"].values, [[1.25, 1.5, 0.6666667], [1.0, 1.25, 1.5], [1.75, 1.0, 1.25]])

@@ -58,6 +58,9 @@ SIGNATURES = {
                               c_i32, c_f64, c_i64, c_i64, c_p]),
     "xrs_affine": (c_int, [c_p, c_p, c_i32, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f64, c_f64, c_f64, c_f64,
                            c_i32, c_f64, c_i32, c_i32, c_i32, c_i32, c_p]),
+    "xrs_has_nan": (c_int, [c_p, c_i32, c_i64, c_i64, c_i64, c_i64, c_i64, c_p, c_p]),
+    "xrs_affine_recover": (c_int, [c_p, c_p, c_i32, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f64, c_f64, c_f64,
+                                   c_f64, c_f64, c_i32, c_i32, c_i32, c_i32, c_p]),
     "xrs_coarsen": (c_int, [c_p, c_p, c_i32, c_i64, c_i64, c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, c_p]),
 }
 

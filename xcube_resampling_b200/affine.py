@@ -43,8 +43,22 @@ def _np_dtype(t: torch.Tensor) -> np.dtype:
     return np.dtype(str(t.dtype).replace("torch.", ""))
 
 
+def has_nan_dev(src: torch.Tensor) -> bool:
+    """``da.any(da.isnan(array))`` (affine.py:347-349) -- one pass, one 4-byte read-back."""
+    lib = load()
+    src3 = src.unsqueeze(0) if src.dim() == 2 else src
+    if src3.stride(2) != 1:
+        src3 = src3.contiguous()
+    n, h, w = src3.shape
+    flag = torch.zeros(1, dtype=torch.int32, device=src3.device)
+    slice_stride = src3.stride(0) if n > 1 else h * src3.stride(1)
+    check(lib.xrs_has_nan(_dev.ptr(src3), DTYPE_CODES[_np_dtype(src3)], n, h, w, src3.stride(1), slice_stride,
+                          _dev.ptr(flag), _dev.stream_ptr(src3.device)), "xrs_has_nan")
+    return bool(flag.item())
+
+
 def affine_resample_dev(src: torch.Tensor, scale_ji, offset_ji, out_hw, order: int, cval, agg: str = "mean",
-                        factors=(1, 1), slice_blend: bool | None = None) -> torch.Tensor:
+                        factors=(1, 1), slice_blend: bool | None = None, recover: bool = False) -> torch.Tensor:
     """``xrs_affine`` on device buffers.
 
     src: (h, w) or (n, h, w) device tensor; source index = intermediate index * scale + offset,
@@ -64,10 +78,18 @@ def affine_resample_dev(src: torch.Tensor, scale_ji, offset_ji, out_hw, order: i
     is_float = dt.kind == "f"
     out_int64 = f_j * f_i > 1 and (agg in _INT64_OUT_AGGS or (not is_float and agg in ("sum", "prod")))
     out_dtype = np.dtype(np.int64) if out_int64 else dt
-    out = _dev.empty((n, int(out_hw[0]), int(out_hw[1])), out_dtype, src3.device)
     if slice_blend is None:
         slice_blend = not squeeze
     slice_stride = src3.stride(0) if n > 1 else h * src3.stride(1)
+    if recover:  # affine.py:344-360; the result is float64 (filtered image / float64 filtered mask)
+        out = _dev.empty((n, int(out_hw[0]), int(out_hw[1])), np.float64, src3.device)
+        check(lib.xrs_affine_recover(_dev.ptr(src3), _dev.ptr(out), DTYPE_CODES[dt], n, h, w, src3.stride(1),
+                                     slice_stride, int(out_hw[0]), int(out_hw[1]), float(scale_ji[0]),
+                                     float(offset_ji[0]), float(scale_ji[1]), float(offset_ji[1]), float(cval),
+                                     AGG_CODES[agg], f_j, f_i, int(bool(slice_blend)), _dev.stream_ptr(src3.device)),
+              "xrs_affine_recover")
+        return out[0] if squeeze else out
+    out = _dev.empty((n, int(out_hw[0]), int(out_hw[1])), out_dtype, src3.device)
     check(lib.xrs_affine(_dev.ptr(src3), _dev.ptr(out), DTYPE_CODES[dt], n, h, w, src3.stride(1), slice_stride,
                          int(out_hw[0]), int(out_hw[1]), float(scale_ji[0]), float(offset_ji[0]), float(scale_ji[1]),
                          float(offset_ji[1]), int(order), float(cval), AGG_CODES[agg], f_j, f_i, int(bool(slice_blend)),
@@ -91,16 +113,16 @@ def _resample_array_dev(src: torch.Tensor, affine_matrix, output_hw, interp_meth
     ((i_scale, _, i_off), (m10, j_scale, j_off)) = affine_matrix
     if interp_method > 1:
         raise ValueError(_ORDER_ERROR)
-    if recover_nan and interp_method > 0:
-        raise NotImplementedError("recover_nans is not implemented by the B200 path yet")
+    recover = bool(recover_nan) and interp_method > 0 and _np_dtype(src).kind == "f" and has_nan_dev(src)
     # affine.py:253 tests matrix[1][0] (always 0) instead of the y scale: only the x scale (or a
     # non-zero shear term) triggers aggregation -- kept as is for drop-in behaviour
     if (i_scale > 1 or m10 > 1) and interp_method != 0:
         j_div = math.ceil(abs(j_scale))
         i_div = math.ceil(abs(i_scale))
         return affine_resample_dev(src, (j_scale / j_div, i_scale / i_div), (j_off, i_off), output_hw, interp_method,
-                                   fill_value, agg_method, (j_div, i_div))
-    return affine_resample_dev(src, (j_scale, i_scale), (j_off, i_off), output_hw, interp_method, fill_value)
+                                   fill_value, agg_method, (j_div, i_div), recover=recover)
+    return affine_resample_dev(src, (j_scale, i_scale), (j_off, i_off), output_hw, interp_method, fill_value,
+                               recover=recover)
 
 
 def resample_dataset(dataset, affine_matrix, yx_dims, target_size, target_tile_size, interp_methods=None,

@@ -179,6 +179,44 @@ __device__ __forceinline__ OutT reduce_window(T *w, int f_j, int f_i, int agg) {
     }
 }
 
+// NaN recovery (affine.py:344-360): the zero-filled image and the validity mask go through the same
+// order-1 filter; the sample is their quotient, NaN where the mask weight is ~0.  scipy returns the
+// filtered image in the array's dtype and the filtered mask in float64, numpy divides in float64.
+template <typename T>
+__device__ __forceinline__ double affine_sample_recover(const T *__restrict__ sl, const T *__restrict__ nx, int64_t J,
+                                                        int64_t I, const AffineGeom &g) {
+    const double cj = dadd(dmul(static_cast<double>(J), g.j_scale), g.j_off);
+    const double ci = dadd(dmul(static_cast<double>(I), g.i_scale), g.i_off);
+    const Axis1 aj = axis_order1(cj, g.src_h), ai = axis_order1(ci, g.src_w);
+    double im, norm;
+    if (!aj.inside || !ai.inside) {
+        im = static_cast<double>(scipy_cast<T>(g.cval));
+        norm = g.cval;
+    } else {
+        const T v[4] = {__ldg(sl + aj.k0 * g.src_pitch + ai.k0), __ldg(sl + aj.k0 * g.src_pitch + ai.k1),
+                        __ldg(sl + aj.k1 * g.src_pitch + ai.k0), __ldg(sl + aj.k1 * g.src_pitch + ai.k1)};
+        const double wj[4] = {aj.w0, aj.w0, aj.w1, aj.w1}, wi[4] = {ai.w0, ai.w1, ai.w0, ai.w1};
+        double t = 0.0, n = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool nan = v[k] != v[k];
+            t = dadd(t, dmul(dmul(nan ? 0.0 : static_cast<double>(v[k]), wj[k]), wi[k]));
+            n = dadd(n, dmul(dmul(nan ? 0.0 : 1.0, wj[k]), wi[k]));
+        }
+        if (nx != nullptr) {  // zero-weight taps of the next slice: only +-inf survives the zero filling
+            const T u[4] = {__ldg(nx + aj.k0 * g.src_pitch + ai.k0), __ldg(nx + aj.k0 * g.src_pitch + ai.k1),
+                            __ldg(nx + aj.k1 * g.src_pitch + ai.k0), __ldg(nx + aj.k1 * g.src_pitch + ai.k1)};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (u[k] == u[k] && non_finite(u[k])) t = NAN;
+        }
+        im = static_cast<double>(scipy_cast<T>(t));
+        norm = n;
+    }
+    if (fabs(norm) <= 1e-8) return NAN;  // np.isclose(scaled_norm, 0.0)
+    return ddiv(im, norm);
+}
+
 // ---------------------------------------------------------------------------
 // generic kernel: one thread per output pixel and slice
 // ---------------------------------------------------------------------------
@@ -205,6 +243,56 @@ __global__ void __launch_bounds__(256) k4_affine_generic(const T *__restrict__ s
     for (int a = 0; a < g.f_j; ++a)
         for (int b = 0; b < g.f_i; ++b) w[a * g.f_i + b] = affine_sample<T>(cur, nx, oj * g.f_j + a, oi * g.f_i + b, g);
     *out = reduce_window<T, OutT>(w, g.f_j, g.f_i, g.agg);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k4_affine_recover(const T *__restrict__ src, double *__restrict__ dst, AffineGeom g) {
+    const int64_t oi = static_cast<int64_t>(blockIdx.x) * 32 + threadIdx.x;
+    const int64_t oj = static_cast<int64_t>(blockIdx.y) * 8 + threadIdx.y;
+    const int64_t sl = blockIdx.z;
+    if (oi >= g.dst_w || oj >= g.dst_h) return;
+    const T *cur = src + sl * g.src_slice_stride;
+    const T *nx = nullptr;
+    if (g.slice_blend && g.n_slices > 1) {
+        int64_t nsl = sl + 1;
+        if (nsl >= g.n_slices) nsl = g.n_slices > 2 ? g.n_slices - 2 : 0;
+        if (nsl != sl) nx = src + nsl * g.src_slice_stride;
+    }
+    double *out = dst + (sl * g.dst_h + oj) * g.dst_w + oi;
+    const int n = g.f_j * g.f_i;
+    if (n == 1) {
+        *out = affine_sample_recover<T>(cur, nx, oj, oi, g);
+        return;
+    }
+    double w[RS_MAX_WINDOW];
+    for (int a = 0; a < g.f_j; ++a)
+        for (int b = 0; b < g.f_i; ++b) w[a * g.f_i + b] = affine_sample_recover<T>(cur, nx, oj * g.f_j + a, oi * g.f_i + b, g);
+    *out = reduce_window<double, double>(w, g.f_j, g.f_i, g.agg);
+}
+
+__global__ void __launch_bounds__(256) k4_has_nan_f32(const float *__restrict__ p, int64_t h, int64_t w, int64_t pitch,
+                                                      int64_t slice_stride, int32_t *flag) {
+    const float *base = p + blockIdx.z * slice_stride;
+    bool any = false;
+    for (int64_t r = blockIdx.y; r < h; r += gridDim.y)
+        for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < w;
+             c += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+            const float v = __ldg(base + r * pitch + c);
+            any = any || (v != v);
+        }
+    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+__global__ void __launch_bounds__(256) k4_has_nan_f64(const double *__restrict__ p, int64_t h, int64_t w, int64_t pitch,
+                                                      int64_t slice_stride, int32_t *flag) {
+    const double *base = p + blockIdx.z * slice_stride;
+    bool any = false;
+    for (int64_t r = blockIdx.y; r < h; r += gridDim.y)
+        for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < w;
+             c += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+            const double v = __ldg(base + r * pitch + c);
+            any = any || (v != v);
+        }
+    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
 static bool agg_outputs_int64(int agg, bool is_float) {
@@ -273,6 +361,50 @@ int xrs_coarsen(const void *src, void *dst, int32_t dtype, int64_t n_slices, int
     // identity nearest-neighbour "resample" + aggregation == dask.array.coarsen
     return xrs_affine(src, dst, dtype, n_slices, src_h, src_w, src_pitch, src_slice_stride, src_h / f_j, src_w / f_i, 1.0,
                       0.0, 1.0, 0.0, 0, 0.0, agg, f_j, f_i, 0, stream);
+}
+
+int xrs_has_nan(const void *src, int32_t dtype, int64_t n_slices, int64_t src_h, int64_t src_w, int64_t src_pitch,
+                int64_t src_slice_stride, int32_t *flag, void *stream) {
+    if (!src || !flag) return fail("xrs_has_nan: null pointer");
+    if (n_slices < 1 || src_h < 1 || src_w < 1 || src_pitch < src_w || n_slices > 65535) return fail("xrs_has_nan: bad shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    XRS_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), st));
+    if (dtype != XRS_F32 && dtype != XRS_F64) return 0;  // integers hold no NaN
+    const dim3 grid(static_cast<unsigned>(std::min<int64_t>(ceil_div(src_w, 256), 64)),
+                    static_cast<unsigned>(std::min<int64_t>(src_h, 1024)), static_cast<unsigned>(n_slices));
+    if (dtype == XRS_F32)
+        XRS_TIMED("k4_has_nan", st, k4_has_nan_f32<<<grid, 256, 0, st>>>(static_cast<const float *>(src), src_h, src_w, src_pitch, src_slice_stride, flag));
+    else
+        XRS_TIMED("k4_has_nan", st, k4_has_nan_f64<<<grid, 256, 0, st>>>(static_cast<const double *>(src), src_h, src_w, src_pitch, src_slice_stride, flag));
+    XRS_LAUNCH_CHECK("k4_has_nan");
+    return 0;
+}
+
+int xrs_affine_recover(const void *src, double *dst, int32_t dtype, int64_t n_slices, int64_t src_h, int64_t src_w,
+                       int64_t src_pitch, int64_t src_slice_stride, int64_t dst_h, int64_t dst_w, double j_scale,
+                       double j_off, double i_scale, double i_off, double cval, int32_t agg, int32_t f_j, int32_t f_i,
+                       int32_t slice_blend, void *stream) {
+    if (!src || !dst) return fail("xrs_affine_recover: null pointer");
+    if (dtype != XRS_F32 && dtype != XRS_F64) return fail("xrs_affine_recover: floating-point data only");
+    if (n_slices < 1 || src_h < 1 || src_w < 1 || src_pitch < src_w || dst_h < 1 || dst_w < 1) return fail("xrs_affine_recover: bad shape");
+    if (f_j < 1 || f_i < 1 || static_cast<int64_t>(f_j) * f_i > RS_MAX_WINDOW || f_i > 128) return fail("xrs_affine_recover: bad aggregation factors");
+    if (f_j * f_i > 1 && (agg < XRS_AGG_CENTER || agg > XRS_AGG_VAR || agg == XRS_AGG_MODE || agg == XRS_AGG_COUNT))
+        return fail("xrs_affine_recover: aggregation method not available for floating-point NaN recovery");
+    if (n_slices > 65535 || ceil_div(dst_h, 8) > 65535) return fail("xrs_affine_recover: too many slices or rows for one launch");
+    AffineGeom g;
+    g.n_slices = n_slices; g.src_h = src_h; g.src_w = src_w; g.src_pitch = src_pitch; g.src_slice_stride = src_slice_stride;
+    g.dst_h = dst_h; g.dst_w = dst_w;
+    g.j_scale = j_scale; g.j_off = j_off; g.i_scale = i_scale; g.i_off = i_off; g.cval = cval;
+    g.order = 1; g.agg = agg; g.f_j = f_j; g.f_i = f_i; g.slice_blend = slice_blend;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const dim3 block(32, 8);
+    const dim3 grid(static_cast<unsigned>(ceil_div(dst_w, 32)), static_cast<unsigned>(ceil_div(dst_h, 8)), static_cast<unsigned>(n_slices));
+    if (dtype == XRS_F32)
+        XRS_TIMED("k4_affine_recover", st, k4_affine_recover<float><<<grid, block, 0, st>>>(static_cast<const float *>(src), dst, g));
+    else
+        XRS_TIMED("k4_affine_recover", st, k4_affine_recover<double><<<grid, block, 0, st>>>(static_cast<const double *>(src), dst, g));
+    XRS_LAUNCH_CHECK("k4_affine_recover");
+    return 0;
 }
 
 }  // extern "C"
