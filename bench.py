@@ -144,6 +144,13 @@ def run_cpu(steps, warmup, scale):
 
     oracle.build()
     lon, lat, bands, size, xy_min, res = make_scene(scale=scale)
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would
+    # otherwise make the CPU arm single-threaded)
+    try:
+        n_host = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        n_host = os.cpu_count() or 1
+    oracle.lib().xrso_set_num_threads(n_host)
     cores = oracle.lib().xrso_num_threads()
     for _ in range(warmup):
         cpu_scene_pass(orect, ogrid, lon, lat, bands, size, xy_min, res)
