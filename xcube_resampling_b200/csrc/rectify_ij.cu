@@ -149,10 +149,34 @@ __device__ __forceinline__ void load_tile_ctx(const IjGeom &g, int ty, int tx, T
                      : dsub(g.y_max, dmul(static_cast<double>(t.r0), g.y_res));
 }
 
-__global__ void k1_init_claims(uint4 *claims, int64_t n_vec, unsigned int *slow_count) {
+// Claim words <- "no claim"; block 0 also resets the slow-quad counter and reduces the source quad
+// rows the requested target rows can see: the union of the source windows of the reference tiles
+// that intersect [row_begin, row_end) (rectify.py:397-399 -- a tile only ever looks at the quads of
+// its own window).  k1_scatter skips every quad row outside that range, which is what makes a
+// row-band call cost its footprint instead of the whole swath.
+__global__ void k1_init_claims(uint4 *claims, int64_t n_vec, unsigned int *slow_count, IjGeom g) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n_vec) claims[i] = make_uint4(K1_NOCLAIM, K1_NOCLAIM, K1_NOCLAIM, K1_NOCLAIM);
-    if (i == 0) *slow_count = 0u;
+    if (blockIdx.x != 0) return;
+    int *range = reinterpret_cast<int *>(slow_count) + 1;  // [qj_min, qj_max]
+    if (threadIdx.x == 0) {
+        *slow_count = 0u;
+        range[0] = INT32_MAX;
+        range[1] = -1;
+    }
+    __syncthreads();
+    const int ty0 = static_cast<int>(g.row_begin / g.tile_h), ty1 = static_cast<int>((g.row_end - 1) / g.tile_h);
+    int lo = INT32_MAX, hi = -1;
+    for (int t = ty0 * g.ntx + threadIdx.x; t < (ty1 + 1) * g.ntx; t += blockDim.x) {
+        const int64_t *bb = g.tile_boxes + 4 * static_cast<int64_t>(t);
+        if (__ldg(bb) == -1) continue;
+        lo = min(lo, static_cast<int>(__ldg(bb + 1)));
+        hi = max(hi, static_cast<int>(min(__ldg(bb + 3) + 1, g.src_h)) - 2);
+    }
+    if (lo <= hi) {
+        atomicMin(range, lo);
+        atomicMax(range + 1, hi);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -376,8 +400,11 @@ __global__ void __launch_bounds__(K1S_WARPS * 32, 2) k1_scatter(IjGeom g) {
     const int64_t strip = static_cast<int64_t>(blockIdx.x) * K1S_WARPS + (threadIdx.x >> 5);
     if (strip * 31 >= nqi) return;  // whole warp out of range
     const int64_t col = strip * 31 + lane;  // vertex column of this lane
-    const int64_t j_begin = static_cast<int64_t>(blockIdx.y) * K1S_ROWS;
-    const int64_t j_end = min(j_begin + K1S_ROWS, nqj);  // quad rows [j_begin, j_end)
+    const int *qj_range = reinterpret_cast<const int *>(g.slow_count) + 1;  // from k1_init_claims
+    const int64_t j_begin = max(static_cast<int64_t>(blockIdx.y) * K1S_ROWS, static_cast<int64_t>(qj_range[0]));
+    const int64_t j_end = min(min(static_cast<int64_t>(blockIdx.y + 1) * K1S_ROWS, nqj),
+                              static_cast<int64_t>(qj_range[1]) + 1);  // quad rows [j_begin, j_end)
+    if (j_begin >= j_end) return;
     const bool col_ok = col < g.src_w;
     const bool quad_lane = lane < 31 && col < nqi;
 
@@ -571,7 +598,7 @@ int xrs_rectify_ij(const double *x, const double *y, int64_t src_h, int64_t src_
     g.slow_count = reinterpret_cast<unsigned int *>(g.slow_list + (src_h - 1) * (src_w - 1));
 
     const int64_t n_vec = ceil_div(n_rows * dst_w, 4);
-    XRS_TIMED("k1_init_claims", st, k1_init_claims<<<static_cast<unsigned>(ceil_div(n_vec, 256)), 256, 0, st>>>(reinterpret_cast<uint4 *>(g.claims), n_vec, g.slow_count));
+    XRS_TIMED("k1_init_claims", st, k1_init_claims<<<static_cast<unsigned>(ceil_div(n_vec, 256)), 256, 0, st>>>(reinterpret_cast<uint4 *>(g.claims), n_vec, g.slow_count, g));
     XRS_LAUNCH_CHECK("k1_init_claims");
     const dim3 sgrid(static_cast<unsigned>(ceil_div(ceil_div(src_w - 1, 31), K1S_WARPS)),
                      static_cast<unsigned>(ceil_div(src_h - 1, K1S_ROWS)));
