@@ -362,39 +362,77 @@ __device__ __forceinline__ void scatter_quad_generic(const IjGeom &g, const Scat
         }
 }
 
-// A vertex's pixel index in the reference tile that (approximately) contains it.  For a vertex that
-// is non-finite or outside the target image, tile = -(1 + outcode): bit 0 left, 1 right, 2 above,
-// 3 below the image by more than 2 px, bit 4 non-finite.
-struct VertexPx {
-    int pi, pj, tile;
+// ---------------------------------------------------------------------------
+// k1_scatter, pixel-space form
+//
+// Barycentric coordinates are invariant under the affine map CRS -> target pixel coordinates, so
+// the acceptance conditions u >= lo, v >= lo, u + v <= hi can be evaluated with the vertices
+// expressed in (fractional) GLOBAL pixel coordinates f = (x - x_min) / x_res: no tile-local
+// offsets, no exact floor divisions, and the edge functions step by plain vertex differences.
+// The reference's own arithmetic (tile-local offsets, CRS units, divided form) differs from this
+// by rounding only (< 1e-11 relative to |det|); a pixel whose edge functions do not all clear a
+// margin well above that sends its quad to the generic kernel, which IS the reference's arithmetic.  The
+// reference's pixel box needs no separate test: a pixel centre inside the triangles grown by the
+// uv tolerance lies inside [floor(min f), floor(max f)] as long as uv_delta * extent < 0.5 px
+// (quads larger than K1_MAX_EXTENT pixels take the generic path).
+// ---------------------------------------------------------------------------
+constexpr double K1_MAX_EXTENT = 64.0;
+
+struct TileWin {
+    int id;                          // ty * ntx + tx, -1 = nothing cached
+    int qi_lo, qi_hi, qj_lo, qj_hi;  // quads inside the tile's source window (rectify.py:397-399)
+    bool has;
 };
 
-__device__ __forceinline__ VertexPx vertex_px(const IjGeom &g, const ScatterConst &k, double vx, double vy,
-                                              double inv_xr, double inv_yr, float inv_tw, float inv_th, TileCtx &tc) {
-    VertexPx v;
-    v.pi = v.pj = 0;
-    v.tile = -1;
-    const double fx = (vx - g.x_min) * inv_xr;
-    const double fy = g.j_up ? (vy - g.y_min) * inv_yr : (g.y_max - vy) * inv_yr;
-    const double W = static_cast<double>(g.dst_w), H = static_cast<double>(g.dst_h);
-    if (!(fx >= 0.0 && fx < W && fy >= 0.0 && fy < H)) {
-        int code = (isfinite(fx) && isfinite(fy)) ? 0 : 16;
-        if (fx < -2.0) code |= 1;
-        if (fx >= W + 2.0) code |= 2;
-        if (fy < -2.0) code |= 4;
-        if (fy >= H + 2.0) code |= 8;
-        v.tile = -(1 + code);
-        return v;
-    }
-    const int tx = fast_div(static_cast<int>(fx), g.tile_w, inv_tw), ty = fast_div(static_cast<int>(fy), g.tile_h, inv_th);
-    if (tc.id != ty * g.ntx + tx) load_tile_ctx(g, ty, tx, tc);
-    v.tile = tc.id;
-    v.pi = floor_px_div(dsub(vx, tc.x_off), k.x_scale, k.inv_xs);
-    v.pj = floor_px_div(dsub(vy, tc.y_off), k.y_scale, k.inv_ys);
-    return v;
+__device__ __forceinline__ void load_tile_win(const IjGeom &g, int ty, int tx, TileWin &t) {
+    t.id = ty * g.ntx + tx;
+    const int64_t *bb = g.tile_boxes + 4 * static_cast<int64_t>(t.id);
+    const int64_t b0 = __ldg(bb), b1 = __ldg(bb + 1), b2 = __ldg(bb + 2), b3 = __ldg(bb + 3);
+    t.has = b0 != -1;
+    t.qi_lo = static_cast<int>(b0); t.qj_lo = static_cast<int>(b1);
+    t.qi_hi = static_cast<int>(min(b2 + 1, g.src_w)) - 2;
+    t.qj_hi = static_cast<int>(min(b3 + 1, g.src_h)) - 2;
 }
 
-__global__ void __launch_bounds__(K1S_WARPS * 32, 2) k1_scatter(IjGeom g) {
+// Edge functions of one triangle in pixel space, referred to the centre of pixel (i_ref, j_ref):
+//   e1 = s*nu - lo*|det| - m,  e2 = s*nv - lo*|det| - m  (m = decision margin), stepped per pixel;
+//   the third condition hi*|det| - s*(nu + nv) - m > 0 is e1 + e2 < k3.
+struct PxEdges {
+    double e1, e2;
+    double dx1, dx2;  // per pixel column
+    double dy1, dy2;  // per pixel row
+    double k3, two_m;
+};
+
+// (ax, ay) is the triangle's origin vertex, (bx, by) the u-direction vertex, (cx, cy) the v-direction
+// vertex (_fdet / _fu / _fv of rectify.py:737-757 with pixel coordinates).
+__device__ __forceinline__ PxEdges make_px_edges(double ax, double ay, double bx, double by, double cx, double cy,
+                                                 double pcx, double pcy, double lo, double hi, double coord_bound) {
+    PxEdges f;
+    const double abx = ax - bx, aby = ay - by, acx = ax - cx, acy = ay - cy, apx = ax - pcx, apy = ay - pcy;
+    const double det = abx * acy - acx * aby;
+    const double nu = apx * acy - apy * acx;
+    const double nv = apy * abx - apx * aby;
+    const double s = det < 0.0 ? -1.0 : 1.0, ad = fabs(det);
+    f.dx1 = -s * acy; f.dy1 = s * acx;   // gradient of s*nu
+    f.dx2 = s * aby;  f.dy2 = -s * abx;  // gradient of s*nv
+    const double m = 1e-9 * ad + coord_bound * (fabs(acy) + fabs(acx) + fabs(aby) + fabs(abx));
+    f.e1 = s * nu - lo * ad - m;
+    f.e2 = s * nv - lo * ad - m;
+    f.k3 = (hi - 2.0 * lo) * ad - 3.0 * m;
+    f.two_m = 2.0 * m;
+    return f;
+}
+
+// certain accept: all three conditions clear the margin; certain reject: one fails by more than it
+__device__ __forceinline__ bool px_accepts(const PxEdges &f, double a1, double a2) {
+    return a1 > 0.0 && a2 > 0.0 && a1 + a2 < f.k3;
+}
+__device__ __forceinline__ bool px_rejects(const PxEdges &f, double a1, double a2) {
+    return a1 < -f.two_m || a2 < -f.two_m || a1 + a2 > f.k3 + f.two_m;
+}
+
+__global__ void __launch_bounds__(K1S_WARPS * 32, 2) k1_scatter(const __grid_constant__ IjGeom g) {
     const int64_t nqi = g.src_w - 1, nqj = g.src_h - 1;
     const int lane = threadIdx.x & 31;
     const int64_t strip = static_cast<int64_t>(blockIdx.x) * K1S_WARPS + (threadIdx.x >> 5);
@@ -408,64 +446,102 @@ __global__ void __launch_bounds__(K1S_WARPS * 32, 2) k1_scatter(IjGeom g) {
     const bool col_ok = col < g.src_w;
     const bool quad_lane = lane < 31 && col < nqi;
 
-    ScatterConst k;
-    k.x_scale = g.x_res; k.y_scale = g.j_up ? g.y_res : -g.y_res;
-    k.inv_xs = 1.0 / k.x_scale; k.inv_ys = 1.0 / k.y_scale;
-    k.uv_lo = -g.uv_delta; k.uv_hi = dadd(1.0, dmul(2.0, g.uv_delta));
     const double inv_xr = 1.0 / g.x_res, inv_yr = 1.0 / g.y_res;
+    const double uv_lo = -g.uv_delta, uv_hi = dadd(1.0, dmul(2.0, g.uv_delta));
     const float inv_tw = 1.0f / static_cast<float>(g.tile_w), inv_th = 1.0f / static_cast<float>(g.tile_h);
+    const int W = static_cast<int>(g.dst_w), R0 = static_cast<int>(g.row_begin), R1 = static_cast<int>(g.row_end);
+    const double clamp_hi = static_cast<double>(max(g.dst_w, g.dst_h)) + 8.0;
+    // rounding of a pixel coordinate (two roundings of a value up to the image size) seen through an
+    // edge function's gradient, with a factor 8 to spare
+    const double coord_bound = 8.0 * 2.3e-16 * clamp_hi;
+    const bool small_tolerance = g.uv_delta * (K1_MAX_EXTENT + 2.0) < 0.25;
     const int qi = static_cast<int>(col);
 
-    TileCtx tc;
-    tc.id = -1;
-    // previous vertex row: this lane's vertex (x0, y0, v0) and its right neighbour (x1, y1, v1)
-    double x0 = col_ok ? __ldg(g.x + j_begin * g.src_pitch + col) : NAN;
-    double y0 = col_ok ? __ldg(g.y + j_begin * g.src_pitch + col) : NAN;
-    VertexPx v0 = vertex_px(g, k, x0, y0, inv_xr, inv_yr, inv_tw, inv_th, tc);
-    double x1 = __shfl_down_sync(0xffffffffu, x0, 1), y1 = __shfl_down_sync(0xffffffffu, y0, 1);
-    VertexPx v1;
-    v1.pi = __shfl_down_sync(0xffffffffu, v0.pi, 1);
-    v1.pj = __shfl_down_sync(0xffffffffu, v0.pj, 1);
-    v1.tile = __shfl_down_sync(0xffffffffu, v0.tile, 1);
+    TileWin tw;
+    tw.id = -1;
+    // A vertex in pixel space: fractional coordinates and their floors (pixel indices, clamped to a
+    // band around the image so that they fit an int).  `ok` is false for non-finite coordinates.
+    auto to_px = [&](double vx, double vy, double &fx, double &fy, int &pi, int &pj) {
+        fx = (vx - g.x_min) * inv_xr;
+        fy = g.j_up ? (vy - g.y_min) * inv_yr : (g.y_max - vy) * inv_yr;
+        pi = __double2int_rd(fmin(fmax(fx, -8.0), clamp_hi));
+        pj = __double2int_rd(fmin(fmax(fy, -8.0), clamp_hi));
+        return fabs(fx) < 1e9 && fabs(fy) < 1e9;  // false for NaN / inf
+    };
+    double fx0, fy0;
+    int pi0, pj0;
+    bool ok0 = to_px(col_ok ? __ldg(g.x + j_begin * g.src_pitch + col) : NAN,
+                     col_ok ? __ldg(g.y + j_begin * g.src_pitch + col) : NAN, fx0, fy0, pi0, pj0);
+    double fx1 = __shfl_down_sync(0xffffffffu, fx0, 1), fy1 = __shfl_down_sync(0xffffffffu, fy0, 1);
+    int pi1 = __shfl_down_sync(0xffffffffu, pi0, 1), pj1 = __shfl_down_sync(0xffffffffu, pj0, 1);
+    bool ok1 = (__ballot_sync(0xffffffffu, ok0) >> ((lane + 1) & 31)) & 1u;
 
     // the next vertex row is fetched one iteration ahead so that its latency hides behind the
     // pixel scans of the current row
-    double xn = (col_ok && j_begin < j_end) ? __ldg(g.x + (j_begin + 1) * g.src_pitch + col) : NAN;
-    double yn = (col_ok && j_begin < j_end) ? __ldg(g.y + (j_begin + 1) * g.src_pitch + col) : NAN;
+    double xn = col_ok ? __ldg(g.x + (j_begin + 1) * g.src_pitch + col) : NAN;
+    double yn = col_ok ? __ldg(g.y + (j_begin + 1) * g.src_pitch + col) : NAN;
     for (int64_t j = j_begin; j < j_end; ++j) {
-        const double x2 = xn, y2 = yn;
+        double fx2, fy2;
+        int pi2, pj2;
+        const bool ok2 = to_px(xn, yn, fx2, fy2, pi2, pj2);
         if (j + 1 < j_end) {
             xn = col_ok ? __ldg(g.x + (j + 2) * g.src_pitch + col) : NAN;
             yn = col_ok ? __ldg(g.y + (j + 2) * g.src_pitch + col) : NAN;
         }
-        const VertexPx v2 = vertex_px(g, k, x2, y2, inv_xr, inv_yr, inv_tw, inv_th, tc);
-        const double x3 = __shfl_down_sync(0xffffffffu, x2, 1), y3 = __shfl_down_sync(0xffffffffu, y2, 1);
-        VertexPx v3;
-        v3.pi = __shfl_down_sync(0xffffffffu, v2.pi, 1);
-        v3.pj = __shfl_down_sync(0xffffffffu, v2.pj, 1);
-        v3.tile = __shfl_down_sync(0xffffffffu, v2.tile, 1);
-        bool slow = quad_lane;
+        const double fx3 = __shfl_down_sync(0xffffffffu, fx2, 1), fy3 = __shfl_down_sync(0xffffffffu, fy2, 1);
+        const int pi3 = __shfl_down_sync(0xffffffffu, pi2, 1), pj3 = __shfl_down_sync(0xffffffffu, pj2, 1);
+        const bool ok3 = (__ballot_sync(0xffffffffu, ok2) >> ((lane + 1) & 31)) & 1u;
+        bool slow = false;
         if (quad_lane) {
-            const uint32_t qkey = static_cast<uint32_t>(j * nqi + col);
-            const int qj = static_cast<int>(j);
-            const int i_lo = min(min(v0.pi, v1.pi), min(v2.pi, v3.pi)), i_hi = max(max(v0.pi, v1.pi), max(v2.pi, v3.pi));
-            const int j_lo = min(min(v0.pj, v1.pj), min(v2.pj, v3.pj)), j_hi = max(max(v0.pj, v1.pj), max(v2.pj, v3.pj));
-            // Fast path: all four vertices were indexed in the lane's cached tile and the pixel box stays
-            // at least one pixel inside it, so no other tile can see the quad (tile-local and neighbouring
-            // tile arithmetic differ by less than one pixel) and the box needs no tile clipping.
-            const bool same_tile = v2.tile >= 0 && v2.tile == tc.id && v0.tile == v2.tile && v1.tile == v2.tile &&
-                                   v3.tile == v2.tile;
-            if (same_tile && i_lo >= 1 && j_lo >= 1 && i_hi <= tc.tw - 2 && j_hi <= tc.th - 2) {
-                if (tc.has_window && qi >= tc.qi_lo && qi <= tc.qi_hi && qj >= tc.qj_lo && qj <= tc.qj_hi) {
-                    const int jl = max(j_lo, tc.dj_lo), jh = min(j_hi, tc.dj_hi);  // requested rows
-                    if (jl <= jh) claim_pixels_fast(g, tc, k, x0, y0, x1, y1, x2, y2, x3, y3, i_lo, i_hi, jl, jh, qkey);
+            const int bi_lo = min(min(pi0, pi1), min(pi2, pi3)), bi_hi = max(max(pi0, pi1), max(pi2, pi3));
+            const int bj_lo = min(min(pj0, pj1), min(pj2, pj3)), bj_hi = max(max(pj0, pj1), max(pj2, pj3));
+            if (!(ok0 && ok1 && ok2 && ok3) || !small_tolerance) {
+                slow = true;  // non-finite vertices: generic path (it also rejects far-away quads)
+            } else if (!(bi_hi < 0 || bi_lo >= W || bj_hi < R0 || bj_lo >= R1)) {
+                if (bi_hi - bi_lo >= static_cast<int>(K1_MAX_EXTENT) || bj_hi - bj_lo >= static_cast<int>(K1_MAX_EXTENT)) {
+                    slow = true;
+                } else {
+                    const int i_lo = max(bi_lo, 0), i_hi = min(bi_hi, W - 1), j_lo = max(bj_lo, R0), j_hi = min(bj_hi, R1 - 1);
+                    const uint32_t qkey = static_cast<uint32_t>(j * nqi + col);
+                    const int qj = static_cast<int>(j);
+                    const double pcx = static_cast<double>(i_lo) + 0.5, pcy = static_cast<double>(j_lo) + 0.5;
+                    // triangle A: origin p0, u towards p1, v towards p2; triangle B: origin p3, u towards p2, v towards p1
+                    const PxEdges fa = make_px_edges(fx0, fy0, fx1, fy1, fx2, fy2, pcx, pcy, uv_lo, uv_hi, coord_bound);
+                    const PxEdges fb = make_px_edges(fx3, fy3, fx2, fy2, fx1, fy1, pcx, pcy, uv_lo, uv_hi, coord_bound);
+                    const int tx_a = fast_div(i_lo, g.tile_w, inv_tw), ty_a = fast_div(j_lo, g.tile_h, inv_th);
+                    const int tx_b = (i_hi < (tx_a + 1) * g.tile_w) ? tx_a : fast_div(i_hi, g.tile_w, inv_tw);
+                    const int ty_b = (j_hi < (ty_a + 1) * g.tile_h) ? ty_a : fast_div(j_hi, g.tile_h, inv_th);
+                    for (int ty = ty_a; ty <= ty_b; ++ty) {
+                        const int ja = max(j_lo, ty * g.tile_h), jb = min(j_hi, (ty + 1) * g.tile_h - 1);
+                        for (int tx = tx_a; tx <= tx_b; ++tx) {
+                            if (tw.id != ty * g.ntx + tx) load_tile_win(g, ty, tx, tw);
+                            if (!tw.has || qi < tw.qi_lo || qi > tw.qi_hi || qj < tw.qj_lo || qj > tw.qj_hi) continue;
+                            const int ia = max(i_lo, tx * g.tile_w), ib = min(i_hi, (tx + 1) * g.tile_w - 1);
+                            const double ci = static_cast<double>(ia - i_lo);
+                            const double a1c = fma(ci, fa.dx1, fa.e1), a2c = fma(ci, fa.dx2, fa.e2);
+                            const double b1c = fma(ci, fb.dx1, fb.e1), b2c = fma(ci, fb.dx2, fb.e2);
+                            uint32_t *claim_row = g.claims + (static_cast<int64_t>(ja) - g.row_begin) * g.dst_w;
+                            for (int gj = ja; gj <= jb; ++gj, claim_row += g.dst_w) {
+                                const double rj = static_cast<double>(gj - j_lo);
+                                double a1 = fma(rj, fa.dy1, a1c), a2 = fma(rj, fa.dy2, a2c);
+                                double b1 = fma(rj, fb.dy1, b1c), b2 = fma(rj, fb.dy2, b2c);
+                                for (int gi = ia; gi <= ib; ++gi) {
+                                    bool acc = px_accepts(fa, a1, a2);
+                                    if (!acc) {
+                                        const bool rej_a = px_rejects(fa, a1, a2);
+                                        acc = rej_a && px_accepts(fb, b1, b2);
+                                        // within the margin of an edge: the whole quad is redone by the
+                                        // generic kernel with the reference's arithmetic (atomicMin is idempotent)
+                                        if (!acc && !(rej_a && px_rejects(fb, b1, b2))) slow = true;
+                                    }
+                                    if (acc) atomicMin(claim_row + gi, qkey);
+                                    a1 += fa.dx1; a2 += fa.dx2;
+                                    b1 += fb.dx1; b2 += fb.dx2;
+                                }
+                            }
+                        }
+                    }
                 }
-                slow = false;
-            } else if (v0.tile < 0 && v1.tile < 0 && v2.tile < 0 && v3.tile < 0) {
-                // all four vertices outside the target: if they are finite and share an outside
-                // half-plane (with 2 px to spare) the quad cannot reach any target pixel
-                const int c0 = -v0.tile - 1, c1 = -v1.tile - 1, c2 = -v2.tile - 1, c3 = -v3.tile - 1;
-                if (((c0 | c1 | c2 | c3) & 16) == 0 && (c0 & c1 & c2 & c3 & 15) != 0) slow = false;
             }
         }
         // quads for the generic path are queued (warp-aggregated append) and handled by k1_scatter_slow,
@@ -477,8 +553,9 @@ __global__ void __launch_bounds__(K1S_WARPS * 32, 2) k1_scatter(IjGeom g) {
             base = __shfl_sync(0xffffffffu, base, 0);
             if (slow) g.slow_list[base + __popc(slow_mask & ((1u << lane) - 1u))] = static_cast<uint32_t>(j * nqi + col);
         }
-        x0 = x2; y0 = y2; x1 = x3; y1 = y3;
-        v0 = v2; v1 = v3;
+        fx0 = fx2; fy0 = fy2; fx1 = fx3; fy1 = fy3;
+        pi0 = pi2; pj0 = pj2; pi1 = pi3; pj1 = pj3;
+        ok0 = ok2; ok1 = ok3;
     }
 }
 
