@@ -28,7 +28,7 @@ namespace xrs {
 
 constexpr uint32_t K1_NOCLAIM = 0xffffffffu;
 constexpr int K1_SENTINEL = INT32_MIN;  // stands for np.int64 min (non-finite vertex)
-constexpr int K1S_ROWS = 64;            // quad rows marched by one warp
+constexpr int K1S_ROWS = 32;            // quad rows marched by one warp
 constexpr int K1S_WARPS = 8;
 constexpr int K1R_THREADS = 256;
 
