@@ -357,10 +357,13 @@ def ours(args):
         lat_p[...] = lat
         bands_p = _dev.pinned_empty((nb, fj1 - fj0, w), np.float32)
         bands_p[...] = bands[:, fj0:fj1, :]
-        e2e_steps = max(1, min(args.steps, 3))
+        e2e_steps = max(1, min(args.steps, 10))
 
         ds = xrs.Dataset(data_vars=dict(bands=(("band", "y", "x"), bands_p)),
                          coords=dict(lon=(("y", "x"), lon_p), lat=(("y", "x"), lat_p)))
+        # the grid mapping of the end-to-end leg wraps the page-locked coordinate arrays (it is what
+        # rectify_dataset uploads), so every host buffer of the call is pinned
+        source_gm = xrs.GridMapping.from_coords(lon_p, lat_p, "EPSG:4326", xy_res=res, xy_dim_names=("x", "y"))
 
         def e2e_step():
             n = 0
@@ -375,7 +378,8 @@ def ours(args):
                     n += out.size
             return n
 
-        e2e_step()
+        for _ in range(2):  # warm-up: pinned output buffers enter the host allocator's cache
+            e2e_step()
         barrier()
         t0 = time.perf_counter()
         n_units = 0
