@@ -376,3 +376,19 @@ def test_resample_in_space_dispatches_to_reproject(xrs):
     tgt = xrs.GridMapping.regular(size=(5, 5), xy_min=(4320080, 3382480), xy_res=80, crs="epsg:3035")
     out = xrs.resample_in_space(_ds_5x5(xrs), target_gm=tgt)
     np.testing.assert_array_equal(out.band_1.values, EXPECTED_5X5)
+
+
+def test_band_pipeline_equals_plain_path(xrs, monkeypatch):
+    """reproject_dataset streams large variables in band chunks; same bytes as the plain path."""
+    src_gm, tgt_gm = _case_utm_from_geographic(xrs, n=160, tile=64)
+    rng = np.random.default_rng(8)
+    data = rng.random((7, src_gm.height, src_gm.width)).astype(np.float32)
+    ds = xrs.Dataset(data_vars=dict(v=xrs.DataArray(data, dims=("band", "lat", "lon"))),
+                     coords=dict(lon=xrs.DataArray(src_gm.x_values, dims="lon"),
+                                 lat=xrs.DataArray(src_gm.y_values, dims="lat")))
+    for method in ("nearest", "bilinear"):
+        plain = xrs.reproject_dataset(ds, tgt_gm, source_gm=src_gm, interp_methods=method)["v"].values
+        monkeypatch.setattr(xrs.rep, "_PIPELINE_MIN_BYTES", 0)
+        piped = xrs.reproject_dataset(ds, tgt_gm, source_gm=src_gm, interp_methods=method)["v"].values
+        monkeypatch.undo()
+        assert_same(piped, plain, method)

@@ -265,12 +265,31 @@ def reproject_dataset(
             assert len(var.dims) in (2, 3), f"Data variable {var_name} has {len(var.dims)} dimensions."
             fill_value = _get_fill_value(fill_values, var_name, var)
             interp_method = _get_interp_method_str(interp_methods, var_name, var)
-            out = _dev.to_host(plan.run(_dev.to_device(var.values), interp_method, fill_value))
+            out = _reproject_from_host(plan, var.values, interp_method, fill_value)
             dims = t_dims if len(var.dims) == 2 else (var.dims[0],) + t_dims
             target_ds[var_name] = DataArray(out, dims=dims, attrs=var.attrs, name=var_name)
         elif yx_dims[0] not in var.dims and yx_dims[1] not in var.dims:
             target_ds[var_name] = var
     return to_like(target_ds, user_ds)
+
+
+_PIPELINE_MIN_BYTES = 64 << 20
+
+
+def _reproject_from_host(plan: ReprojectPlan, values: np.ndarray, interp_method: str, fill_value) -> np.ndarray:
+    """K3 for one host variable; large (bands, y, x) variables stream through the device in band
+    chunks with upload, kernel and download overlapped (``_dev.BandPipeline``)."""
+    if interp_method not in INTERP_CODES:
+        raise NotImplementedError(
+            f"interp_methods must be one of 0, 1, 'nearest', 'bilinear', "
+            f"'triangular', was '{interp_method}'."
+        )
+    if values.ndim == 3 and values.shape[0] > 1 and values.nbytes >= _PIPELINE_MIN_BYTES:
+        out_dtype = np.float64 if interp_method == "bilinear" else values.dtype
+        gm = plan.target_gm
+        pipe = _dev.BandPipeline(values, (plan.rows[1] - plan.rows[0], gm.width), out_dtype, plan.device)
+        return pipe.run(lambda src, out: plan.run(src, interp_method, fill_value, out=out))
+    return _dev.to_host(plan.run(_dev.to_device(values, plan.device), interp_method, fill_value))
 
 
 def _flip_y(ds: Dataset, y_dim: str) -> Dataset:
