@@ -203,95 +203,11 @@ __device__ __forceinline__ void claim_pixels(const IjGeom &g, const TileCtx &tc,
         const double py = dadd(tc.y_off, dmul(dadd(static_cast<double>(dj), 0.5), k.y_scale));
         for (int di = i_lo; di <= i_hi; ++di) {
             const double px = dadd(tc.x_off, dmul(dadd(static_cast<double>(di), 0.5), k.x_scale));
-            bool acc = tri_accepts(ta, tri_u(px, py, x0, y0, x2, y2), tri_v(px, py, x0, y0, x1, y1), k.uv_lo, k.uv_hi);
-            if (!acc) acc = tri_accepts(tb, tri_u(px, py, x3, y3, x1, y1), tri_v(px, py, x3, y3, x2, y2), k.uv_lo, k.uv_hi);
-            if (acc) atomicMin(claim_row + di, qkey);
-        }
-    }
-}
-
-// The same scan for quads whose vertices are all finite (the fast path of k1_scatter), with the
-// three acceptance conditions of each triangle kept as affine "edge functions" of the pixel index:
-//   e1 = s*nu - lo*|det| >= 0,  e2 = s*nv - lo*|det| >= 0,  e3 = hi*|det| - s*(nu + nv) >= 0.
-// They are evaluated once at the box corner (from the reference's own expressions) and then stepped
-// by constant increments -- 3 additions per triangle and pixel instead of two 7-operation
-// determinants.  A pixel is decided by the edge functions only when all of them clear a margin
-// that bounds (a) the rounding drift of the stepping and (b) the difference between the stepped
-// pixel centre and the reference's rounded x_off + (i + 0.5) * x_scale; anything closer to an edge
-// is decided by the reference's exact divided form, so the claims are identical.
-struct EdgeFn {
-    double e1, e2, e3;     // values at the current pixel, margin already subtracted
-    double dx1, dx2, dx3;  // step per pixel column
-    double dy1, dy2, dy3;  // step per pixel row
-    double two_m;          // twice the margin
-    bool live;
-};
-
-__device__ __forceinline__ EdgeFn make_edge_fn(double det, double nu, double nv, double gu_x, double gu_y, double gv_x,
-                                               double gv_y, double lo, double hi, double x_scale, double y_scale,
-                                               double px_abs, double py_abs) {
-    EdgeFn f;
-    f.live = det != 0.0;
-    const double s = det < 0.0 ? -1.0 : 1.0, ad = fabs(det);
-    f.dx1 = s * gu_x * x_scale; f.dy1 = s * gu_y * y_scale;
-    f.dx2 = s * gv_x * x_scale; f.dy2 = s * gv_y * y_scale;
-    f.dx3 = -(f.dx1 + f.dx2);   f.dy3 = -(f.dy1 + f.dy2);
-    const double gx = fabs(gu_x) + fabs(gv_x), gy = fabs(gu_y) + fabs(gv_y);
-    const double m = 1e-11 * ad + 4e-15 * (px_abs * gx + py_abs * gy);
-    f.e1 = s * nu - lo * ad - m;
-    f.e2 = s * nv - lo * ad - m;
-    f.e3 = hi * ad - s * (nu + nv) - m;
-    f.two_m = 2.0 * m;
-    return f;
-}
-
-__device__ __forceinline__ void claim_pixels_fast(const IjGeom &g, const TileCtx &tc, const ScatterConst &k, double x0,
-                                                  double y0, double x1, double y1, double x2, double y2, double x3,
-                                                  double y3, int i_lo, int i_hi, int j_lo, int j_hi, uint32_t qkey) {
-    // rectify.py:528-542
-    const double det_a = tri_det(x0, y0, x1, y1, x2, y2);
-    const double det_b = tri_det(x3, y3, x2, y2, x1, y1);
-    if (det_a == 0.0 && det_b == 0.0) return;
-    // pixel centre of the box corner, the reference's expression (rectify.py:545,554)
-    const double px0 = dadd(tc.x_off, dmul(dadd(static_cast<double>(i_lo), 0.5), k.x_scale));
-    const double py0 = dadd(tc.y_off, dmul(dadd(static_cast<double>(j_lo), 0.5), k.y_scale));
-    const double px_abs = fmax(fabs(px0), fabs(px0 + (i_hi - i_lo) * k.x_scale));
-    const double py_abs = fmax(fabs(py0), fabs(py0 + (j_hi - j_lo) * k.y_scale));
-    // gradients of nu, nv with respect to the pixel centre (from _fu / _fv, rectify.py:744-757)
-    const EdgeFn fa = make_edge_fn(det_a, tri_u(px0, py0, x0, y0, x2, y2), tri_v(px0, py0, x0, y0, x1, y1),
-                                   -(y0 - y2), (x0 - x2), (y0 - y1), -(x0 - x1), k.uv_lo, k.uv_hi, k.x_scale, k.y_scale,
-                                   px_abs, py_abs);
-    const EdgeFn fb = make_edge_fn(det_b, tri_u(px0, py0, x3, y3, x1, y1), tri_v(px0, py0, x3, y3, x2, y2),
-                                   -(y3 - y1), (x3 - x1), (y3 - y2), -(x3 - x2), k.uv_lo, k.uv_hi, k.x_scale, k.y_scale,
-                                   px_abs, py_abs);
-    uint32_t *claim_row = g.claims + (static_cast<int64_t>(tc.r0) + j_lo - g.row_begin) * g.dst_w + tc.c0;
-    for (int dj = j_lo; dj <= j_hi; ++dj, claim_row += g.dst_w) {
-        const double rj = static_cast<double>(dj - j_lo);
-        double a1 = fa.e1 + rj * fa.dy1, a2 = fa.e2 + rj * fa.dy2, a3 = fa.e3 + rj * fa.dy3;
-        double b1 = fb.e1 + rj * fb.dy1, b2 = fb.e2 + rj * fb.dy2, b3 = fb.e3 + rj * fb.dy3;
-        for (int di = i_lo; di <= i_hi; ++di) {
-            bool acc = fa.live && a1 > 0.0 && a2 > 0.0 && a3 > 0.0;
-            bool exact = false;
-            if (!acc) {
-                const bool rej_a = !fa.live || a1 < -fa.two_m || a2 < -fa.two_m || a3 < -fa.two_m;
-                acc = fb.live && b1 > 0.0 && b2 > 0.0 && b3 > 0.0 && rej_a;
-                if (!acc) {
-                    const bool rej_b = !fb.live || b1 < -fb.two_m || b2 < -fb.two_m || b3 < -fb.two_m;
-                    exact = !(rej_a && rej_b);
-                }
-            }
-            if (exact) {  // within the margin of an edge: the reference's own arithmetic decides
-                const double px = dadd(tc.x_off, dmul(dadd(static_cast<double>(di), 0.5), k.x_scale));
-                const double py = dadd(tc.y_off, dmul(dadd(static_cast<double>(dj), 0.5), k.y_scale));
-                acc = fa.live && tri_accepts_exact(tri_u(px, py, x0, y0, x2, y2), tri_v(px, py, x0, y0, x1, y1), det_a,
-                                                   k.uv_lo, k.uv_hi);
-                if (!acc)
-                    acc = fb.live && tri_accepts_exact(tri_u(px, py, x3, y3, x1, y1), tri_v(px, py, x3, y3, x2, y2),
-                                                       det_b, k.uv_lo, k.uv_hi);
-            }
-            if (acc) atomicMin(claim_row + di, qkey);
-            a1 += fa.dx1; a2 += fa.dx2; a3 += fa.dx3;
-            b1 += fb.dx1; b2 += fb.dx2; b3 += fb.dx3;
+            const bool acc_a = tri_accepts(ta, tri_u(px, py, x0, y0, x2, y2), tri_v(px, py, x0, y0, x1, y1), k.uv_lo, k.uv_hi);
+            const bool acc_b = !acc_a && tri_accepts(tb, tri_u(px, py, x3, y3, x1, y1), tri_v(px, py, x3, y3, x2, y2),
+                                                     k.uv_lo, k.uv_hi);
+            // claim word: quad index and, in bit 0, which triangle accepted (A is tried first)
+            if (acc_a || acc_b) atomicMin(claim_row + di, (qkey << 1) | (acc_b ? 1u : 0u));
         }
     }
 }
@@ -526,15 +442,16 @@ __global__ void __launch_bounds__(K1S_WARPS * 32, 2) k1_scatter(const __grid_con
                                 double a1 = fma(rj, fa.dy1, a1c), a2 = fma(rj, fa.dy2, a2c);
                                 double b1 = fma(rj, fb.dy1, b1c), b2 = fma(rj, fb.dy2, b2c);
                                 for (int gi = ia; gi <= ib; ++gi) {
-                                    bool acc = px_accepts(fa, a1, a2);
-                                    if (!acc) {
+                                    const bool acc_a = px_accepts(fa, a1, a2);
+                                    bool acc_b = false;
+                                    if (!acc_a) {
                                         const bool rej_a = px_rejects(fa, a1, a2);
-                                        acc = rej_a && px_accepts(fb, b1, b2);
+                                        acc_b = rej_a && px_accepts(fb, b1, b2);
                                         // within the margin of an edge: the whole quad is redone by the
                                         // generic kernel with the reference's arithmetic (atomicMin is idempotent)
-                                        if (!acc && !(rej_a && px_rejects(fb, b1, b2))) slow = true;
+                                        if (!acc_b && !(rej_a && px_rejects(fb, b1, b2))) slow = true;
                                     }
-                                    if (acc) atomicMin(claim_row + gi, qkey);
+                                    if (acc_a || acc_b) atomicMin(claim_row + gi, (qkey << 1) | (acc_b ? 1u : 0u));
                                     a1 += fa.dx1; a2 += fa.dx2;
                                     b1 += fb.dx1; b2 += fb.dx2;
                                 }
@@ -586,42 +503,37 @@ __global__ void __launch_bounds__(K1R_THREADS) k1_resolve(IjGeom g) {
     if (c >= g.dst_w) return;
     const int64_t n_rows = g.row_end - g.row_begin;
     const int64_t o = static_cast<int64_t>(blockIdx.y) * g.dst_w + c;
-    const uint32_t qkey = __ldcs(g.claims + o);
+    const uint32_t claim = __ldcs(g.claims + o);
     double oi = NAN, oj = NAN;
-    if (qkey != K1_NOCLAIM) {
-        const int64_t nqi = g.src_w - 1;
-        const int64_t j0 = qkey / nqi, i0 = qkey - j0 * nqi;
+    if (claim != K1_NOCLAIM) {
+        const uint32_t qkey = claim >> 1, nqi = static_cast<uint32_t>(g.src_w - 1);
+        const bool tri_b = claim & 1u;  // which triangle the scatter accepted (A is tried first, rectify.py:556-573)
+        const uint32_t j0 = qkey / nqi, i0 = qkey - j0 * nqi;
         const int ty = static_cast<int>(r) / g.tile_h, tx = static_cast<int>(c) / g.tile_w;
-        const int64_t r0 = static_cast<int64_t>(ty) * g.tile_h, c0 = static_cast<int64_t>(tx) * g.tile_w;
+        const int r0 = ty * g.tile_h, c0 = tx * g.tile_w;
         const int64_t *bb = g.tile_boxes + 4 * (static_cast<int64_t>(ty) * g.ntx + tx);
-        const int64_t bb0 = __ldg(bb), bb1 = __ldg(bb + 1);
+        const int bb0 = static_cast<int>(__ldg(bb)), bb1 = static_cast<int>(__ldg(bb + 1));
         const double x_off = dadd(g.x_min, dmul(static_cast<double>(c0), g.x_res));
         const double y_off = g.j_up ? dadd(g.y_min, dmul(static_cast<double>(r0), g.y_res))
                                     : dsub(g.y_max, dmul(static_cast<double>(r0), g.y_res));
         const double x_scale = g.x_res, y_scale = g.j_up ? g.y_res : -g.y_res;
-        const double uv_lo = -g.uv_delta, uv_hi = dadd(1.0, dmul(2.0, g.uv_delta));
-        const double px = dadd(x_off, dmul(dadd(static_cast<double>(c - c0), 0.5), x_scale));
-        const double py = dadd(y_off, dmul(dadd(static_cast<double>(r - r0), 0.5), y_scale));
-        const int64_t s0 = j0 * g.src_pitch + i0, s2 = s0 + g.src_pitch;
-        const double x0 = __ldg(g.x + s0), x1 = __ldg(g.x + s0 + 1), x2 = __ldg(g.x + s2), x3 = __ldg(g.x + s2 + 1);
-        const double y0 = __ldg(g.y + s0), y1 = __ldg(g.y + s0 + 1), y2 = __ldg(g.y + s2), y3 = __ldg(g.y + s2 + 1);
-        double det_a = tri_det(x0, y0, x1, y1, x2, y2);
-        if (det_a != det_a) det_a = 0.0;
-        const double nu_a = tri_u(px, py, x0, y0, x2, y2), nv_a = tri_v(px, py, x0, y0, x1, y1);
-        double u, v;
-        bool tri_b = true;
-        if (tri_accepts(make_tri_test(det_a, uv_lo, uv_hi), nu_a, nv_a, uv_lo, uv_hi)) {
-            u = ddiv(nu_a, det_a); v = ddiv(nv_a, det_a);
-            tri_b = false;
-        } else {  // the claim guarantees that triangle B accepts
-            const double det_b = tri_det(x3, y3, x2, y2, x1, y1);
-            u = ddiv(tri_u(px, py, x3, y3, x1, y1), det_b);
-            v = ddiv(tri_v(px, py, x3, y3, x2, y2), det_b);
-        }
+        const double px = dadd(x_off, dmul(dadd(static_cast<double>(static_cast<int>(c) - c0), 0.5), x_scale));
+        const double py = dadd(y_off, dmul(dadd(static_cast<double>(static_cast<int>(r) - r0), 0.5), y_scale));
+        const int64_t s0 = static_cast<int64_t>(j0) * g.src_pitch + i0, s2 = s0 + g.src_pitch;
+        // origin vertex o, u-direction vertex pu, v-direction vertex pv of the accepted triangle:
+        // A = (p0; p1, p2), B = (p3; p2, p1)
+        const int64_t so = tri_b ? s2 + 1 : s0, su = tri_b ? s2 : s0 + 1, sv = tri_b ? s0 + 1 : s2;
+        const double ox = __ldg(g.x + so), oy = __ldg(g.y + so);
+        const double ux = __ldg(g.x + su), uy = __ldg(g.y + su);
+        const double vx = __ldg(g.x + sv), vy = __ldg(g.y + sv);
+        const double det = tri_det(ox, oy, ux, uy, vx, vy);
+        const double u = ddiv(tri_u(px, py, ox, oy, vx, vy), det);
+        const double v = ddiv(tri_v(px, py, ox, oy, ux, uy), det);
         const double fi = clamp01(u), fj = clamp01(v);
         // rectify.py:564-576: window-local index + fraction, then + window origin
-        const double li = tri_b ? dsub(static_cast<double>(i0 + 1 - bb0), fi) : dadd(static_cast<double>(i0 - bb0), fi);
-        const double lj = tri_b ? dsub(static_cast<double>(j0 + 1 - bb1), fj) : dadd(static_cast<double>(j0 - bb1), fj);
+        const int wi = static_cast<int>(i0) - bb0, wj = static_cast<int>(j0) - bb1;
+        const double li = tri_b ? dsub(static_cast<double>(wi + 1), fi) : dadd(static_cast<double>(wi), fi);
+        const double lj = tri_b ? dsub(static_cast<double>(wj + 1), fj) : dadd(static_cast<double>(wj), fj);
         oi = dadd(static_cast<double>(bb0), li);
         oj = dadd(static_cast<double>(bb1), lj);
     }
@@ -656,7 +568,7 @@ int xrs_rectify_ij(const double *x, const double *y, int64_t src_h, int64_t src_
     if (dst_h < 1 || dst_w < 1 || tile_h < 1 || tile_w < 1) return fail("xrs_rectify_ij: bad target shape");
     if (dst_h > (1 << 30) || dst_w > (1 << 30) || src_w > (1 << 30) || src_h > (1 << 30)) return fail("xrs_rectify_ij: image too large");
     if (!(x_res > 0.0) || !(y_res > 0.0)) return fail("xrs_rectify_ij: resolution must be positive");
-    if ((src_h - 1) * (src_w - 1) >= 0xffffffffLL) return fail("xrs_rectify_ij: source has too many quads");
+    if ((src_h - 1) * (src_w - 1) >= 0x7fffffffLL) return fail("xrs_rectify_ij: source has too many quads (2^31 or more)");
     if (reinterpret_cast<uintptr_t>(workspace) & 15) return fail("xrs_rectify_ij: workspace must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     IjGeom g;
