@@ -318,6 +318,7 @@ struct PxEdges {
     double dx1, dx2;  // per pixel column
     double dy1, dy2;  // per pixel row
     double k3, two_m;
+    bool degenerate;
 };
 
 // (ax, ay) is the triangle's origin vertex, (bx, by) the u-direction vertex, (cx, cy) the v-direction
@@ -337,15 +338,23 @@ __device__ __forceinline__ PxEdges make_px_edges(double ax, double ay, double bx
     f.e2 = s * nv - lo * ad - m;
     f.k3 = (hi - 2.0 * lo) * ad - 3.0 * m;
     f.two_m = 2.0 * m;
+    f.degenerate = !(ad > 1e-6);  // (nearly) collapsed triangle: the generic kernel decides
     return f;
 }
 
-// certain accept: all three conditions clear the margin; certain reject: one fails by more than it
-__device__ __forceinline__ bool px_accepts(const PxEdges &f, double a1, double a2) {
-    return a1 > 0.0 && a2 > 0.0 && a1 + a2 < f.k3;
+// The per-pixel decisions read only the SIGN / high word of the three condition values
+// (a1, a2, k3 - (a1 + a2)), i.e. integer instructions instead of fp64 compares:
+//   certain accept  all three non-negative (their high words OR-ed have the sign bit clear);
+//   certain reject  one of them below -4m: for negative doubles the high word, read as unsigned,
+//                   grows with the magnitude, so `hi > hi(-4m)` is that test to within 2^-20 relative,
+//                   which the factor 2 between the 2m the argument needs and the 4m used here absorbs.
+__device__ __forceinline__ bool px_accepts(double a1, double a2, double t3) {
+    return (__double2hiint(a1) | __double2hiint(a2) | __double2hiint(t3)) >= 0;
 }
-__device__ __forceinline__ bool px_rejects(const PxEdges &f, double a1, double a2) {
-    return a1 < -f.two_m || a2 < -f.two_m || a1 + a2 > f.k3 + f.two_m;
+__device__ __forceinline__ bool px_rejects(uint32_t neg_thresh_hi, double a1, double a2, double t3) {
+    return static_cast<uint32_t>(__double2hiint(a1)) > neg_thresh_hi ||
+           static_cast<uint32_t>(__double2hiint(a2)) > neg_thresh_hi ||
+           static_cast<uint32_t>(__double2hiint(t3)) > neg_thresh_hi;
 }
 
 __global__ void __launch_bounds__(K1S_WARPS * 32, 2) k1_scatter(const __grid_constant__ IjGeom g) {
@@ -424,10 +433,13 @@ __global__ void __launch_bounds__(K1S_WARPS * 32, 2) k1_scatter(const __grid_con
                     // triangle A: origin p0, u towards p1, v towards p2; triangle B: origin p3, u towards p2, v towards p1
                     const PxEdges fa = make_px_edges(fx0, fy0, fx1, fy1, fx2, fy2, pcx, pcy, uv_lo, uv_hi, coord_bound);
                     const PxEdges fb = make_px_edges(fx3, fy3, fx2, fy2, fx1, fy1, pcx, pcy, uv_lo, uv_hi, coord_bound);
+                    if (fa.degenerate || fb.degenerate) slow = true;
+                    const uint32_t rej_hi_a = static_cast<uint32_t>(__double2hiint(-2.0 * fa.two_m));
+                    const uint32_t rej_hi_b = static_cast<uint32_t>(__double2hiint(-2.0 * fb.two_m));
                     const int tx_a = fast_div(i_lo, g.tile_w, inv_tw), ty_a = fast_div(j_lo, g.tile_h, inv_th);
                     const int tx_b = (i_hi < (tx_a + 1) * g.tile_w) ? tx_a : fast_div(i_hi, g.tile_w, inv_tw);
                     const int ty_b = (j_hi < (ty_a + 1) * g.tile_h) ? ty_a : fast_div(j_hi, g.tile_h, inv_th);
-                    for (int ty = ty_a; ty <= ty_b; ++ty) {
+                    for (int ty = ty_a; ty <= ty_b && !slow; ++ty) {
                         const int ja = max(j_lo, ty * g.tile_h), jb = min(j_hi, (ty + 1) * g.tile_h - 1);
                         for (int tx = tx_a; tx <= tx_b; ++tx) {
                             if (tw.id != ty * g.ntx + tx) load_tile_win(g, ty, tx, tw);
@@ -442,14 +454,16 @@ __global__ void __launch_bounds__(K1S_WARPS * 32, 2) k1_scatter(const __grid_con
                                 double a1 = fma(rj, fa.dy1, a1c), a2 = fma(rj, fa.dy2, a2c);
                                 double b1 = fma(rj, fb.dy1, b1c), b2 = fma(rj, fb.dy2, b2c);
                                 for (int gi = ia; gi <= ib; ++gi) {
-                                    const bool acc_a = px_accepts(fa, a1, a2);
+                                    const double a3 = fa.k3 - (a1 + a2);
+                                    const bool acc_a = px_accepts(a1, a2, a3);
                                     bool acc_b = false;
                                     if (!acc_a) {
-                                        const bool rej_a = px_rejects(fa, a1, a2);
-                                        acc_b = rej_a && px_accepts(fb, b1, b2);
+                                        const double b3 = fb.k3 - (b1 + b2);
+                                        const bool rej_a = px_rejects(rej_hi_a, a1, a2, a3);
+                                        acc_b = rej_a && px_accepts(b1, b2, b3);
                                         // within the margin of an edge: the whole quad is redone by the
                                         // generic kernel with the reference's arithmetic (atomicMin is idempotent)
-                                        if (!acc_b && !(rej_a && px_rejects(fb, b1, b2))) slow = true;
+                                        if (!acc_b && !(rej_a && px_rejects(rej_hi_b, b1, b2, b3))) slow = true;
                                     }
                                     if (acc_a || acc_b) atomicMin(claim_row + gi, (qkey << 1) | (acc_b ? 1u : 0u));
                                     a1 += fa.dx1; a2 += fa.dx2;
