@@ -30,8 +30,8 @@ def xrs():
     return pkg
 
 
-def _gm(xrs, g: ogrid.RegularGrid):
-    return xrs.GridMapping.regular((g.width, g.height), (g.x_min, g.y_min), (g.x_res, g.y_res), "EPSG:4326",
+def _gm(xrs, g: ogrid.RegularGrid, crs="EPSG:4326"):
+    return xrs.GridMapping.regular((g.width, g.height), (g.x_min, g.y_min), (g.x_res, g.y_res), crs,
                                    tile_size=(g.tile_w, g.tile_h), is_j_axis_up=g.is_j_axis_up)
 
 
@@ -273,3 +273,67 @@ def test_band_pipeline_equals_plain_path(xrs, monkeypatch):
         piped = xrs.rectify_dataset(ds, target_gm=target_gm, source_gm=source_gm, interp_methods=method)["bands"].values
         monkeypatch.undo()
         assert_same(piped, plain, method)
+
+
+# ---------------------------------------------------------------------------
+# adversarial geometry for the pixel-space scatter (edge functions + margins)
+# ---------------------------------------------------------------------------
+def _ij_equal(xrs, x, y, g, crs="EPSG:4326"):
+    gm = _gm(xrs, g, crs)
+    windows, ij = _device_rectify(xrs, x, y, gm)
+    assert_same(windows, orect.source_windows(x, y, g), "K0 windows")
+    assert_same(xrs.dev.to_host(ij), orect.rectify_ij(x, y, g), "K1 ij")
+
+
+@pytest.mark.parametrize("tile", [None, 16, (24, 10)])
+@pytest.mark.parametrize("ratio", [1.0, 2.0, 0.5, 3.0])
+def test_axis_aligned_source_on_pixel_centres(xrs, tile, ratio):
+    """Regular source whose vertices sit exactly on target pixel centres / corners: every triangle
+    edge passes through pixel centres (u, v exactly 0 or 1) -- the margin / exact-arithmetic path."""
+    res = 0.25
+    w, h = 41, 33
+    x = np.broadcast_to(10.0 + ratio * res * (np.arange(w) + 0.5), (h, w)).copy()
+    y = np.broadcast_to((50.0 - ratio * res * (np.arange(h) + 0.5))[:, None], (h, w)).copy()
+    size = (int(w * ratio) + 4, int(h * ratio) + 4)
+    g = ogrid.regular_grid(size, (10.0 - 2 * res, 50.0 - (size[1] - 2) * res), res, tile_size=tile)
+    _ij_equal(xrs, x, y, g)
+
+
+def test_holes_duplicates_and_folds(xrs):
+    """NaN holes, duplicated rows / columns (zero-area quads) and a fold (negative determinants)."""
+    x, y = swath(180, 150, theta=25.0, seed=11)
+    x[20:24, 30:50] = nan
+    y[20:24, 30:50] = nan
+    x[70, :] = x[69, :]
+    y[70, :] = y[69, :]          # duplicated row
+    x[:, 100] = x[:, 99]
+    y[:, 100] = y[:, 99]         # duplicated column
+    x[110:130] = x[110:130][::-1].copy()
+    y[110:130] = y[110:130][::-1].copy()  # folded strip
+    x[5, 5] = np.inf
+    res = 0.0027
+    size, xy_min = covering_grid_args(x, y, res)
+    g = ogrid.regular_grid(size, xy_min, res, tile_size=64)
+    _ij_equal(xrs, x, y, g)
+
+
+def test_projected_coordinate_magnitudes(xrs):
+    """UTM-like metres: coordinates ~5e5 / 6e6 with 300 m pixels (rounding of the pixel-space
+    transform is largest relative to the quad size here)."""
+    lon, lat = swath(300, 260, theta=-8.0, seed=13)
+    x = 500000.0 + (lon - 10.0) * 78000.0
+    y = 5000000.0 + (lat - 45.0) * 111000.0
+    res = 300.0
+    size, xy_min = covering_grid_args(x, y, res)
+    for tile in (None, 100):
+        g = ogrid.regular_grid(size, xy_min, res, tile_size=tile)
+        _ij_equal(xrs, x, y, g, "EPSG:32632")
+
+
+def test_huge_quads_take_the_generic_path(xrs):
+    """Quads spanning > 64 target pixels (K1_MAX_EXTENT) and a loose uv tolerance."""
+    x, y = swath(12, 10, theta=33.0, seed=17)
+    res = 0.0027 / 90.0
+    size, xy_min = covering_grid_args(x, y, res)
+    g = ogrid.regular_grid(size, xy_min, res, tile_size=256)
+    _ij_equal(xrs, x, y, g)
