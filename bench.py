@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the scene (debugging only; 1.0 = BASELINE config)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (debugging only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (debugging only)")
+    ap.add_argument("--no-graph", action="store_true", help="N > 1: launch eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -275,16 +276,41 @@ def ours(args):
         sampler.start()
     launches0 = lib.xrs_launch_count()
     _lib.profile_collect()
-    _lib.profile_enable(True)  # per-kernel CUDA events inside libxrs, on the launching stream
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
+    use_graph = world > 1 and not args.no_graph
+    if not use_graph:
+        # N = 1: eager launches, per-kernel CUDA events inside libxrs over the timed region itself
+        _lib.profile_enable(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step(record=True)
+        e1.record()
+        torch.cuda.synchronize()
+        _lib.profile_enable(False)
+        kernel_times = _lib.profile_collect()
+        launches = lib.xrs_launch_count() - launches0
+    else:
+        # N > 1: a rank's band kernels are short (0.01-0.15 ms), so the step (N scenes x 2 methods x
+        # 9 launches) is captured once in a CUDA graph and replayed; the per-kernel breakdown comes
+        # from one extra eager step after the timed region
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        launches_per_step = lib.xrs_launch_count() - launches0
+        graph.replay()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        launches = launches_per_step * args.steps
+        _lib.profile_enable(True)
         step(record=True)
-    e1.record()
-    torch.cuda.synchronize()
-    _lib.profile_enable(False)
-    kernel_times = _lib.profile_collect()
-    launches = lib.xrs_launch_count() - launches0
+        torch.cuda.synchronize()
+        _lib.profile_enable(False)
+        kernel_times = _lib.profile_collect()
     my_ms = e0.elapsed_time(e1)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -296,7 +322,7 @@ def ours(args):
         phase_ms["k0"] += evs[0].elapsed_time(evs[1])
         phase_ms["k1"] += evs[1].elapsed_time(evs[2])
         phase_ms["k2_" + m] += evs[2].elapsed_time(evs[3])
-    n_pass = args.steps * world
+    n_pass = (args.steps if not use_graph else 1) * world
     phase_ms = {k: v / n_pass / (len(METHODS) if k in ("k0", "k1") else 1) for k, v in phase_ms.items()}
 
     # ---- roofline of the dominant kernel (largest share of the timed region) ------------
@@ -344,7 +370,9 @@ def ours(args):
                           "workload (profiles/r01_*_ncu_full.txt)" if traffic else None,
         "algorithmic_bytes_per_launch": top["algorithmic_bytes_per_launch"], "bytes_model": top["bytes_model"],
         "ms_per_launch": top["ms_per_launch"], "share_of_kernel_time": top["share_of_kernel_time"],
-        "timing": "CUDA events recorded by libxrs around every launch on the launching stream, timed region only",
+        "timing": ("CUDA events recorded by libxrs around every launch on the launching stream, timed region only"
+                   if not use_graph else
+                   "timed region = CUDA-graph replays of the step; per-kernel CUDA events from one extra eager step"),
         "kernels": kernels, "phase_ms_per_rectify": phase_ms,
     }
 

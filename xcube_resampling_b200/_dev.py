@@ -115,6 +115,17 @@ def ptr_array(tensors) -> ctypes.Array:
     return arr
 
 
+def plane_ptr_array(t: torch.Tensor) -> ctypes.Array:
+    """Pointers to the planes t[0], t[1], ... of a (bands, h, w) tensor, computed from the base
+    pointer and the band stride (no per-band tensor views: this sits on the per-call hot path)."""
+    n = t.shape[0]
+    base, step = t.data_ptr(), t.stride(0) * t.element_size()
+    arr = (ctypes.c_void_p * n)()
+    for k in range(n):
+        arr[k] = base + k * step
+    return arr
+
+
 class BandPipeline:
     """Host -> device -> host streaming of a (bands, h, w) variable in band chunks.
 

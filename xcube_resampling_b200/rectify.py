@@ -198,8 +198,8 @@ def gather_ij(src: torch.Tensor, ij: torch.Tensor, interp_method: str, fill_valu
     _, H, W = ij.shape
     if out is None:
         out = torch.empty((bands, H, W), dtype=src3.dtype, device=src3.device)
-    src_planes = _dev.ptr_array([src3[b] for b in range(bands)])
-    dst_planes = _dev.ptr_array([out[b] for b in range(bands)])
+    src_planes = _dev.plane_ptr_array(src3)
+    dst_planes = _dev.plane_ptr_array(out)
     fill = float(fill_value)
     check(lib.xrs_gather_ij(src_planes, dst_planes, bands, DTYPE_CODES[np_dtype], h, w, src3.stride(1),
                             int(window_origin[0]), int(window_origin[1]), win_w, win_h, _dev.ptr(ij), H, W,

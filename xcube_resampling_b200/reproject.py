@@ -205,8 +205,8 @@ class ReprojectPlan:
         n_rows = self.rows[1] - self.rows[0]
         if out is None:
             out = _dev.empty((bands, n_rows, gm.width), out_np_dtype, src3.device)
-        src_planes = _dev.ptr_array([src3[b] for b in range(bands)])
-        dst_planes = _dev.ptr_array([out[b] for b in range(bands)])
+        src_planes = _dev.plane_ptr_array(src3)
+        dst_planes = _dev.plane_ptr_array(out)
         check(self.lib.xrs_reproject(
             src_planes, dst_planes, bands, DTYPE_CODES[np_dtype], DTYPE_CODES[out_np_dtype], sgm.height, sgm.width,
             src3.stride(1), int(window_origin[0]), int(window_origin[1]), win_w, win_h,
