@@ -125,3 +125,19 @@ def test_median_nan_patterns(xrs):
         ref = np.asarray(ores.coarsen(a, f, f, "median"))
         got = xrs.dev.to_host(xrs.aff.coarsen_dev(xrs.dev.to_device(a), (f, f), "median"))
         assert_same(got, ref.astype(np.float32), f"median f={f}")
+
+
+@pytest.mark.parametrize("f", [2, 4, 8])
+@pytest.mark.parametrize("agg", ["mean", "min", "max", "median", "mode", "first", "last", "center", "sum", "count"])
+def test_uint8_packed_path(xrs, f, agg):
+    """uint8 rasters with 4-aligned output width take the SIMD-in-a-word kernel (4 windows / thread)."""
+    rng = np.random.default_rng(100 + f)
+    h, w = 7 * f, 16 * f * 3
+    a = rng.integers(0, 256, size=(2, h, w)).astype(np.uint8)
+    a[0, : 2 * f] = rng.integers(0, 4, size=(2 * f, w)).astype(np.uint8)  # few classes: mode ties, zeros for count
+    a[1, 3 * f: 4 * f] = 255
+    ref = np.asarray(ores.coarsen(a, f, f, agg))
+    got, used = _kernels_used(xrs, lambda: xrs.dev.to_host(xrs.aff.coarsen_dev(xrs.dev.to_device(a), (f, f), agg)))
+    assert used == ({"k5_u8x2_sort"} if agg in ("median", "mode") else {"k5_u8x4_reduce"}), used
+    assert got.dtype == (np.int64 if agg in ("mode", "sum", "count") else np.uint8)
+    assert np.array_equal(got.astype(np.int64), ref.astype(np.int64)), f"{agg} f={f}"

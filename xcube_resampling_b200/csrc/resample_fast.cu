@@ -60,6 +60,17 @@ __device__ __forceinline__ void load_row(const T *__restrict__ p, T (&out)[F], b
 }
 
 // ---- sorting network ---------------------------------------------------------------------------
+// NaNs never reach the network (mapped to +inf before sorting), so the IEEE min / max instructions
+// order the values exactly like the comparison-based exchange; +0 and -0 compare equal in numpy's
+// sort as well, so which of them ends up first is immaterial to the reducers.
+__device__ __forceinline__ float sort_min(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ float sort_max(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double sort_min(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ double sort_max(double a, double b) { return fmax(a, b); }
+template <typename T>
+__device__ __forceinline__ T sort_min(T a, T b) { return a < b ? a : b; }
+template <typename T>
+__device__ __forceinline__ T sort_max(T a, T b) { return a < b ? b : a; }
 template <int N, typename T>
 __device__ __forceinline__ void bitonic_sort(T (&a)[N]) {
 #pragma unroll
@@ -69,12 +80,12 @@ __device__ __forceinline__ void bitonic_sort(T (&a)[N]) {
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 const int l = i ^ j;
-                if (l > i) {
+                if (l > i) {  // compare-exchange as a min / max pair (FMNMX / VIMNMX: 2 instructions)
                     const bool up = (i & k) == 0;
                     const T x = a[i], y = a[l];
-                    const bool sw = up ? (x > y) : (x < y);
-                    a[i] = sw ? y : x;
-                    a[l] = sw ? x : y;
+                    const T lo = sort_min(x, y), hi = sort_max(x, y);
+                    a[i] = up ? lo : hi;
+                    a[l] = up ? hi : lo;
                 }
             }
         }
@@ -291,6 +302,303 @@ __global__ void __launch_bounds__(256) k5_window_reduce(const T *__restrict__ sr
     dst[(sl * g.dst_h + oj) * g.dst_w + oi] = r;
 }
 
+// ---------------------------------------------------------------------------
+// uint8 rasters (class maps, masks): four horizontally adjacent windows per thread, SIMD-in-a-word.
+//
+// A thread reads 4*F bytes per window row with one or two 16-byte loads and transposes them with
+// byte permutes into N = F*F registers t[p], byte lane k of t[p] = pixel p of window k.  min / max,
+// the sorting network of median and mode (vminu4 / vmaxu4), run-length counting (vcmpeq4 / vadd4 /
+// vcmpgtu4) and the pick reducers then work on four windows per instruction; sums use dp4a on the
+// untransposed rows.  Results: 4 bytes, or 4 int64 for mode / count / sum, per thread.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void transpose4x4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t &r0, uint32_t &r1,
+                                             uint32_t &r2, uint32_t &r3) {
+    const uint32_t t0 = __byte_perm(a, b, 0x5140), t1 = __byte_perm(a, b, 0x7362);
+    const uint32_t t2 = __byte_perm(c, d, 0x5140), t3 = __byte_perm(c, d, 0x7362);
+    r0 = __byte_perm(t0, t2, 0x5410); r1 = __byte_perm(t0, t2, 0x7632);
+    r2 = __byte_perm(t1, t3, 0x5410); r3 = __byte_perm(t1, t3, 0x7632);
+}
+
+template <int N>
+__device__ __forceinline__ void bitonic_sort_u8x4(uint32_t (&a)[N]) {
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const uint32_t lo = __vminu4(a[i], a[l]), hi = __vmaxu4(a[i], a[l]);
+                    a[i] = up ? lo : hi;
+                    a[l] = up ? hi : lo;
+                }
+            }
+        }
+    }
+}
+
+// rint(sum / N) for N = 4, 16, 64 (np.mean in float64 is exact here, np.rint rounds half to even)
+template <int N>
+__device__ __forceinline__ uint32_t mean_half_even(uint32_t sum) {
+    const uint32_t q = sum / N, rem = sum % N;
+    return q + ((rem > N / 2 || (rem == N / 2 && (q & 1u))) ? 1u : 0u);
+}
+
+template <int F>
+__global__ void __launch_bounds__(256) k5_u8x4_reduce(const uint8_t *__restrict__ src, void *__restrict__ dst, FastGeom g) {
+    constexpr int N = F * F;
+    constexpr int WORDS = F;  // 32-bit words per loaded row (4 windows x F bytes)
+    const int64_t og = static_cast<int64_t>(blockIdx.x) * 32 + threadIdx.x;  // group of 4 output columns
+    const int64_t oj = static_cast<int64_t>(blockIdx.y) * 8 + threadIdx.y;
+    const int64_t sl = blockIdx.z;
+    const int64_t oi = og * 4;
+    if (oi >= g.dst_w || oj >= g.dst_h) return;
+    const uint8_t *base = src + sl * g.src_slice_stride + (oj * F + g.j_off) * g.src_pitch + oi * F + g.i_off;
+    uint32_t rows[F][WORDS];
+#pragma unroll
+    for (int a = 0; a < F; ++a) {
+        const uint8_t *p = base + a * g.src_pitch;
+        if constexpr (F == 2) {
+            const uint2 v = __ldcs(reinterpret_cast<const uint2 *>(p));
+            rows[a][0] = v.x; rows[a][1] = v.y;
+        } else {
+#pragma unroll
+            for (int q = 0; q < WORDS / 4; ++q) {
+                const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(p) + q);
+                rows[a][4 * q + 0] = v.x; rows[a][4 * q + 1] = v.y; rows[a][4 * q + 2] = v.z; rows[a][4 * q + 3] = v.w;
+            }
+        }
+    }
+    const int agg = g.agg;
+    const int64_t o = (sl * g.dst_h + oj) * g.dst_w + oi;
+    // ---- sums on the untransposed rows: window k owns F consecutive bytes of every row ----------
+    if (agg == XRS_AGG_SUM || agg == XRS_AGG_MEAN) {
+        uint32_t sum[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int a = 0; a < F; ++a) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if constexpr (F == 2) {
+                    const uint32_t w = rows[a][k >> 1];
+                    sum[k] += (k & 1) ? ((w >> 16) & 0xffu) + (w >> 24) : (w & 0xffu) + ((w >> 8) & 0xffu);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < F / 4; ++q) sum[k] = __dp4a(rows[a][k * (F / 4) + q], 0x01010101u, sum[k]);
+                }
+            }
+        }
+        if (agg == XRS_AGG_SUM) {
+            int64_t *out = static_cast<int64_t *>(dst) + o;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) out[k] = sum[k];
+        } else {
+            const uint32_t r = mean_half_even<N>(sum[0]) | (mean_half_even<N>(sum[1]) << 8) |
+                               (mean_half_even<N>(sum[2]) << 16) | (mean_half_even<N>(sum[3]) << 24);
+            *reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(dst) + o) = r;
+        }
+        return;
+    }
+    // ---- transposed registers: t[p], byte lane k = pixel p (row-major in the window) of window k ---
+    uint32_t t[N];
+#pragma unroll
+    for (int a = 0; a < F; ++a) {
+        if constexpr (F == 2) {
+            t[2 * a + 0] = __byte_perm(rows[a][0], rows[a][1], 0x6420);
+            t[2 * a + 1] = __byte_perm(rows[a][0], rows[a][1], 0x7531);
+        } else {
+#pragma unroll
+            for (int h = 0; h < F / 4; ++h)
+                transpose4x4(rows[a][0 * (F / 4) + h], rows[a][1 * (F / 4) + h], rows[a][2 * (F / 4) + h],
+                             rows[a][3 * (F / 4) + h], t[F * a + 4 * h + 0], t[F * a + 4 * h + 1], t[F * a + 4 * h + 2],
+                             t[F * a + 4 * h + 3]);
+        }
+    }
+    uint32_t r = 0;       // 4 uint8 results
+    uint32_t cnt = 0;     // 4 byte-sized counts (count reducer)
+    bool wide = false;    // results are int64 (mode, count)
+    switch (agg) {
+    case XRS_AGG_FIRST: r = t[0]; break;
+    case XRS_AGG_LAST: r = t[N - 1]; break;
+    case XRS_AGG_CENTER: r = t[(F / 2) * F + F / 2]; break;
+    case XRS_AGG_MIN:
+        r = t[0];
+#pragma unroll
+        for (int k = 1; k < N; ++k) r = __vminu4(r, t[k]);
+        break;
+    case XRS_AGG_MAX:
+        r = t[0];
+#pragma unroll
+        for (int k = 1; k < N; ++k) r = __vmaxu4(r, t[k]);
+        break;
+    case XRS_AGG_COUNT:  // np.count_nonzero
+#pragma unroll
+        for (int k = 0; k < N; ++k) cnt = __vadd4(cnt, __vcmpne4(t[k], 0u) & 0x01010101u);
+        r = cnt;
+        wide = true;
+        break;
+    case XRS_AGG_MEDIAN: {  // mean of the two middle values in float64, np.rint (half to even)
+        bitonic_sort_u8x4<N>(t);
+        const uint32_t a = t[N / 2 - 1], b = t[N / 2];
+        const uint32_t q = __vhaddu4(a, b);  // floor((a + b) / 2)
+        r = __vadd4(q, (a ^ b) & q & 0x01010101u);
+        break;
+    }
+    default: {  // mode (coarsen.py:138-155): most frequent value, lowest value wins ties
+        bitonic_sort_u8x4<N>(t);
+        uint32_t run = 0x01010101u, best_n = 0x01010101u, best = t[0];
+#pragma unroll
+        for (int k = 1; k < N; ++k) {
+            const uint32_t eq = __vcmpeq4(t[k], t[k - 1]);
+            run = __vadd4(run & eq, 0x01010101u);
+            const uint32_t better = __vcmpgtu4(run, best_n);
+            best_n = (run & better) | (best_n & ~better);
+            best = (t[k] & better) | (best & ~better);
+        }
+        r = best;
+        wide = true;
+        break;
+    }
+    }
+    if (wide) {
+        int64_t *out = static_cast<int64_t *>(dst) + o;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out[k] = (r >> (8 * k)) & 0xffu;
+    } else {
+        *reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(dst) + o) = r;
+    }
+}
+
+// Median and mode of uint8 windows: two windows per thread as 16-bit lanes (u16x2), because the
+// packed 16-bit min / max are single instructions on sm_100a (VIMNMX.U16x2) while the byte-wise
+// vminu4 / vmaxu4 are emulated with ~6 logic operations each.
+template <int N>
+__device__ __forceinline__ void bitonic_sort_u16x2(uint32_t (&a)[N]) {
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const uint32_t lo = __vminu2(a[i], a[l]), hi = __vmaxu2(a[i], a[l]);
+                    a[i] = up ? lo : hi;
+                    a[l] = up ? hi : lo;
+                }
+            }
+        }
+    }
+}
+
+template <int F>
+__global__ void __launch_bounds__(256) k5_u8x2_sort(const uint8_t *__restrict__ src, void *__restrict__ dst, FastGeom g) {
+    constexpr int N = F * F;
+    const int64_t og = static_cast<int64_t>(blockIdx.x) * 32 + threadIdx.x;  // pair of output columns
+    const int64_t oj = static_cast<int64_t>(blockIdx.y) * 8 + threadIdx.y;
+    const int64_t sl = blockIdx.z;
+    const int64_t oi = og * 2;
+    if (oi >= g.dst_w || oj >= g.dst_h) return;
+    const uint8_t *base = src + sl * g.src_slice_stride + (oj * F + g.j_off) * g.src_pitch + oi * F + g.i_off;
+    // u[p]: low half-word = pixel p of window 0, high half-word = pixel p of window 1
+    uint32_t u[N];
+#pragma unroll
+    for (int a = 0; a < F; ++a) {
+        const uint8_t *p = base + a * g.src_pitch;
+        if constexpr (F == 2) {
+            const uint32_t w = __ldcs(reinterpret_cast<const uint32_t *>(p));
+            u[2 * a + 0] = __byte_perm(w, w, 0x2200) & 0x00ff00ffu;
+            u[2 * a + 1] = __byte_perm(w, w, 0x3311) & 0x00ff00ffu;
+        } else if constexpr (F == 4) {
+            const uint2 w = __ldcs(reinterpret_cast<const uint2 *>(p));
+            u[4 * a + 0] = __byte_perm(w.x, w.y, 0x4400) & 0x00ff00ffu;
+            u[4 * a + 1] = __byte_perm(w.x, w.y, 0x5511) & 0x00ff00ffu;
+            u[4 * a + 2] = __byte_perm(w.x, w.y, 0x6622) & 0x00ff00ffu;
+            u[4 * a + 3] = __byte_perm(w.x, w.y, 0x7733) & 0x00ff00ffu;
+        } else {
+            const uint4 w = __ldcs(reinterpret_cast<const uint4 *>(p));
+            u[8 * a + 0] = __byte_perm(w.x, w.z, 0x4400) & 0x00ff00ffu;
+            u[8 * a + 1] = __byte_perm(w.x, w.z, 0x5511) & 0x00ff00ffu;
+            u[8 * a + 2] = __byte_perm(w.x, w.z, 0x6622) & 0x00ff00ffu;
+            u[8 * a + 3] = __byte_perm(w.x, w.z, 0x7733) & 0x00ff00ffu;
+            u[8 * a + 4] = __byte_perm(w.y, w.w, 0x4400) & 0x00ff00ffu;
+            u[8 * a + 5] = __byte_perm(w.y, w.w, 0x5511) & 0x00ff00ffu;
+            u[8 * a + 6] = __byte_perm(w.y, w.w, 0x6622) & 0x00ff00ffu;
+            u[8 * a + 7] = __byte_perm(w.y, w.w, 0x7733) & 0x00ff00ffu;
+        }
+    }
+    bitonic_sort_u16x2<N>(u);
+    const int64_t o = (sl * g.dst_h + oj) * g.dst_w + oi;
+    if (g.agg == XRS_AGG_MEDIAN) {  // float64 mean of the two middle values, np.rint (half to even)
+        const uint32_t sum = u[N / 2 - 1] + u[N / 2];  // lanes <= 510: no carry between them
+        const uint32_t q = (sum >> 1) & 0x7fff7fffu;
+        const uint32_t r = q + (sum & q & 0x00010001u);
+        *reinterpret_cast<uint16_t *>(static_cast<uint8_t *>(dst) + o) =
+            static_cast<uint16_t>((r & 0xffu) | ((r >> 8) & 0xff00u));
+        return;
+    }
+    // mode (coarsen.py:138-155): most frequent value, lowest value wins ties.  Per lane the key
+    // (run length << 8) | (255 - value) is maximal for the longest run and, among equal runs, for the
+    // smallest value, so one packed max per element tracks the winner.
+    uint32_t run = 0x00010001u;
+    uint32_t best = 0x01000100u | (0x00ff00ffu - u[0]);
+#pragma unroll
+    for (int k = 1; k < N; ++k) {
+        const uint32_t x = u[k] ^ u[k - 1];
+        const uint32_t differs = ((x + 0x7fff7fffu) >> 15) & 0x00010001u;  // 1 per lane whose value changed
+        const uint32_t same_mask = (differs ^ 0x00010001u) * 0xffffu;
+        run = (run & same_mask) + 0x00010001u;
+        best = __vmaxu2(best, (run << 8) | (0x00ff00ffu - u[k]));
+    }
+    int64_t *out = static_cast<int64_t *>(dst) + o;
+    out[0] = 255 - static_cast<int64_t>(best & 0xffu);
+    out[1] = 255 - static_cast<int64_t>((best >> 16) & 0xffu);
+}
+
+template <int F>
+static int launch_u8x2_sort(const void *src, void *dst, const FastGeom &g, cudaStream_t st) {
+    const dim3 block(32, 8);
+    const dim3 grid(static_cast<unsigned>(ceil_div(g.dst_w / 2, 32)), static_cast<unsigned>(ceil_div(g.dst_h, 8)),
+                    static_cast<unsigned>(g.n_slices));
+    XRS_TIMED("k5_u8x2_sort", st, k5_u8x2_sort<F><<<grid, block, 0, st>>>(static_cast<const uint8_t *>(src), dst, g));
+    XRS_LAUNCH_CHECK("k5_u8x2_sort");
+    return 0;
+}
+
+static bool u8x2_sort_applicable(const void *src, const void *dst, const FastGeom &g, int F) {
+    if (g.agg != XRS_AGG_MEDIAN && g.agg != XRS_AGG_MODE) return false;
+    if (g.dst_w % 2 != 0) return false;
+    const int64_t align = 2 * F;  // bytes per row segment of a thread
+    const uintptr_t p = reinterpret_cast<uintptr_t>(src);
+    if (p % align || g.src_pitch % align || g.src_slice_stride % align || g.i_off % align) return false;
+    return reinterpret_cast<uintptr_t>(dst) % (g.agg == XRS_AGG_MODE ? 8 : 2) == 0;
+}
+
+template <int F>
+static int launch_u8x4(const void *src, void *dst, const FastGeom &g, cudaStream_t st) {
+    const dim3 block(32, 8);
+    const dim3 grid(static_cast<unsigned>(ceil_div(g.dst_w / 4, 32)), static_cast<unsigned>(ceil_div(g.dst_h, 8)),
+                    static_cast<unsigned>(g.n_slices));
+    XRS_TIMED("k5_u8x4_reduce", st, k5_u8x4_reduce<F><<<grid, block, 0, st>>>(static_cast<const uint8_t *>(src), dst, g));
+    XRS_LAUNCH_CHECK("k5_u8x4_reduce");
+    return 0;
+}
+
+// the packed path needs 4 whole windows per thread, 16-byte (8 for F = 2) aligned row segments and
+// a 4-byte aligned output row
+static bool u8x4_applicable(const void *src, const void *dst, const FastGeom &g, int F) {
+    const int agg = g.agg;
+    if (agg == XRS_AGG_PROD || agg == XRS_AGG_STD || agg == XRS_AGG_VAR) return false;
+    if (g.dst_w % 4 != 0) return false;
+    const int64_t align = F == 2 ? 8 : 16;
+    const uintptr_t p = reinterpret_cast<uintptr_t>(src);
+    if (p % align || g.src_pitch % align || g.src_slice_stride % align || g.i_off % align) return false;
+    const bool wide = agg == XRS_AGG_MODE || agg == XRS_AGG_COUNT || agg == XRS_AGG_SUM;
+    return reinterpret_cast<uintptr_t>(dst) % (wide ? 8 : 4) == 0;
+}
+
 static bool fast_outputs_int64(int agg, bool is_float) {
     if (agg == XRS_AGG_MODE || agg == XRS_AGG_COUNT) return true;
     return !is_float && (agg == XRS_AGG_SUM || agg == XRS_AGG_PROD);
@@ -351,6 +659,24 @@ static int launch_t(const void *src, void *dst, const AffineGeom &a, cudaStream_
     const uintptr_t p = reinterpret_cast<uintptr_t>(src);
     g.vec = (p % align == 0 && (a.src_pitch * sizeof(T)) % align == 0 && (a.src_slice_stride * sizeof(T)) % align == 0 &&
              (g.i_off * sizeof(T)) % align == 0) ? 1 : 0;
+    if constexpr (std::is_same<T, uint8_t>::value) {
+        if (u8x2_sort_applicable(src, dst, g, F)) {
+            *handled = true;
+            switch (F) {
+            case 2: return launch_u8x2_sort<2>(src, dst, g, st);
+            case 4: return launch_u8x2_sort<4>(src, dst, g, st);
+            default: return launch_u8x2_sort<8>(src, dst, g, st);
+            }
+        }
+        if (u8x4_applicable(src, dst, g, F)) {
+            *handled = true;
+            switch (F) {
+            case 2: return launch_u8x4<2>(src, dst, g, st);
+            case 4: return launch_u8x4<4>(src, dst, g, st);
+            default: return launch_u8x4<8>(src, dst, g, st);
+            }
+        }
+    }
     const int mode = (a.order == 1 && FLT) ? MODE_BLEND : MODE_PLAIN;
     const int cls = (a.agg == XRS_AGG_MEDIAN || a.agg == XRS_AGG_MODE) ? CLASS_SORT : CLASS_SIMPLE;
     switch (F) {
