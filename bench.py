@@ -360,14 +360,16 @@ def ours(args):
     top = kernels[0] if kernels else {"kernel": "none", "ms_per_launch": 0.0, "achieved_gbs": 0.0, "frac": 0.0,
                                       "algorithmic_bytes_per_launch": 0.0, "bytes_model": "n/a",
                                       "share_of_kernel_time": 0.0}
-    traffic = {"k1_scatter": 533.7e6, "k2_gather_staged<bilinear>": 5672.8e6, "k2_gather_staged<nearest>": 5695.0e6,
-               "k1_resolve": 1063.0e6}.get(top["kernel"]) if (world == 1 and args.scale == 1.0) else None
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this
+    # exact workload (profiles/r01_final_k0_k1_ncu_full.txt, r01_final_k2_gather_ncu_full.txt)
+    traffic = {"k1_scatter": 524.5e6, "k2_gather_staged<bilinear>": 5671.3e6, "k2_gather_staged<nearest>": 5693.2e6,
+               "k0_tile_windows": 326.8e6}.get(top["kernel"]) if (world == 1 and args.scale == 1.0) else None
     roofline = {
         "bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_gbs"], "peak": peak,
         "peak_kind": peak_kind, "unit": "GB/s", "frac": top["frac"],
         "traffic": traffic,
         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of this "
-                          "workload (profiles/r01_*_ncu_full.txt)" if traffic else None,
+                          "workload (profiles/r01_final_*_ncu_full.txt)" if traffic else None,
         "algorithmic_bytes_per_launch": top["algorithmic_bytes_per_launch"], "bytes_model": top["bytes_model"],
         "ms_per_launch": top["ms_per_launch"], "share_of_kernel_time": top["share_of_kernel_time"],
         "timing": ("CUDA events recorded by libxrs around every launch on the launching stream, timed region only"
