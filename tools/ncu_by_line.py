@@ -46,7 +46,8 @@ def main():
             cur_b["hdr"] = r
         elif cur_b is not None and cur_b["hdr"] and len(r) == len(cur_b["hdr"]):
             cur_b["rows"].append(r)
-    b = blocks[0]
+    match = [blk for blk in blocks if kernel.split("EN")[0].lstrip("_Z0123456789N").replace("3xrs", "") in blk["name"]]
+    b = match[0] if match else blocks[0]
     h = b["hdr"]
     i_ex, i_s = h.index("Instructions Executed"), h.index("# Samples")
     if len(b["rows"]) != len(lines):

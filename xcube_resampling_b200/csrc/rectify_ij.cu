@@ -5,23 +5,26 @@
 // The reference scatters every source quad's two triangles onto the target tile sequentially and
 // lets the FIRST writer win.  Whether a quad accepts a pixel never depends on earlier writes, so
 // the result equals "per pixel, the accepting quad with the smallest row-major index wins".  That
-// form is order-free and runs as two kernels:
+// form is order-free and runs as four kernels:
 //
-//   k1_scatter  one lane per source quad.  A warp marches down a strip of 31 quad columns, keeping
-//               the previous vertex row in registers (every coordinate is loaded once, coalesced).
-//               The quad's pixel box is scanned with division-free half-plane tests and each
-//               accepted pixel receives atomicMin(claim, quad index).
-//   k1_resolve  one thread per target pixel: the winning quad recomputes its barycentric
-//               coordinates with the reference's exact expressions and writes (i, j).
+//   k1_init_claims   claim words <- "none"; source quad rows visible to the requested target rows.
+//   k1_scatter       one lane per source quad, in target pixel space.  A warp marches down a strip
+//                    of 31 quad columns (vertex rows kept in registers / prefetched, every
+//                    coordinate loaded once, coalesced); the quad's pixel box is scanned with
+//                    stepped edge functions and sign-bit decisions; accepted pixels receive
+//                    atomicMin(claim, 2 * quad index + triangle).
+//   k1_scatter_slow  the generic path in the reference's exact arithmetic for queued quads
+//                    (non-finite vertices, degenerate or huge quads, pixels within rounding
+//                    distance of an edge).
+//   k1_resolve       one thread per target pixel: the winning triangle recomputes its barycentric
+//                    coordinates with the reference's exact expressions and writes (i, j).
 //
 // All parity-critical arithmetic uses round-to-nearest intrinsics in the reference's expression
 // order (no FMA contraction) and the reference TILE-LOCAL offsets (rectify.py:402-416), so the ij
 // image is bit-identical to the numba kernel's for any reference tile size.
 //
-// (A first version gathered per target tile with the source window staged in shared memory by
-// bulk copies; it measured 3.0 ms on the OLCI scene against the scatter form's fraction of that,
-// because window over-fetch, two passes over the quads and divergent pixel loops cost ~100
-// warp-instructions per quad.  See DESIGN.md.)
+// (History: a gather form -- CTA per target tile, source window staged in shared memory by bulk
+// copies -- measured 3.0 ms on the OLCI scene; a CRS-space scatter 2.1 ms; this form 1.45 ms.)
 #include "common.cuh"
 
 namespace xrs {
