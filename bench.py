@@ -69,7 +69,8 @@ def workload_config(w, h, nb, size, n_gpus):
         "target": f"{size[0]}x{size[1]} @0.0027deg, reference tile_size {TILE}",
         "scene_pass": "rectify(nearest)+rectify(bilinear); each = K0 tile windows + K1 ij image + K2 gather",
         "scenes_per_step": n_gpus,
-        "partition": "target row bands, rank r = band r of every scene, no collective",
+        "partition": "target row bands of equal work (valid pixels per row), rank r = band r of every scene, "
+                     "no collective",
         "l2": "inputs (2.0 GB) and outputs (3.3 GB per method) exceed the 126 MB L2; no explicit flush",
     }
 
@@ -230,12 +231,21 @@ def ours(args):
     target_gm = xrs.GridMapping.regular(size, xy_min, res, "EPSG:4326", tile_size=TILE)
     source_gm = xrs.GridMapping.from_coords(lon, lat, "EPSG:4326", xy_res=res, xy_dim_names=("x", "y"))
     W_t, H_t = target_gm.size
-    rows = xbands.row_bands(H_t, world, align=32)[rank]
+    x_dev = _dev.to_device(lon)
+    y_dev = _dev.to_device(lat)
+    if world == 1:
+        rows = (0, H_t)
+    else:
+        # Row bands of equal WORK, not equal height: a rotated swath leaves the top and bottom rows of
+        # the target mostly empty.  The weights come from one full ij image (valid pixels per row plus
+        # a constant for the fill writes); every rank derives the same partition.
+        ij_full = xrect.RectifyPlan(target_gm, dev).ij(x_dev, y_dev)
+        valid_per_row = (~torch.isnan(ij_full[0])).sum(dim=1).cpu().numpy().astype(np.float64)
+        del ij_full
+        rows = xbands.weighted_row_bands(valid_per_row + 0.15 * W_t, world, align=32)[rank]
     band_px = (rows[1] - rows[0]) * W_t
 
     # ---- device residency: full coordinates + the band's source footprint of all bands ----
-    x_dev = _dev.to_device(lon)
-    y_dev = _dev.to_device(lat)
     plan = xrect.RectifyPlan(target_gm, dev, rows=rows)
     boxes_host = _dev.to_host(plan.windows(x_dev, y_dev))
     fp = xbands.rectify_band_footprint(boxes_host, target_gm, rows, (w, h)) or (0, 0, w, min(h, 2))
@@ -418,8 +428,9 @@ def ours(args):
         torch.cuda.synchronize()
         dt_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
         n_units = sum_over_ranks(float(n_units))
-        h2d = world * len(METHODS) * (lon_p.nbytes + lat_p.nbytes + bands_p.nbytes)
-        d2h = world * len(METHODS) * nb * band_px * 4
+        # bytes copied per step by the whole job: every rank handles `world` scenes x 2 methods
+        h2d = sum_over_ranks(float(world * len(METHODS) * (lon_p.nbytes + lat_p.nbytes + bands_p.nbytes)))
+        d2h = sum_over_ranks(float(world * len(METHODS) * nb * band_px * 4))
         e2e = {"value": n_units / (dt_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": dt_ms / e2e_steps,
                "api": ("rectify_dataset(ds, target_gm, source_gm, interp_methods)" if world == 1 else

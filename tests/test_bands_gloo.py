@@ -41,6 +41,20 @@ def test_row_bands_partition():
         xbands.row_bands(10, 0)
 
 
+def test_weighted_row_bands_balance():
+    h = 5013
+    r = np.arange(h)
+    weights = np.exp(-((r - h / 2) / (h / 4)) ** 2) + 0.1  # a rotated swath: heavy middle rows
+    for n in (2, 4, 8):
+        bands = xbands.weighted_row_bands(weights, n, align=32)
+        assert bands[0][0] == 0 and bands[-1][1] == h and all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+        loads = [weights[a:b].sum() for a, b in bands]
+        equal = [weights[a:b].sum() for a, b in xbands.row_bands(h, n, align=32)]
+        assert max(loads) < 1.1 * sum(loads) / n
+        assert max(loads) <= max(equal)
+    assert xbands.weighted_row_bands(np.zeros(100), 4, 32)[-1][1] == 100
+
+
 def _rectify_worker(rank, world, port, result_dir):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)

@@ -24,6 +24,29 @@ def row_bands(height: int, n_bands: int, align: int = 32) -> list[tuple[int, int
     return [(edges[k], edges[k + 1]) for k in range(n_bands)]
 
 
+def weighted_row_bands(row_weights, n_bands: int, align: int = 32) -> list[tuple[int, int]]:
+    """Contiguous row bands of (approximately) equal total weight, boundaries on multiples of
+    ``align``.  ``row_weights[r]`` is the cost of target row r -- for a rotated swath the rows near
+    the middle of the image hold far more valid pixels than those at the top and bottom, so equal
+    row counts would leave the outer ranks idle."""
+    w = np.asarray(row_weights, dtype=np.float64)
+    height = w.shape[0]
+    if n_bands < 1:
+        raise ValueError("n_bands must be >= 1")
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    total = cum[-1]
+    edges = [0]
+    for k in range(1, n_bands):
+        if total > 0:
+            r = int(np.searchsorted(cum, total * k / n_bands, side="left"))
+        else:
+            r = height * k // n_bands
+        r = min(height, max(edges[-1], align * int(round(r / align))))
+        edges.append(r)
+    edges.append(height)
+    return [(edges[k], edges[k + 1]) for k in range(n_bands)]
+
+
 def band_tile_rows(target_gm: GridMapping, rows: tuple[int, int]) -> tuple[int, int]:
     """Reference tile rows [ty0, ty1) intersecting target rows [r0, r1)."""
     r0, r1 = rows
