@@ -180,6 +180,27 @@ __global__ void k1_init_claims(uint4 *claims, int64_t n_vec, unsigned int *slow_
         atomicMin(range, lo);
         atomicMax(range + 1, hi);
     }
+    // ... and, per block of K1S_ROWS quad rows, the quad COLUMNS those windows cover: for a rotated
+    // swath a target row band maps to a diagonal strip of the source, so most of every source row
+    // lies outside it
+    int *col_range = range + 3;  // after [qj_min, qj_max, pad]
+    const int n_rb = static_cast<int>((g.src_h - 1 + K1S_ROWS - 1) / K1S_ROWS);
+    for (int rb = threadIdx.x; rb < n_rb; rb += blockDim.x) {
+        const int rb_lo = rb * K1S_ROWS, rb_hi = rb_lo + K1S_ROWS - 1;
+        int clo = INT32_MAX, chi = -1;
+        for (int t = ty0 * g.ntx; t < (ty1 + 1) * g.ntx; ++t) {
+            const int64_t *bb = g.tile_boxes + 4 * static_cast<int64_t>(t);
+            const int64_t b0 = __ldg(bb);
+            if (b0 == -1) continue;
+            const int qj_lo = static_cast<int>(__ldg(bb + 1));
+            const int qj_hi = static_cast<int>(min(__ldg(bb + 3) + 1, g.src_h)) - 2;
+            if (qj_lo > rb_hi || qj_hi < rb_lo) continue;
+            clo = min(clo, static_cast<int>(b0));
+            chi = max(chi, static_cast<int>(min(__ldg(bb + 2) + 1, g.src_w)) - 2);
+        }
+        col_range[2 * rb] = clo;
+        col_range[2 * rb + 1] = chi;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -371,6 +392,11 @@ __global__ void __launch_bounds__(K1S_WARPS * 32, 2) k1_scatter(const __grid_con
     const int64_t j_end = min(min(static_cast<int64_t>(blockIdx.y + 1) * K1S_ROWS, nqj),
                               static_cast<int64_t>(qj_range[1]) + 1);  // quad rows [j_begin, j_end)
     if (j_begin >= j_end) return;
+    {   // quad columns visible to the requested target rows in this block of quad rows
+        const int *col_range = qj_range + 3 + 2 * blockIdx.y;
+        const int64_t c_lo = col_range[0], c_hi = col_range[1];
+        if (strip * 31 + 30 < c_lo || strip * 31 > c_hi) return;  // warp-uniform
+    }
     const bool col_ok = col < g.src_w;
     const bool quad_lane = lane < 31 && col < nqi;
 
@@ -568,10 +594,12 @@ static int64_t claims_bytes(int64_t rows, int64_t dst_w) {
     return (rows * dst_w * static_cast<int64_t>(sizeof(uint32_t)) + 15) / 16 * 16;
 }
 
-// layout: [claims: 4 B per target pixel of the row band][slow-quad queue: 4 B per source quad][counter]
+// layout: [claims: 4 B per target pixel of the row band][slow-quad queue: 4 B per source quad]
+// [counter, quad-row range: 16 B][quad-column range per block of K1S_ROWS quad rows: 8 B each]
 int64_t xrs_rectify_ij_workspace_bytes(int64_t src_h, int64_t src_w, int64_t dst_rows, int64_t dst_w) {
     if (src_h < 2 || src_w < 2 || dst_rows < 1 || dst_w < 1) return 0;
-    return claims_bytes(dst_rows, dst_w) + (src_h - 1) * (src_w - 1) * static_cast<int64_t>(sizeof(uint32_t)) + 16;
+    return claims_bytes(dst_rows, dst_w) + (src_h - 1) * (src_w - 1) * static_cast<int64_t>(sizeof(uint32_t)) + 16 +
+           8 * ceil_div(src_h - 1, K1S_ROWS);
 }
 
 int xrs_rectify_ij(const double *x, const double *y, int64_t src_h, int64_t src_w, int64_t src_pitch,
