@@ -242,7 +242,7 @@ def ours(args):
         ij_full = xrect.RectifyPlan(target_gm, dev).ij(x_dev, y_dev)
         valid_per_row = (~torch.isnan(ij_full[0])).sum(dim=1).cpu().numpy().astype(np.float64)
         del ij_full
-        rows = xbands.weighted_row_bands(valid_per_row + 0.15 * W_t, world, align=32)[rank]
+        rows = xbands.weighted_row_bands(valid_per_row + 0.3 * W_t, world, align=32)[rank]
     band_px = (rows[1] - rows[0]) * W_t
 
     # ---- device residency: full coordinates + the band's source footprint of all bands ----
