@@ -14,7 +14,7 @@ namespace xrs {
 // K0: per-tile source windows
 // ===========================================================================
 constexpr int K0_THREADS = 256;       // one source column per thread
-constexpr int K0_ROWS = 64;           // consecutive source rows marched by one block
+constexpr int K0_ROWS = 32;           // consecutive source rows marched by one block
 constexpr int K0_UNROLL = 4;          // rows in flight per thread
 constexpr int K0_SMEM_TILES = 2048;   // tile table kept in shared memory up to this many tiles
 
