@@ -483,17 +483,18 @@ __global__ void __launch_bounds__(K1S_WARPS * 32, 2) k1_scatter(const __grid_con
                                 double a1 = fma(rj, fa.dy1, a1c), a2 = fma(rj, fa.dy2, a2c);
                                 double b1 = fma(rj, fb.dy1, b1c), b2 = fma(rj, fb.dy2, b2c);
                                 for (int gi = ia; gi <= ib; ++gi) {
-                                    const double a3 = fa.k3 - (a1 + a2);
-                                    const bool acc_a = px_accepts(a1, a2, a3);
-                                    bool acc_b = false;
-                                    if (!acc_a) {
-                                        const double b3 = fb.k3 - (b1 + b2);
-                                        const bool rej_a = px_rejects(rej_hi_a, a1, a2, a3);
-                                        acc_b = rej_a && px_accepts(b1, b2, b3);
-                                        // within the margin of an edge: the whole quad is redone by the
-                                        // generic kernel with the reference's arithmetic (atomicMin is idempotent)
-                                        if (!acc_b && !(rej_a && px_rejects(rej_hi_b, b1, b2, b3))) slow = true;
-                                    }
+                                    // straight-line decisions (no nested branches): both triangles are
+                                    // evaluated, the atomic is the only predicated operation
+                                    const double a3 = fa.k3 - (a1 + a2), b3 = fb.k3 - (b1 + b2);
+                                    const uint32_t ha1 = __double2hiint(a1), ha2 = __double2hiint(a2), ha3 = __double2hiint(a3);
+                                    const uint32_t hb1 = __double2hiint(b1), hb2 = __double2hiint(b2), hb3 = __double2hiint(b3);
+                                    const bool acc_a = static_cast<int>(ha1 | ha2 | ha3) >= 0;
+                                    const bool rej_a = max(max(ha1, ha2), ha3) > rej_hi_a;
+                                    const bool acc_b = !acc_a && rej_a && static_cast<int>(hb1 | hb2 | hb3) >= 0;
+                                    const bool rej_b = max(max(hb1, hb2), hb3) > rej_hi_b;
+                                    // within the margin of an edge: the whole quad is redone by the generic
+                                    // kernel with the reference's arithmetic (atomicMin is idempotent)
+                                    slow = slow || (!acc_a && !acc_b && !(rej_a && rej_b));
                                     if (acc_a || acc_b) atomicMin(claim_row + gi, (qkey << 1) | (acc_b ? 1u : 0u));
                                     a1 += fa.dx1; a2 += fa.dx2;
                                     b1 += fb.dx1; b2 += fb.dx2;
