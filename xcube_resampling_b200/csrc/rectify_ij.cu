@@ -463,6 +463,7 @@ __global__ void __launch_bounds__(K1S_WARPS * 32, 2) k1_scatter(const __grid_con
                     const PxEdges fa = make_px_edges(fx0, fy0, fx1, fy1, fx2, fy2, pcx, pcy, uv_lo, uv_hi, coord_bound);
                     const PxEdges fb = make_px_edges(fx3, fy3, fx2, fy2, fx1, fy1, pcx, pcy, uv_lo, uv_hi, coord_bound);
                     if (fa.degenerate || fb.degenerate) slow = true;
+                    const double dx3_a = -(fa.dx1 + fa.dx2), dx3_b = -(fb.dx1 + fb.dx2);
                     const uint32_t rej_hi_a = static_cast<uint32_t>(__double2hiint(-2.0 * fa.two_m));
                     const uint32_t rej_hi_b = static_cast<uint32_t>(__double2hiint(-2.0 * fb.two_m));
                     const int tx_a = fast_div(i_lo, g.tile_w, inv_tw), ty_a = fast_div(j_lo, g.tile_h, inv_th);
@@ -482,10 +483,10 @@ __global__ void __launch_bounds__(K1S_WARPS * 32, 2) k1_scatter(const __grid_con
                                 const double rj = static_cast<double>(gj - j_lo);
                                 double a1 = fma(rj, fa.dy1, a1c), a2 = fma(rj, fa.dy2, a2c);
                                 double b1 = fma(rj, fb.dy1, b1c), b2 = fma(rj, fb.dy2, b2c);
+                                double a3 = fa.k3 - (a1 + a2), b3 = fb.k3 - (b1 + b2);  // third condition, stepped too
                                 for (int gi = ia; gi <= ib; ++gi) {
                                     // straight-line decisions (no nested branches): both triangles are
                                     // evaluated, the atomic is the only predicated operation
-                                    const double a3 = fa.k3 - (a1 + a2), b3 = fb.k3 - (b1 + b2);
                                     const uint32_t ha1 = __double2hiint(a1), ha2 = __double2hiint(a2), ha3 = __double2hiint(a3);
                                     const uint32_t hb1 = __double2hiint(b1), hb2 = __double2hiint(b2), hb3 = __double2hiint(b3);
                                     const bool acc_a = static_cast<int>(ha1 | ha2 | ha3) >= 0;
@@ -496,8 +497,8 @@ __global__ void __launch_bounds__(K1S_WARPS * 32, 2) k1_scatter(const __grid_con
                                     // kernel with the reference's arithmetic (atomicMin is idempotent)
                                     slow = slow || (!acc_a && !acc_b && !(rej_a && rej_b));
                                     if (acc_a || acc_b) atomicMin(claim_row + gi, (qkey << 1) | (acc_b ? 1u : 0u));
-                                    a1 += fa.dx1; a2 += fa.dx2;
-                                    b1 += fb.dx1; b2 += fb.dx2;
+                                    a1 += fa.dx1; a2 += fa.dx2; a3 += dx3_a;
+                                    b1 += fb.dx1; b2 += fb.dx2; b3 += dx3_b;
                                 }
                             }
                         }
