@@ -141,3 +141,27 @@ def test_uint8_packed_path(xrs, f, agg):
     assert used == ({"k5_u8x2_sort"} if agg in ("median", "mode") else {"k5_u8x4_reduce"}), used
     assert got.dtype == (np.int64 if agg in ("mode", "sum", "count") else np.uint8)
     assert np.array_equal(got.astype(np.int64), ref.astype(np.int64)), f"{agg} f={f}"
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("agg", ["mean", "max", "min", "sum", "first", "center", "std"])
+def test_blend2_four_windows_per_thread(xrs, dtype, agg):
+    """2x2 windows of order-1 samples with a 4-aligned output width: k5_blend2_x4."""
+    rng = np.random.default_rng(77)
+    h, w = 2 * 9 + 2, 2 * 24 + 4
+    a = rng.normal(size=(h, w)).astype(dtype)
+    a[rng.random(a.shape) < 0.04] = nan
+    a[rng.random(a.shape) < 0.02] = inf
+    a[rng.random(a.shape) < 0.02] = -0.0
+    a[h - 1, 5] = nan
+    a[3, w - 1] = -inf
+    for off, out_hw in (((0, 0), (10, 24)), ((2, 4), (9, 24)), ((0, 0), (9, 24))):
+        matrix = ((2.0, 0.0, float(off[1])), (0.0, 2.0, float(off[0])))
+        ref = np.asarray(ores.resample_array(a, matrix, out_hw, 1, agg, False, nan))
+        got, used = _kernels_used(xrs, lambda: xrs.dev.to_host(
+            xrs.aff._resample_array_dev(xrs.dev.to_device(a), matrix, out_hw, 1, agg, False, nan)))
+        assert used == {"k5_blend2_x4"}, used
+        if agg == "std":
+            np.testing.assert_allclose(got, ref.astype(got.dtype), rtol=1e-6, equal_nan=True)
+        else:
+            assert_same(got, ref.astype(got.dtype), f"{agg} off={off} out={out_hw}")

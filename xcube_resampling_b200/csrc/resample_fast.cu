@@ -303,6 +303,72 @@ __global__ void __launch_bounds__(256) k5_window_reduce(const T *__restrict__ sr
 }
 
 // ---------------------------------------------------------------------------
+// 2x2 windows of order-1 samples (the 2x bilinear down-scaling of affine.py:277-313 on aligned
+// grids, BASELINE config C1): four adjacent output pixels per thread.  The 3 x 9 neighbourhood
+// (two window rows + the lower tap row, eight window columns + the right tap column) comes in with
+// six 16-byte loads and three scalar ones, instead of six loads per single window.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k5_blend2_x4(const T *__restrict__ src, T *__restrict__ dst, FastGeom g) {
+    const int64_t og = static_cast<int64_t>(blockIdx.x) * 32 + threadIdx.x;  // group of 4 output columns
+    const int64_t oj = static_cast<int64_t>(blockIdx.y) * 8 + threadIdx.y;
+    const int64_t sl = blockIdx.z;
+    const int64_t oi = og * 4;
+    if (oi >= g.dst_w || oj >= g.dst_h) return;
+    const T *base = src + sl * g.src_slice_stride;
+    const int64_t j0 = oj * 2 + g.j_off, i0 = oi * 2 + g.i_off;
+    const int64_t jr = next_tap(j0 + 1, g.src_h), ic = next_tap(i0 + 7, g.src_w);
+    const int64_t rows[3] = {j0, j0 + 1, jr};
+    T v[3][9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const T *p = base + rows[a] * g.src_pitch + i0;
+        T seg[8];
+        load_row<T, 8>(p, seg, true);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) v[a][b] = seg[b];
+        v[a][8] = __ldg(base + rows[a] * g.src_pitch + ic);
+    }
+    bool nf[3][9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 9; ++b) nf[a][b] = non_finite(v[a][b]);
+    T out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        T w[4];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int c = 2 * k + b;
+                T x = v[a][c];
+                x = (x == T(0)) ? T(0) : x;  // 0.0 + (-0.0) = +0.0 in scipy's accumulation
+                w[a * 2 + b] = (nf[a][c + 1] || nf[a + 1][c] || nf[a + 1][c + 1]) ? static_cast<T>(NAN) : x;
+            }
+        out[k] = reduce_simple<T, T, 2>(w, g.agg);
+    }
+    T *q = dst + (sl * g.dst_h + oj) * g.dst_w + oi;
+    if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<uint4 *>(q) = *reinterpret_cast<const uint4 *>(out);
+    } else {
+        reinterpret_cast<uint4 *>(q)[0] = reinterpret_cast<const uint4 *>(out)[0];
+        reinterpret_cast<uint4 *>(q)[1] = reinterpret_cast<const uint4 *>(out)[1];
+    }
+}
+
+template <typename T>
+static bool blend2_x4_applicable(const void *src, const void *dst, const FastGeom &g, int agg_class) {
+    if (agg_class != CLASS_SIMPLE || g.agg == XRS_AGG_COUNT) return false;  // count writes int64
+    if (g.dst_w % 4 != 0) return false;
+    const uintptr_t p = reinterpret_cast<uintptr_t>(src);
+    const int64_t es = sizeof(T);
+    if (p % 16 || (g.src_pitch * es) % 16 || (g.src_slice_stride * es) % 16 || (g.i_off * es) % 16) return false;
+    return reinterpret_cast<uintptr_t>(dst) % 16 == 0;
+}
+
+// ---------------------------------------------------------------------------
 // uint8 rasters (class maps, masks): four horizontally adjacent windows per thread, SIMD-in-a-word.
 //
 // A thread reads 4*F bytes per window row with one or two 16-byte loads and transposes them with
@@ -639,7 +705,20 @@ static int launch_f(const void *src, void *dst, const FastGeom &g, int mode, int
     }
     *handled = true;
     if constexpr (FLT) {
-        if (mode == MODE_BLEND) return launch_one<T, F, MODE_BLEND, CLASS_SIMPLE>(src, dst, g, st);
+        if (mode == MODE_BLEND) {
+            if constexpr (F == 2) {
+                if (blend2_x4_applicable<T>(src, dst, g, cls)) {
+                    const dim3 block(32, 8);
+                    const dim3 grid(static_cast<unsigned>(ceil_div(g.dst_w / 4, 32)),
+                                    static_cast<unsigned>(ceil_div(g.dst_h, 8)), static_cast<unsigned>(g.n_slices));
+                    XRS_TIMED("k5_blend2_x4", st, k5_blend2_x4<T><<<grid, block, 0, st>>>(
+                                  static_cast<const T *>(src), static_cast<T *>(dst), g));
+                    XRS_LAUNCH_CHECK("k5_blend2_x4");
+                    return 0;
+                }
+            }
+            return launch_one<T, F, MODE_BLEND, CLASS_SIMPLE>(src, dst, g, st);
+        }
     }
     return launch_one<T, F, MODE_PLAIN, CLASS_SIMPLE>(src, dst, g, st);
 }
