@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the scene (debugging only; 1.0 = BASELINE config)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (debugging only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (debugging only)")
+    ap.add_argument("--two-step", action="store_true",
+                    help="device-resident leg: xrs_rectify_ij + xrs_gather_ij instead of the fused xrs_rectify_gather")
     ap.add_argument("--no-graph", action="store_true", help="N > 1: launch eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -67,7 +69,8 @@ def workload_config(w, h, nb, size, n_gpus):
         "workload": "rectify_dataset: OLCI-shaped swath -> regular 300 m EPSG:4326 grid, nearest + bilinear",
         "source": f"{w}x{h} lon/lat float64, {nb} float32 bands",
         "target": f"{size[0]}x{size[1]} @0.0027deg, reference tile_size {TILE}",
-        "scene_pass": "rectify(nearest)+rectify(bilinear); each = K0 tile windows + K1 ij image + K2 gather",
+        "scene_pass": "rectify(nearest)+rectify(bilinear); each = K0 tile windows + K1 claims + K2 gather of "
+                      "21 bands (fused xrs_rectify_gather: ij resolved in registers)",
         "scenes_per_step": n_gpus,
         "partition": "target row bands of equal work (valid pixels per row), rank r = band r of every scene, "
                      "no collective",
@@ -265,10 +268,16 @@ def ours(args):
             boxes = plan.windows(x_dev, y_dev)
             if record:
                 evs[1].record()
-            ij = plan.ij(x_dev, y_dev, boxes)
-            if record:
-                evs[2].record()
-            xrect.gather_ij(src_dev, ij, m, np.nan, out=outs[m], window_origin=(fi0, fj0), full_size=(w, h))
+            if args.two_step:  # xrs_rectify_ij + xrs_gather_ij (the ij image goes through HBM)
+                ij = plan.ij(x_dev, y_dev, boxes)
+                if record:
+                    evs[2].record()
+                xrect.gather_ij(src_dev, ij, m, np.nan, out=outs[m], window_origin=(fi0, fj0), full_size=(w, h))
+            else:              # xrs_rectify_gather: one variable per call, ij resolved in registers
+                if record:
+                    evs[2].record()
+                plan.rectify_gather(x_dev, y_dev, src_dev, m, np.nan, out=outs[m], tile_boxes=boxes,
+                                    window_origin=(fi0, fj0), full_size=(w, h))
             if record:
                 evs[3].record()
                 pending.append((m, evs))
@@ -347,16 +356,19 @@ def ours(args):
     s_used = float((fj1 - fj0) * w)       # source pixels of the data bands resident for this row band
     T = float(band_px)
     # algorithmic (compulsory) bytes per launch, DESIGN.md "Kernels"
+    if args.two_step:
+        k2_index_bytes, k2_model = 16.0 * T, "16*T (ij) + 4*B*S_used (source once) + 4*B*T (output once)"
+    else:
+        k2_index_bytes = 4.0 * T + 16.0 * S
+        k2_model = "4*T (claims) + 16*S (winning quads' vertices) + 4*B*S_used (source once) + 4*B*T (output once)"
     models = {
         "k0_tile_windows": (16.0 * S, "16*S (lon+lat fp64 read once)"),
         "k1_init_claims": (4.0 * T, "4*T (claim word per target pixel)"),
         "k1_scatter": (16.0 * S + 4.0 * T, "16*S (lon+lat fp64 read once) + 4*T (claim word per target pixel)"),
         "k1_scatter_slow": (0.0, "queue of border quads, no compulsory traffic of its own"),
         "k1_resolve": (4.0 * T + 16.0 * T + 16.0 * S, "4*T (claims) + 16*T (ij fp64 out) + 16*S (winning quads' vertices)"),
-        "k2_gather_staged<nearest>": (16.0 * T + 4.0 * nb * s_used + 4.0 * nb * T,
-                                      "16*T (ij) + 4*B*S_used (source once) + 4*B*T (output once)"),
-        "k2_gather_staged<bilinear>": (16.0 * T + 4.0 * nb * s_used + 4.0 * nb * T,
-                                       "16*T (ij) + 4*B*S_used (source once) + 4*B*T (output once)"),
+        "k2_gather_staged<nearest>": (k2_index_bytes + 4.0 * nb * s_used + 4.0 * nb * T, k2_model),
+        "k2_gather_staged<bilinear>": (k2_index_bytes + 4.0 * nb * s_used + 4.0 * nb * T, k2_model),
     }
     total_kernel_ms = sum(v[0] for v in kernel_times.values()) or 1.0
     kernels = []

@@ -147,6 +147,21 @@ int xrs_gather_ij(const void *const *src_planes_host, void *const *dst_planes_ho
                   int64_t win_w, int64_t win_h, const double *ij, int64_t dst_h, int64_t dst_w, int32_t method,
                   double fill, void *stream);
 
+/* K1 + K2 fused -- xrs_rectify_ij followed by xrs_gather_ij without materialising the ij image:
+ * the claim stage of K1 runs as usual, then the gather kernel resolves each pixel's fractional
+ * source index in registers (same arithmetic, same results) and gathers all bands.  Saves the
+ * 16 bytes per target pixel that K1 would write and K2 read back; meant for calls that gather ONE
+ * variable (rectify_dataset uses xrs_rectify_ij + xrs_gather_ij when several variables share the
+ * ij image).  Arguments as for the two functions; `data_pitch` is the row pitch of the data planes,
+ * dst planes are (row_end - row_begin, dst_w); workspace as for xrs_rectify_ij. */
+int xrs_rectify_gather(const double *x, const double *y, int64_t src_h, int64_t src_w, int64_t src_pitch,
+                       const int64_t *tile_boxes, int64_t dst_h, int64_t dst_w, int32_t tile_h, int32_t tile_w,
+                       double x_min, double y_min, double y_max, double x_res, double y_res, int32_t is_j_axis_up,
+                       double uv_delta, int64_t row_begin, int64_t row_end, void *workspace,
+                       const void *const *src_planes_host, void *const *dst_planes_host, int32_t n_bands, int32_t dtype,
+                       int64_t data_pitch, int64_t win_i0, int64_t win_j0, int64_t win_w, int64_t win_h, int32_t method,
+                       double fill, void *stream);
+
 /* ------------------------------------------------------------------------
  * Reprojection (reproject.py) and CRS point transforms
  * --------------------------------------------------------------------- */

@@ -337,3 +337,29 @@ def test_huge_quads_take_the_generic_path(xrs):
     size, xy_min = covering_grid_args(x, y, res)
     g = ogrid.regular_grid(size, xy_min, res, tile_size=256)
     _ij_equal(xrs, x, y, g)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.uint8, np.int16, np.float64])
+@pytest.mark.parametrize("tile", [None, 96])
+def test_fused_rectify_gather_equals_two_step_path(xrs, dtype, tile):
+    """xrs_rectify_gather (claims -> resolve in registers -> gather) == xrs_rectify_ij + xrs_gather_ij."""
+    w, h = 333, 260
+    x, y = swath(w, h, theta=-22.0, seed=21)
+    x[40:44, 100:120] = nan
+    res = 0.0027
+    size, xy_min = covering_grid_args(x, y, res)
+    g = ogrid.regular_grid(size, xy_min, res, tile_size=tile)
+    gm = _gm(xrs, g)
+    rng = np.random.default_rng(2)
+    src = (rng.random((5, h, w)) * 200).astype(dtype)
+    fill = nan if np.issubdtype(dtype, np.floating) else 255 if dtype == np.uint8 else -1
+    xd, yd = xrs.dev.to_device(x), xrs.dev.to_device(y)
+    for pitched in (True, False):  # TMA-staged and direct kernels
+        sd = xrs.dev.to_device_pitched(src) if pitched else xrs.dev.to_device(src)
+        for rows in (None, (64, 160)):
+            plan = xrs.rect.RectifyPlan(gm, xd.device, rows=rows)
+            ij = plan.ij(xd, yd)
+            for method in ("nearest", "bilinear", "triangular"):
+                want = xrs.dev.to_host(xrs.rect.gather_ij(sd, ij, method, fill))
+                got = xrs.dev.to_host(plan.rectify_gather(xd, yd, sd, method, fill))
+                assert_same(got, want, f"{np.dtype(dtype).name} {method} rows={rows} pitched={pitched}")

@@ -12,7 +12,7 @@
 //   * k2_gather_direct: plain per-pixel global loads, for sources whose pitch TMA cannot describe.
 #include <cuda.h>
 
-#include "common.cuh"
+#include "rectify_common.cuh"
 
 namespace xrs {
 
@@ -66,6 +66,27 @@ __device__ __forceinline__ Taps make_taps(double fi, double fj, int64_t src_w, i
 template <typename T>
 __device__ __forceinline__ double ld_f64(const T *p) { return static_cast<double>(__ldg(p)); }
 
+// Where a gather kernel gets the fractional source index of a target pixel from: the ij image of
+// xrs_rectify_ij, or -- fused mode (xrs_rectify_gather) -- straight from K1's claim words, running
+// the resolve step (rectify_common.cuh) in registers so that the 16 bytes per pixel of ij are neither
+// written nor read back.
+struct IjSource {
+    const double *ij;  // (2, dst_h, dst_w), or nullptr in fused mode
+    IjGeom geom;       // fused mode: claims, source coordinates, tile windows, target grid
+};
+
+template <bool FUSED>
+__device__ __forceinline__ void load_ij(const IjSource &s, int64_t r, int64_t c, int64_t dst_h, int64_t dst_w,
+                                        double &fi, double &fj) {
+    const int64_t o = r * dst_w + c;
+    if (!FUSED) {
+        fi = ld_stream(s.ij + o);
+        fj = ld_stream(s.ij + dst_h * dst_w + o);
+    } else {
+        resolve_pixel(s.geom, s.geom.row_begin + r, c, __ldcs(s.geom.claims + o), fi, fj);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // direct kernel
 // ---------------------------------------------------------------------------
@@ -77,15 +98,17 @@ struct PlaneTable {
     T *dst[K2_MAX_BANDS];
 };
 
-template <typename T, int METHOD>
+template <typename T, int METHOD, bool FUSED>
 __global__ void __launch_bounds__(K2_BX *K2_BY)
 k2_gather_direct(PlaneTable<T> planes, int n_bands, int64_t src_h, int64_t src_w, int64_t src_pitch, int64_t win_i0,
-                 int64_t win_j0, const double *__restrict__ ij, int64_t dst_h, int64_t dst_w, T fill) {
+                 int64_t win_j0, const __grid_constant__ IjSource ijs, int64_t dst_h, int64_t dst_w, T fill) {
     const int64_t c = static_cast<int64_t>(blockIdx.x) * K2_BX + threadIdx.x;
     const int64_t r = static_cast<int64_t>(blockIdx.y) * K2_BY + threadIdx.y;
     if (c >= dst_w || r >= dst_h) return;
     const int64_t o = r * dst_w + c;
-    const Taps t = make_taps<METHOD>(ld_stream(ij + o), ld_stream(ij + dst_h * dst_w + o), src_w, src_h);
+    double fi_, fj_;
+    load_ij<FUSED>(ijs, r, c, dst_h, dst_w, fi_, fj_);
+    const Taps t = make_taps<METHOD>(fi_, fj_, src_w, src_h);
     if (!t.valid) {
         for (int b = 0; b < n_bands; ++b) st_stream(planes.dst[b] + o, fill);
         return;
@@ -132,10 +155,10 @@ __device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *m
         : "memory");
 }
 
-template <typename T, int METHOD>
-__global__ void __launch_bounds__(K2S_THREADS)
+template <typename T, int METHOD, bool FUSED>
+__global__ void __launch_bounds__(K2S_THREADS, (!FUSED && METHOD == XRS_NEAREST) ? 4 : 3)
 k2_gather_staged(const __grid_constant__ StagedParams<T> p, int n_bands, int64_t src_h, int64_t src_w,
-                 int64_t src_pitch, int64_t win_i0, int64_t win_j0, const double *__restrict__ ij, int64_t dst_h,
+                 int64_t src_pitch, int64_t win_i0, int64_t win_j0, const __grid_constant__ IjSource ijs, int64_t dst_h,
                  int64_t dst_w, T fill) {
     // TMA tensor copies need a 128-byte aligned shared-memory destination; static __shared__
     // variables would shift the dynamic segment, so everything lives in it behind an aligned base.
@@ -151,7 +174,6 @@ k2_gather_staged(const __grid_constant__ StagedParams<T> p, int n_bands, int64_t
     const int64_t c = static_cast<int64_t>(blockIdx.x) * K2S_TW + tx;
     const int64_t r_base = static_cast<int64_t>(blockIdx.y) * K2S_TH + ty;  // rows r_base + k * K2S_ROW_STEP
     const bool col_in = c < dst_w;
-    const int64_t plane = dst_h * dst_w;
 
     // ---- this thread's pixels: source taps and fractions --------------------------------
     double fi[K2S_PX], fj[K2S_PX];
@@ -159,8 +181,8 @@ k2_gather_staged(const __grid_constant__ StagedParams<T> p, int n_bands, int64_t
     for (int k = 0; k < K2S_PX; ++k) {
         const int64_t r = r_base + k * K2S_ROW_STEP;
         const bool in = col_in && r < dst_h;
-        fi[k] = in ? ld_stream(ij + r * dst_w + c) : NAN;
-        fj[k] = in ? ld_stream(ij + plane + r * dst_w + c) : NAN;
+        fi[k] = fj[k] = NAN;
+        if (in) load_ij<FUSED>(ijs, r, c, dst_h, dst_w, fi[k], fj[k]);
     }
     Taps t[K2S_PX];
     int i_lo = INT32_MAX, i_hi = -1, j_lo = INT32_MAX, j_hi = -1;
@@ -317,25 +339,25 @@ static T cast_fill(double fill) {
     return static_cast<T>(static_cast<long long>(fill));
 }
 
-template <typename T, int METHOD>
+template <typename T, int METHOD, bool FUSED>
 static int launch_staged(const StagedParams<T> &sp, int nb, int64_t src_h, int64_t src_w, int64_t src_pitch,
-                         int64_t win_i0, int64_t win_j0, const double *ij, int64_t dst_h, int64_t dst_w, T fill,
+                         int64_t win_i0, int64_t win_j0, const IjSource &ij, int64_t dst_h, int64_t dst_w, T fill,
                          cudaStream_t st) {
     const size_t smem = static_cast<size_t>(K2S_STAGES) * K2S_BOX_W * K2S_BOX_H * sizeof(T) +
                         K2S_STAGES * sizeof(uint64_t) + 4 * (K2S_THREADS / 32) * sizeof(int) + 128;
-    XRS_CUDA(cudaFuncSetAttribute(k2_gather_staged<T, METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    XRS_CUDA(cudaFuncSetAttribute(k2_gather_staged<T, METHOD, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
     const dim3 grid(static_cast<unsigned>(ceil_div(dst_w, K2S_TW)), static_cast<unsigned>(ceil_div(dst_h, K2S_TH)));
-    XRS_TIMED(METHOD == XRS_NEAREST ? "k2_gather_staged<nearest>" : METHOD == XRS_BILINEAR ? "k2_gather_staged<bilinear>" : "k2_gather_staged<triangular>", st, k2_gather_staged<T, METHOD><<<grid, K2S_THREADS, smem, st>>>(sp, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij,
+    XRS_TIMED(METHOD == XRS_NEAREST ? "k2_gather_staged<nearest>" : METHOD == XRS_BILINEAR ? "k2_gather_staged<bilinear>" : "k2_gather_staged<triangular>", st, k2_gather_staged<T, METHOD, FUSED><<<grid, K2S_THREADS, smem, st>>>(sp, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij,
                                                                  dst_h, dst_w, fill));
     XRS_LAUNCH_CHECK("k2_gather_staged");
     return 0;
 }
 
-template <typename T>
+template <typename T, bool FUSED>
 static int launch_gather(const void *const *src_planes, void *const *dst_planes, int n_bands, int64_t src_h,
                          int64_t src_w, int64_t src_pitch, int64_t win_i0, int64_t win_j0, int64_t win_w,
-                         int64_t win_h, const double *ij, int64_t dst_h, int64_t dst_w, int method, double fill,
+                         int64_t win_h, const IjSource &ij, int64_t dst_h, int64_t dst_w, int method, double fill,
                          cudaStream_t st) {
     const T fill_t = cast_fill<T>(fill);
     // TMA needs 16-byte aligned plane bases and row strides
@@ -371,13 +393,13 @@ static int launch_gather(const void *const *src_planes, void *const *dst_planes,
                 int rc;
                 switch (method) {
                 case XRS_NEAREST:
-                    rc = launch_staged<T, XRS_NEAREST>(sp, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fill_t, st);
+                    rc = launch_staged<T, XRS_NEAREST, FUSED>(sp, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fill_t, st);
                     break;
                 case XRS_BILINEAR:
-                    rc = launch_staged<T, XRS_BILINEAR>(sp, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fill_t, st);
+                    rc = launch_staged<T, XRS_BILINEAR, FUSED>(sp, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fill_t, st);
                     break;
                 default:
-                    rc = launch_staged<T, XRS_TRIANGULAR>(sp, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fill_t, st);
+                    rc = launch_staged<T, XRS_TRIANGULAR, FUSED>(sp, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fill_t, st);
                     break;
                 }
                 if (rc) return rc;
@@ -394,13 +416,13 @@ static int launch_gather(const void *const *src_planes, void *const *dst_planes,
         const dim3 grid(static_cast<unsigned>(ceil_div(dst_w, K2_BX)), static_cast<unsigned>(ceil_div(dst_h, K2_BY)));
         switch (method) {
         case XRS_NEAREST:
-            XRS_TIMED("k2_gather_direct", st, k2_gather_direct<T, XRS_NEAREST><<<grid, block, 0, st>>>(pt, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fill_t));
+            XRS_TIMED("k2_gather_direct", st, k2_gather_direct<T, XRS_NEAREST, FUSED><<<grid, block, 0, st>>>(pt, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fill_t));
             break;
         case XRS_BILINEAR:
-            XRS_TIMED("k2_gather_direct", st, k2_gather_direct<T, XRS_BILINEAR><<<grid, block, 0, st>>>(pt, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fill_t));
+            XRS_TIMED("k2_gather_direct", st, k2_gather_direct<T, XRS_BILINEAR, FUSED><<<grid, block, 0, st>>>(pt, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fill_t));
             break;
         default:
-            XRS_TIMED("k2_gather_direct", st, k2_gather_direct<T, XRS_TRIANGULAR><<<grid, block, 0, st>>>(pt, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fill_t));
+            XRS_TIMED("k2_gather_direct", st, k2_gather_direct<T, XRS_TRIANGULAR, FUSED><<<grid, block, 0, st>>>(pt, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fill_t));
             break;
         }
         XRS_LAUNCH_CHECK("k2_gather_direct");
@@ -430,7 +452,40 @@ int xrs_gather_ij(const void *const *src_planes_host, void *const *dst_planes_ho
     for (int b = 0; b < n_bands; ++b)
         if (!src_planes_host[b] || !dst_planes_host[b]) return fail("xrs_gather_ij: null plane pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    XRS_DISPATCH_DTYPE(dtype, T, return launch_gather<T>(src_planes_host, dst_planes_host, n_bands, src_h, src_w, src_pitch, win_i0, win_j0, win_w, win_h, ij, dst_h, dst_w, method, fill, st));
+    IjSource ijs;
+    memset(&ijs, 0, sizeof(ijs));
+    ijs.ij = ij;
+    XRS_DISPATCH_DTYPE(dtype, T, return launch_gather<T, false>(src_planes_host, dst_planes_host, n_bands, src_h, src_w, src_pitch, win_i0, win_j0, win_w, win_h, ijs, dst_h, dst_w, method, fill, st));
+    return 0;
+}
+
+int xrs_rectify_gather(const double *x, const double *y, int64_t src_h, int64_t src_w, int64_t src_pitch,
+                       const int64_t *tile_boxes, int64_t dst_h, int64_t dst_w, int32_t tile_h, int32_t tile_w,
+                       double x_min, double y_min, double y_max, double x_res, double y_res, int32_t is_j_axis_up,
+                       double uv_delta, int64_t row_begin, int64_t row_end, void *workspace,
+                       const void *const *src_planes_host, void *const *dst_planes_host, int32_t n_bands, int32_t dtype,
+                       int64_t data_pitch, int64_t win_i0, int64_t win_j0, int64_t win_w, int64_t win_h, int32_t method,
+                       double fill, void *stream) {
+    if (!src_planes_host || !dst_planes_host) return fail("xrs_rectify_gather: null pointer");
+    if (n_bands < 1) return fail("xrs_rectify_gather: n_bands must be >= 1");
+    if (method != XRS_NEAREST && method != XRS_BILINEAR && method != XRS_TRIANGULAR)
+        return fail("interp_methods must be one of 0, 1, 'nearest', 'bilinear', 'triangular'");
+    if (src_w > INT32_MAX || src_h > INT32_MAX) return fail("xrs_rectify_gather: source too large");
+    if (win_i0 < 0 || win_j0 < 0 || win_w < 1 || win_h < 1 || win_i0 + win_w > src_w || win_j0 + win_h > src_h ||
+        data_pitch < win_w)
+        return fail("xrs_rectify_gather: bad source window");
+    for (int b = 0; b < n_bands; ++b)
+        if (!src_planes_host[b] || !dst_planes_host[b]) return fail("xrs_rectify_gather: null plane pointer");
+    IjSource ijs;
+    memset(&ijs, 0, sizeof(ijs));
+    if (int rc = k1_make_geom("xrs_rectify_gather", x, y, src_h, src_w, src_pitch, tile_boxes, dst_h, dst_w, tile_h, tile_w,
+                              x_min, y_min, y_max, x_res, y_res, is_j_axis_up, uv_delta, row_begin, row_end, workspace,
+                              &ijs.geom))
+        return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (int rc = k1_enqueue_claims(ijs.geom, st)) return rc;
+    const int64_t n_rows = row_end - row_begin;
+    XRS_DISPATCH_DTYPE(dtype, T, return launch_gather<T, true>(src_planes_host, dst_planes_host, n_bands, src_h, src_w, data_pitch, win_i0, win_j0, win_w, win_h, ijs, n_rows, dst_w, method, fill, st));
     return 0;
 }
 

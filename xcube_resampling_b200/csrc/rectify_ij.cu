@@ -25,42 +25,9 @@
 //
 // (History: a gather form -- CTA per target tile, source window staged in shared memory by bulk
 // copies -- measured 3.0 ms on the OLCI scene; a CRS-space scatter 2.1 ms; this form 1.45 ms.)
-#include "common.cuh"
+#include "rectify_common.cuh"
 
 namespace xrs {
-
-constexpr uint32_t K1_NOCLAIM = 0xffffffffu;
-constexpr int K1_SENTINEL = INT32_MIN;  // stands for np.int64 min (non-finite vertex)
-constexpr int K1S_ROWS = 32;            // quad rows marched by one warp
-constexpr int K1S_WARPS = 8;
-constexpr int K1R_THREADS = 256;
-
-struct IjGeom {
-    const double *x, *y;
-    int64_t src_h, src_w, src_pitch;
-    const int64_t *tile_boxes;
-    double *ij;
-    uint32_t *claims;  // (row_end - row_begin, dst_w): smallest accepting quad index per pixel
-    int64_t dst_h, dst_w;
-    int tile_h, tile_w, ntx, nty;
-    double x_min, y_min, y_max, x_res, y_res;
-    int j_up;
-    double uv_delta;
-    int64_t row_begin, row_end;  // target rows computed by this call
-    uint32_t *slow_list;         // quads that need the generic (multi-tile) treatment
-    unsigned int *slow_count;
-};
-
-__device__ __forceinline__ double tri_det(double ax, double ay, double bx, double by, double cx, double cy) {
-    return dsub(dmul(dsub(ax, bx), dsub(ay, cy)), dmul(dsub(ax, cx), dsub(ay, by)));
-}
-__device__ __forceinline__ double tri_u(double px, double py, double ax, double ay, double cx, double cy) {
-    return dsub(dmul(dsub(ax, px), dsub(ay, cy)), dmul(dsub(ay, py), dsub(ax, cx)));
-}
-__device__ __forceinline__ double tri_v(double px, double py, double ax, double ay, double bx, double by) {
-    return dsub(dmul(dsub(ay, py), dsub(ax, bx)), dmul(dsub(ax, px), dsub(ay, by)));
-}
-__device__ __forceinline__ double clamp01(double t) { return t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t); }
 
 // np.floor(v).astype(np.int64) reduced to int32: non-finite / out-of-range -> sentinel
 // (x86 gives INT64_MIN for those), everything else clamped to +-2^30, which preserves
@@ -548,42 +515,62 @@ __global__ void __launch_bounds__(K1R_THREADS) k1_resolve(IjGeom g) {
     if (c >= g.dst_w) return;
     const int64_t n_rows = g.row_end - g.row_begin;
     const int64_t o = static_cast<int64_t>(blockIdx.y) * g.dst_w + c;
-    const uint32_t claim = __ldcs(g.claims + o);
-    double oi = NAN, oj = NAN;
-    if (claim != K1_NOCLAIM) {
-        const uint32_t qkey = claim >> 1, nqi = static_cast<uint32_t>(g.src_w - 1);
-        const bool tri_b = claim & 1u;  // which triangle the scatter accepted (A is tried first, rectify.py:556-573)
-        const uint32_t j0 = qkey / nqi, i0 = qkey - j0 * nqi;
-        const int ty = static_cast<int>(r) / g.tile_h, tx = static_cast<int>(c) / g.tile_w;
-        const int r0 = ty * g.tile_h, c0 = tx * g.tile_w;
-        const int64_t *bb = g.tile_boxes + 4 * (static_cast<int64_t>(ty) * g.ntx + tx);
-        const int bb0 = static_cast<int>(__ldg(bb)), bb1 = static_cast<int>(__ldg(bb + 1));
-        const double x_off = dadd(g.x_min, dmul(static_cast<double>(c0), g.x_res));
-        const double y_off = g.j_up ? dadd(g.y_min, dmul(static_cast<double>(r0), g.y_res))
-                                    : dsub(g.y_max, dmul(static_cast<double>(r0), g.y_res));
-        const double x_scale = g.x_res, y_scale = g.j_up ? g.y_res : -g.y_res;
-        const double px = dadd(x_off, dmul(dadd(static_cast<double>(static_cast<int>(c) - c0), 0.5), x_scale));
-        const double py = dadd(y_off, dmul(dadd(static_cast<double>(static_cast<int>(r) - r0), 0.5), y_scale));
-        const int64_t s0 = static_cast<int64_t>(j0) * g.src_pitch + i0, s2 = s0 + g.src_pitch;
-        // origin vertex o, u-direction vertex pu, v-direction vertex pv of the accepted triangle:
-        // A = (p0; p1, p2), B = (p3; p2, p1)
-        const int64_t so = tri_b ? s2 + 1 : s0, su = tri_b ? s2 : s0 + 1, sv = tri_b ? s0 + 1 : s2;
-        const double ox = __ldg(g.x + so), oy = __ldg(g.y + so);
-        const double ux = __ldg(g.x + su), uy = __ldg(g.y + su);
-        const double vx = __ldg(g.x + sv), vy = __ldg(g.y + sv);
-        const double det = tri_det(ox, oy, ux, uy, vx, vy);
-        const double u = ddiv(tri_u(px, py, ox, oy, vx, vy), det);
-        const double v = ddiv(tri_v(px, py, ox, oy, ux, uy), det);
-        const double fi = clamp01(u), fj = clamp01(v);
-        // rectify.py:564-576: window-local index + fraction, then + window origin
-        const int wi = static_cast<int>(i0) - bb0, wj = static_cast<int>(j0) - bb1;
-        const double li = tri_b ? dsub(static_cast<double>(wi + 1), fi) : dadd(static_cast<double>(wi), fi);
-        const double lj = tri_b ? dsub(static_cast<double>(wj + 1), fj) : dadd(static_cast<double>(wj), fj);
-        oi = dadd(static_cast<double>(bb0), li);
-        oj = dadd(static_cast<double>(bb1), lj);
-    }
+    double oi, oj;
+    resolve_pixel(g, r, c, __ldcs(g.claims + o), oi, oj);
     st_stream(g.ij + o, oi);
     st_stream(g.ij + n_rows * g.dst_w + o, oj);
+}
+
+static int64_t claims_bytes_of(int64_t rows, int64_t dst_w) {
+    return (rows * dst_w * static_cast<int64_t>(sizeof(uint32_t)) + 15) / 16 * 16;
+}
+
+int k1_make_geom(const char *who, const double *x, const double *y, int64_t src_h, int64_t src_w, int64_t src_pitch,
+                 const int64_t *tile_boxes, int64_t dst_h, int64_t dst_w, int32_t tile_h, int32_t tile_w, double x_min,
+                 double y_min, double y_max, double x_res, double y_res, int32_t is_j_axis_up, double uv_delta,
+                 int64_t row_begin, int64_t row_end, void *workspace, IjGeom *out) {
+    const std::string w(who);
+    if (!x || !y || !tile_boxes || !workspace) return fail(w + ": null pointer");
+    if (row_begin < 0 || row_end > dst_h || row_begin >= row_end) return fail(w + ": bad row range");
+    if (src_h < 2 || src_w < 2 || src_pitch < src_w) return fail(w + ": source must be at least 2x2");
+    if (dst_h < 1 || dst_w < 1 || tile_h < 1 || tile_w < 1) return fail(w + ": bad target shape");
+    if (dst_h > (1 << 30) || dst_w > (1 << 30) || src_w > (1 << 30) || src_h > (1 << 30)) return fail(w + ": image too large");
+    if (!(x_res > 0.0) || !(y_res > 0.0)) return fail(w + ": resolution must be positive");
+    if ((src_h - 1) * (src_w - 1) >= 0x7fffffffLL) return fail(w + ": source has too many quads (2^31 or more)");
+    if (reinterpret_cast<uintptr_t>(workspace) & 15) return fail(w + ": workspace must be 16-byte aligned");
+    if (ceil_div(src_h - 1, K1S_ROWS) > 65535) return fail(w + ": source too tall");
+    IjGeom g;
+    g.x = x; g.y = y; g.src_h = src_h; g.src_w = src_w; g.src_pitch = src_pitch;
+    g.tile_boxes = tile_boxes; g.ij = nullptr; g.claims = static_cast<uint32_t *>(workspace);
+    g.dst_h = dst_h; g.dst_w = dst_w;
+    g.tile_h = static_cast<int>(std::min<int64_t>(tile_h, dst_h));
+    g.tile_w = static_cast<int>(std::min<int64_t>(tile_w, dst_w));
+    g.ntx = static_cast<int>(ceil_div(dst_w, g.tile_w));
+    g.nty = static_cast<int>(ceil_div(dst_h, g.tile_h));
+    g.x_min = x_min; g.y_min = y_min; g.y_max = y_max; g.x_res = x_res; g.y_res = y_res;
+    g.j_up = is_j_axis_up ? 1 : 0; g.uv_delta = uv_delta;
+    g.row_begin = row_begin; g.row_end = row_end;
+    g.slow_list = reinterpret_cast<uint32_t *>(static_cast<char *>(workspace) + claims_bytes_of(row_end - row_begin, dst_w));
+    g.slow_count = reinterpret_cast<unsigned int *>(g.slow_list + (src_h - 1) * (src_w - 1));
+    *out = g;
+    return 0;
+}
+
+int k1_enqueue_claims(const IjGeom &g, cudaStream_t st) {
+    const int64_t n_rows = g.row_end - g.row_begin;
+    const int64_t n_vec = ceil_div(n_rows * g.dst_w, 4);
+    XRS_TIMED("k1_init_claims", st, k1_init_claims<<<static_cast<unsigned>(ceil_div(n_vec, 256)), 256, 0, st>>>(reinterpret_cast<uint4 *>(g.claims), n_vec, g.slow_count, g));
+    XRS_LAUNCH_CHECK("k1_init_claims");
+    const dim3 sgrid(static_cast<unsigned>(ceil_div(ceil_div(g.src_w - 1, 31), K1S_WARPS)),
+                     static_cast<unsigned>(ceil_div(g.src_h - 1, K1S_ROWS)));
+    XRS_TIMED("k1_scatter", st, k1_scatter<<<sgrid, K1S_WARPS * 32, 0, st>>>(g));
+    XRS_LAUNCH_CHECK("k1_scatter");
+    int dev = 0, sms = 0;
+    XRS_CUDA(cudaGetDevice(&dev));
+    XRS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    XRS_TIMED("k1_scatter_slow", st, k1_scatter_slow<<<static_cast<unsigned>(sms * 4), 256, 0, st>>>(g));
+    XRS_LAUNCH_CHECK("k1_scatter_slow");
+    return 0;
 }
 
 }  // namespace xrs
@@ -609,43 +596,16 @@ int xrs_rectify_ij(const double *x, const double *y, int64_t src_h, int64_t src_
                    int32_t tile_w, double x_min, double y_min, double y_max, double x_res, double y_res,
                    int32_t is_j_axis_up, double uv_delta, int64_t row_begin, int64_t row_end, void *workspace,
                    void *stream) {
-    if (!x || !y || !tile_boxes || !ij || !workspace) return fail("xrs_rectify_ij: null pointer");
-    if (row_begin < 0 || row_end > dst_h || row_begin >= row_end) return fail("xrs_rectify_ij: bad row range");
-    if (src_h < 2 || src_w < 2 || src_pitch < src_w) return fail("xrs_rectify_ij: source must be at least 2x2");
-    if (dst_h < 1 || dst_w < 1 || tile_h < 1 || tile_w < 1) return fail("xrs_rectify_ij: bad target shape");
-    if (dst_h > (1 << 30) || dst_w > (1 << 30) || src_w > (1 << 30) || src_h > (1 << 30)) return fail("xrs_rectify_ij: image too large");
-    if (!(x_res > 0.0) || !(y_res > 0.0)) return fail("xrs_rectify_ij: resolution must be positive");
-    if ((src_h - 1) * (src_w - 1) >= 0x7fffffffLL) return fail("xrs_rectify_ij: source has too many quads (2^31 or more)");
-    if (reinterpret_cast<uintptr_t>(workspace) & 15) return fail("xrs_rectify_ij: workspace must be 16-byte aligned");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!ij) return fail("xrs_rectify_ij: null pointer");
     IjGeom g;
-    g.x = x; g.y = y; g.src_h = src_h; g.src_w = src_w; g.src_pitch = src_pitch;
-    g.tile_boxes = tile_boxes; g.ij = ij; g.claims = static_cast<uint32_t *>(workspace);
-    g.dst_h = dst_h; g.dst_w = dst_w;
-    g.tile_h = static_cast<int>(std::min<int64_t>(tile_h, dst_h));
-    g.tile_w = static_cast<int>(std::min<int64_t>(tile_w, dst_w));
-    g.ntx = static_cast<int>(ceil_div(dst_w, g.tile_w));
-    g.nty = static_cast<int>(ceil_div(dst_h, g.tile_h));
-    g.x_min = x_min; g.y_min = y_min; g.y_max = y_max; g.x_res = x_res; g.y_res = y_res;
-    g.j_up = is_j_axis_up ? 1 : 0; g.uv_delta = uv_delta;
-    g.row_begin = row_begin; g.row_end = row_end;
+    if (int rc = k1_make_geom("xrs_rectify_ij", x, y, src_h, src_w, src_pitch, tile_boxes, dst_h, dst_w, tile_h, tile_w,
+                              x_min, y_min, y_max, x_res, y_res, is_j_axis_up, uv_delta, row_begin, row_end, workspace,
+                              &g))
+        return rc;
+    g.ij = ij;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (int rc = k1_enqueue_claims(g, st)) return rc;
     const int64_t n_rows = row_end - row_begin;
-    g.slow_list = reinterpret_cast<uint32_t *>(static_cast<char *>(workspace) + claims_bytes(n_rows, dst_w));
-    g.slow_count = reinterpret_cast<unsigned int *>(g.slow_list + (src_h - 1) * (src_w - 1));
-
-    const int64_t n_vec = ceil_div(n_rows * dst_w, 4);
-    XRS_TIMED("k1_init_claims", st, k1_init_claims<<<static_cast<unsigned>(ceil_div(n_vec, 256)), 256, 0, st>>>(reinterpret_cast<uint4 *>(g.claims), n_vec, g.slow_count, g));
-    XRS_LAUNCH_CHECK("k1_init_claims");
-    const dim3 sgrid(static_cast<unsigned>(ceil_div(ceil_div(src_w - 1, 31), K1S_WARPS)),
-                     static_cast<unsigned>(ceil_div(src_h - 1, K1S_ROWS)));
-    if (sgrid.y > 65535) return fail("xrs_rectify_ij: source too tall");
-    XRS_TIMED("k1_scatter", st, k1_scatter<<<sgrid, K1S_WARPS * 32, 0, st>>>(g));
-    XRS_LAUNCH_CHECK("k1_scatter");
-    int dev = 0, sms = 0;
-    XRS_CUDA(cudaGetDevice(&dev));
-    XRS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    XRS_TIMED("k1_scatter_slow", st, k1_scatter_slow<<<static_cast<unsigned>(sms * 4), 256, 0, st>>>(g));
-    XRS_LAUNCH_CHECK("k1_scatter_slow");
     if (n_rows > 65535) return fail("xrs_rectify_ij: more than 65535 target rows per call");
     const dim3 rgrid(static_cast<unsigned>(ceil_div(dst_w, K1R_THREADS)), static_cast<unsigned>(n_rows));
     XRS_TIMED("k1_resolve", st, k1_resolve<<<rgrid, K1R_THREADS, 0, st>>>(g));

@@ -125,6 +125,55 @@ class RectifyPlan:
             _dev.ptr(self._ws1), _dev.stream_ptr(self.device)), "xrs_rectify_ij")
         return self.ij_buf
 
+    def rectify_gather(self, x: torch.Tensor, y: torch.Tensor, src: torch.Tensor, interp_method: str, fill_value,
+                       out: torch.Tensor | None = None, tile_boxes: torch.Tensor | None = None,
+                       window_origin: tuple[int, int] = (0, 0), full_size: tuple[int, int] | None = None):
+        """Fused K1 + K2 for ONE variable (see :func:`_rectify_gather_dev`)."""
+        return _rectify_gather_dev(self, x, y, src, interp_method, fill_value, out, tile_boxes, window_origin, full_size)
+
+
+def _rectify_gather_dev(plan: "RectifyPlan", x: torch.Tensor, y: torch.Tensor, src: torch.Tensor, interp_method: str,
+                        fill_value, out: torch.Tensor | None = None, tile_boxes: torch.Tensor | None = None,
+                        window_origin: tuple[int, int] = (0, 0), full_size: tuple[int, int] | None = None):
+    """K0 (unless ``tile_boxes`` is given) + K1 claim stage + fused resolve / gather
+    (``xrs_rectify_gather``): the ij image is never written.  Same results as
+    ``gather_ij(src, plan.ij(x, y), ...)``; for calls that gather a single variable."""
+    lib = plan.lib
+    _check_coords(x, y)
+    if interp_method not in INTERP_CODES:
+        raise NotImplementedError(
+            f"interp_methods must be one of 0, 1, 'nearest', 'bilinear', "
+            f"'triangular', was '{interp_method}'."
+        )
+    if tile_boxes is None:
+        tile_boxes = plan.windows(x, y)
+    gm = plan.gm
+    x_min, y_min, x_max, y_max = gm.xy_bbox
+    h, w = x.shape
+    n_rows = plan.rows[1] - plan.rows[0]
+    need = lib.xrs_rectify_ij_workspace_bytes(h, w, n_rows, gm.width)
+    if plan._ws1 is None or plan._ws1.numel() < need:
+        plan._ws1 = _dev.workspace(need, plan.device)
+    squeeze = src.dim() == 2
+    src3 = src.unsqueeze(0) if squeeze else src
+    if src3.stride(2) != 1 or (src3.shape[0] > 1 and src3.stride(0) < src3.stride(1) * src3.shape[1]):
+        src3 = src3.contiguous()
+    np_dtype = np.dtype(str(src3.dtype).replace("torch.", ""))
+    bands, win_h, win_w = src3.shape
+    full_w, full_h = (win_w, win_h) if full_size is None else (int(full_size[0]), int(full_size[1]))
+    if (full_w, full_h) != (w, h):
+        raise ValueError("data variable and coordinates must describe the same source image")
+    if out is None:
+        out = torch.empty((bands, n_rows, gm.width), dtype=src3.dtype, device=src3.device)
+    check(lib.xrs_rectify_gather(
+        _dev.ptr(x), _dev.ptr(y), h, w, x.stride(0), _dev.ptr(tile_boxes), gm.height, gm.width, gm.tile_height,
+        gm.tile_width, float(x_min), float(y_min), float(y_max), float(gm.x_res), float(gm.y_res),
+        int(bool(gm.is_j_axis_up)), plan.uv_delta, plan.rows[0], plan.rows[1], _dev.ptr(plan._ws1),
+        _dev.plane_ptr_array(src3), _dev.plane_ptr_array(out), bands, DTYPE_CODES[np_dtype], src3.stride(1),
+        int(window_origin[0]), int(window_origin[1]), win_w, win_h, INTERP_CODES[interp_method], float(fill_value),
+        _dev.stream_ptr(plan.device)), "xrs_rectify_gather")
+    return out[0] if squeeze else out
+
 
 def _check_coords(x: torch.Tensor, y: torch.Tensor):
     if x.dtype != torch.float64 or y.dtype != torch.float64:
@@ -278,7 +327,8 @@ def rectify_dataset(
             source_ds, source_gm, x_dev, y_dev, x_scale, y_scale,
             _prep_interp_methods_downscale(interp_methods), agg_methods, recover_nans)
 
-    ij = compute_target_source_ij(x_dev, y_dev, target_gm, UV_DELTA)
+    plan = RectifyPlan(target_gm, x_dev.device, uv_delta=UV_DELTA)
+    ij = None  # computed on first need; a single small variable takes the fused K1 + K2 path instead
 
     # output coordinates (rectify.py:148-157)
     sx_name, sy_name = source_gm.xy_var_names
@@ -292,6 +342,7 @@ def rectify_dataset(
 
     yx_dims = (source_gm.xy_dim_names[1], source_gm.xy_dim_names[0])
     t_dims = (target_gm.xy_dim_names[1], target_gm.xy_dim_names[0])
+    n_spatial = sum(1 for _n, v in source_ds.items() if v.dims[-2:] == yx_dims)
     for var_name, var in source_ds.items():
         if var.dims[-2:] == yx_dims:
             assert len(var.dims) in (2, 3), f"Data variable {var_name} has {len(var.dims)} dimensions."
@@ -302,7 +353,14 @@ def rectify_dataset(
                     f"interp_methods must be one of 0, 1, 'nearest', 'bilinear', "
                     f"'triangular', was '{interp_method}'."
                 )
-            out = _gather_from_host(var.values, ij, interp_method, fill_value)
+            if n_spatial == 1 and var.values.nbytes < _PIPELINE_MIN_BYTES:
+                # one variable, small enough not to be streamed: ij is resolved in registers
+                src = _dev.to_device_pitched(var.values, x_dev.device)
+                out = _dev.to_host(plan.rectify_gather(x_dev, y_dev, src, interp_method, fill_value))
+            else:
+                if ij is None:
+                    ij = plan.ij(x_dev, y_dev)
+                out = _gather_from_host(var.values, ij, interp_method, fill_value)
             dims = t_dims if len(var.dims) == 2 else (var.dims[0],) + t_dims
             target_ds[var_name] = DataArray(out, dims=dims, attrs=var.attrs, name=var_name)
         elif yx_dims[0] not in var.dims and yx_dims[1] not in var.dims:
