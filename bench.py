@@ -82,49 +82,103 @@ def workload_config(w, h, nb, size, n_gpus):
 # clocks
 # ---------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled while the timed region runs.
+
+    In-process NVML (the counters behind nvidia-smi's clocks.sm / clocks_event_reasons.* columns)
+    every 10 ms from a thread that is joined before the end-to-end leg starts; falls back to an
+    ``nvidia-smi -lms 100`` child when the NVML binding is missing.  (A lingering nvidia-smi child
+    was measured to stall page-locked copies of the following leg for 0.2-0.4 s at a time, hence the
+    in-process sampler and the kill + wait in the fallback.)"""
+
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASON_BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.lines = []
         self.proc = None
+        self.thread = None
+        self.stop_flag = threading.Event()
+        self.sm, self.smax, self.reasons = [], [], set()
+        self.source = None
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            handle = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.smax.append(float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+
+            def loop():
+                while not self.stop_flag.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+                        mask = int(reasons_fn(handle))
+                        self.reasons.update(name for name, bit in self.REASON_BITS.items() if mask & bit)
+                    except pynvml.NVMLError:
+                        pass
+                    self.stop_flag.wait(0.01)
+
+            self.source = "nvml"
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # no NVML binding: the nvidia-smi child below
+            self.thread = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
                  str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
+
+    def _nvml_index(self):
+        # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a list of indices
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.gpu])
+            except (ValueError, IndexError):
+                pass
+        return self.gpu
 
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [t.strip() for t in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join()
+        elif self.proc is not None:
+            time.sleep(0.15)
+            self.proc.kill()
+            self.proc.wait()
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for ln in self.lines:
+                f = [t.strip() for t in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    self.sm.append(float(f[1]))
+                    self.smax.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        self.reasons.add(name)
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                "sm_max_mhz": max(self.smax) if self.smax else None, "samples": len(self.sm),
+                "source": self.source, "reasons": sorted(self.reasons)}
 
 
 # ---------------------------------------------------------------------------
@@ -199,6 +253,30 @@ def reference_arm(args):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+def pin_to_gpu_numa_node(gpu_index):
+    """Restrict this process to the CPUs NVML reports as local to the GPU, so that page-locked host
+    buffers (first touched here) sit on the NUMA node of the GPU's PCIe root.  Returns the original
+    CPU set (restored before the CPU baseline runs); a no-op when NVML is unavailable."""
+    try:
+        original = os.sched_getaffinity(0)
+    except (AttributeError, OSError):
+        return None
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_words = (max(original) // 64) + 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, n_words)
+        local = {64 * k + b for k, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        local &= original
+        if local:
+            os.sched_setaffinity(0, local)
+    except Exception:  # NVML missing or not permitted: keep the inherited affinity
+        pass
+    return original
+
+
 def ours(args):
     import torch
     import torch.distributed as dist
@@ -211,6 +289,7 @@ def ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    all_cpus = pin_to_gpu_numa_node(local_rank)  # pinned host buffers land next to the GPU's PCIe root
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -435,8 +514,11 @@ def ours(args):
         barrier()
         t0 = time.perf_counter()
         n_units = 0
+        step_ms = []
         for _ in range(e2e_steps):
+            ts = time.perf_counter()
             n_units += e2e_step()
+            step_ms.append(round((time.perf_counter() - ts) * 1e3, 2))
         torch.cuda.synchronize()
         dt_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
         n_units = sum_over_ranks(float(n_units))
@@ -445,6 +527,7 @@ def ours(args):
         d2h = sum_over_ranks(float(world * len(METHODS) * nb * band_px * 4))
         e2e = {"value": n_units / (dt_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": dt_ms / e2e_steps,
+               "rank0_step_ms": step_ms,
                "api": ("rectify_dataset(ds, target_gm, source_gm, interp_methods)" if world == 1 else
                        "rectify_band_host (rectify_dataset's device pipeline on this rank's row band)")
                       + ": pinned host arrays in, pinned host arrays out, host clock around synchronised calls"}
@@ -452,6 +535,8 @@ def ours(args):
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        if all_cpus:
+            os.sched_setaffinity(0, all_cpus)  # the CPU arm uses every host core again
         v, cores, sample, _ms, _ = run_cpu(steps=5, warmup=1, scale=args.scale)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
