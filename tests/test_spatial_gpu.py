@@ -121,3 +121,41 @@ def test_ref_spatial_logs_and_passthrough(xrs, caplog):
                for m in caplog.messages)
     out = xrs.resample_in_space(ds, target_gm=xrs.GridMapping.from_dataset(ds))
     assert out is ds
+
+
+def test_ref_gridmapping_transform(xrs):
+    """tests/gridmapping/test_transform.py:35-64: CRS84 3x3 grid -> UTM 32N, 7 decimals."""
+    gm = xrs.GridMapping.regular(size=(3, 3), xy_min=(10, 53), xy_res=0.1, crs="CRS84")
+    gm_t = gm.transform(crs="EPSG:32632")
+    assert gm_t.crs == xrs.CRS.from_epsg(32632)
+    assert gm_t.is_regular is False
+    assert gm_t.xy_var_names == ("transformed_x", "transformed_y")
+    assert gm_t.xy_dim_names == ("lon", "lat")
+    xy = gm_t.xy_coords.values
+    np.testing.assert_almost_equal(xy[0], np.array([
+        [570057.076286, 576728.9360228, 583400.7295284],
+        [570220.3304187, 576907.7404859, 583595.0849538],
+        [570383.3684844, 577086.3083212, 583789.1831954]]))
+    np.testing.assert_almost_equal(xy[1], np.array([
+        [5900595.928991, 5900698.5746648, 5900810.5532744],
+        [5889471.9033896, 5889574.6540572, 5889686.7472201],
+        [5878348.0594403, 5878450.9138481, 5878563.1201969]]))
+
+
+def test_ref_gridmapping_transform_names_and_noop(xrs):
+    """tests/gridmapping/test_transform.py:66-110."""
+    gm = xrs.GridMapping.regular(size=(3, 3), xy_min=(10, 53), xy_res=0.1, crs="CRS84")
+    gm_t = gm.transform(crs="EPSG:32632", xy_var_names=("x", "y"))
+    assert gm_t.xy_var_names == ("x", "y")
+    assert gm_t.xy_dim_names == ("lon", "lat")
+    assert gm.transform(gm.crs) is gm
+    assert gm.transform(crs=gm.crs, xy_var_names=("x", "y")).xy_var_names == ("x", "y")
+    # a projected regular grid to both geographic CRSs, and an explicit resolution (bbox from densified edges)
+    utm = xrs.GridMapping.regular(size=(20, 10), xy_min=(500000, 5900000), xy_res=100, crs="EPSG:32632")
+    for crs in ("CRS84", "EPSG:4326"):
+        assert utm.transform(crs).crs.is_geographic
+    geo = utm.transform("EPSG:4326", xy_res=0.001)
+    assert geo.xy_res == (0.001, 0.001)
+    x0, y0, x1, y1 = geo.xy_bbox
+    xy = geo.xy_coords.values
+    assert x0 < xy[0].min() and xy[0].max() < x1 and y0 < xy[1].min() and xy[1].max() < y1

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Attribute an ncu source-page capture to CUDA source lines.
 
-    python tools/ncu_by_line.py report.ncu-rep object.o kernel_mangled_name [top_n]
+    python tools/ncu_by_line.py report.ncu-rep object.o kernel_mangled_name [top_n] [ncu_kernel_name_substring]
 
 ncu's CSV source page is per SASS instruction; `nvdisasm -g` of the same cubin carries the
 line table.  Both list the kernel's instructions in address order, so they are joined by index.
@@ -46,7 +46,8 @@ def main():
             cur_b["hdr"] = r
         elif cur_b is not None and cur_b["hdr"] and len(r) == len(cur_b["hdr"]):
             cur_b["rows"].append(r)
-    match = [blk for blk in blocks if kernel.split("EN")[0].lstrip("_Z0123456789N").replace("3xrs", "") in blk["name"]]
+    want = sys.argv[5] if len(sys.argv) > 5 else kernel.split("EN")[0].lstrip("_Z0123456789N").replace("3xrs", "")
+    match = [blk for blk in blocks if want in blk["name"]]
     b = match[0] if match else blocks[0]
     h = b["hdr"]
     i_ex, i_s = h.index("Instructions Executed"), h.index("# Samples")

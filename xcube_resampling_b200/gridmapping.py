@@ -479,6 +479,37 @@ class GridMapping:
         return GridMapping.regular(size=(width, height), xy_min=(x_min, y_min), xy_res=xy_res, crs=self.crs,
                                    tile_size=tile_size, is_j_axis_up=is_j_axis_up)
 
+    def transform(self, crs, *, xy_res=None, tile_size=None, xy_var_names=None,
+                  tolerance: float = DEFAULT_TOLERANCE) -> "GridMapping":
+        """base.py:884-913 -> transform.py:57-125: this grid mapping with its coordinates expressed in
+        another CRS.  The point transform runs on the device (xrs_transform_points), the bounding box
+        of a given ``xy_res`` comes from edges densified with 101 points (transform.py:89)."""
+        from .reproject import transform_bounds, transform_points  # device code; imported late (cycle)
+
+        target_crs = normalize_crs(crs)
+        if xy_var_names:
+            _assert_valid_xy_names(xy_var_names, name="xy_var_names")
+        if self.crs == target_crs:
+            if tile_size is not None or xy_var_names is not None:
+                return self.derive(tile_size=tile_size, xy_var_names=xy_var_names)
+            return self
+        xy = self.xy_coords.values
+        x2, y2 = transform_points(np.ascontiguousarray(xy[0], dtype=np.float64),
+                                  np.ascontiguousarray(xy[1], dtype=np.float64), self.crs, target_crs)
+        xy_bbox = None
+        if xy_res is not None:
+            box = transform_bounds(self.crs, target_crs, np.asarray([self.xy_bbox], dtype=np.float64),
+                                   densify_pts=101)[0]
+            x_res, y_res = _normalize_number_pair(xy_res)
+            xy_bbox = (float(box[0]) - x_res / 2, float(box[1]) - y_res / 2,
+                       float(box[2]) + x_res / 2, float(box[3]) + y_res / 2)
+        names = tuple(xy_var_names) if xy_var_names else ("transformed_x", "transformed_y")
+        dims = (self.xy_dim_names[1], self.xy_dim_names[0])
+        return GridMapping.from_coords(DataArray(x2, dims=dims, name=names[0]), DataArray(y2, dims=dims, name=names[1]),
+                                       target_crs, xy_res=xy_res, xy_bbox=xy_bbox,
+                                       tile_size=tile_size if tile_size is not None else self.tile_size,
+                                       tolerance=tolerance)
+
     @classmethod
     def from_coords(cls, x_coords, y_coords, crs, *, xy_res=None, xy_bbox=None, tile_size=None,
                     tolerance: float = DEFAULT_TOLERANCE, xy_var_names=None, xy_dim_names=None) -> "GridMapping":
