@@ -419,19 +419,23 @@ def ours(args):
                     n += out.size
             return n
 
-        # Warm-up to steady state: the first two steps page-lock the output buffers (seconds); for a
-        # second or two after that, single steps were measured to take 1.5-3x longer on this pool
-        # (host-side, independent of the kernels).  Warm-up ends when three consecutive steps agree
-        # within 3 % on every rank (at most 20 steps); the timed steps that follow are consecutive
-        # and all counted, and their individual times are reported.
+        # Warm-up to steady state.  The first step page-locks the output buffers (seconds); for two to
+        # three seconds after that, single steps were measured to take 1.5-4x longer at random on
+        # this pool (host-side: the kernels and the copies of such a step are not slower when timed
+        # alone).  Warm-up therefore runs for at least 4 s after the first step AND until three
+        # consecutive steps agree within 3 % on every rank (at most 60 steps).  The timed steps that
+        # follow are consecutive and all counted; every warm-up and timed step time is reported.
         warm_ms = []
-        while len(warm_ms) < 20:
+        t_first = None
+        while len(warm_ms) < 60:
             ts = time.perf_counter()
             e2e_step()
             warm_ms.append(round((time.perf_counter() - ts) * 1e3, 2))
+            if t_first is None:
+                t_first = time.perf_counter()
             last = warm_ms[-3:]
-            unsteady = 0.0 if (len(warm_ms) >= 5 and max(last) <= 1.03 * min(last)) else 1.0
-            if max_over_ranks(unsteady) == 0.0:
+            steady = len(warm_ms) >= 4 and max(last) <= 1.03 * min(last) and time.perf_counter() - t_first >= 4.0
+            if max_over_ranks(0.0 if steady else 1.0) == 0.0:
                 break
         barrier()
         t0 = time.perf_counter()
