@@ -12,6 +12,11 @@ A scene pass = rectify(nearest) + rectify(bilinear), each a complete K0 (tile wi
 image) + K2 (gather of all 21 bands).  ``value`` is output Mpix*band/s with the inputs resident in
 HBM; ``e2e`` is the same metric through ``rectify_dataset`` with host (pinned) inputs and host
 outputs, copies inside the timed region.  Rank 0 prints ONE JSON line.
+
+The device-resident part is timed twice over K steps each: eagerly, launch after launch, with a
+CUDA event pair around every kernel (the per-kernel durations of ``roofline``), then as K replays
+of a CUDA graph of the same step in which the two methods' passes run as concurrent chains
+(``value``; ``--no-graph`` takes it from the eager region instead).
 """
 
 import argparse
@@ -45,7 +50,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (debugging only)")
     ap.add_argument("--two-step", action="store_true",
                     help="device-resident leg: xrs_rectify_ij + xrs_gather_ij instead of the fused xrs_rectify_gather")
-    ap.add_argument("--no-graph", action="store_true", help="N > 1: launch eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-graph", action="store_true", help="take `value` from the eager, sequential region instead of the CUDA-graph replays")
     return ap.parse_args()
 
 
@@ -73,7 +78,7 @@ def workload_config(w, h, nb, size, n_gpus):
                       "21 bands (fused xrs_rectify_gather: ij resolved in registers)",
         "scenes_per_step": n_gpus,
         "partition": "target row bands of equal work (valid pixels per row), rank r = band r of every scene, "
-                     "no collective; N>1: the step is one CUDA graph, nearest and bilinear passes on two streams",
+                     "no collective; the timed step is one CUDA graph, nearest and bilinear passes as two chains on two streams",
         "l2": "inputs (2.0 GB) and outputs (3.3 GB per method) exceed the 126 MB L2; no explicit flush",
     }
 
@@ -364,7 +369,7 @@ def ours(args):
             evs[3].record()
             pending.append((m, evs))
 
-    chains = [torch.cuda.Stream(dev) for _ in METHODS] if world > 1 and not args.no_graph else None
+    chains = [torch.cuda.Stream(dev) for _ in METHODS]
 
     def step(record=False, concurrent=False):
         if not concurrent:
@@ -465,29 +470,34 @@ def ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = lib.xrs_launch_count()
     _lib.profile_collect()
-    use_graph = world > 1 and not args.no_graph
-    if not use_graph:
-        # N = 1: eager launches, per-kernel CUDA events inside libxrs over the timed region itself
-        _lib.profile_enable(True)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            step(record=True)
-        e1.record()
-        torch.cuda.synchronize()
-        _lib.profile_enable(False)
-        kernel_times = _lib.profile_collect()
-        launches = lib.xrs_launch_count() - launches0
-    else:
-        # N > 1: a rank's band kernels are short (0.01-0.15 ms), so the step (N scenes x 2 methods x
-        # 9 launches) is captured once in a CUDA graph and replayed; the per-kernel breakdown comes
-        # from one extra eager step after the timed region
+    use_graph = not args.no_graph
+    # Region A (every N): K eager steps, one launch after the other on one stream, with libxrs's
+    # per-launch CUDA events -- the per-kernel durations behind `roofline` and the step time of the
+    # plain sequential form.
+    launches0 = lib.xrs_launch_count()
+    _lib.profile_enable(True)
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(args.steps):
+        step(record=True)
+    a1.record()
+    torch.cuda.synchronize()
+    _lib.profile_enable(False)
+    kernel_times = _lib.profile_collect()
+    launches = lib.xrs_launch_count() - launches0
+    eager_ms = max_over_ranks(a0.elapsed_time(a1))
+    e0, e1 = a0, a1
+    if use_graph:
+        # Region B, the one `value` is computed from: the same step captured once in a CUDA graph --
+        # the nearest and the bilinear passes as two chains on two streams (K0 and the K1 scatter are
+        # latency-bound and leave bandwidth for the other chain's gather; at N > 1 a rank's band
+        # kernels are only 10-140 us) -- and replayed K times.
+        launches0 = lib.xrs_launch_count()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             step(concurrent=True)
-        launches_per_step = lib.xrs_launch_count() - launches0
+        launches = (lib.xrs_launch_count() - launches0) * args.steps
         graph.replay()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -496,12 +506,6 @@ def ours(args):
             graph.replay()
         e1.record()
         torch.cuda.synchronize()
-        launches = launches_per_step * args.steps
-        _lib.profile_enable(True)
-        step(record=True)
-        torch.cuda.synchronize()
-        _lib.profile_enable(False)
-        kernel_times = _lib.profile_collect()
     my_ms = e0.elapsed_time(e1)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -513,7 +517,7 @@ def ours(args):
         phase_ms["k0"] += evs[0].elapsed_time(evs[1])
         phase_ms["k1"] += evs[1].elapsed_time(evs[2])
         phase_ms["k2_" + m] += evs[2].elapsed_time(evs[3])
-    n_pass = (args.steps if not use_graph else 1) * world
+    n_pass = args.steps * world
     phase_ms = {k: v / n_pass / (len(METHODS) if k in ("k0", "k1") else 1) for k, v in phase_ms.items()}
 
     # ---- roofline of the dominant kernel (largest share of the timed region) ------------
@@ -571,9 +575,11 @@ def ours(args):
                           "workload (profiles/r01_final_*_ncu_full.txt)" if traffic else None,
         "algorithmic_bytes_per_launch": top["algorithmic_bytes_per_launch"], "bytes_model": top["bytes_model"],
         "ms_per_launch": top["ms_per_launch"], "share_of_kernel_time": top["share_of_kernel_time"],
-        "timing": ("CUDA events recorded by libxrs around every launch on the launching stream, timed region only"
-                   if not use_graph else
-                   "timed region = CUDA-graph replays of the step; per-kernel CUDA events from one extra eager step"),
+        "timing": "CUDA events recorded by libxrs around every launch on the launching stream over K eager, "
+                  "sequential steps (ms_per_step_eager)" +
+                  ("; `value` is timed over K CUDA-graph replays of the same step with the nearest and bilinear "
+                   "passes as two concurrent chains" if use_graph else "; `value` is that region"),
+        "ms_per_step_eager": eager_ms / args.steps,
         "kernels": kernels, "phase_ms_per_rectify": phase_ms,
     }
 
