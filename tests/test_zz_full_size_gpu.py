@@ -1,0 +1,257 @@
+"""Parity at the FULL sizes of BASELINE.json's configurations (C1..C5), through the C ABI.
+
+The other GPU test modules compare against the oracle at sizes it finishes in a blink; here the
+device runs every configuration at its real size and the result is checked
+
+* against the oracle itself where it is fast enough (C2: the C restatement does the whole 40 Mpx
+  scene in seconds; C1: scipy on 4096^2),
+* against the oracle on strips / reference tiles cut out of the full-size result (C3, C4, C5), and
+* through size-independent properties: a row-band split reproduces the whole image bit for bit,
+  the fused and the two-step rectify forms agree bit for bit.
+
+Tolerances are those of the north star: ij, nearest, min/max/median/mode bit-exact; bilinear
+through a real projection 1e-6 relative, nearest there < 1e-4 rounding-tie mismatches.
+(The file name sorts last on purpose: these are the long tests.)
+"""
+
+import numpy as np
+import pytest
+
+from oracle import grid as ogrid
+from oracle import proj as oproj
+from oracle import rectify as orect
+from oracle import reproject as orep
+from oracle import resample as ores
+
+from .helpers import assert_same
+
+pytestmark = pytest.mark.gpu
+nan = np.nan
+
+
+@pytest.fixture(scope="module")
+def xrs():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import xcube_resampling_b200 as pkg
+    from xcube_resampling_b200 import _dev, affine, rectify, reproject
+
+    pkg.dev, pkg.rect, pkg.rep, pkg.aff = _dev, rectify, reproject, affine
+    yield pkg
+    torch.cuda.empty_cache()
+
+
+def _bits(t):
+    """Bit pattern view of a float tensor (NaN == NaN under torch.equal)."""
+    import torch
+
+    return t.contiguous().view(torch.int64 if t.dtype == torch.float64 else torch.int32)
+
+
+# ---------------------------------------------------------------------------
+# C2: rectify of the OLCI-shaped swath (4865 x 4091 -> ~7992 x 5013), reference tile 512
+# ---------------------------------------------------------------------------
+def test_c2_rectify_full_size(xrs):
+    import torch
+    from xcube_resampling_b200 import synthetic as syn
+
+    w, h, res = syn.OLCI_WIDTH, syn.OLCI_HEIGHT, syn.OLCI_RES_DEG
+    lon, lat = syn.swath(w, h, res=res, theta=12.0, seed=0)
+    size, xy_min = syn.covering_grid_args(lon, lat, res)
+    g = ogrid.regular_grid(size, xy_min, res, tile_size=512)
+    gm = xrs.GridMapping.regular(size, xy_min, res, "EPSG:4326", tile_size=512)
+    xd, yd = xrs.dev.to_device(lon), xrs.dev.to_device(lat)
+    plan = xrs.rect.RectifyPlan(gm, xd.device)
+    windows = plan.windows(xd, yd)
+    ref_windows = orect.source_windows(lon, lat, g)
+    assert_same(xrs.dev.to_host(windows), ref_windows, "C2 K0 windows")
+    ij = plan.ij(xd, yd, windows)
+    ref_ij = orect.rectify_ij(lon, lat, g, windows=ref_windows)
+    ij_host = xrs.dev.to_host(ij)
+    valid = float(np.mean(~np.isnan(ij_host[0])))
+    assert 0.5 < valid < 0.9, valid  # rotated swath: ~71 % of the covering grid
+    assert_same(ij_host, ref_ij, "C2 K1 ij (40 Mpx, bit-exact)")
+    del ij_host, ref_ij
+
+    # row bands of uneven height reproduce the whole image
+    parts = []
+    for rows in ((0, 1000), (1000, 1536), (1536, gm.height)):
+        parts.append(xrs.rect.RectifyPlan(gm, xd.device, rows=rows).ij(xd, yd).clone())
+    assert torch.equal(_bits(torch.cat(parts, dim=1)), _bits(ij)), "C2 ij: row-band split differs from the whole image"
+    del parts
+
+    # gathers: two-step == fused == oracle, 3 bands (one with NaN holes)
+    bands = syn.band_stack(3, h, w, seed=0)
+    bands[1, np.random.default_rng(3).random((h, w)) < 0.01] = nan
+    sd = xrs.dev.to_device_pitched(bands)
+    ij_np = xrs.dev.to_host(ij)
+    for method in ("nearest", "bilinear"):
+        two = xrs.rect.gather_ij(sd, ij, method, nan)
+        fused = plan.rectify_gather(xd, yd, sd, method, nan, tile_boxes=windows)
+        assert torch.equal(_bits(two), _bits(fused)), f"C2 {method}: fused form differs from the two-step form"
+        assert_same(xrs.dev.to_host(two), orect.gather(bands, ij_np, method, nan), f"C2 K2 {method}")
+        del two, fused
+
+
+# ---------------------------------------------------------------------------
+# reproject helpers: one reference tile (or a block of it) of a full-size target from the oracle
+# ---------------------------------------------------------------------------
+def _oracle_grid(gm):
+    return ogrid.regular_grid(gm.size, (gm.x_min, gm.y_min), gm.xy_res, tile_size=gm.tile_size,
+                              is_j_axis_up=gm.is_j_axis_up)
+
+
+def _oracle_tile_block(src_gm, tgt_gm, data, data_origin, method, fill, src_epsg, tgt_epsg, ty, tx, n_rows):
+    """Rows [0, n_rows) of reference tile (ty, tx) of the target, from the oracle.
+
+    ``data`` holds the source rows/columns starting at ``data_origin=(i0, j0)`` of the full source
+    (everything the tile's window reaches must be inside it or outside the source)."""
+    g = _oracle_grid(tgt_gm)
+    xs, ys = src_gm.x_values, src_gm.y_values
+    tp, sp = oproj.from_epsg(tgt_epsg), oproj.from_epsg(src_epsg)
+    win = orep.source_windows(float(xs[0]), float(ys[0]), src_gm.x_res, src_gm.y_res, float(ys[1] - ys[0]),
+                              src_gm.width, src_gm.height, g, tp, sp)
+    r0, c0 = ty * g.tile_h, tx * g.tile_w
+    r1, c1 = min(r0 + n_rows, r0 + g.tile_h, g.height), min(c0 + g.tile_w, g.width)
+    xx, yy = np.meshgrid(ogrid.x_centres(g)[c0:c1], ogrid.y_centres(g)[r0:r1])
+    xx, yy = oproj.transform(tp, sp, xx, yy)
+    wj, wi, wh, ww = int(win["j0"][ty, tx]), int(win["i0"][ty, tx]), win["win_h"], win["win_w"]
+    # the tile's window of the fill-padded source (reproject.py:499-530) without padding the whole image
+    window = np.full((data.shape[0], wh, ww), fill, dtype=data.dtype)
+    oi, oj = data_origin
+    js, je = max(wj, 0), min(wj + wh, src_gm.height)
+    is_, ie = max(wi, 0), min(wi + ww, src_gm.width)
+    assert oj <= js and je <= oj + data.shape[1] and oi <= is_ and ie <= oi + data.shape[2], "window outside the data"
+    window[:, js - wj:je - wj, is_ - wi:ie - wi] = data[:, js - oj:je - oj, is_ - oi:ie - oi]
+    block = orep.sample_window(xx, yy, window, win["x0"][ty, tx], win["y0"][ty, tx], src_gm.x_res, src_gm.y_res, method)
+    return (r0, r1, c0, c1), block
+
+
+def _compare_projected(got, want, method, what):
+    assert got.shape == want.shape and got.dtype == want.dtype, (what, got.shape, want.shape, got.dtype, want.dtype)
+    if method == "nearest":
+        frac = float(np.mean(~((got == want) | (np.isnan(got) & np.isnan(want)))))
+        print(f"{what}: nearest mismatch fraction (rounding ties) {frac:.3g}")
+        assert frac < 1e-4, (what, frac)
+    else:
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-9, equal_nan=True, err_msg=what)
+
+
+# ---------------------------------------------------------------------------
+# C3: 0.0001 deg EPSG:4326 -> UTM 32N 10980^2 Sentinel-2 tile, reference tile 2048
+# ---------------------------------------------------------------------------
+def test_c3_reproject_full_size(xrs):
+    import torch
+
+    tgt = xrs.GridMapping.regular((10980, 10980), (399960.0, 990240.0), 10.0, "EPSG:32632", tile_size=2048)
+    box = oproj.transform_bounds(oproj.from_epsg(32632), oproj.from_epsg(4326), *tgt.xy_bbox)
+    res = 0.0001
+    x_min = float(np.floor(box[0] / res) * res) - 4 * res
+    y_min = float(np.floor(box[1] / res) * res) - 4 * res
+    w = int(np.ceil((box[2] - x_min) / res)) + 4
+    h = int(np.ceil((box[3] - y_min) / res)) + 4
+    src = xrs.GridMapping.regular((w, h), (x_min, y_min), res, "EPSG:4326")
+    rng = np.random.default_rng(7)
+    data = np.empty((2, h, w), dtype=np.float32)
+    for b in range(2):
+        rng.random(out=data[b], dtype=np.float32)
+    sd = xrs.dev.to_device(data)
+    plan = xrs.rep.ReprojectPlan(src, tgt)
+    for method in ("bilinear", "nearest"):
+        full = plan.run(sd, method, nan)
+        assert tuple(full.shape) == (2, 10980, 10980)
+        assert full.dtype == (torch.float64 if method == "bilinear" else torch.float32)
+        # an interior reference tile and the ragged last one (rows 10240.., cols 10240..)
+        for ty, tx in ((2, 3), (5, 5)):
+            (r0, r1, c0, c1), want = _oracle_tile_block(src, tgt, data, (0, 0), method, nan, 4326, 32632, ty, tx, 384)
+            got = full[:, r0:r1, c0:c1].cpu().numpy()
+            _compare_projected(got, want, method, f"C3 {method} tile ({ty},{tx})")
+        # a row band fed with its source footprint only reproduces the rows of the whole image
+        rows = (4096, 6144)
+        band_plan = xrs.rep.ReprojectPlan(src, tgt, rows=rows)
+        i0, j0, i1, j1 = band_plan.footprint()
+        assert (j1 - j0) < 0.3 * h, "C3: a 2048-row band needs only a fraction of the source rows"
+        part = band_plan.run(sd[:, j0:j1, i0:i1].contiguous(), method, nan, window_origin=(i0, j0))
+        assert torch.equal(_bits(part), _bits(full[:, rows[0]:rows[1]])), f"C3 {method}: row band differs"
+        del full, part
+
+
+# ---------------------------------------------------------------------------
+# C5: global 0.01 deg grid -> EPSG:3857 36000^2, reference tile 4500, one of the 8 row bands
+# ---------------------------------------------------------------------------
+def test_c5_reproject_row_band_full_size(xrs):
+    ext = 20037508.342789244
+    tgt = xrs.GridMapping.regular((36000, 36000), (-ext, -ext), 2 * ext / 36000, "EPSG:3857", tile_size=4500)
+    src = xrs.GridMapping.regular((36000, 18000), (-180.0, -90.0), 0.01, "EPSG:4326")
+    windows = xrs.rep.get_source_windows(src, tgt)
+    band = 3  # rows 13500..18000, just north of the equator
+    rows = (band * 4500, (band + 1) * 4500)
+    plan = xrs.rep.ReprojectPlan(src, tgt, rows=rows, windows=windows)
+    i0, j0, i1, j1 = plan.footprint()
+    assert (i0, i1) == (0, 36000) and 3500 < (j1 - j0) < 5000, (i0, j0, i1, j1)
+    rng = np.random.default_rng(11)
+    data = np.empty((1, j1 - j0, i1 - i0), dtype=np.float32)
+    rng.random(out=data[0], dtype=np.float32)
+    sd = xrs.dev.to_device(data)
+    for method in ("bilinear", "nearest"):
+        out = plan.run(sd, method, nan, window_origin=(i0, j0))
+        assert tuple(out.shape) == (1, 4500, 36000)
+        # interior tile columns: the target columns coincide with source columns here (0.01 deg both), so
+        # at the dateline tiles rounding noise decides whether a tap at index -0 / w-1+0 reads fill --
+        # legitimately different between two implementations; the pad rules are covered at small sizes
+        for tx in (1, 4, 6):
+            (r0, r1, c0, c1), want = _oracle_tile_block(src, tgt, data, (i0, j0), method, nan, 4326, 3857, band, tx, 256)
+            got = out[:, r0 - rows[0]:r1 - rows[0], c0:c1].cpu().numpy()
+            _compare_projected(got, want, method, f"C5 {method} tile ({band},{tx})")
+        del out
+
+
+# ---------------------------------------------------------------------------
+# C4: coarsen 20000^2 float32 / uint8 by 4 and 8; oracle on the first and last strips
+# ---------------------------------------------------------------------------
+def test_c4_coarsen_full_size(xrs):
+    import torch
+
+    n, strip = 20000, 800
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(4)
+    f32 = torch.rand((n, n), dtype=torch.float32, device="cuda", generator=gen)
+    f32[::97, ::89] = nan  # sparse NaNs: nan-reducers and the median's valid-count path
+    coarse = torch.randint(0, 20, (n // 11 + 1, n // 11 + 1), dtype=torch.uint8, device="cuda", generator=gen)
+    u8 = coarse.repeat_interleave(11, 0).repeat_interleave(11, 1)[:n, :n].contiguous()  # blocky class raster
+    noise = torch.rand((n, n), device="cuda", generator=gen) < 0.05
+    u8[noise] = torch.randint(0, 20, (int(noise.sum()),), dtype=torch.uint8, device="cuda", generator=gen)
+    del noise, coarse
+    host = {"f32": (f32[:strip].cpu().numpy(), f32[n - strip:].cpu().numpy()),
+            "u8": (u8[:strip].cpu().numpy(), u8[n - strip:].cpu().numpy())}
+    for f in (4, 8):
+        for name, src, aggs in (("f32", f32, ("mean", "min", "max", "median")), ("u8", u8, ("mode", "min", "max"))):
+            for agg in aggs:
+                out = xrs.aff.coarsen_dev(src, (f, f), agg)
+                assert tuple(out.shape) == (n // f, n // f)
+                top = out[: strip // f].cpu().numpy()
+                bottom = out[(n - strip) // f:].cpu().numpy()
+                for got, a, where in ((top, host[name][0], "first"), (bottom, host[name][1], "last")):
+                    want = np.asarray(ores.coarsen(a, f, f, agg))
+                    assert_same(got, want.astype(got.dtype), f"C4 {name} /{f} {agg} ({where} strip)")
+                del out
+
+
+# ---------------------------------------------------------------------------
+# C1: affine_transform_dataset, 2x bilinear downsample of 4096^2 float32
+# ---------------------------------------------------------------------------
+def test_c1_affine_full_size(xrs):
+    rng = np.random.default_rng(0)
+    n = 4096
+    a = rng.random((n, n)).astype(np.float32)
+    a[rng.random((n, n)) < 0.001] = nan
+    src = ogrid.regular_grid((n, n), (0, 0), 0.01, tile_size=1024)
+    tgt = ogrid.regular_grid((n // 2, n // 2), (0, 0), 0.02, tile_size=1024)
+    ref = ores.affine_transform(a, src, tgt, interp=1)
+    source_gm = xrs.GridMapping.regular((n, n), (0, 0), 0.01, "EPSG:4326", tile_size=1024)
+    target_gm = xrs.GridMapping.regular((n // 2, n // 2), (0, 0), 0.02, "EPSG:4326", tile_size=1024)
+    ds = xrs.Dataset(data_vars=dict(refl=(("lat", "lon"), a)),
+                     coords=dict(lon=source_gm.x_coords.values, lat=source_gm.y_coords.values))
+    out = xrs.affine_transform_dataset(ds, target_gm, source_gm=source_gm, interp_methods=1)
+    assert_same(out["refl"].values, ref, "C1 4096^2 -> 2048^2")

@@ -83,14 +83,30 @@ def _edge_points(boxes: np.ndarray, densify_pts: int = _DENSIFY_PTS):
     return xs, ys
 
 
+def _unwrap_longitudes(lon: np.ndarray) -> np.ndarray:
+    """Remove +-360 degree jumps between consecutive samples along the last axis (NaNs pass through)."""
+    lon = np.asarray(lon, dtype=np.float64)
+    with np.errstate(invalid="ignore"):
+        step = np.diff(lon, axis=-1)
+        turn = np.where(np.abs(step) > 180.0, -np.sign(step) * 360.0, 0.0)
+    shift = np.concatenate([np.zeros(lon.shape[:-1] + (1,)), np.cumsum(turn, axis=-1)], axis=-1)
+    return lon + shift
+
+
 def transform_bounds(from_crs, to_crs, boxes, densify_pts: int = _DENSIFY_PTS, device=None) -> np.ndarray:
     """``Transformer.transform_bounds`` for a batch of (x_min, y_min, x_max, y_max) boxes: densified
     edges through the device transform, then min / max over the finite results.  (n, 4) float64.
 
-    PROJ's special cases for geographic output crossing the antimeridian or enclosing a pole are
-    not reproduced."""
+    Geographic output: the point transform wraps longitudes into [-180, 180] like PROJ, so a box
+    that touches the antimeridian (e.g. a web-Mercator tile ending at x = +20037508.34) would get
+    a boundary sample at -180 next to ones at +179.99.  Consecutive samples are never half a turn
+    apart, so such jumps are undone (the walk stays contiguous: 179.99 -> 180.00001) and the box
+    keeps its real extent.  PROJ's own antimeridian result (x_min > x_max) and its pole-enclosing
+    case are not reproduced."""
     xs, ys = _edge_points(boxes, densify_pts)
     tx, ty = transform_points(xs, ys, from_crs, to_crs, device)
+    if normalize_crs(to_crs).is_geographic:
+        tx = _unwrap_longitudes(tx)
     ok = np.isfinite(tx) & np.isfinite(ty)
     big = np.inf
     out = np.stack([np.where(ok, tx, big).min(axis=1), np.where(ok, ty, big).min(axis=1),
