@@ -51,3 +51,27 @@ def test_global_web_mercator_windows_at_the_antimeridian(monkeypatch):
     assert np.array_equal(w.i0, win["i0"]) and np.array_equal(w.j0, win["j0"])
     assert np.array_equal(w.x0, win["x0"]) and np.array_equal(w.y0, win["y0"])
     assert w.x0.dtype == np.float32
+
+
+def test_gridmapping_transform_and_to_regular(monkeypatch):
+    """tests/gridmapping/test_base.py:326-404 with the device transform replaced by the oracle's."""
+    import xcube_resampling_b200.reproject as rep
+    from xcube_resampling_b200.crs import CRS
+    from xcube_resampling_b200.gridmapping import GridMapping
+
+    monkeypatch.setattr(rep, "transform_points", _fake_transform_points)
+    gm = GridMapping.regular((400, 200), (20, 56), 0.01, "EPSG:4326")
+    t = gm.transform("EPSG:32633")
+    assert t is not gm and t.crs == CRS.from_epsg(32633) and t.is_regular is False
+    assert (t.size, t.tile_size, t.is_j_axis_up) == ((400, 200), (400, 200), False)
+    assert t.xy_var_names == ("transformed_x", "transformed_y") and t.xy_dim_names == ("lon", "lat")
+
+    t = gm.derive(tile_size=(200, 200)).transform("EPSG:32633", xy_res=1000)
+    assert (t.size, t.tile_size, t.xy_res, t.is_j_axis_up) == ((400, 200), (200, 200), (1000, 1000), False)
+    r = t.to_regular()
+    assert r.is_regular and r.crs == CRS.from_epsg(32633)
+    assert (r.size, r.tile_size, r.xy_res, r.is_j_axis_up) == ((267, 249), (200, 200), (1000, 1000), False)
+    assert r.xy_var_names == ("x", "y") and r.xy_dim_names == ("x", "y")
+
+    r = GridMapping.regular((1000, 1000), (9.6, 47.6), 0.0002, "EPSG:4326").transform("EPSG:32633").to_regular()
+    assert (r.size, r.tile_size, r.is_j_axis_up, r.is_lon_360) == ((827, 1163), (1000, 1000), False, False)

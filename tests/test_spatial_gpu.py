@@ -159,3 +159,34 @@ def test_ref_gridmapping_transform_names_and_noop(xrs):
     x0, y0, x1, y1 = geo.xy_bbox
     xy = geo.xy_coords.values
     assert x0 < xy[0].min() and xy[0].max() < x1 and y0 < xy[1].min() and xy[1].max() < y1
+
+
+def test_ref_gridmapping_transform_to_regular(xrs):
+    """tests/gridmapping/test_base.py:348-404 with the device point transform."""
+    gm = xrs.GridMapping.regular((400, 200), (20, 56), 0.01, "EPSG:4326", tile_size=(200, 200))
+    t = gm.transform("EPSG:32633", xy_res=1000)
+    assert (t.size, t.tile_size, t.xy_res, t.is_j_axis_up) == ((400, 200), (200, 200), (1000, 1000), False)
+    r = t.to_regular()
+    assert (r.size, r.tile_size, r.xy_res, r.is_j_axis_up) == ((267, 249), (200, 200), (1000, 1000), False)
+    assert r.xy_var_names == ("x", "y") and r.xy_dim_names == ("x", "y")
+    r = xrs.GridMapping.regular((1000, 1000), (9.6, 47.6), 0.0002, "EPSG:4326").transform("EPSG:32633").to_regular()
+    assert (r.size, r.tile_size, r.is_j_axis_up, r.is_lon_360) == ((827, 1163), (1000, 1000), False, False)
+
+
+def test_ref_ij_bbox_from_xy_bbox(xrs):
+    """tests/gridmapping/test_base.py:456-512: source-index boxes of xy boxes on a global 0.5 deg grid (K0)."""
+    gm = xrs.GridMapping.regular((720, 360), (-180.0, -90.0), 0.5, "EPSG:4326", tile_size=(360, 180))
+    assert gm.ij_bbox_from_xy_bbox((-180, -90, 180, 90)) == (0, 0, 720, 360)
+    assert gm.ij_bbox_from_xy_bbox((-180, -90, 0, 0)) == (0, 180, 360, 360)
+    assert gm.ij_bbox_from_xy_bbox((0, 0, 180, 90)) == (360, 0, 720, 180)
+    assert gm.ij_bbox_from_xy_bbox((-180, -90, 0, 0), ij_border=1) == (0, 179, 361, 360)
+    assert gm.ij_bbox_from_xy_bbox((0, 0, 180, 90), ij_border=1) == (359, 0, 720, 181)
+    assert gm.ij_bbox_from_xy_bbox((-190, -100, -170, -80), ij_border=1) == (0, 339, 21, 360)
+    assert gm.ij_bbox_from_xy_bbox((-190, -100, -180, -90), ij_border=1) == (-1, -1, -1, -1)
+    # a batch of arbitrary boxes (not the tiles of one grid): one K0 pass per box
+    boxes = np.array([[-180, -90, 180, 90], [-180, -90, 0, 0], [0, 0, 180, 90], [-180, -90, 0, 0], [0, 0, 180, 90],
+                      [-190, -100, -170, -80], [-190, -100, -180, -90]], dtype=np.float32)
+    want = np.array([[0, 0, 720, 360], [0, 180, 360, 360], [360, 0, 720, 180], [0, 180, 360, 360], [360, 0, 720, 180],
+                     [0, 340, 20, 360], [-1, -1, -1, -1]], dtype=np.int64)
+    got = gm.ij_bboxes_from_xy_bboxes(boxes)
+    assert got.dtype == np.int64 and np.array_equal(got, want)

@@ -207,7 +207,13 @@ def tile_source_windows_for_boxes(source_gm: GridMapping, xy_bboxes: np.ndarray,
     xy = source_gm.xy_coords.values
     x = _dev.to_device(xy[0], dtype=np.float64)
     y = _dev.to_device(xy[1], dtype=np.float64)
-    return _dev.to_host(tile_source_windows_dev(x, y, xy_bboxes, xy_border, ij_border))
+    xy_bboxes = np.asarray(xy_bboxes, dtype=np.float64).reshape(-1, 4)
+    try:
+        return _dev.to_host(tile_source_windows_dev(x, y, xy_bboxes, xy_border, ij_border))
+    except NotImplementedError:
+        # arbitrary boxes (not the row-major tiles of one grid): one pass per box over the resident coordinates
+        parts = [tile_source_windows_dev(x, y, xy_bboxes[k:k + 1], xy_border, ij_border) for k in range(len(xy_bboxes))]
+        return _dev.to_host(torch.cat(parts, dim=0))
 
 
 def compute_target_source_ij(x: torch.Tensor, y: torch.Tensor, target_gm: GridMapping,
