@@ -1,0 +1,50 @@
+"""Host-side pieces of bench.py that run without a GPU: the reference arm (CPU port of the
+reference kernels on a bounded sample), its JSON contract, and the helpers' behaviour when NVML /
+nvidia-smi are absent."""
+
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(args, env_extra=None):
+    env = dict(os.environ, **(env_extra or {}))
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True,
+                          cwd=ROOT, env=env, timeout=300)
+
+
+def test_reference_arm_json_line():
+    r = _run(["--impl", "reference", "--scale", "0.05", "--steps", "1", "--warmup", "0", "--gpus", "2"])
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "output Mpix*band/s" and line["unit"] == "Mpix*band/s"
+    assert line["higher_is_better"] is True and line["n_gpus"] == 2 and line["gpu_launches"] == 0
+    assert line["value"] > 0 and line["e2e"]["value"] == line["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    cpu = line["cpu_baseline"]
+    assert cpu["kind"] == "port" and cpu["cores"] >= 1 and cpu["value"] == line["value"] and "swath" in cpu["sample"]
+    assert "workload" in line["config"] and "bounded_sample" in line["config"]
+    assert line["config"]["scenes_per_step"] == 2
+
+
+def test_reference_arm_only_rank_zero_works():
+    r = _run(["--impl", "reference", "--scale", "0.05", "--steps", "1", "--warmup", "0"], {"RANK": "1", "WORLD_SIZE": "2"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_helpers_without_nvml():
+    sys.path.insert(0, ROOT)
+    import bench
+
+    sampler = bench.ClockSampler(0)
+    sampler.start()
+    clocks = sampler.stop()
+    assert set(clocks) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    before = os.sched_getaffinity(0)
+    assert bench.pin_to_gpu_numa_node(0) == before
+    assert os.sched_getaffinity(0) == before  # no NVML here: affinity untouched
+    cfg = bench.workload_config(4865, 4091, 21, (7992, 5013), 8)
+    assert cfg["scenes_per_step"] == 8 and "rectify_dataset" in cfg["workload"]
