@@ -102,3 +102,29 @@ def test_to_coords_keeps_the_dtype_of_reused_coordinates():
                                   DataArray(cv["y"].values.astype(np.float32), dims="y"), gm.crs)
     cv2 = gm2.to_coords(xy_var_names=("a", "b"), xy_dim_names=("u", "v"), reuse_coords=True)
     assert cv2["a"].values.dtype == np.float32 and cv2["b"].values.dtype == np.float32
+
+
+def test_from_dataset_non_regular_cube():
+    """tests/gridmapping/test_dataset.py:40-66: 2-D float32 lon/lat variables of a swath."""
+    from xcube_resampling_b200.dataset import Dataset
+
+    lon = np.array([[8, 9.3, 10.6, 11.9], [8, 9.2, 10.4, 11.6], [8, 9.1, 10.2, 11.3]], dtype=np.float32)
+    lat = np.array([[56, 56.1, 56.2, 56.3], [55, 55.2, 55.4, 55.6], [54, 54.3, 54.6, 54.9]], dtype=np.float32)
+    rad = np.random.default_rng(0).random((3, 4))
+    ds = Dataset(dict(lon=DataArray(lon, dims=("y", "x")), lat=DataArray(lat, dims=("y", "x")),
+                      rad=DataArray(rad, dims=("y", "x"))))
+    gm = GridMapping.from_dataset(ds)
+    assert (gm.size, gm.tile_size, gm.crs) == ((4, 3), (4, 3), GEO)
+    assert (gm.is_regular, gm.is_lon_360, gm.is_j_axis_up) == (False, False, False)
+    assert gm.xy_coords.shape == (2, 3, 4) and gm.xy_coords.dims == ("coord", "y", "x")
+    assert gm.xy_res == (0.8, 0.8)
+
+
+def test_from_dataset_explicit_crs():
+    """tests/gridmapping/test_dataset.py:68-82."""
+    from xcube_resampling_b200.dataset import Dataset
+
+    ds = Dataset(data_vars={"var": (("lat", "lon"), np.random.default_rng(1).random((2, 2)))},
+                 coords={"lon": ("lon", np.array([0.0, 1.0])), "lat": ("lat", np.array([0.0, 1.0]))})
+    gm = GridMapping.from_dataset(ds, crs="EPSG:4326")
+    assert gm.is_regular and gm.crs == GEO
