@@ -202,6 +202,28 @@ def make_rectify(R, B):
     print("rectify.npz:", cases)
 
 
+def make_rectify_f32_coords(R, B):
+    """float32 coordinate images fed to the reference kernels as they are (rectify.py:480-501 builds
+    its vertex arrays in the coordinates' dtype).  Pins that up-casting float32 coordinates to
+    float64 first, as the C ABI requires, changes nothing."""
+    out = {}
+    cases = []
+    for name, w, h, theta, tile, j_up in [("f32_tiled32", 96, 80, 12.0, 32, False),
+                                          ("f32_tiled_17x40_jup", 70, 64, -25.0, (17, 40), True)]:
+        x, y = swath(w, h, theta=theta, seed=3)
+        x32, y32 = x.astype(np.float32), y.astype(np.float32)
+        g = regular_params(x32.astype(np.float64), y32.astype(np.float64), 0.0027, tile, j_up)
+        windows, ij = reference_rectify(R, B, x32, y32, g)
+        out[f"{name}/x"], out[f"{name}/y"] = x32, y32
+        out[f"{name}/grid"] = np.array([g["width"], g["height"], g["tile_w"], g["tile_h"], g["x_min"], g["y_min"],
+                                        g["x_max"], g["y_max"], g["x_res"], g["y_res"], float(g["j_up"])])
+        out[f"{name}/windows"], out[f"{name}/ij"] = windows, ij
+        cases.append(name)
+    out["cases"] = np.array(cases)
+    np.savez_compressed(os.path.join(HERE, "rectify_f32coords.npz"), **out)
+    print("rectify_f32coords.npz:", cases)
+
+
 def make_ij_bboxes(B):
     """compute_ij_bboxes on the fixture of tests/gridmapping/test_bboxes.py plus random boxes."""
     out = {}
@@ -231,6 +253,7 @@ def main():
     import xcube_resampling.rectify as R
 
     make_rectify(R, B)
+    make_rectify_f32_coords(R, B)
     make_ij_bboxes(B)
     try:
         from make_golden_resample import make_all as make_resample  # added with the affine/coarsen/reproject paths

@@ -40,6 +40,20 @@ def test_rectify_gather_matches_reference_kernels(case, method):
         assert_same(out, z[f"{case}/out_{vname}_{method}"], f"{vname}/{method}")
 
 
+@pytest.mark.parametrize("case", ["f32_tiled32", "f32_tiled_17x40_jup"])
+def test_rectify_float32_coordinates(case):
+    """The reference kernels were run on float32 coordinate images (rectify.py:480-501 keeps the
+    coordinates' dtype for the vertex arrays); the C ABI takes float64 only, so callers up-cast --
+    which must give the same windows and the same ij image, bit for bit."""
+    z = load_golden("rectify_f32coords.npz")
+    g = grid_from_golden(z[f"{case}/grid"])
+    x, y = z[f"{case}/x"], z[f"{case}/y"]
+    assert x.dtype == np.float32 and y.dtype == np.float32
+    x64, y64 = x.astype(np.float64), y.astype(np.float64)
+    assert_same(orect.source_windows(x64, y64, g), z[f"{case}/windows"], "windows")
+    assert_same(orect.rectify_ij(x64, y64, g), z[f"{case}/ij"], "ij")
+
+
 def test_ij_bboxes_match_reference_kernel():
     z = load_golden("ij_bboxes.npz")
     for k in range(int(z["n_cases"])):

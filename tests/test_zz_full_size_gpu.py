@@ -255,3 +255,25 @@ def test_c1_affine_full_size(xrs):
                      coords=dict(lon=source_gm.x_coords.values, lat=source_gm.y_coords.values))
     out = xrs.affine_transform_dataset(ds, target_gm, source_gm=source_gm, interp_methods=1)
     assert_same(out["refl"].values, ref, "C1 4096^2 -> 2048^2")
+
+
+# ---------------------------------------------------------------------------
+# float32 coordinate images (golden from the reference kernels run on float32 arrays)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["f32_tiled32", "f32_tiled_17x40_jup"])
+def test_rectify_float32_coordinates_golden(xrs, case):
+    """rectify_dataset up-casts float32 lon/lat to the float64 the C ABI takes; the reference, fed the
+    float32 arrays directly, produces the same windows and ij image (tests/golden/make_golden.py)."""
+    from .helpers import grid_from_golden, load_golden
+
+    z = load_golden("rectify_f32coords.npz")
+    g = grid_from_golden(z[f"{case}/grid"])
+    gm = xrs.GridMapping.regular((g.width, g.height), (g.x_min, g.y_min), (g.x_res, g.y_res), "EPSG:4326",
+                                 tile_size=(g.tile_w, g.tile_h), is_j_axis_up=g.is_j_axis_up)
+    assert (gm.x_min, gm.y_min, gm.y_max, gm.x_res, gm.y_res) == (g.x_min, g.y_min, g.y_max, g.x_res, g.y_res)
+    xd = xrs.dev.to_device(z[f"{case}/x"], dtype=np.float64)
+    yd = xrs.dev.to_device(z[f"{case}/y"], dtype=np.float64)
+    plan = xrs.rect.RectifyPlan(gm, xd.device)
+    windows = plan.windows(xd, yd)
+    assert_same(xrs.dev.to_host(windows), z[f"{case}/windows"], "K0 windows (float32 coordinates)")
+    assert_same(xrs.dev.to_host(plan.ij(xd, yd, windows)), z[f"{case}/ij"], "K1 ij (float32 coordinates)")
