@@ -102,6 +102,55 @@ int xrs_tile_src_bboxes(const double *x, const double *y, int64_t src_h, int64_t
                         const double *y_hi, int32_t nty, int32_t ij_border, int64_t *out_boxes, void *workspace,
                         void *stream);
 
+/* K0 over a ROW SLAB of the swath (multi-GPU: every GPU scans 1/N of the source rows), merged
+ * afterwards.  `minform_table` is (ntx*nty, 4) int32 in "min-form" -- (i_min, j_min, -i_max1, -j_max1)
+ * in whole-image indices, INT32_MAX = nothing seen (xrs_minform_init) -- so partial tables of
+ * different slabs combine with an element-wise MIN: one all-reduce(MIN) between processes, one
+ * numpy.minimum between threads.  x / y point at row `j_offset` of the (src_h, src_w) images.
+ * xrs_tile_src_bboxes_finalize turns the merged table into the int64 boxes of xrs_tile_src_bboxes
+ * (grown by ij_border, clipped to the whole image, bboxes.py:90-106).  The only exchange step of
+ * the rectification path. */
+int xrs_minform_init(int32_t *table, int64_t n, void *stream);
+int xrs_tile_src_bboxes_partial(const double *x, const double *y, int64_t slab_h, int64_t src_w, int64_t src_pitch,
+                                int64_t j_offset, const double *x_lo, const double *x_hi, int32_t ntx,
+                                const double *y_lo, const double *y_hi, int32_t nty, int32_t *minform_table,
+                                void *workspace, void *stream);
+int xrs_tile_src_bboxes_finalize(const int32_t *minform_table, int32_t n_tiles, int32_t ij_border, int64_t src_w,
+                                 int64_t src_h, int64_t *out_boxes, void *stream);
+
+/* Source footprint of target ROW BANDS (multi-GPU partition; the reference's per-tile
+ * source slicing is rectify.py:397-399).  For band b = target rows [band_edges[b], band_edges[b+1])
+ * and every group g of xrs_quad_row_group() source quad rows, minform_fp[(b*n_groups + g)*2 ..] holds
+ * (c_min, -c_max) over the quads of the scanned slab whose pixel box (grown by 2 px + 1 % of its
+ * extent) overlaps the band; INT32_MAX = none.  Every quad that can claim a pixel of the band is
+ * inside, so K1 restricted to the footprint (src_col_ranges) gives the same claims as K1 on the
+ * whole swath.  n_groups = ceil((src_h - 1) / group); the slab is rows [j_offset, j_offset + slab_h)
+ * of the image (include the first row of the next slab so that no quad row is lost) and j_offset
+ * must be a multiple of the group size.  Tables of different slabs merge with MIN. */
+int32_t xrs_quad_row_group(void);
+int xrs_band_quad_footprints(const double *x, const double *y, int64_t slab_h, int64_t src_w, int64_t src_pitch,
+                             int64_t j_offset, int64_t src_h, int64_t dst_h, int64_t dst_w, double x_min, double y_min,
+                             double y_max, double x_res, double y_res, int32_t is_j_axis_up,
+                             const int32_t *band_edges, int32_t n_bands, int32_t *minform_fp, void *stream);
+
+/* Strided copies between host and device on the copy engines: `slices` windows of `rows` rows of
+ * `width_bytes`, row pitches and slice strides in bytes on either side (cudaMemcpy2DAsync per slice,
+ * direction inferred from the pointers; host memory should be page-locked).  Ragged footprint
+ * uploads and row-band downloads into one shared host array go through this. */
+int xrs_copy2d_slices(void *dst, int64_t dst_pitch_bytes, int64_t dst_slice_bytes, const void *src,
+                      int64_t src_pitch_bytes, int64_t src_slice_bytes, int64_t width_bytes, int64_t rows,
+                      int64_t slices, void *stream);
+
+/* Statistics of 2-D coordinate images that stay on the device (CRS-transformed or pre-downscaled
+ * swath coordinates inside rectify_dataset): what GridMapping.from_coords needs from the WHOLE
+ * images.  out4 (device, 4 x uint64): [0] 1 if any x > 180 (coords.py:102-103), [1] / [2] bit
+ * patterns of the smallest / largest positive cell area of coords.py:226-252 (geographic grids:
+ * the reference's metre conversion), ~0 / 0 if there is none, [3] reserved.
+ * xrs_lon_360: x < 0 -> x + 360 in place (helpers.py to_lon_360). */
+int xrs_coords_stats(const double *x, const double *y, int64_t h, int64_t w, int64_t pitch, int32_t is_geographic,
+                     uint64_t *out4, void *stream);
+int xrs_lon_360(double *x, int64_t h, int64_t w, int64_t pitch, void *stream);
+
 /* K1 -- source-index (ij) image of a regular target grid.
  * Replaces _compute_target_source_ij / _compute_target_source_ij_block /
  * _compute_target_source_ij_sequential / _line (rectify.py:312-576) including
@@ -118,14 +167,18 @@ int xrs_tile_src_bboxes(const double *x, const double *y, int64_t src_h, int64_t
  *   row_begin/end only target rows [row_begin, row_end) are computed (multi-GPU row
  *                 bands); ij then is (2, row_end-row_begin, dst_w).  Results do not
  *                 depend on the band split.
+ *   src_col_ranges  NULL, or the band's row of the table of xrs_band_quad_footprints: per group
+ *                 of xrs_quad_row_group() source quad rows (c_min, -c_max) of the quads whose
+ *                 coordinates the caller made resident.  Only those quads are read -- x and y
+ *                 may then be buffers in which just the footprint has been uploaded.
  * workspace: xrs_rectify_ij_workspace_bytes(src_h, src_w, row_end - row_begin, dst_w) bytes,
  *            16-byte aligned. */
 int64_t xrs_rectify_ij_workspace_bytes(int64_t src_h, int64_t src_w, int64_t dst_rows, int64_t dst_w);
 int xrs_rectify_ij(const double *x, const double *y, int64_t src_h, int64_t src_w, int64_t src_pitch,
                    const int64_t *tile_boxes, double *ij, int64_t dst_h, int64_t dst_w, int32_t tile_h,
                    int32_t tile_w, double x_min, double y_min, double y_max, double x_res, double y_res,
-                   int32_t is_j_axis_up, double uv_delta, int64_t row_begin, int64_t row_end, void *workspace,
-                   void *stream);
+                   int32_t is_j_axis_up, double uv_delta, int64_t row_begin, int64_t row_end,
+                   const int32_t *src_col_ranges, void *workspace, void *stream);
 
 /* K2 -- gather of all bands through the ij image.
  * Replaces _compute_var_image / _compute_var_image_block /
@@ -157,8 +210,8 @@ int xrs_gather_ij(const void *const *src_planes_host, void *const *dst_planes_ho
 int xrs_rectify_gather(const double *x, const double *y, int64_t src_h, int64_t src_w, int64_t src_pitch,
                        const int64_t *tile_boxes, int64_t dst_h, int64_t dst_w, int32_t tile_h, int32_t tile_w,
                        double x_min, double y_min, double y_max, double x_res, double y_res, int32_t is_j_axis_up,
-                       double uv_delta, int64_t row_begin, int64_t row_end, void *workspace,
-                       const void *const *src_planes_host, void *const *dst_planes_host, int32_t n_bands, int32_t dtype,
+                       double uv_delta, int64_t row_begin, int64_t row_end, const int32_t *src_col_ranges,
+                       void *workspace, const void *const *src_planes_host, void *const *dst_planes_host, int32_t n_bands, int32_t dtype,
                        int64_t data_pitch, int64_t win_i0, int64_t win_j0, int64_t win_w, int64_t win_h, int32_t method,
                        double fill, void *stream);
 

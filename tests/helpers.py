@@ -32,3 +32,49 @@ def assert_same(a, b, what=""):
         idx = np.argwhere(bad)[:5]
         raise AssertionError(f"{what}: {bad.sum()} of {a.size} elements differ, first at {idx.tolist()}: "
                              f"{a[bad][:5]} vs {b[bad][:5]}")
+
+
+INT32_MAX = np.iinfo(np.int32).max
+
+
+def quad_footprints_np(x, y, g, band_edges, group=32, rows=None):
+    """numpy restatement of ``xrs_band_quad_footprints`` (csrc/bands.cu) -- our own partition logic,
+    not reference code: per target row band and per group of ``group`` source quad rows, the
+    min-form (c_min, -c_max) over the quads whose grown pixel box overlaps the band.  ``rows``
+    restricts the scan to the quad rows of vertex rows [rows[0], rows[1]) (a slab)."""
+    h, w = x.shape
+    n_bands = len(band_edges) - 1
+    n_groups = -(-(h - 1) // group)
+    out = np.full((n_bands, n_groups, 2), INT32_MAX, dtype=np.int32)
+    r0, r1 = (0, h) if rows is None else rows
+    inv_xr, inv_yr = 1.0 / g.x_res, 1.0 / g.y_res
+    with np.errstate(invalid="ignore", over="ignore"):
+        fx = (x[r0:r1] - g.x_min) * inv_xr
+        fy = (y[r0:r1] - g.y_min) * inv_yr if g.is_j_axis_up else (g.y_max - y[r0:r1]) * inv_yr
+        ok = (np.abs(fx) < 1e15) & (np.abs(fy) < 1e15)
+    corners = [(slice(0, -1), slice(0, -1)), (slice(0, -1), slice(1, None)), (slice(1, None), slice(0, -1)),
+               (slice(1, None), slice(1, None))]
+    n_ok = sum(ok[c].astype(np.int32) for c in corners)
+    lo_x = np.minimum.reduce([np.where(ok[c], fx[c], np.inf) for c in corners])
+    hi_x = np.maximum.reduce([np.where(ok[c], fx[c], -np.inf) for c in corners])
+    lo_y = np.minimum.reduce([np.where(ok[c], fy[c], np.inf) for c in corners])
+    hi_y = np.maximum.reduce([np.where(ok[c], fy[c], -np.inf) for c in corners])
+    with np.errstate(invalid="ignore"):
+        mrg = 2.0 + 0.01 * np.maximum(hi_x - lo_x, hi_y - lo_y)
+        lo_x, hi_x = np.floor(lo_x) - mrg, np.floor(hi_x) + mrg
+        lo_y, hi_y = np.floor(lo_y) - mrg, np.floor(hi_y) + mrg
+        hit = (n_ok >= 3) & (hi_x >= 0.0) & (lo_x < g.width) & (hi_y >= 0.0) & (lo_y < g.height)
+        r_lo = np.where(hit, np.maximum(lo_y, 0.0), 0).astype(np.int64)
+        r_hi = np.where(hit, np.minimum(hi_y, g.height - 1.0), -1).astype(np.int64)
+    qj, qi = np.nonzero(hit)
+    for b in range(n_bands):
+        e0, e1 = band_edges[b], band_edges[b + 1]
+        if e0 >= e1:
+            continue
+        sel = (r_lo[qj, qi] < e1) & (r_hi[qj, qi] >= e0)
+        gj = (qj[sel] + r0) // group
+        for gi in np.unique(gj):
+            cols = qi[sel][gj == gi]
+            out[b, gi, 0] = min(out[b, gi, 0], cols.min())
+            out[b, gi, 1] = min(out[b, gi, 1], -cols.max())
+    return out

@@ -129,7 +129,76 @@ def _reproject_worker(rank, world, port, result_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("worker", [_rectify_worker, _reproject_worker])
+def _footprint_worker(rank, world, port, result_dir):
+    """The product multi-GPU path's host logic (multigpu.py) with the kernels stood in for by numpy /
+    the oracle: slab scans, the MIN exchange over the process group, ragged upload plan, and the
+    claim that a band computed from ONLY its footprint equals the whole-image result."""
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from xcube_resampling_b200 import multigpu
+
+        from .helpers import INT32_MAX, quad_footprints_np
+
+        w, h, res, tile, group = 200, 170, 0.0027, 64, 32
+        lon, lat = swath(w, h, res=res, theta=-17.0, seed=5)
+        lon[60:63, 40:70] = np.nan  # a hole: quads with fewer than three finite vertices do not count
+        size, xy_min = covering_grid_args(lon, lat, res)
+        gm = GridMapping.regular(size, xy_min, res, "EPSG:4326", tile_size=tile)
+        g = ogrid.regular_grid(size, xy_min, res, tile_size=tile)
+        edges = multigpu.default_band_edges(gm.height, world)
+        assert edges[0] == 0 and edges[-1] == gm.height and len(edges) == world + 1
+        # slab scan (numpy stand-in for xrs_band_quad_footprints) + exchange
+        slabs = multigpu.source_slabs(h, world, group)
+        assert slabs[0][0] == 0 and slabs[-1][1] == h and all(a[1] == b[0] and a[0] % group == 0 for a, b in zip(slabs, slabs[1:]))
+        s0, s1 = slabs[rank]
+        part = quad_footprints_np(lon, lat, g, edges, group, rows=(s0, min(h, s1 + 1)))
+        merged = multigpu.DistExchange().merge(rank, torch.from_numpy(part.copy())).numpy()
+        whole = quad_footprints_np(lon, lat, g, edges, group)
+        assert np.array_equal(merged, whole), "merged slab tables differ from the whole-swath table"
+        assert np.array_equal(multigpu.merge_minform_host([part, whole]), whole)
+        # upload plan of this rank's band
+        window, segments, n_px = multigpu.footprint_segments(merged[rank], h, w, group, merge_groups=2, align=8)
+        assert window is not None and 0 < n_px < h * w, (window, n_px)
+        assert segments[0][0] == window[0] and segments[-1][1] == window[1]
+        assert all(a[1] <= b[0] for a, b in zip(segments, segments[1:])), "segments overlap"
+        keep = np.zeros((h, w), dtype=bool)
+        for j0, j1, i0, i1 in segments:
+            keep[j0:j1, i0:i1] = True
+        # every vertex of a footprint quad and every tap reachable through it (+2) is uploaded
+        fp = merged[rank].astype(np.int64)
+        for gi in range(fp.shape[0]):
+            if fp[gi, 0] == INT32_MAX:
+                continue
+            lo, hi = fp[gi, 0], -fp[gi, 1]
+            rows_needed = slice(gi * group, min(h, gi * group + group + 2))
+            assert keep[rows_needed, lo:min(w, hi + 3)].all(), f"group {gi}: footprint not covered by the segments"
+        # K1 restricted to the footprint (quads outside never read) + gather from the uploaded data only
+        rows = (edges[rank], edges[rank + 1])
+        boxes = orect.source_windows(lon, lat, g)
+        vert = np.zeros((h, w), dtype=bool)
+        for gi in range(fp.shape[0]):
+            if fp[gi, 0] == INT32_MAX:
+                continue
+            lo, hi = fp[gi, 0], -fp[gi, 1]
+            vert[gi * group:min(h, gi * group + group + 1), lo:hi + 2] = True
+        assert not (vert & ~keep).any()
+        lon_m, lat_m = np.where(vert, lon, np.nan), np.where(vert, lat, np.nan)
+        ij_full = orect.rectify_ij(lon, lat, g, windows=boxes)
+        ij_band = orect.rectify_ij(lon_m, lat_m, g, windows=boxes)[:, rows[0]:rows[1]]
+        assert np.array_equal(ij_band, ij_full[:, rows[0]:rows[1]], equal_nan=True), "band ij from the footprint differs"
+        data = np.random.default_rng(0).random((3, h, w)).astype(np.float32)
+        masked = np.where(keep[None], data, np.float32(-777.0))
+        for method in ("nearest", "bilinear", "triangular"):
+            part_out = orect.gather(masked, ij_band, method, np.nan)
+            full_out = orect.gather(data, ij_full, method, np.nan)[:, rows[0]:rows[1]]
+            assert np.array_equal(part_out, full_out, equal_nan=True), (rank, method)
+        open(os.path.join(result_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("worker", [_rectify_worker, _reproject_worker, _footprint_worker])
 def test_two_rank_row_bands_gloo(worker, tmp_path):
     world = 2
     mp.spawn(worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)

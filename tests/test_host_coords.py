@@ -128,3 +128,21 @@ def test_from_dataset_explicit_crs():
                  coords={"lon": ("lon", np.array([0.0, 1.0])), "lat": ("lat", np.array([0.0, 1.0]))})
     gm = GridMapping.from_dataset(ds, crs="EPSG:4326")
     assert gm.is_regular and gm.crs == GEO
+
+
+def test_from_coords_skips_nan_in_the_edge_rows_and_columns():
+    """xarray's .min() / .max() skip NaN (coords.py:272-281): NaN-padded swath edges must not break
+    the bounding box (np.min / np.max raised 'cannot convert float NaN to integer')."""
+    from xcube_resampling_b200.synthetic import swath
+
+    lon, lat = swath(40, 30, theta=15.0, seed=1)
+    clean = GridMapping.from_coords(lon, lat, "EPSG:4326", xy_res=0.0027, xy_dim_names=("x", "y"))
+    for (j, i) in ((0, 3), (29, 0), (10, 0), (5, 39), (29, 39)):
+        x, y = lon.copy(), lat.copy()
+        x[j, i] = np.nan
+        y[j, i] = np.nan
+        gm = GridMapping.from_coords(x, y, "EPSG:4326", xy_res=0.0027, xy_dim_names=("x", "y"))
+        assert all(np.isfinite(v) for v in gm.xy_bbox)
+        assert gm.size == clean.size
+        for a, b in zip(gm.xy_bbox, clean.xy_bbox):
+            assert abs(a - b) < 0.01

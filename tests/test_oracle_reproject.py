@@ -62,6 +62,39 @@ def test_webmerc_known_values():
     np.testing.assert_allclose(y, [0.0, 20037508.342789244], atol=1e-5)
 
 
+# EPSG:3857 has no vector in the reference's own tests; these are the published ones:
+# IOGP Guidance Note 7-2, section 3.5.1 "Popular Visualisation Pseudo-Mercator" worked example
+# (forward and reverse), and the square world extent +-pi * 6378137 m at latitude
+# atan(sinh(pi)) = 85.0511287798066 deg that EPSG:3857 tilings are defined on.
+GN7_2_LON, GN7_2_LAT = -(100 + 20 / 60), 24 + 22 / 60 + 54.433 / 3600
+GN7_2_E, GN7_2_N = -11169055.58, 2800000.00
+GN7_2_REV_N, GN7_2_REV_LAT = 2810000.00, 24 + 27 / 60 + 48.889 / 3600
+WORLD = 20037508.342789244
+
+
+def test_webmerc_guidance_note_7_2_example():
+    x, y = oproj.transform(oproj.from_epsg(4326), WEBMERC, np.array([GN7_2_LON]), np.array([GN7_2_LAT]))
+    assert abs(x[0] - GN7_2_E) < 0.005 and abs(y[0] - GN7_2_N) < 0.005  # published to the centimetre
+    lon, lat = oproj.transform(WEBMERC, oproj.from_epsg(4326), np.array([GN7_2_E]), np.array([GN7_2_REV_N]))
+    assert abs(lon[0] - GN7_2_LON) < 5e-8 and abs(lat[0] - GN7_2_REV_LAT) < 5e-8  # published to 0.001 arc second
+    x, y = oproj.transform(oproj.from_epsg(4326), WEBMERC, np.array([180.0, -180.0]),
+                           np.array([85.0511287798066, -85.0511287798066]))
+    np.testing.assert_allclose(x, [WORLD, -WORLD], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(y, [WORLD, -WORLD], rtol=0, atol=2e-6)
+
+
+def test_transform_bounds_webmerc_tile_at_the_antimeridian():
+    """The easternmost tile of config C5 (36000^2 over the world extent, tile 4500): its box ends on
+    x = +WORLD, i.e. on the antimeridian.  The densified boundary must come back as a contiguous
+    longitude interval ending at 180 (not wrapped to -180), latitudes from the closed form."""
+    t = 2 * WORLD / 8
+    box = oproj.transform_bounds(WEBMERC, oproj.from_epsg(4326), WORLD - t, 0.0, WORLD, t)
+    assert abs(box[0] - 135.0) < 1e-9 and abs(box[2] - 180.0) < 1e-9
+    assert box[1] == 0.0 and abs(box[3] - np.degrees(np.arctan(np.sinh(t / 6378137.0)))) < 1e-12
+    west = oproj.transform_bounds(WEBMERC, oproj.from_epsg(4326), -WORLD, -t, -WORLD + t, 0.0)
+    assert abs(west[0] + 180.0) < 1e-9 and abs(west[2] + 135.0) < 1e-9
+
+
 # ---------------------------------------------------------------------------
 # _reproject_block
 # ---------------------------------------------------------------------------

@@ -254,7 +254,8 @@ def test_c_abi_rejects_bad_arguments(xrs):
 
 
 def test_band_pipeline_equals_plain_path(xrs, monkeypatch):
-    """Chunked upload / gather / download overlap (BandPipeline) gives the same bytes."""
+    """The band-chunk pipeline (upload / gather / download overlapped, shared ij image) gives the same
+    bytes as the fused single-variable path (ij resolved in registers) -- and both match the oracle."""
     from xcube_resampling_b200 import rectify as xrect
 
     w, h = 300, 220
@@ -273,6 +274,8 @@ def test_band_pipeline_equals_plain_path(xrs, monkeypatch):
         piped = xrs.rectify_dataset(ds, target_gm=target_gm, source_gm=source_gm, interp_methods=method)["bands"].values
         monkeypatch.undo()
         assert_same(piped, plain, method)
+        g = ogrid.regular_grid(size, xy_min, res, tile_size=128)
+        assert_same(piped, orect.gather(bands, orect.rectify_ij(x, y, g), method, nan), f"{method} vs oracle")
 
 
 # ---------------------------------------------------------------------------

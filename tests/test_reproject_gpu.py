@@ -112,6 +112,34 @@ def test_transform_bounds_matches_oracle(xrs):
         np.testing.assert_allclose(got[k], want, rtol=0, atol=1e-11)
 
 
+def test_webmerc_published_known_answers(xrs):
+    """EPSG:3857 has no vector in the reference's tests: IOGP Guidance Note 7-2 section 3.5.1 worked example
+    (forward and reverse) and the world-extent corners, through the device transform."""
+    lon, lat = -(100 + 20 / 60), 24 + 22 / 60 + 54.433 / 3600
+    x, y = xrs.rep.transform_points([lon], [lat], "EPSG:4326", "EPSG:3857")
+    assert abs(x[0] + 11169055.58) < 0.005 and abs(y[0] - 2800000.00) < 0.005
+    lon2, lat2 = xrs.rep.transform_points([-11169055.58], [2810000.00], "EPSG:3857", "EPSG:4326")
+    assert abs(lon2[0] - lon) < 5e-8 and abs(lat2[0] - (24 + 27 / 60 + 48.889 / 3600)) < 5e-8
+    world = 20037508.342789244
+    x, y = xrs.rep.transform_points([180.0, -180.0], [85.0511287798066, -85.0511287798066], "EPSG:4326", "EPSG:3857")
+    np.testing.assert_allclose(x, [world, -world], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(y, [world, -world], rtol=0, atol=2e-6)
+
+
+def test_transform_bounds_webmerc_tiles_at_the_antimeridian(xrs):
+    """Config C5's easternmost / westernmost tiles touch x = +-world extent: contiguous longitude
+    intervals ending at +-180, equal to the oracle's."""
+    world = 20037508.342789244
+    t = 2 * world / 8
+    boxes = np.array([[world - t, 0.0, world, t], [-world, -t, -world + t, 0.0], [-t, -t, t, t]])
+    got = xrs.rep.transform_bounds("EPSG:3857", "EPSG:4326", boxes)
+    for k in range(3):
+        want = oproj.transform_bounds(oproj.from_epsg(3857), oproj.from_epsg(4326), *boxes[k])
+        np.testing.assert_allclose(got[k], want, rtol=0, atol=1e-10)
+    assert abs(got[0][2] - 180.0) < 1e-9 and abs(got[0][0] - 135.0) < 1e-9
+    assert abs(got[1][0] + 180.0) < 1e-9 and abs(got[1][2] + 135.0) < 1e-9
+
+
 # ---------------------------------------------------------------------------
 # kernel arithmetic, identity transform: bit-exact
 # ---------------------------------------------------------------------------
@@ -378,17 +406,18 @@ def test_resample_in_space_dispatches_to_reproject(xrs):
     np.testing.assert_array_equal(out.band_1.values, EXPECTED_5X5)
 
 
-def test_band_pipeline_equals_plain_path(xrs, monkeypatch):
-    """reproject_dataset streams large variables in band chunks; same bytes as the plain path."""
+def test_band_pipeline_equals_plain_path(xrs):
+    """reproject_dataset streams every variable through the device in band chunks (1, 2, 4, ... bands,
+    upload / kernel / download overlapped); same bytes as one plain kernel call on the whole stack."""
     src_gm, tgt_gm = _case_utm_from_geographic(xrs, n=160, tile=64)
     rng = np.random.default_rng(8)
     data = rng.random((7, src_gm.height, src_gm.width)).astype(np.float32)
     ds = xrs.Dataset(data_vars=dict(v=xrs.DataArray(data, dims=("band", "lat", "lon"))),
                      coords=dict(lon=xrs.DataArray(src_gm.x_values, dims="lon"),
                                  lat=xrs.DataArray(src_gm.y_values, dims="lat")))
+    plan = xrs.rep.ReprojectPlan(src_gm, tgt_gm)
+    sd = xrs.dev.to_device(data)
     for method in ("nearest", "bilinear"):
-        plain = xrs.reproject_dataset(ds, tgt_gm, source_gm=src_gm, interp_methods=method)["v"].values
-        monkeypatch.setattr(xrs.rep, "_PIPELINE_MIN_BYTES", 0)
+        plain = xrs.dev.to_host(plan.run(sd, method, np.nan))
         piped = xrs.reproject_dataset(ds, tgt_gm, source_gm=src_gm, interp_methods=method)["v"].values
-        monkeypatch.undo()
         assert_same(piped, plain, method)

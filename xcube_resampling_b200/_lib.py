@@ -49,12 +49,22 @@ SIGNATURES = {
                                     c_p, c_p]),
     "xrs_rectify_ij_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64, c_i64]),
     "xrs_rectify_ij": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_i64, c_i64, c_i32, c_i32, c_f64, c_f64,
-                               c_f64, c_f64, c_f64, c_i32, c_f64, c_i64, c_i64, c_p, c_p]),
+                               c_f64, c_f64, c_f64, c_i32, c_f64, c_i64, c_i64, c_p, c_p, c_p]),
     "xrs_gather_ij": (c_int, [c_p, c_p, c_i32, c_i32, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_p, c_i64,
                               c_i64, c_i32, c_f64, c_p]),
     "xrs_rectify_gather": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, c_p, c_i64, c_i64, c_i32, c_i32, c_f64, c_f64, c_f64,
-                                   c_f64, c_f64, c_i32, c_f64, c_i64, c_i64, c_p, c_p, c_p, c_i32, c_i32, c_i64, c_i64,
+                                   c_f64, c_f64, c_i32, c_f64, c_i64, c_i64, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i64, c_i64,
                                    c_i64, c_i64, c_i64, c_i32, c_f64, c_p]),
+    "xrs_minform_init": (c_int, [c_p, c_i64, c_p]),
+    "xrs_tile_src_bboxes_partial": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_p, c_p, c_i32, c_p, c_p, c_i32,
+                                            c_p, c_p, c_p]),
+    "xrs_tile_src_bboxes_finalize": (c_int, [c_p, c_i32, c_i32, c_i64, c_i64, c_p, c_p]),
+    "xrs_quad_row_group": (c_i32, []),
+    "xrs_band_quad_footprints": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f64, c_f64,
+                                         c_f64, c_f64, c_f64, c_i32, c_p, c_i32, c_p, c_p]),
+    "xrs_coords_stats": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, c_i32, c_p, c_p]),
+    "xrs_lon_360": (c_int, [c_p, c_i64, c_i64, c_i64, c_p]),
+    "xrs_copy2d_slices": (c_int, [c_p, c_i64, c_i64, c_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_p]),
     "xrs_transform_points": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p]),
     "xrs_reproject": (c_int, [c_p, c_p, c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_p, c_p,
                               c_p, c_p, c_i64, c_i64, c_i32, c_i32, c_p, c_p, c_p, c_p, c_i32, c_i32, c_f64, c_f64,

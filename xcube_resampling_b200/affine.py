@@ -125,6 +125,18 @@ def _resample_array_dev(src: torch.Tensor, affine_matrix, output_hw, interp_meth
                                recover=recover)
 
 
+def resample_coords_dev(src: torch.Tensor, var_name, var, affine_matrix, target_size, interp_methods=None,
+                        agg_methods=None, recover_nans=False) -> torch.Tensor:
+    """What :func:`resample_dataset` does to ONE variable, device buffer in, device buffer out: the
+    per-variable option resolution of affine.py:176-205 followed by ``_resample_array``.  Used for the
+    2-D coordinate images of rectify's pre-downscale (rectify.py:234-260), which stay on the device."""
+    interp = _get_interp_method_int(interp_methods, var_name, var)
+    agg = _get_agg_method(agg_methods, var_name, var)
+    recover = _get_recover_nan(recover_nans, var_name, var)
+    fill = _get_fill_value(None, var_name, var)
+    return _resample_array_dev(src, affine_matrix, (target_size[1], target_size[0]), interp, agg, recover, fill)
+
+
 def resample_dataset(dataset, affine_matrix, yx_dims, target_size, target_tile_size, interp_methods=None,
                      agg_methods=None, recover_nans=False, fill_values=None) -> Dataset:
     """Resample every variable (data variables AND coordinates) with trailing ``yx_dims``.
@@ -147,6 +159,10 @@ def resample_dataset(dataset, affine_matrix, yx_dims, target_size, target_tile_s
             src = _dev.to_device(var.values)
             out = _resample_array_dev(src, affine_matrix, (target_size[1], target_size[0]), interp, agg, recover, fill)
             out_np = _dev.to_host(out).reshape(lead + (target_size[1], target_size[0]))
+            if out_np.dtype == np.int64 and var.dtype.kind == "u" and agg in ("sum", "prod"):
+                # np.nansum / np.nanprod of unsigned data return uint64 (coarsen.py:50-90); the kernel's
+                # two's-complement int64 accumulator holds the same bits
+                out_np = out_np.view(np.uint64)
             new_var = DataArray(out_np, dims=var.dims, attrs=var.attrs, name=var_name)
         elif yx_dims[0] not in var.dims and yx_dims[1] not in var.dims:
             new_var = var

@@ -29,6 +29,8 @@ SOURCES = {
     "capi.cu": [],
     "rectify.cu": ["-fmad=false"],
     "rectify_ij.cu": ["-fmad=false"],
+    "bands.cu": ["-fmad=false"],
+    "coords.cu": ["-fmad=false"],
     "gather.cu": ["-fmad=false"],
     "resample.cu": ["-fmad=false"],
     "resample_fast.cu": ["-fmad=false"],

@@ -1,0 +1,161 @@
+// bands.cu -- target row bands across GPUs: what a band needs from the source, and how it gets there.
+//
+// The reference fans rectification out over target tiles (rectify.py:263-309, dask.py:41-135) and
+// every tile task slices its source window out of the whole coordinate / data arrays
+// (rectify.py:397-399).  Here one GPU owns one target ROW BAND and must be handed, over PCIe, only
+// the part of the swath that can reach it:
+//
+//   xrs_band_quad_footprints   per band and per group of K1S_ROWS source quad rows, the range of quad
+//                              columns whose pixel box touches the band -- a ragged (diagonal, for a
+//                              rotated swath) footprint instead of the bounding box of tile windows.
+//                              Scans a row slab of the swath; slabs scanned on different GPUs are
+//                              merged with MIN (maxima stored negated, see rectify.cu "min-form").
+//   xrs_minform_init           fill a min-form table with "nothing seen"
+//   xrs_copy2d_slices          strided host<->device copies of (slices, rows, width) windows on the
+//                              copy engines (ragged footprint uploads, row-band downloads into one
+//                              host array)
+#include "rectify_common.cuh"
+
+namespace xrs {
+
+constexpr int KB_THREADS = 256;
+constexpr int KB_MAX_BANDS = 64;
+
+__global__ void kb_fill_i32(int32_t *p, int64_t n, int32_t v) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+struct BandGrid {
+    double x_min, y_min, y_max, inv_xr, inv_yr;
+    int j_up;
+    int64_t dst_w, dst_h;
+};
+
+// One block = KB_THREADS quad columns x K1S_ROWS quad rows (one row group); a thread marches down its
+// quad column.  A quad counts for every band its pixel box (grown by a margin that covers the
+// barycentric tolerance and the +-1 px between tile-local and global pixel arithmetic) overlaps.
+// Quads with fewer than three finite vertices cannot accept a pixel (both triangles hold a NaN).
+__global__ void __launch_bounds__(KB_THREADS)
+kb_quad_footprints(const double *__restrict__ x, const double *__restrict__ y, int64_t slab_h, int64_t src_w,
+                   int64_t pitch, int64_t j_offset, BandGrid g, const int32_t *__restrict__ band_edges, int n_bands,
+                   int n_groups, int32_t *__restrict__ fp) {
+    __shared__ int s_edges[KB_MAX_BANDS + 1];
+    __shared__ int s_tab[KB_MAX_BANDS][2];
+    for (int k = threadIdx.x; k <= n_bands; k += blockDim.x) s_edges[k] = band_edges[k];
+    for (int k = threadIdx.x; k < n_bands; k += blockDim.x) { s_tab[k][0] = INT32_MAX; s_tab[k][1] = INT32_MAX; }
+    __syncthreads();
+    const int64_t nqi = src_w - 1;
+    const int64_t n_col_chunks = ceil_div(nqi, KB_THREADS);
+    const int64_t chunk = blockIdx.x % n_col_chunks, row_chunk = blockIdx.x / n_col_chunks;
+    const int64_t qi = chunk * KB_THREADS + threadIdx.x;
+    const int64_t q0 = row_chunk * K1S_ROWS, q1 = min(q0 + K1S_ROWS, slab_h - 1);  // local quad rows
+    if (qi < nqi && q0 < q1) {
+        auto px = [&](double vx, double vy, double &fx, double &fy) {
+            fx = (vx - g.x_min) * g.inv_xr;
+            fy = g.j_up ? (vy - g.y_min) * g.inv_yr : (g.y_max - vy) * g.inv_yr;
+            return fabs(fx) < 1e15 && fabs(fy) < 1e15;  // false for NaN / inf
+        };
+        double ax, ay, bx, by;  // upper vertices of the current quad row
+        bool ok_a = px(__ldg(x + q0 * pitch + qi), __ldg(y + q0 * pitch + qi), ax, ay);
+        bool ok_b = px(__ldg(x + q0 * pitch + qi + 1), __ldg(y + q0 * pitch + qi + 1), bx, by);
+        const int ci = static_cast<int>(qi);
+        for (int64_t q = q0; q < q1; ++q) {
+            double cx, cy, dx, dy;
+            const bool ok_c = px(__ldg(x + (q + 1) * pitch + qi), __ldg(y + (q + 1) * pitch + qi), cx, cy);
+            const bool ok_d = px(__ldg(x + (q + 1) * pitch + qi + 1), __ldg(y + (q + 1) * pitch + qi + 1), dx, dy);
+            if (static_cast<int>(ok_a) + ok_b + ok_c + ok_d >= 3) {
+                double lo_x = INFINITY, hi_x = -INFINITY, lo_y = INFINITY, hi_y = -INFINITY;
+                if (ok_a) { lo_x = fmin(lo_x, ax); hi_x = fmax(hi_x, ax); lo_y = fmin(lo_y, ay); hi_y = fmax(hi_y, ay); }
+                if (ok_b) { lo_x = fmin(lo_x, bx); hi_x = fmax(hi_x, bx); lo_y = fmin(lo_y, by); hi_y = fmax(hi_y, by); }
+                if (ok_c) { lo_x = fmin(lo_x, cx); hi_x = fmax(hi_x, cx); lo_y = fmin(lo_y, cy); hi_y = fmax(hi_y, cy); }
+                if (ok_d) { lo_x = fmin(lo_x, dx); hi_x = fmax(hi_x, dx); lo_y = fmin(lo_y, dy); hi_y = fmax(hi_y, dy); }
+                const double mrg = 2.0 + 0.01 * fmax(hi_x - lo_x, hi_y - lo_y);
+                lo_x = floor(lo_x) - mrg; hi_x = floor(hi_x) + mrg;
+                lo_y = floor(lo_y) - mrg; hi_y = floor(hi_y) + mrg;
+                if (hi_x >= 0.0 && lo_x < static_cast<double>(g.dst_w) && hi_y >= 0.0 &&
+                    lo_y < static_cast<double>(g.dst_h)) {
+                    const int r_lo = static_cast<int>(fmax(lo_y, 0.0));
+                    const int r_hi = static_cast<int>(fmin(hi_y, static_cast<double>(g.dst_h - 1)));
+                    for (int b = 0; b < n_bands; ++b) {
+                        if (s_edges[b + 1] <= r_lo || s_edges[b] > r_hi || s_edges[b] >= s_edges[b + 1]) continue;
+                        atomicMin(&s_tab[b][0], ci);
+                        atomicMin(&s_tab[b][1], -ci);
+                    }
+                }
+            }
+            ax = cx; ay = cy; bx = dx; by = dy; ok_a = ok_c; ok_b = ok_d;
+        }
+    }
+    __syncthreads();
+    const int64_t group = j_offset / K1S_ROWS + row_chunk;
+    if (group < n_groups)
+        for (int b = threadIdx.x; b < n_bands; b += blockDim.x)
+            if (s_tab[b][0] != INT32_MAX) {
+                int32_t *e = fp + (static_cast<int64_t>(b) * n_groups + group) * 2;
+                atomicMin(e, s_tab[b][0]);
+                atomicMin(e + 1, s_tab[b][1]);
+            }
+}
+
+}  // namespace xrs
+
+using namespace xrs;
+
+extern "C" {
+
+int32_t xrs_quad_row_group(void) { return K1S_ROWS; }
+
+int xrs_minform_init(int32_t *table, int64_t n, void *stream) {
+    if (!table || n < 1) return fail("xrs_minform_init: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    XRS_TIMED("kb_fill_i32", st, kb_fill_i32<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, st>>>(table, n, INT32_MAX));
+    XRS_LAUNCH_CHECK("kb_fill_i32");
+    return 0;
+}
+
+int xrs_band_quad_footprints(const double *x, const double *y, int64_t slab_h, int64_t src_w, int64_t src_pitch,
+                             int64_t j_offset, int64_t src_h, int64_t dst_h, int64_t dst_w, double x_min, double y_min,
+                             double y_max, double x_res, double y_res, int32_t is_j_axis_up,
+                             const int32_t *band_edges, int32_t n_bands, int32_t *minform_fp, void *stream) {
+    if (!x || !y || !band_edges || !minform_fp) return fail("xrs_band_quad_footprints: null pointer");
+    if (slab_h < 2 || src_w < 2 || src_pitch < src_w || src_h < 2) return fail("xrs_band_quad_footprints: slab must hold at least 2x2 vertices");
+    if (j_offset < 0 || j_offset % K1S_ROWS != 0 || j_offset + slab_h > src_h)
+        return fail("xrs_band_quad_footprints: slab must start on a multiple of the quad row group and lie inside the source");
+    if (n_bands < 1 || n_bands > KB_MAX_BANDS) return fail("xrs_band_quad_footprints: 1..64 bands");
+    if (!(x_res > 0.0) || !(y_res > 0.0) || dst_h < 1 || dst_w < 1) return fail("xrs_band_quad_footprints: bad target grid");
+    if (src_w > INT32_MAX - 1 || src_h > INT32_MAX - 1) return fail("xrs_band_quad_footprints: source too large");
+    BandGrid g;
+    g.x_min = x_min; g.y_min = y_min; g.y_max = y_max; g.inv_xr = 1.0 / x_res; g.inv_yr = 1.0 / y_res;
+    g.j_up = is_j_axis_up ? 1 : 0; g.dst_w = dst_w; g.dst_h = dst_h;
+    const int n_groups = static_cast<int>(ceil_div(src_h - 1, K1S_ROWS));
+    const int64_t n_blocks = ceil_div(src_w - 1, KB_THREADS) * ceil_div(slab_h - 1, K1S_ROWS);
+    if (n_blocks > 0x7fffffffLL) return fail("xrs_band_quad_footprints: slab too large");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    XRS_TIMED("kb_quad_footprints", st, kb_quad_footprints<<<static_cast<unsigned>(n_blocks), KB_THREADS, 0, st>>>(x, y, slab_h, src_w, src_pitch, j_offset, g, band_edges, n_bands, n_groups, minform_fp));
+    XRS_LAUNCH_CHECK("kb_quad_footprints");
+    return 0;
+}
+
+int xrs_copy2d_slices(void *dst, int64_t dst_pitch_bytes, int64_t dst_slice_bytes, const void *src,
+                      int64_t src_pitch_bytes, int64_t src_slice_bytes, int64_t width_bytes, int64_t rows,
+                      int64_t slices, void *stream) {
+    if (!dst || !src) return fail("xrs_copy2d_slices: null pointer");
+    if (width_bytes < 0 || rows < 0 || slices < 0) return fail("xrs_copy2d_slices: negative extent");
+    if (width_bytes == 0 || rows == 0 || slices == 0) return 0;
+    if (dst_pitch_bytes < width_bytes || src_pitch_bytes < width_bytes) return fail("xrs_copy2d_slices: pitch smaller than the row width");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int64_t s = 0; s < slices; ++s) {
+        char *d = static_cast<char *>(dst) + s * dst_slice_bytes;
+        const char *p = static_cast<const char *>(src) + s * src_slice_bytes;
+        if (dst_pitch_bytes == width_bytes && src_pitch_bytes == width_bytes) {
+            XRS_CUDA(cudaMemcpyAsync(d, p, static_cast<size_t>(width_bytes) * rows, cudaMemcpyDefault, st));
+        } else {
+            XRS_CUDA(cudaMemcpy2DAsync(d, static_cast<size_t>(dst_pitch_bytes), p, static_cast<size_t>(src_pitch_bytes),
+                                       static_cast<size_t>(width_bytes), static_cast<size_t>(rows), cudaMemcpyDefault, st));
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -462,8 +462,8 @@ int xrs_gather_ij(const void *const *src_planes_host, void *const *dst_planes_ho
 int xrs_rectify_gather(const double *x, const double *y, int64_t src_h, int64_t src_w, int64_t src_pitch,
                        const int64_t *tile_boxes, int64_t dst_h, int64_t dst_w, int32_t tile_h, int32_t tile_w,
                        double x_min, double y_min, double y_max, double x_res, double y_res, int32_t is_j_axis_up,
-                       double uv_delta, int64_t row_begin, int64_t row_end, void *workspace,
-                       const void *const *src_planes_host, void *const *dst_planes_host, int32_t n_bands, int32_t dtype,
+                       double uv_delta, int64_t row_begin, int64_t row_end, const int32_t *src_col_ranges,
+                       void *workspace, const void *const *src_planes_host, void *const *dst_planes_host, int32_t n_bands, int32_t dtype,
                        int64_t data_pitch, int64_t win_i0, int64_t win_j0, int64_t win_w, int64_t win_h, int32_t method,
                        double fill, void *stream) {
     if (!src_planes_host || !dst_planes_host) return fail("xrs_rectify_gather: null pointer");
@@ -482,6 +482,7 @@ int xrs_rectify_gather(const double *x, const double *y, int64_t src_h, int64_t 
                               x_min, y_min, y_max, x_res, y_res, is_j_axis_up, uv_delta, row_begin, row_end, workspace,
                               &ijs.geom))
         return rc;
+    ijs.geom.fp_cols = src_col_ranges;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (int rc = k1_enqueue_claims(ijs.geom, st)) return rc;
     const int64_t n_rows = row_end - row_begin;

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(K0_THREADS)
 k0_tile_windows(const double *__restrict__ x, const double *__restrict__ y, int64_t h, int64_t w, int64_t pitch,
                 const double *__restrict__ g_x_lo, const double *__restrict__ g_x_hi, int ntx,
                 const double *__restrict__ g_y_lo, const double *__restrict__ g_y_hi, int nty,
-                int4 *__restrict__ table) {
+                int4 *__restrict__ table, int j_offset) {
     extern __shared__ __align__(16) unsigned char k0_smem[];
     double *s_x_lo = reinterpret_cast<double *>(k0_smem);
     double *s_x_hi = s_x_lo + ntx;
@@ -113,9 +113,9 @@ k0_tile_windows(const double *__restrict__ x, const double *__restrict__ y, int6
                 for (int tx = rx.a; tx <= rx.b; ++tx) {
                     int *e = reinterpret_cast<int *>(tab + ty * ntx + tx);
                     atomicMin(e + 0, ci);
-                    atomicMin(e + 1, j_first);
+                    atomicMin(e + 1, j_first + j_offset);
                     atomicMax(e + 2, ci + 1);
-                    atomicMax(e + 3, j_last + 1);
+                    atomicMax(e + 3, j_last + 1 + j_offset);
                 }
             }
         };
@@ -179,6 +179,40 @@ __global__ void k0_finalize(const int4 *__restrict__ table, int n, int ij_border
     out[4 * t + 0] = b0; out[4 * t + 1] = b1; out[4 * t + 2] = b2; out[4 * t + 3] = b3;
 }
 
+// "Min-form" tables: every entry is merged across partial scans (row slabs of the swath handled by
+// different GPUs) with MIN alone -- maxima are stored negated -- so that one all-reduce(MIN) or one
+// element-wise minimum on the host combines them.  A tile entry is (i_min, j_min, -i_max1, -j_max1);
+// INT32_MAX everywhere = no source point seen.
+__global__ void k0_fold_minform(const int4 *__restrict__ table, int n, int32_t *__restrict__ minform) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int4 e = table[t];
+    if (e.z < 0) return;
+    atomicMin(minform + 4 * t + 0, e.x);
+    atomicMin(minform + 4 * t + 1, e.y);
+    atomicMin(minform + 4 * t + 2, -e.z);
+    atomicMin(minform + 4 * t + 3, -e.w);
+}
+
+__global__ void k0_finalize_minform(const int32_t *__restrict__ minform, int n, int ij_border, int64_t w, int64_t h,
+                                    int64_t *__restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int64_t b0 = -1, b1 = -1, b2 = -1, b3 = -1;
+    if (minform[4 * t] != INT32_MAX) {
+        b0 = minform[4 * t]; b1 = minform[4 * t + 1]; b2 = -static_cast<int64_t>(minform[4 * t + 2]);
+        b3 = -static_cast<int64_t>(minform[4 * t + 3]);
+        if (ij_border != 0) {  // bboxes.py:90-106
+            b0 -= ij_border; b1 -= ij_border; b2 += ij_border; b3 += ij_border;
+            if (b0 < 0) b0 = 0;
+            if (b1 < 0) b1 = 0;
+            if (b2 > w) b2 = w;
+            if (b3 > h) b3 = h;
+        }
+    }
+    out[4 * t + 0] = b0; out[4 * t + 1] = b1; out[4 * t + 2] = b2; out[4 * t + 3] = b3;
+}
+
 }  // namespace xrs
 
 using namespace xrs;
@@ -189,36 +223,74 @@ int64_t xrs_tile_src_bboxes_workspace_bytes(int32_t ntx, int32_t nty) {
     return static_cast<int64_t>(ntx) * nty * static_cast<int64_t>(sizeof(int4));
 }
 
-int xrs_tile_src_bboxes(const double *x, const double *y, int64_t src_h, int64_t src_w, int64_t src_pitch,
-                        const double *x_lo, const double *x_hi, int32_t ntx, const double *y_lo,
-                        const double *y_hi, int32_t nty, int32_t ij_border, int64_t *out_boxes, void *workspace,
-                        void *stream) {
-    if (!x || !y || !x_lo || !x_hi || !y_lo || !y_hi || !out_boxes || !workspace) return fail("xrs_tile_src_bboxes: null pointer");
-    if (src_h < 1 || src_w < 1 || src_pitch < src_w) return fail("xrs_tile_src_bboxes: bad source shape");
-    if (ntx < 1 || nty < 1 || ntx > 65535 || nty > 65535) return fail("xrs_tile_src_bboxes: tile counts must be in [1, 65535]");
-    if (src_w > INT32_MAX - 1 || src_h > INT32_MAX - 1) return fail("xrs_tile_src_bboxes: source too large");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int k0_scan(const char *who, const double *x, const double *y, int64_t src_h, int64_t src_w, int64_t src_pitch,
+                   int64_t j_offset, const double *x_lo, const double *x_hi, int32_t ntx, const double *y_lo,
+                   const double *y_hi, int32_t nty, int4 *table, cudaStream_t st) {
+    const std::string w(who);
+    if (!x || !y || !x_lo || !x_hi || !y_lo || !y_hi || !table) return fail(w + ": null pointer");
+    if (src_h < 1 || src_w < 1 || src_pitch < src_w) return fail(w + ": bad source shape");
+    if (ntx < 1 || nty < 1 || ntx > 65535 || nty > 65535) return fail(w + ": tile counts must be in [1, 65535]");
+    if (src_w > INT32_MAX - 1 || src_h + j_offset > INT32_MAX - 1 || j_offset < 0) return fail(w + ": source too large");
     const int n_tiles = ntx * nty;
-    int4 *table = static_cast<int4 *>(workspace);
     XRS_TIMED("k0_init_table", st, k0_init_table<<<static_cast<unsigned>(ceil_div(n_tiles, 256)), 256, 0, st>>>(table, n_tiles));
     XRS_LAUNCH_CHECK("k0_init_table");
 
     const int64_t n_blocks = ceil_div(src_w, K0_THREADS) * ceil_div(src_h, K0_ROWS);
-    if (n_blocks > 0x7fffffffLL) return fail("xrs_tile_src_bboxes: source too large");
+    if (n_blocks > 0x7fffffffLL) return fail(w + ": source too large");
     const unsigned grid = static_cast<unsigned>(n_blocks);
     const size_t axis_bytes = static_cast<size_t>(2 * ntx + 2 * nty) * sizeof(double);
+    const int joff = static_cast<int>(j_offset);
     if (n_tiles <= K0_SMEM_TILES) {
         const size_t smem = axis_bytes + static_cast<size_t>(n_tiles) * sizeof(int4);
         XRS_CUDA(cudaFuncSetAttribute(k0_tile_windows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        XRS_TIMED("k0_tile_windows", st, k0_tile_windows<true><<<grid, K0_THREADS, smem, st>>>(x, y, src_h, src_w, src_pitch, x_lo, x_hi, ntx, y_lo, y_hi, nty, table));
+        XRS_TIMED("k0_tile_windows", st, k0_tile_windows<true><<<grid, K0_THREADS, smem, st>>>(x, y, src_h, src_w, src_pitch, x_lo, x_hi, ntx, y_lo, y_hi, nty, table, joff));
     } else {
-        if (axis_bytes > 200 * 1024) return fail("xrs_tile_src_bboxes: too many tile rows/columns");
+        if (axis_bytes > 200 * 1024) return fail(w + ": too many tile rows/columns");
         XRS_CUDA(cudaFuncSetAttribute(k0_tile_windows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(axis_bytes)));
-        XRS_TIMED("k0_tile_windows", st, k0_tile_windows<false><<<grid, K0_THREADS, axis_bytes, st>>>(x, y, src_h, src_w, src_pitch, x_lo, x_hi, ntx, y_lo, y_hi, nty, table));
+        XRS_TIMED("k0_tile_windows", st, k0_tile_windows<false><<<grid, K0_THREADS, axis_bytes, st>>>(x, y, src_h, src_w, src_pitch, x_lo, x_hi, ntx, y_lo, y_hi, nty, table, joff));
     }
     XRS_LAUNCH_CHECK("k0_tile_windows");
+    return 0;
+}
+
+int xrs_tile_src_bboxes(const double *x, const double *y, int64_t src_h, int64_t src_w, int64_t src_pitch,
+                        const double *x_lo, const double *x_hi, int32_t ntx, const double *y_lo,
+                        const double *y_hi, int32_t nty, int32_t ij_border, int64_t *out_boxes, void *workspace,
+                        void *stream) {
+    if (!out_boxes || !workspace) return fail("xrs_tile_src_bboxes: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int4 *table = static_cast<int4 *>(workspace);
+    if (int rc = k0_scan("xrs_tile_src_bboxes", x, y, src_h, src_w, src_pitch, 0, x_lo, x_hi, ntx, y_lo, y_hi, nty, table, st))
+        return rc;
+    const int n_tiles = ntx * nty;
     XRS_TIMED("k0_finalize", st, k0_finalize<<<static_cast<unsigned>(ceil_div(n_tiles, 256)), 256, 0, st>>>(table, n_tiles, ij_border, src_w, src_h, out_boxes));
     XRS_LAUNCH_CHECK("k0_finalize");
+    return 0;
+}
+
+int xrs_tile_src_bboxes_partial(const double *x, const double *y, int64_t slab_h, int64_t src_w, int64_t src_pitch,
+                                int64_t j_offset, const double *x_lo, const double *x_hi, int32_t ntx,
+                                const double *y_lo, const double *y_hi, int32_t nty, int32_t *minform_table,
+                                void *workspace, void *stream) {
+    if (!minform_table || !workspace) return fail("xrs_tile_src_bboxes_partial: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int4 *table = static_cast<int4 *>(workspace);
+    if (int rc = k0_scan("xrs_tile_src_bboxes_partial", x, y, slab_h, src_w, src_pitch, j_offset, x_lo, x_hi, ntx, y_lo,
+                         y_hi, nty, table, st))
+        return rc;
+    const int n_tiles = ntx * nty;
+    XRS_TIMED("k0_fold_minform", st, k0_fold_minform<<<static_cast<unsigned>(ceil_div(n_tiles, 256)), 256, 0, st>>>(table, n_tiles, minform_table));
+    XRS_LAUNCH_CHECK("k0_fold_minform");
+    return 0;
+}
+
+int xrs_tile_src_bboxes_finalize(const int32_t *minform_table, int32_t n_tiles, int32_t ij_border, int64_t src_w,
+                                 int64_t src_h, int64_t *out_boxes, void *stream) {
+    if (!minform_table || !out_boxes) return fail("xrs_tile_src_bboxes_finalize: null pointer");
+    if (n_tiles < 1) return fail("xrs_tile_src_bboxes_finalize: n_tiles must be >= 1");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    XRS_TIMED("k0_finalize", st, k0_finalize_minform<<<static_cast<unsigned>(ceil_div(n_tiles, 256)), 256, 0, st>>>(minform_table, n_tiles, ij_border, src_w, src_h, out_boxes));
+    XRS_LAUNCH_CHECK("k0_finalize_minform");
     return 0;
 }
 

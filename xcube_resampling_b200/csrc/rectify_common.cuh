@@ -27,6 +27,8 @@ struct IjGeom {
     int64_t row_begin, row_end;  // target rows computed by this call
     uint32_t *slow_list;         // quads that need the generic (multi-tile) treatment
     unsigned int *slow_count;
+    const int32_t *fp_cols;      // optional: per group of K1S_ROWS quad rows (c_min, -c_max) of the quads the
+                                 // caller made resident (xrs_band_quad_footprints); nullptr = whole swath
 };
 
 __device__ __forceinline__ double tri_det(double ax, double ay, double bx, double by, double cx, double cy) {

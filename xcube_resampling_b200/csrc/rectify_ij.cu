@@ -165,6 +165,11 @@ __global__ void k1_init_claims(uint4 *claims, int64_t n_vec, unsigned int *slow_
             clo = min(clo, static_cast<int>(b0));
             chi = max(chi, static_cast<int>(min(__ldg(bb + 2) + 1, g.src_w)) - 2);
         }
+        if (g.fp_cols) {  // caller-supplied footprint of the row band (min-form: c_min, -c_max)
+            clo = max(clo, static_cast<int>(__ldg(g.fp_cols + 2 * rb)));
+            const int neg_hi = __ldg(g.fp_cols + 2 * rb + 1);
+            chi = neg_hi == INT32_MAX ? -1 : min(chi, -neg_hi);
+        }
         col_range[2 * rb] = clo;
         col_range[2 * rb + 1] = chi;
     }
@@ -359,22 +364,28 @@ __global__ void __launch_bounds__(K1S_WARPS * 32, 2) k1_scatter(const __grid_con
     const int64_t j_end = min(min(static_cast<int64_t>(blockIdx.y + 1) * K1S_ROWS, nqj),
                               static_cast<int64_t>(qj_range[1]) + 1);  // quad rows [j_begin, j_end)
     if (j_begin >= j_end) return;
-    {   // quad columns visible to the requested target rows in this block of quad rows
-        const int *col_range = qj_range + 3 + 2 * blockIdx.y;
-        const int64_t c_lo = col_range[0], c_hi = col_range[1];
-        if (strip * 31 + 30 < c_lo || strip * 31 > c_hi) return;  // warp-uniform
-    }
-    const bool col_ok = col < g.src_w;
-    const bool quad_lane = lane < 31 && col < nqi;
+    // quad columns visible to the requested target rows in this block of quad rows: quads outside
+    // lie in no source window of the band's tiles (and outside the caller's footprint, whose
+    // coordinates need not even be resident), so neither they nor their vertices are touched
+    const int *col_range = qj_range + 3 + 2 * blockIdx.y;
+    const int64_t c_lo = col_range[0], c_hi = col_range[1];
+    if (strip * 31 + 30 < c_lo || strip * 31 > c_hi) return;  // warp-uniform
+    const bool col_ok = col < g.src_w && col >= c_lo && col <= c_hi + 1;
+    const bool quad_lane = lane < 31 && col < nqi && col >= c_lo && col <= c_hi;
 
     const double inv_xr = 1.0 / g.x_res, inv_yr = 1.0 / g.y_res;
     const double uv_lo = -g.uv_delta, uv_hi = dadd(1.0, dmul(2.0, g.uv_delta));
     const float inv_tw = 1.0f / static_cast<float>(g.tile_w), inv_th = 1.0f / static_cast<float>(g.tile_h);
     const int W = static_cast<int>(g.dst_w), R0 = static_cast<int>(g.row_begin), R1 = static_cast<int>(g.row_end);
     const double clamp_hi = static_cast<double>(max(g.dst_w, g.dst_h)) + 8.0;
-    // rounding of a pixel coordinate (two roundings of a value up to the image size) seen through an
-    // edge function's gradient, with a factor 8 to spare
-    const double coord_bound = 8.0 * 2.3e-16 * clamp_hi;
+    // rounding of a pixel coordinate seen through an edge function's gradient, with a factor 8 to
+    // spare.  Two sources: this kernel's own pixel coordinates (two roundings of a value up to the
+    // image size) and the reference's pixel centres x_off + (i + 0.5) * res (rectify.py:516-523), whose
+    // rounding error is an ulp of the CRS coordinate itself -- |x| / res pixels, which for metre grids
+    // (UTM northings of 5e6 m at 10 m) is far larger than the image size.
+    const double crs_mag = fmax(fmax(fabs(g.x_min), fabs(g.x_min + static_cast<double>(g.dst_w) * g.x_res)) * inv_xr,
+                                fmax(fabs(g.y_min), fabs(g.y_max)) * inv_yr);
+    const double coord_bound = 8.0 * 2.3e-16 * fmax(clamp_hi, crs_mag);
     const bool small_tolerance = g.uv_delta * (K1_MAX_EXTENT + 2.0) < 0.25;
     const int qi = static_cast<int>(col);
 
@@ -550,6 +561,7 @@ int k1_make_geom(const char *who, const double *x, const double *y, int64_t src_
     g.x_min = x_min; g.y_min = y_min; g.y_max = y_max; g.x_res = x_res; g.y_res = y_res;
     g.j_up = is_j_axis_up ? 1 : 0; g.uv_delta = uv_delta;
     g.row_begin = row_begin; g.row_end = row_end;
+    g.fp_cols = nullptr;
     g.slow_list = reinterpret_cast<uint32_t *>(static_cast<char *>(workspace) + claims_bytes_of(row_end - row_begin, dst_w));
     g.slow_count = reinterpret_cast<unsigned int *>(g.slow_list + (src_h - 1) * (src_w - 1));
     *out = g;
@@ -594,8 +606,8 @@ int64_t xrs_rectify_ij_workspace_bytes(int64_t src_h, int64_t src_w, int64_t dst
 int xrs_rectify_ij(const double *x, const double *y, int64_t src_h, int64_t src_w, int64_t src_pitch,
                    const int64_t *tile_boxes, double *ij, int64_t dst_h, int64_t dst_w, int32_t tile_h,
                    int32_t tile_w, double x_min, double y_min, double y_max, double x_res, double y_res,
-                   int32_t is_j_axis_up, double uv_delta, int64_t row_begin, int64_t row_end, void *workspace,
-                   void *stream) {
+                   int32_t is_j_axis_up, double uv_delta, int64_t row_begin, int64_t row_end,
+                   const int32_t *src_col_ranges, void *workspace, void *stream) {
     if (!ij) return fail("xrs_rectify_ij: null pointer");
     IjGeom g;
     if (int rc = k1_make_geom("xrs_rectify_ij", x, y, src_h, src_w, src_pitch, tile_boxes, dst_h, dst_w, tile_h, tile_w,
@@ -603,6 +615,7 @@ int xrs_rectify_ij(const double *x, const double *y, int64_t src_h, int64_t src_
                               &g))
         return rc;
     g.ij = ij;
+    g.fp_cols = src_col_ranges;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (int rc = k1_enqueue_claims(g, st)) return rc;
     const int64_t n_rows = row_end - row_begin;

@@ -148,8 +148,10 @@ class Dataset:
                 v = DataArray(arr, dims=(), name=name)
             else:
                 raise ValueError(f"variable {name!r}: give a DataArray or a (dims, data) tuple")
-        else:
+        elif type(v) is DataArray:
             v = DataArray(v, name=name)
+        else:  # a DataArray subclass (e.g. a device-resident coordinate placeholder) is kept as it is
+            v.name = name
         self._vars[name] = v
         if is_coord:
             self._coord_names.add(name)

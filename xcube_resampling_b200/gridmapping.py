@@ -199,6 +199,7 @@ class GridMapping:
         self._x_coords = None if x_coords is None else np.asarray(x_coords)
         self._y_coords = None if y_coords is None else np.asarray(y_coords)
         self._coords_lazy = x_coords is None and y_coords is None
+        self._x_dev = self._y_dev = None  # 2-D coordinates resident on a GPU (from_device_coords)
 
     # -- derived instances --------------------------------------------------
     def derive(self, /, xy_var_names=None, xy_dim_names=None, tile_size=None, is_j_axis_up=None) -> "GridMapping":
@@ -281,11 +282,19 @@ class GridMapping:
 
     def _new_x(self) -> np.ndarray:
         """regular.py:44-52."""
+        if self._x_dev is not None:  # device-resident 2-D coordinates: fetched only when asked for
+            from . import _dev
+
+            return _dev.to_host(self._x_dev)
         self._assert_regular()
         return _tiled_linspace(self.x_min + self.x_res / 2, self.x_max - self.x_res / 2, self.width, self.tile_width)
 
     def _new_y(self) -> np.ndarray:
         """regular.py:54-63."""
+        if self._y_dev is not None:
+            from . import _dev
+
+            return _dev.to_host(self._y_dev)
         self._assert_regular()
         y1, y2 = self.y_min + self.y_res / 2, self.y_max - self.y_res / 2
         if not self.is_j_axis_up:
@@ -587,20 +596,117 @@ class GridMapping:
         x_res, y_res = _to_int_or_float(x_res), _to_int_or_float(y_res)
         if xy_bbox is None:
             xh, yh = x_res / 2, y_res / 2
-            x_min = _to_int_or_float(np.min(x[..., 0]) - xh)
-            x_max = _to_int_or_float(np.max(x[..., -1]) + xh)
+            # xarray's .min() / .max() skip NaN (coords.py:272-281): NaN-padded swath edges are legal input
+            x_min = _to_int_or_float(float(np.nanmin(x[..., 0])) - xh)
+            x_max = _to_int_or_float(float(np.nanmax(x[..., -1])) + xh)
             if is_j_axis_up:
-                y_min = _to_int_or_float(float(np.min(y[0, ...])) - yh)
-                y_max = _to_int_or_float(float(np.max(y[-1, ...])) + yh)
+                y_min = _to_int_or_float(float(np.nanmin(y[0, ...])) - yh)
+                y_max = _to_int_or_float(float(np.nanmax(y[-1, ...])) + yh)
             else:
-                y_min = _to_int_or_float(float(np.min(y[-1, ...])) - yh)
-                y_max = _to_int_or_float(float(np.max(y[0, ...])) + yh)
+                y_min = _to_int_or_float(float(np.nanmin(y[-1, ...])) - yh)
+                y_max = _to_int_or_float(float(np.nanmax(y[0, ...])) + yh)
             xy_bbox = (x_min, y_min, x_max, y_max)
         if xy_dim_names is None:
             xy_dim_names = (str(x_dim), str(y_dim))
         return cls(x_coords=x, y_coords=y, crs=crs, size=size, tile_size=tile_size, xy_bbox=xy_bbox,
                    xy_res=(x_res, y_res), xy_var_names=tuple(xy_var_names), xy_dim_names=tuple(xy_dim_names),
                    is_regular=is_regular, is_lon_360=is_lon_360, is_j_axis_up=is_j_axis_up)
+
+    @property
+    def device_coords(self):
+        """(x, y) float64 device tensors when the 2-D coordinates live on a GPU, else ``None``."""
+        return None if self._x_dev is None else (self._x_dev, self._y_dev)
+
+    @classmethod
+    def from_device_coords(cls, x_dev, y_dev, crs, *, xy_res=None, xy_bbox=None, tile_size=None,
+                           tolerance: float = DEFAULT_TOLERANCE, xy_var_names=None,
+                           xy_dim_names=None) -> "GridMapping":
+        """:meth:`from_coords` (coords.py:99-337) for 2-D float64 coordinate images that are resident on
+        a GPU and stay there.  What the derivation needs from the whole images -- ``any(x > 180)`` and
+        the extreme cell areas behind the resolution estimate -- is reduced by one device pass
+        (``xrs_coords_stats``); the regularity test, bounding box and axis direction read the first /
+        last rows and columns only, which are the only values copied to the host.  ``x_values`` /
+        ``y_values`` fetch the images on demand."""
+        import torch
+
+        from . import _dev
+        from ._lib import check, load
+
+        lib = load()
+        crs = normalize_crs(crs)
+        if x_dev.dim() != 2 or x_dev.shape != y_dev.shape or x_dev.dtype != torch.float64 or y_dev.dtype != torch.float64:
+            raise ValueError("x_dev and y_dev must be 2-D float64 device tensors of equal shape")
+        if x_dev.stride(1) != 1 or y_dev.stride() != x_dev.stride():
+            x_dev, y_dev = x_dev.contiguous(), y_dev.contiguous()
+        if not isinstance(tolerance, float):
+            raise TypeError(f"tolerance must be an instance of {float}, was {type(tolerance)}")
+        if not tolerance > 0.0:
+            raise ValueError("tolerance must be greater zero")
+        height, width = x_dev.shape
+        if xy_var_names is None:
+            xy_var_names = ("lon", "lat") if crs.is_geographic else ("x", "y")
+        tile_size = _normalize_int_pair(tile_size, default=None)
+
+        def stats():
+            out = torch.empty(4, dtype=torch.int64, device=x_dev.device)
+            check(lib.xrs_coords_stats(_dev.ptr(x_dev), _dev.ptr(y_dev), height, width, x_dev.stride(0),
+                                       int(bool(crs.is_geographic)), _dev.ptr(out), _dev.stream_ptr(x_dev.device)),
+                  "xrs_coords_stats")
+            raw = _dev.to_host(out).view(np.uint64)
+            areas = raw[1:3].copy().view(np.float64)
+            return bool(raw[0]), (float(areas[0]) if raw[1] != np.uint64(0xFFFFFFFFFFFFFFFF) else math.nan,
+                                  float(areas[1]) if raw[2] != 0 else math.nan)
+
+        def edges():
+            parts = [x_dev[0], x_dev[-1], y_dev[0], y_dev[-1], x_dev[:, 0], x_dev[:, -1], y_dev[:, 0], y_dev[:, -1]]
+            flat = _dev.to_host(torch.cat([p.reshape(-1) for p in parts]))
+            out, pos = [], 0
+            for n in (width,) * 4 + (height,) * 4:
+                out.append(flat[pos:pos + n])
+                pos += n
+            return out
+
+        any_gt_180, areas = stats()
+        x_r0, x_r1, y_r0, y_r1, x_c0, x_c1, y_c0, y_c1 = edges()
+        is_lon_360 = any_gt_180 if crs.is_geographic else None
+        x_x_diff, x_y_diff = _abs_no_nan(np.diff(x_r0)), _abs_no_nan(np.diff(x_c0))
+        y_x_diff, y_y_diff = _abs_no_nan(np.diff(y_r0)), _abs_no_nan(np.diff(y_c0))
+        if not is_lon_360 and crs.is_geographic and (np.max(x_x_diff) > 180 or np.max(x_y_diff) > 180):
+            x_dev = x_dev.clone()
+            check(lib.xrs_lon_360(_dev.ptr(x_dev), height, width, x_dev.stride(0), _dev.stream_ptr(x_dev.device)),
+                  "xrs_lon_360")
+            _, areas = stats()
+            x_r0, x_r1, y_r0, y_r1, x_c0, x_c1, y_c0, y_c1 = edges()
+            x_x_diff, x_y_diff = _abs_no_nan(np.diff(x_r0)), _abs_no_nan(np.diff(x_c0))
+            is_lon_360 = True
+        if xy_res is not None:
+            x_res, y_res = _normalize_number_pair(xy_res)
+        else:
+            x_res, y_res = x_x_diff[0], y_y_diff[0]
+        is_regular = bool(np.allclose(x_x_diff, x_res, atol=tolerance) and np.allclose(y_y_diff, y_res, atol=tolerance)
+                          and np.allclose(x_y_diff, 0, atol=tolerance) and np.allclose(y_x_diff, 0, atol=tolerance))
+        if not is_regular and xy_res is None:
+            # coords.py:253-264 from the extreme areas
+            xy = 0.7 * math.sqrt(areas[0]) + 0.3 * math.sqrt(areas[1])
+            if crs.is_geographic:
+                xy = math.degrees(xy / _ER)
+            x_res = y_res = float(round_to_fraction(xy, digits=1, resolution=0.5))
+        is_j_axis_up = bool(np.all(y_r0 < y_r1))
+        if not (x_res > 0 and y_res > 0):
+            raise RuntimeError("internal error: x_res and y_res could not be determined")
+        x_res, y_res = _to_int_or_float(x_res), _to_int_or_float(y_res)
+        if xy_bbox is None:
+            xh, yh = x_res / 2, y_res / 2
+            y_first, y_last = (y_r0, y_r1) if is_j_axis_up else (y_r1, y_r0)
+            xy_bbox = (_to_int_or_float(float(np.nanmin(x_c0)) - xh), _to_int_or_float(float(np.nanmin(y_first)) - yh),
+                       _to_int_or_float(float(np.nanmax(x_c1)) + xh), _to_int_or_float(float(np.nanmax(y_last)) + yh))
+        if xy_dim_names is None:
+            xy_dim_names = ("x", "y")
+        gm = cls(crs=crs, size=(width, height), tile_size=tile_size, xy_bbox=xy_bbox, xy_res=(x_res, y_res),
+                 xy_var_names=tuple(xy_var_names), xy_dim_names=tuple(xy_dim_names), is_regular=is_regular,
+                 is_lon_360=is_lon_360, is_j_axis_up=is_j_axis_up)
+        gm._x_dev, gm._y_dev = x_dev, y_dev
+        return gm
 
     @classmethod
     def from_dataset(cls, dataset: Any, *, crs=None, tile_size=None, prefer_is_regular: bool = True, prefer_crs=None,

@@ -15,6 +15,7 @@ and return torch tensors used purely as device buffers.
 
 from __future__ import annotations
 
+import ctypes
 from collections.abc import Iterable
 
 import numpy as np
@@ -73,10 +74,10 @@ def _separable_axes(xy_bboxes: np.ndarray, xy_border: float):
 class RectifyPlan:
     """Device-resident constants and scratch buffers of one (source shape, target grid) pair.
 
-    Building the plan uploads the tile axis tables once and allocates the K0/K1 workspaces and
-    the ij buffer; afterwards :meth:`windows` and :meth:`ij` only enqueue kernels (no allocation,
-    no host<->device traffic, no synchronisation), which is what the steady state of a
-    scene-after-scene service looks like.
+    Building the plan uploads the tile axis tables once and allocates the K0 workspace; the K1
+    workspace and the ij buffer are allocated on first use.  Afterwards :meth:`windows` and
+    :meth:`ij` only enqueue kernels (no allocation, no host<->device traffic, no synchronisation),
+    which is what the steady state of a scene-after-scene service looks like.
     """
 
     def __init__(self, target_gm: GridMapping, device=None, rows: tuple[int, int] | None = None,
@@ -93,37 +94,99 @@ class RectifyPlan:
         self._axes = _dev.to_device(np.concatenate([x_lo, x_hi, y_lo, y_hi]), self.device)
         self.tile_boxes = _dev.empty((self.ntx * self.nty, 4), np.int64, self.device)
         self._ws0 = _dev.workspace(lib.xrs_tile_src_bboxes_workspace_bytes(self.ntx, self.nty), self.device)
-        self._ws1 = None  # K1 workspace, sized on first use (depends on the source shape)
-        self.ij_buf = _dev.empty((2, self.rows[1] - self.rows[0], W), np.float64, self.device)
+        self._ws1 = None      # K1 workspace, sized on first use (depends on the source shape)
+        self._ij_buf = None   # (2, rows, W) float64, allocated by the first ij() call
+        self._edges = None    # (band edges tuple, device tensor) of the last scan_slab call
+
+    @property
+    def ij_buf(self) -> torch.Tensor:
+        if self._ij_buf is None:
+            self._ij_buf = _dev.empty((2, self.rows[1] - self.rows[0], self.gm.width), np.float64, self.device)
+        return self._ij_buf
+
+    def _axes_ptrs(self):
+        base, ntx, nty = self._axes.data_ptr(), self.ntx, self.nty
+        return base, base + 8 * ntx, base + 16 * ntx, base + 16 * ntx + 8 * nty
 
     def windows(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         """K0: per-reference-tile source windows, (n_tiles, 4) int64 on the device."""
         _check_coords(x, y)
         h, w = x.shape
-        base, ntx, nty = self._axes.data_ptr(), self.ntx, self.nty
+        x_lo, x_hi, y_lo, y_hi = self._axes_ptrs()
         check(self.lib.xrs_tile_src_bboxes(
-            _dev.ptr(x), _dev.ptr(y), h, w, x.stride(0), base, base + 8 * ntx, ntx, base + 16 * ntx,
-            base + 16 * ntx + 8 * nty, nty, self.ij_border, _dev.ptr(self.tile_boxes), _dev.ptr(self._ws0),
-            _dev.stream_ptr(self.device)), "xrs_tile_src_bboxes")
+            _dev.ptr(x), _dev.ptr(y), h, w, x.stride(0), x_lo, x_hi, self.ntx, y_lo, y_hi, self.nty, self.ij_border,
+            _dev.ptr(self.tile_boxes), _dev.ptr(self._ws0), _dev.stream_ptr(self.device)), "xrs_tile_src_bboxes")
         return self.tile_boxes
+
+    # -- multi-GPU pieces (multigpu.py): slab scan -> exchange -> finalize ------------------
+    def scan_slab(self, xs: torch.Tensor, ys: torch.Tensor, j_offset: int, n_point_rows: int, src_h: int, src_w: int,
+                  band_edges, table: torch.Tensor) -> None:
+        """Scan rows ``j_offset ...`` of the swath held in ``xs`` / ``ys`` (which may carry one extra
+        vertex row that closes the slab's last quad row): K0 over the first ``n_point_rows`` rows and
+        the bands' quad footprints over all of them, both folded into the min-form ``table``
+        ([4 * n_tiles tile entries | 2 * n_bands * n_groups footprint entries], int32)."""
+        _check_coords(xs, ys)
+        edges = tuple(int(e) for e in band_edges)
+        if self._edges is None or self._edges[0] != edges:
+            self._edges = (edges, _dev.to_device(np.asarray(edges, dtype=np.int32), self.device))
+        n_tiles = self.ntx * self.nty
+        gm = self.gm
+        x_min, y_min, x_max, y_max = gm.xy_bbox
+        x_lo, x_hi, y_lo, y_hi = self._axes_ptrs()
+        st = _dev.stream_ptr(self.device)
+        check(self.lib.xrs_tile_src_bboxes_partial(
+            _dev.ptr(xs), _dev.ptr(ys), int(n_point_rows), src_w, xs.stride(0), int(j_offset), x_lo, x_hi, self.ntx,
+            y_lo, y_hi, self.nty, _dev.ptr(table), _dev.ptr(self._ws0), st), "xrs_tile_src_bboxes_partial")
+        if xs.shape[0] >= 2:
+            check(self.lib.xrs_band_quad_footprints(
+                _dev.ptr(xs), _dev.ptr(ys), xs.shape[0], src_w, xs.stride(0), int(j_offset), src_h, gm.height,
+                gm.width, float(x_min), float(y_min), float(y_max), float(gm.x_res), float(gm.y_res),
+                int(bool(gm.is_j_axis_up)), _dev.ptr(self._edges[1]), len(edges) - 1,
+                ctypes.c_void_p(table.data_ptr() + 16 * n_tiles), st), "xrs_band_quad_footprints")
+
+    def finalize_windows(self, table: torch.Tensor, src_w: int, src_h: int) -> torch.Tensor:
+        """Merged min-form tile entries -> the int64 tile boxes K1 reads (same values as :meth:`windows`)."""
+        check(self.lib.xrs_tile_src_bboxes_finalize(
+            _dev.ptr(table), self.ntx * self.nty, self.ij_border, src_w, src_h, _dev.ptr(self.tile_boxes),
+            _dev.stream_ptr(self.device)), "xrs_tile_src_bboxes_finalize")
+        return self.tile_boxes
+
+    def _ij_call(self, x_addr: int, y_addr: int, h: int, w: int, pitch: int, tile_boxes: torch.Tensor,
+                 col_ranges: torch.Tensor | None) -> torch.Tensor:
+        gm = self.gm
+        x_min, y_min, x_max, y_max = gm.xy_bbox
+        need = self.lib.xrs_rectify_ij_workspace_bytes(h, w, self.rows[1] - self.rows[0], gm.width)
+        if self._ws1 is None or self._ws1.numel() < need:
+            self._ws1 = _dev.workspace(need, self.device)
+        ij = self.ij_buf
+        check(self.lib.xrs_rectify_ij(
+            ctypes.c_void_p(x_addr), ctypes.c_void_p(y_addr), h, w, pitch, _dev.ptr(tile_boxes), _dev.ptr(ij), gm.height,
+            gm.width, gm.tile_height, gm.tile_width, float(x_min), float(y_min), float(y_max), float(gm.x_res),
+            float(gm.y_res), int(bool(gm.is_j_axis_up)), self.uv_delta, self.rows[0], self.rows[1],
+            None if col_ranges is None else _dev.ptr(col_ranges), _dev.ptr(self._ws1),
+            _dev.stream_ptr(self.device)), "xrs_rectify_ij")
+        return ij
 
     def ij(self, x: torch.Tensor, y: torch.Tensor, tile_boxes: torch.Tensor | None = None) -> torch.Tensor:
         """K0 (unless ``tile_boxes`` is given) + K1: the source-index image of ``rows``."""
         _check_coords(x, y)
         if tile_boxes is None:
             tile_boxes = self.windows(x, y)
-        gm = self.gm
-        x_min, y_min, x_max, y_max = gm.xy_bbox
         h, w = x.shape
-        need = self.lib.xrs_rectify_ij_workspace_bytes(h, w, self.rows[1] - self.rows[0], gm.width)
-        if self._ws1 is None or self._ws1.numel() < need:
-            self._ws1 = _dev.workspace(need, self.device)
-        check(self.lib.xrs_rectify_ij(
-            _dev.ptr(x), _dev.ptr(y), h, w, x.stride(0), _dev.ptr(tile_boxes), _dev.ptr(self.ij_buf), gm.height,
-            gm.width, gm.tile_height, gm.tile_width, float(x_min), float(y_min), float(y_max), float(gm.x_res),
-            float(gm.y_res), int(bool(gm.is_j_axis_up)), self.uv_delta, self.rows[0], self.rows[1],
-            _dev.ptr(self._ws1), _dev.stream_ptr(self.device)), "xrs_rectify_ij")
-        return self.ij_buf
+        return self._ij_call(x.data_ptr(), y.data_ptr(), h, w, x.stride(0), tile_boxes, None)
+
+    def ij_window(self, xw: torch.Tensor, yw: torch.Tensor, j0: int, src_h: int, src_w: int, tile_boxes: torch.Tensor,
+                  col_ranges: torch.Tensor) -> torch.Tensor:
+        """K1 when only a footprint of the coordinates is resident: ``xw`` / ``yw`` hold source rows
+        ``j0 : j0 + xw.shape[0]`` at full pitch and only the quads listed in ``col_ranges`` (the
+        band's row of the footprint table, min-form, int32 on the device) are read.  Indices in the
+        result refer to the whole image."""
+        _check_coords(xw, yw)
+        if col_ranges.dtype != torch.int32 or not col_ranges.is_contiguous():
+            raise TypeError("col_ranges must be a contiguous int32 device tensor")
+        off = int(j0) * xw.stride(0) * 8
+        return self._ij_call(xw.data_ptr() - off, yw.data_ptr() - off, src_h, src_w, xw.stride(0), tile_boxes,
+                             col_ranges)
 
     def rectify_gather(self, x: torch.Tensor, y: torch.Tensor, src: torch.Tensor, interp_method: str, fill_value,
                        out: torch.Tensor | None = None, tile_boxes: torch.Tensor | None = None,
@@ -168,7 +231,7 @@ def _rectify_gather_dev(plan: "RectifyPlan", x: torch.Tensor, y: torch.Tensor, s
     check(lib.xrs_rectify_gather(
         _dev.ptr(x), _dev.ptr(y), h, w, x.stride(0), _dev.ptr(tile_boxes), gm.height, gm.width, gm.tile_height,
         gm.tile_width, float(x_min), float(y_min), float(y_max), float(gm.x_res), float(gm.y_res),
-        int(bool(gm.is_j_axis_up)), plan.uv_delta, plan.rows[0], plan.rows[1], _dev.ptr(plan._ws1),
+        int(bool(gm.is_j_axis_up)), plan.uv_delta, plan.rows[0], plan.rows[1], None, _dev.ptr(plan._ws1),
         _dev.plane_ptr_array(src3), _dev.plane_ptr_array(out), bands, DTYPE_CODES[np_dtype], src3.stride(1),
         int(window_origin[0]), int(window_origin[1]), win_w, win_h, INTERP_CODES[interp_method], float(fill_value),
         _dev.stream_ptr(plan.device)), "xrs_rectify_gather")
@@ -266,20 +329,20 @@ def gather_ij(src: torch.Tensor, ij: torch.Tensor, interp_method: str, fill_valu
 def rectify_band_host(x: np.ndarray, y: np.ndarray, src_window: np.ndarray, window_origin: tuple[int, int],
                       full_size: tuple[int, int], target_gm: GridMapping, rows: tuple[int, int], interp_method: str,
                       fill_value, device=None) -> np.ndarray:
-    """Rectify one target row band from host buffers to a host buffer (multi-GPU building block).
+    """Rectify one target row band from host buffers to a host buffer, the band's source window
+    given by the caller (building block kept for callers that cut their own windows; the
+    multi-GPU entry points go through :func:`xcube_resampling_b200.multigpu.rectify_band`).
 
-    x, y: full (h, w) source coordinates (needed to find the band's source windows);
-    src_window: (bands, wh, ww) window of the data variable whose element (0, 0, 0) is pixel
-    ``window_origin=(i0, j0)`` of the full ``full_size=(width, height)`` image and which covers
-    :func:`xcube_resampling_b200.bands.rectify_band_footprint` of ``rows``.
-    Returns (bands, rows[1]-rows[0], target width) in (pinned) host memory.
-    """
+    x, y: full (h, w) source coordinates; src_window: (bands, wh, ww) window of the data variable
+    whose element (0, 0, 0) is pixel ``window_origin=(i0, j0)`` of the full
+    ``full_size=(width, height)`` image.  Returns (bands, rows[1]-rows[0], target width)."""
     dev = _dev.require_cuda(device)
     x_dev = _dev.to_device(x, dev, dtype=np.float64)
     y_dev = _dev.to_device(y, dev, dtype=np.float64)
     plan = RectifyPlan(target_gm, dev, rows=rows)
     ij = plan.ij(x_dev, y_dev)
-    return _gather_from_host(np.asarray(src_window), ij, interp_method, fill_value, window_origin, full_size)
+    src = _dev.to_device_pitched(np.asarray(src_window), dev)
+    return _dev.to_host(gather_ij(src, ij, interp_method, fill_value, window_origin=window_origin, full_size=full_size))
 
 
 # ---------------------------------------------------------------------------
@@ -295,11 +358,20 @@ def rectify_dataset(
     recover_nans=False,
     fill_values=None,
     tile_size: int | tuple[int, int] | None = None,
+    *,
+    devices: Iterable | None = None,
 ):
     """Rectify a dataset with 2-D (irregular) coordinates to a regular grid.
 
-    Drop-in for ``xcube_resampling.rectify.rectify_dataset`` (rectify.py:54-179):
-    same arguments, defaults and errors; always eager (numpy in, numpy out).
+    Drop-in for ``xcube_resampling.rectify.rectify_dataset`` (rectify.py:54-179): same
+    arguments, defaults and errors; always eager (numpy in, numpy out).
+
+    ``devices`` (keyword only, not in the reference): CUDA devices to spread the call over, e.g.
+    ``range(8)``.  The target is cut into one row band per device, every device uploads only its
+    band's source footprint and fills its rows of the result (``multigpu.py``); ``None`` = the
+    current device.  The source-index image is computed ONCE per call and shared by all variables
+    (as in the reference, rectify.py:146); variables that are views of the same host array -- the same
+    bands wanted with two interpolation methods -- are uploaded once.
     """
     user_ds = source_ds
     source_ds = from_any(source_ds)
@@ -310,18 +382,21 @@ def rectify_dataset(
     if target_gm is None:
         target_gm = source_gm.to_regular(tile_size=tile_size)
 
-    # source coordinates in the target CRS (rectify.py:126-129)
-    src_x, src_y = source_gm.x_values, source_gm.y_values
-    if src_x.ndim == 1:
-        xy = source_gm.xy_coords.values
-        src_x, src_y = xy[0], xy[1]
-    x_dev = _dev.to_device(src_x, dtype=np.float64)
-    y_dev = _dev.to_device(src_y, dtype=np.float64)
+    # source coordinates in the target CRS (rectify.py:126-129, _transform_coords :182-231): the
+    # original 2-D coordinate variables are dropped, the transformed ones take their place
+    x_dev = y_dev = None
     if not _is_equal_crs(source_gm, target_gm):
         from .reproject import transform_points_dev
 
-        x_dev, y_dev = transform_points_dev(x_dev, y_dev, source_gm.crs, target_gm.crs)
+        xy = source_gm.xy_coords.values
+        x_dev, y_dev = transform_points_dev(_dev.to_device(xy[0], dtype=np.float64),
+                                            _dev.to_device(xy[1], dtype=np.float64), source_gm.crs, target_gm.crs)
+        source_ds = source_ds.drop_vars(source_gm.xy_var_names)
         source_gm = _gm_from_transformed(source_gm, target_gm, x_dev, y_dev)
+        tx, ty = source_gm.xy_var_names
+        source_ds = source_ds.assign_coords({
+            "spatial_ref": DataArray(np.array(0), dims=(), attrs=target_gm.crs.to_cf()),
+            tx: _DeviceCoord(source_gm, 0), ty: _DeviceCoord(source_gm, 1)})
 
     source_ds = _select_variables(source_ds, variables)
 
@@ -333,9 +408,6 @@ def rectify_dataset(
             source_ds, source_gm, x_dev, y_dev, x_scale, y_scale,
             _prep_interp_methods_downscale(interp_methods), agg_methods, recover_nans)
 
-    plan = RectifyPlan(target_gm, x_dev.device, uv_delta=UV_DELTA)
-    ij = None  # computed on first need; a single small variable takes the fused K1 + K2 path instead
-
     # output coordinates (rectify.py:148-157)
     sx_name, sy_name = source_gm.xy_var_names
     coords = {n: v for n, v in source_ds.coords.items() if n not in (sx_name, sy_name)}
@@ -346,9 +418,13 @@ def rectify_dataset(
     coords["spatial_ref"] = DataArray(np.array(0), dims=(), attrs=target_gm.crs.to_cf())
     target_ds = Dataset(coords=coords, attrs=source_ds.attrs)
 
+    # what has to be computed: one Target per spatial variable, grouped by host buffer
+    from ._pipeline import Target, group_by_buffer
+
     yx_dims = (source_gm.xy_dim_names[1], source_gm.xy_dim_names[0])
     t_dims = (target_gm.xy_dim_names[1], target_gm.xy_dim_names[0])
-    n_spatial = sum(1 for _n, v in source_ds.items() if v.dims[-2:] == yx_dims)
+    H, W = target_gm.height, target_gm.width
+    items, results = [], []
     for var_name, var in source_ds.items():
         if var.dims[-2:] == yx_dims:
             assert len(var.dims) in (2, 3), f"Data variable {var_name} has {len(var.dims)} dimensions."
@@ -359,61 +435,137 @@ def rectify_dataset(
                     f"interp_methods must be one of 0, 1, 'nearest', 'bilinear', "
                     f"'triangular', was '{interp_method}'."
                 )
-            if n_spatial == 1 and var.values.nbytes < _PIPELINE_MIN_BYTES:
-                # one variable, small enough not to be streamed: ij is resolved in registers
-                src = _dev.to_device_pitched(var.values, x_dev.device)
-                out = _dev.to_host(plan.rectify_gather(x_dev, y_dev, src, interp_method, fill_value))
-            else:
-                if ij is None:
-                    ij = plan.ij(x_dev, y_dev)
-                out = _gather_from_host(var.values, ij, interp_method, fill_value)
+            values = var.values
+            n_b = 1 if values.ndim == 2 else values.shape[0]
+            out = _dev.pinned_empty((n_b, H, W), values.dtype)
+            items.append((values, Target(str(var_name), interp_method, fill_value, out)))
             dims = t_dims if len(var.dims) == 2 else (var.dims[0],) + t_dims
-            target_ds[var_name] = DataArray(out, dims=dims, attrs=var.attrs, name=var_name)
+            results.append((var_name, out[0] if values.ndim == 2 else out, dims, var.attrs))
         elif yx_dims[0] not in var.dims and yx_dims[1] not in var.dims:
-            target_ds[var_name] = var
+            results.append((var_name, var, None, None))
+    groups = group_by_buffer(items)
+
+    if groups:
+        devs = None if devices is None else list(devices)
+        if devs is not None and len(devs) > 1:
+            _rectify_groups_multi(source_gm, x_dev, y_dev, groups, target_gm, devs)
+        else:
+            dev = _dev.require_cuda(None if not devs else devs[0])
+            _rectify_groups_single(source_gm, x_dev, y_dev, groups, target_gm, dev)
+
+    for var_name, out, dims, attrs in results:
+        target_ds[var_name] = out if dims is None else DataArray(out, dims=dims, attrs=attrs, name=var_name)
     return to_like(target_ds, user_ds)
 
 
-# a variable at least this large is streamed through the device in band chunks (upload, kernels
-# and download overlapped); smaller ones take the plain upload / gather / download sequence
+# a single variable smaller than this is uploaded whole and takes the fused K1 + K2 kernel (ij stays
+# in registers); everything else streams through the band-chunk pipeline
 _PIPELINE_MIN_BYTES = 64 << 20
 
 
-def _gather_from_host(values: np.ndarray, ij: torch.Tensor, interp_method: str, fill_value,
-                      window_origin: tuple[int, int] = (0, 0), full_size: tuple[int, int] | None = None) -> np.ndarray:
-    """K2 for one host variable ((y, x) or (bands, y, x)), result in (pinned) host memory."""
-    if values.ndim == 3 and values.shape[0] > 1 and values.nbytes >= _PIPELINE_MIN_BYTES:
-        pipe = _dev.BandPipeline(values, ij.shape[1:], values.dtype, ij.device)
-        return pipe.run(lambda src, out: gather_ij(src, ij, interp_method, fill_value, out=out,
-                                                   window_origin=window_origin, full_size=full_size))
-    src = _dev.to_device_pitched(values, ij.device)
-    return _dev.to_host(gather_ij(src, ij, interp_method, fill_value, window_origin=window_origin,
-                                  full_size=full_size))
+def _host_coords(source_gm: GridMapping, x_dev, y_dev):
+    """Host float64 (h, w) coordinate arrays of the source grid mapping."""
+    if x_dev is not None:
+        return _dev.to_host(x_dev), _dev.to_host(y_dev)
+    xs, ys = source_gm.x_values, source_gm.y_values
+    if xs.ndim == 1:
+        xy = source_gm.xy_coords.values
+        xs, ys = xy[0], xy[1]
+    return np.asarray(xs, dtype=np.float64), np.asarray(ys, dtype=np.float64)
+
+
+def _rectify_groups_single(source_gm, x_dev, y_dev, groups, target_gm, dev):
+    """One device: coordinates uploaded whole, K0 + K1 once, every variable through K2."""
+    from ._pipeline import GatherPipeline
+
+    with torch.cuda.device(dev):
+        if x_dev is None:
+            xs, ys = _host_coords(source_gm, None, None)
+            x_dev = _dev.to_device(xs, dev, dtype=np.float64)
+            y_dev = _dev.to_device(ys, dev, dtype=np.float64)
+        plan = RectifyPlan(target_gm, dev, uv_delta=UV_DELTA)
+        H, W = target_gm.height, target_gm.width
+        h, w = x_dev.shape
+        if len(groups) == 1 and len(groups[0].targets) == 1 and groups[0].values.nbytes < _PIPELINE_MIN_BYTES:
+            grp = groups[0]
+            tgt = grp.targets[0]
+            src = _dev.to_device_pitched(grp.values, dev)
+            out = plan.rectify_gather(x_dev, y_dev, src, tgt.method, tgt.fill)
+            tgt.out_host[...] = _dev.to_host(out)
+            return
+        ij = plan.ij(x_dev, y_dev)
+        pipe = GatherPipeline(dev, (h, w), W, (0, H))
+
+        def process(src_view, tgt, out_view, b0):
+            gather_ij(src_view, ij, tgt.method, tgt.fill, out=out_view)
+
+        pipe.run(groups, process)
+
+
+def _rectify_groups_multi(source_gm, x_dev, y_dev, groups, target_gm, devices):
+    """Several devices: one target row band per device (multigpu.py)."""
+    from . import multigpu
+
+    xs, ys = _host_coords(source_gm, x_dev, y_dev)
+    edges = multigpu.default_band_edges(target_gm.height, len(devices))
+
+    def worker(k, dev, exchange):
+        multigpu.rectify_band(xs, ys, groups, target_gm, edges, k, exchange, device=dev)
+
+    multigpu.run_on_devices(devices, worker)
+
+
+class _DeviceCoord(DataArray):
+    """Placeholder for a transformed 2-D coordinate variable that lives on the device: its values
+    are fetched only if somebody asks (rectify_dataset itself never does -- the transformed source
+    coordinates are dropped from the result, rectify.py:148-150)."""
+
+    __slots__ = ("_gm", "_axis")
+
+    def __init__(self, gm: GridMapping, axis: int):
+        self._gm, self._axis = gm, axis
+        h, w = gm.height, gm.width
+        dims = (gm.xy_dim_names[1], gm.xy_dim_names[0])
+        # a zero-stride stand-in gives shape / dtype without allocating h*w doubles
+        DataArray.__init__(self, np.broadcast_to(np.float64(0), (h, w)), dims=dims, name=gm.xy_var_names[axis])
+
+    @property
+    def values(self) -> np.ndarray:
+        return self._gm.x_values if self._axis == 0 else self._gm.y_values
+
+    data = values
 
 
 def _gm_from_transformed(source_gm: GridMapping, target_gm: GridMapping, x_dev, y_dev) -> GridMapping:
-    """rectify.py:129: re-derive the source grid mapping from the transformed 2-D coordinates."""
+    """rectify.py:129: re-derive the source grid mapping from the transformed 2-D coordinates,
+    which stay on the device (``GridMapping.from_device_coords``: statistics by one device pass)."""
     names = ("lon", "lat") if target_gm.crs.is_geographic else ("transformed_x", "transformed_y")
     dims = (source_gm.xy_dim_names[1], source_gm.xy_dim_names[0])
-    xs, ys = _dev.to_host(x_dev), _dev.to_host(y_dev)
-    return GridMapping.from_coords(DataArray(xs, dims=dims, name=names[0]), DataArray(ys, dims=dims, name=names[1]),
-                                   target_gm.crs, tile_size=source_gm.tile_size)
+    return GridMapping.from_device_coords(x_dev, y_dev, target_gm.crs, xy_var_names=names,
+                                          xy_dim_names=(dims[1], dims[0]), tile_size=source_gm.tile_size)
 
 
 def _downscale_source(source_ds, source_gm, x_dev, y_dev, x_scale, y_scale, interp_methods, agg_methods,
                       recover_nans):
-    """rectify.py:234-260: affine pre-downscale of every yx variable including the 2-D coordinates."""
-    from .affine import resample_dataset
+    """rectify.py:234-260: affine pre-downscale of every yx variable including the 2-D coordinates.
+    The coordinates are resampled on the device and stay there."""
+    from .affine import resample_coords_dev, resample_dataset
 
     w, h = round(x_scale * source_gm.width), round(y_scale * source_gm.height)
     size = (w if w >= 2 else 2, h if h >= 2 else 2)
     yx_dims = (source_gm.xy_dim_names[1], source_gm.xy_dim_names[0])
     x_name, y_name = source_gm.xy_var_names
-    ds = source_ds.assign_coords({
-        x_name: DataArray(_dev.to_host(x_dev), dims=yx_dims, name=x_name),
-        y_name: DataArray(_dev.to_host(y_dev), dims=yx_dims, name=y_name),
-    })
-    ds = resample_dataset(ds, ((1 / x_scale, 0, 0), (0, 1 / y_scale, 0)), yx_dims, size, source_gm.tile_size,
-                          interp_methods, agg_methods, recover_nans)
-    gm = GridMapping.from_coords(ds[x_name], ds[y_name], source_gm.crs)
-    return ds, gm, _dev.to_device(gm.x_values, dtype=np.float64), _dev.to_device(gm.y_values, dtype=np.float64)
+    matrix = ((1 / x_scale, 0, 0), (0, 1 / y_scale, 0))
+    if x_dev is None:
+        xs, ys = _host_coords(source_gm, None, None)
+        x_dev, y_dev = _dev.to_device(xs, dtype=np.float64), _dev.to_device(ys, dtype=np.float64)
+    x_var = DataArray(np.broadcast_to(np.float64(0), x_dev.shape), dims=yx_dims, name=x_name)
+    y_var = DataArray(np.broadcast_to(np.float64(0), y_dev.shape), dims=yx_dims, name=y_name)
+    x_dev = resample_coords_dev(x_dev, x_name, x_var, matrix, size, interp_methods, agg_methods, recover_nans)
+    y_dev = resample_coords_dev(y_dev, y_name, y_var, matrix, size, interp_methods, agg_methods, recover_nans)
+    ds = source_ds.drop_vars([n for n in (x_name, y_name) if n in source_ds])
+    ds = resample_dataset(ds, matrix, yx_dims, size, source_gm.tile_size, interp_methods, agg_methods, recover_nans)
+    gm = GridMapping.from_device_coords(x_dev, y_dev, source_gm.crs, xy_var_names=(x_name, y_name),
+                                        xy_dim_names=(yx_dims[1], yx_dims[0]))
+    ds = ds.assign_coords({x_name: _DeviceCoord(gm, 0), y_name: _DeviceCoord(gm, 1)})
+    return ds, gm, x_dev, y_dev

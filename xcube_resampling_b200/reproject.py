@@ -246,11 +246,18 @@ def reproject_dataset(
     agg_methods=None,
     recover_nans=False,
     fill_values=None,
+    *,
+    devices: Iterable | None = None,
 ):
     """Reproject a dataset on a regular grid to a regular grid in another CRS.
 
     Drop-in for ``xcube_resampling.reproject.reproject_dataset`` (reproject.py:51-186): same
-    arguments, defaults and errors; always eager (numpy in, numpy out)."""
+    arguments, defaults and errors; always eager (numpy in, numpy out).
+
+    ``devices`` (keyword only, not in the reference): CUDA devices to spread the call over.  The
+    target is cut into one row band per device; every device uploads only the source rectangle its
+    band's tiles can read (``ReprojectPlan.footprint``) and fills its rows of the result.  No
+    exchange step is involved."""
     user_ds = source_ds
     source_ds = from_any(source_ds)
     if source_gm is None:
@@ -263,7 +270,6 @@ def reproject_dataset(
 
     source_ds, source_gm = _downscale_source_dataset(source_ds, source_gm, target_gm, interp_methods, agg_methods,
                                                      recover_nans)
-    plan = ReprojectPlan(source_gm, target_gm)
 
     # output coordinates (reproject.py:152-159)
     sx_name, sy_name = source_gm.xy_var_names
@@ -274,38 +280,85 @@ def reproject_dataset(
     coords["spatial_ref"] = DataArray(np.array(0), dims=(), attrs=target_gm.crs.to_cf())
     target_ds = Dataset(coords=coords, attrs=source_ds.attrs)
 
+    from ._pipeline import Target, group_by_buffer
+
     yx_dims = (source_gm.xy_dim_names[1], source_gm.xy_dim_names[0])
     t_dims = (target_gm.xy_dim_names[1], target_gm.xy_dim_names[0])
+    H, W = target_gm.height, target_gm.width
+    items, results = [], []
     for var_name, var in source_ds.items():
         if var.dims[-2:] == yx_dims:
             assert len(var.dims) in (2, 3), f"Data variable {var_name} has {len(var.dims)} dimensions."
             fill_value = _get_fill_value(fill_values, var_name, var)
             interp_method = _get_interp_method_str(interp_methods, var_name, var)
-            out = _reproject_from_host(plan, var.values, interp_method, fill_value)
+            if interp_method not in INTERP_CODES:
+                raise NotImplementedError(
+                    f"interp_methods must be one of 0, 1, 'nearest', 'bilinear', "
+                    f"'triangular', was '{interp_method}'."
+                )
+            values = var.values
+            n_b = 1 if values.ndim == 2 else values.shape[0]
+            # numpy's promotion in reproject.py:315-328 makes bilinear results float64
+            out_dtype = np.float64 if interp_method == "bilinear" else values.dtype
+            out = _dev.pinned_empty((n_b, H, W), out_dtype)
+            items.append((values, Target(str(var_name), interp_method, fill_value, out)))
             dims = t_dims if len(var.dims) == 2 else (var.dims[0],) + t_dims
-            target_ds[var_name] = DataArray(out, dims=dims, attrs=var.attrs, name=var_name)
+            results.append((var_name, out[0] if values.ndim == 2 else out, dims, var.attrs))
         elif yx_dims[0] not in var.dims and yx_dims[1] not in var.dims:
-            target_ds[var_name] = var
+            results.append((var_name, var, None, None))
+    groups = group_by_buffer(items)
+    if groups:
+        devs = [None] if devices is None else list(devices)
+        reproject_groups(groups, source_gm, target_gm, devs)
+    for var_name, out, dims, attrs in results:
+        target_ds[var_name] = out if dims is None else DataArray(out, dims=dims, attrs=attrs, name=var_name)
     return to_like(target_ds, user_ds)
 
 
-_PIPELINE_MIN_BYTES = 64 << 20
+def reproject_groups(groups, source_gm: GridMapping, target_gm: GridMapping, devices, band_edges=None,
+                     windows: SourceWindows | None = None, chunk_bands: int = 4, stats: list | None = None) -> None:
+    """Fill the targets of ``groups`` (``_pipeline.SourceGroup`` list) on ``devices``: device k
+    computes target rows ``band_edges[k]:band_edges[k+1]`` (default: equal heights on multiples of 32
+    rows) from the source rectangle its tiles can read.  One device = the whole image."""
+    from . import multigpu
+    from ._pipeline import GatherPipeline
 
+    n = len(devices)
+    first = _dev.require_cuda(devices[0])
+    if windows is None:
+        windows = get_source_windows(source_gm, target_gm, first)
+    edges = list(band_edges) if band_edges is not None else multigpu.default_band_edges(target_gm.height, n)
+    h, w = source_gm.height, source_gm.width
 
-def _reproject_from_host(plan: ReprojectPlan, values: np.ndarray, interp_method: str, fill_value) -> np.ndarray:
-    """K3 for one host variable; large (bands, y, x) variables stream through the device in band
-    chunks with upload, kernel and download overlapped (``_dev.BandPipeline``)."""
-    if interp_method not in INTERP_CODES:
-        raise NotImplementedError(
-            f"interp_methods must be one of 0, 1, 'nearest', 'bilinear', "
-            f"'triangular', was '{interp_method}'."
-        )
-    if values.ndim == 3 and values.shape[0] > 1 and values.nbytes >= _PIPELINE_MIN_BYTES:
-        out_dtype = np.float64 if interp_method == "bilinear" else values.dtype
-        gm = plan.target_gm
-        pipe = _dev.BandPipeline(values, (plan.rows[1] - plan.rows[0], gm.width), out_dtype, plan.device)
-        return pipe.run(lambda src, out: plan.run(src, interp_method, fill_value, out=out))
-    return _dev.to_host(plan.run(_dev.to_device(values, plan.device), interp_method, fill_value))
+    def worker(k, dev, _exchange):
+        rows = (int(edges[k]), int(edges[k + 1]))
+        if rows[1] <= rows[0]:
+            return
+        dev = _dev.require_cuda(dev)
+        with torch.cuda.device(dev):
+            plan = ReprojectPlan(source_gm, target_gm, dev, rows=rows, windows=windows)
+            fp = plan.footprint()
+            if fp is None:  # the band lies entirely outside the source
+                for grp in groups:
+                    for tgt in grp.targets:
+                        tgt.out_host[:, rows[0] - tgt.row0:rows[1] - tgt.row0, :] = \
+                            np.asarray(tgt.fill).astype(tgt.out_dtype)
+                return
+            i_lo, j_lo, i_hi, j_hi = fp
+            a = 32  # column range on 128-byte boundaries of 4-byte data
+            i_lo, i_hi = (i_lo // a) * a, min(w, -(-i_hi // a) * a)
+            pipe = GatherPipeline(dev, (h, w), target_gm.width, rows, src_window=(j_lo, j_hi),
+                                  segments=[(j_lo, j_hi, i_lo, i_hi)], chunk_bands=chunk_bands)
+
+            def process(src_view, tgt, out_view, b0):
+                plan.run(src_view, tgt.method, tgt.fill, out=out_view, out_dtype=tgt.out_dtype, window_origin=(0, j_lo))
+
+            pipe.run(groups, process)
+            if stats is not None:
+                stats.append({"device": str(dev), "rows": rows, "footprint": (i_lo, j_lo, i_hi, j_hi),
+                              "h2d_bytes": pipe.h2d_bytes, "d2h_bytes": pipe.d2h_bytes})
+
+    multigpu.run_on_devices([(_dev.require_cuda(d)) for d in devices], worker)
 
 
 def _flip_y(ds: Dataset, y_dim: str) -> Dataset:
