@@ -1,5 +1,5 @@
-"""Host-side pieces of bench.py that run without a GPU: the reference arm (CPU port of the
-reference kernels on a bounded sample), its JSON contract, and the helpers' behaviour when NVML /
+"""Host-side pieces of bench.py that run without a GPU: the reference arm (the reference's own numba
+kernels from oracle/_ref, or the C port of them, on a bounded sample), its JSON contract, and the helpers' behaviour when NVML /
 nvidia-smi are absent."""
 
 import json
@@ -25,9 +25,22 @@ def test_reference_arm_json_line():
     assert line["value"] > 0 and line["e2e"]["value"] == line["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     cpu = line["cpu_baseline"]
-    assert cpu["kind"] == "port" and cpu["cores"] >= 1 and cpu["value"] == line["value"] and "swath" in cpu["sample"]
-    assert "workload" in line["config"] and "bounded_sample" in line["config"]
+    # the reference's own numba kernels when oracle/_ref (or /root/reference) is there, else the C port
+    assert cpu["kind"] in ("reference", "port") and cpu["cores"] >= 1 and cpu["value"] == line["value"]
+    assert "swath" in cpu["sample"]
+    # the config is the GPU arm's, key for key (the bounded sample is described in cpu_baseline)
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert set(line["config"]) == set(bench.workload_config(1, 1, 1, (1, 1), 2))
     assert line["config"]["scenes_per_step"] == 2
+
+
+def test_reference_arm_port_kind():
+    r = _run(["--impl", "reference", "--scale", "0.05", "--steps", "1", "--warmup", "0", "--cpu-kind", "port"])
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
 
 
 def test_reference_arm_only_rank_zero_works():
