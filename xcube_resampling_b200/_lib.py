@@ -11,7 +11,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libxrs.so")
+# XRS_LIB selects an experimental build variant (build.py); the product library otherwise
+LIB_PATH = os.environ.get("XRS_LIB") or os.path.join(_HERE, "libxrs.so")
 
 c_int = ctypes.c_int
 c_i32 = ctypes.c_int32

@@ -56,9 +56,9 @@ def _stamp(src: str, flags) -> str:
     return h.hexdigest()
 
 
-def _compile_one(nvcc, name, extra, verbose):
+def _compile_one(nvcc, name, extra, verbose, obj_dir=None):
     src = os.path.join(CSRC, name)
-    obj = os.path.join(OBJ_DIR, name.replace(".cu", ".o"))
+    obj = os.path.join(obj_dir or OBJ_DIR, name.replace(".cu", ".o"))
     flags = ARCH + COMMON + extra
     stamp_path = obj + ".stamp"
     stamp = _stamp(src, flags)
@@ -75,24 +75,31 @@ def _compile_one(nvcc, name, extra, verbose):
     return obj, True
 
 
-def build(verbose: bool = False, force: bool = False) -> str:
+def build(verbose: bool = False, force: bool = False, variant: str | None = None, defines=()) -> str:
+    """Compile and link ``libxrs.so``.  ``variant`` + ``defines`` (e.g. ``("-DXRS_K1_MINBLOCKS=3",)``) build
+    an experimental ``libxrs_<variant>.so`` beside it (own object directory); ``XRS_LIB=<path>`` makes
+    ``_lib.load()`` pick it up -- used to compare kernel variants in one GPU session."""
     nvcc = _nvcc()
-    os.makedirs(OBJ_DIR, exist_ok=True)
+    obj_dir = OBJ_DIR if not variant else OBJ_DIR + "_" + variant
+    lib_path = LIB_PATH if not variant else os.path.join(HERE, f"libxrs_{variant}.so")
+    os.makedirs(obj_dir, exist_ok=True)
     if force:
-        for f in os.listdir(OBJ_DIR):
-            os.remove(os.path.join(OBJ_DIR, f))
-    present = {n: f for n, f in SOURCES.items() if os.path.exists(os.path.join(CSRC, n))}
+        for f in os.listdir(obj_dir):
+            os.remove(os.path.join(obj_dir, f))
+    present = {n: f + list(defines) for n, f in SOURCES.items() if os.path.exists(os.path.join(CSRC, n))}
     with ThreadPoolExecutor(max_workers=len(present)) as pool:
-        results = list(pool.map(lambda kv: _compile_one(nvcc, kv[0], kv[1], verbose), present.items()))
+        results = list(pool.map(lambda kv: _compile_one(nvcc, kv[0], kv[1], verbose, obj_dir), present.items()))
     objs = [o for o, _ in results]
     changed = any(c for _, c in results)
-    if changed or not os.path.exists(LIB_PATH):
-        cmd = [nvcc] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH] + objs
+    if changed or not os.path.exists(lib_path):
+        cmd = [nvcc] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", lib_path] + objs
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    _variant = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")), None)
+    _defines = tuple(a for a in sys.argv if a.startswith("-D"))
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv, variant=_variant, defines=_defines))

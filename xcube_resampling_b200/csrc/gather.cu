@@ -66,6 +66,15 @@ __device__ __forceinline__ Taps make_taps(double fi, double fj, int64_t src_w, i
 template <typename T>
 __device__ __forceinline__ double ld_f64(const T *p) { return static_cast<double>(__ldg(p)); }
 
+// base + index * sizeof(T) as ONE wide multiply-add (the compiler's shift-and-add pair costs two
+// issue slots per store in the band loop)
+template <typename T>
+__device__ __forceinline__ T *elem_ptr(T *base, uint32_t index) {
+    uint64_t out;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(out) : "r"(index), "n"(sizeof(T)), "l"(reinterpret_cast<uint64_t>(base)));
+    return reinterpret_cast<T *>(out);
+}
+
 // Where a gather kernel gets the fractional source index of a target pixel from: the ij image of
 // xrs_rectify_ij, or -- fused mode (xrs_rectify_gather) -- straight from K1's claim words, running
 // the resolve step (rectify_common.cuh) in registers so that the 16 bytes per pixel of ij are neither
@@ -229,13 +238,31 @@ k2_gather_staged(const __grid_constant__ StagedParams<T> p, int n_bands, int64_t
     const bool staged = (i_hi - i_lo + 1 <= K2S_BOX_W) && (j_hi - j_lo + 1 <= K2S_BOX_H);
 
     if (staged) {
-        int off[K2S_PX], di[K2S_PX], dj[K2S_PX];
+        // Everything that does not depend on the band is computed once: the four tap addresses of each
+        // pixel inside stage 0 (the other stages are compile-time offsets from them -- the band loop is
+        // unrolled over the ring), the output element offsets and the store predicates.  Pixels
+        // without a source read tap (0, 0) with u = v = 0 and are overwritten by `fill` with one
+        // select, so the band loop is branch-free.
+        const T *t00[K2S_PX], *t01[K2S_PX], *t10[K2S_PX], *t11[K2S_PX];
+        uint32_t o32[K2S_PX];
+        uint32_t st_mask = 0;  // bit k: pixel k lies inside the target image (is stored)
 #pragma unroll
         for (int k = 0; k < K2S_PX; ++k) {
-            off[k] = (t[k].j0 - j_lo) * K2S_BOX_W + (t[k].i0 - i_lo);
-            di[k] = t[k].i1 - t[k].i0;
-            dj[k] = (t[k].j1 - t[k].j0) * K2S_BOX_W;
+            const int off = t[k].valid ? (t[k].j0 - j_lo) * K2S_BOX_W + (t[k].i0 - i_lo) : 0;
+            const int di = t[k].valid ? t[k].i1 - t[k].i0 : 0;
+            const int dj = t[k].valid ? (t[k].j1 - t[k].j0) * K2S_BOX_W : 0;
+            t00[k] = stages + off;
+            t01[k] = t00[k] + di;
+            t10[k] = t00[k] + dj;
+            t11[k] = t10[k] + di;
+            const int64_t r = r_base + k * K2S_ROW_STEP;
+            st_mask |= (col_in && r < dst_h) ? (1u << k) : 0u;
+            o32[k] = static_cast<uint32_t>(r * dst_w + c);
+            if (!t[k].valid) t[k].u = t[k].v = 0.0;
         }
+        // opaque to the compiler, so that the band loop tests one bit instead of re-deriving the 64-bit
+        // row / column comparisons for every band and pixel
+        asm volatile("" : "+r"(st_mask));
         constexpr uint32_t STAGE_BYTES = STAGE_ELEMS * sizeof(T);
         if (tid == 0) {
             for (int s = 0; s < K2S_STAGES && s < n_bands; ++s) {
@@ -243,36 +270,37 @@ k2_gather_staged(const __grid_constant__ StagedParams<T> p, int n_bands, int64_t
                 tma_load_2d(stages + s * STAGE_ELEMS, &p.maps[s], box_x, box_y, &full_bar[s]);
             }
         }
-        for (int b = 0; b < n_bands; ++b) {
-            const int s = b % K2S_STAGES;
-            mbar_wait(&full_bar[s], (b / K2S_STAGES) & 1);
-            const T *sm = stages + s * STAGE_ELEMS;
-            T out[K2S_PX];
+        for (int b0 = 0; b0 < n_bands; b0 += K2S_STAGES) {
+            const uint32_t parity = (b0 / K2S_STAGES) & 1;
 #pragma unroll
-            for (int k = 0; k < K2S_PX; ++k) {
-                if (!t[k].valid) {
-                    out[k] = fill;
-                } else if (METHOD == XRS_NEAREST) {
-                    out[k] = sm[off[k]];
-                } else {
-                    const double v00 = static_cast<double>(sm[off[k]]), v01 = static_cast<double>(sm[off[k] + di[k]]);
-                    const double v10 = static_cast<double>(sm[off[k] + dj[k]]);
-                    const double v11 = static_cast<double>(sm[off[k] + dj[k] + di[k]]);
-                    out[k] = cast_from_f64<T>(interp_value<METHOD>(v00, v01, v10, v11, t[k].u, t[k].v));
-                }
-            }
-            if (col_in) {
+            for (int s = 0; s < K2S_STAGES; ++s) {
+                const int b = b0 + s;
+                if (b >= n_bands) break;
+                mbar_wait(&full_bar[s], parity);
+                T out[K2S_PX];
 #pragma unroll
                 for (int k = 0; k < K2S_PX; ++k) {
-                    const int64_t r = r_base + k * K2S_ROW_STEP;
-                    if (r < dst_h) st_stream(p.dst[b] + r * dst_w + c, out[k]);
+                    if (METHOD == XRS_NEAREST) {
+                        out[k] = t00[k][s * STAGE_ELEMS];
+                    } else {
+                        const double v00 = static_cast<double>(t00[k][s * STAGE_ELEMS]);
+                        const double v01 = static_cast<double>(t01[k][s * STAGE_ELEMS]);
+                        const double v10 = static_cast<double>(t10[k][s * STAGE_ELEMS]);
+                        const double v11 = static_cast<double>(t11[k][s * STAGE_ELEMS]);
+                        out[k] = cast_from_f64<T>(interp_value<METHOD>(v00, v01, v10, v11, t[k].u, t[k].v));
+                    }
+                    out[k] = t[k].valid ? out[k] : fill;
                 }
-            }
-            __syncthreads();  // every thread is done with stage s
-            if (tid == 0 && b + K2S_STAGES < n_bands) {
-                fence_proxy_async();
-                mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-                tma_load_2d(stages + s * STAGE_ELEMS, &p.maps[b + K2S_STAGES], box_x, box_y, &full_bar[s]);
+                T *dp = p.dst[b];
+#pragma unroll
+                for (int k = 0; k < K2S_PX; ++k)
+                    if (st_mask & (1u << k)) st_stream(elem_ptr(dp, o32[k]), out[k]);
+                __syncthreads();  // every thread is done with stage s
+                if (tid == 0 && b + K2S_STAGES < n_bands) {
+                    fence_proxy_async();
+                    mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                    tma_load_2d(stages + s * STAGE_ELEMS, &p.maps[b + K2S_STAGES], box_x, box_y, &full_bar[s]);
+                }
             }
         }
         return;
@@ -362,7 +390,7 @@ static int launch_gather(const void *const *src_planes, void *const *dst_planes,
     const T fill_t = cast_fill<T>(fill);
     // TMA needs 16-byte aligned plane bases and row strides
     bool tma_ok = (src_pitch * sizeof(T)) % 16 == 0 && win_w < (1ll << 31) && win_h < (1ll << 31) &&
-                  ceil_div(dst_h, K2S_TH) <= 65535 && get_encode_tiled() != nullptr;
+                  ceil_div(dst_h, K2S_TH) <= 65535 && dst_h * dst_w < (1ll << 32) && get_encode_tiled() != nullptr;
     for (int b = 0; b < n_bands && tma_ok; ++b)
         tma_ok = (reinterpret_cast<uintptr_t>(src_planes[b]) & 15) == 0;
 

@@ -81,15 +81,6 @@ __device__ __forceinline__ bool tri_accepts(const TriTest &t, double nu, double 
     return tri_accepts_exact(nu, nv, t.det, lo, hi);
 }
 
-// floor(g / d) for 0 <= g < 2^30, 1 <= d < 2^30 via a float estimate and one correction step
-__device__ __forceinline__ int fast_div(int g, int d, float inv_d) {
-    int t = static_cast<int>(static_cast<float>(g) * inv_d);
-    const long long p = static_cast<long long>(t) * d;
-    if (p > g) --t;
-    else if (p + d <= g) ++t;
-    return t;
-}
-
 // reference tile geometry a lane keeps cached while its quads stay in the same tile
 struct TileCtx {
     int id;                    // ty * ntx + tx, -1 = nothing cached
@@ -353,7 +344,10 @@ __device__ __forceinline__ bool px_rejects(uint32_t neg_thresh_hi, double a1, do
            static_cast<uint32_t>(__double2hiint(t3)) > neg_thresh_hi;
 }
 
-__global__ void __launch_bounds__(K1S_WARPS * 32, 2) k1_scatter(const __grid_constant__ IjGeom g) {
+#ifndef XRS_K1_MINBLOCKS
+#define XRS_K1_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(K1S_WARPS * 32, XRS_K1_MINBLOCKS) k1_scatter(const __grid_constant__ IjGeom g) {
     const int64_t nqi = g.src_w - 1, nqj = g.src_h - 1;
     const int lane = threadIdx.x & 31;
     const int64_t strip = static_cast<int64_t>(blockIdx.x) * K1S_WARPS + (threadIdx.x >> 5);
@@ -375,7 +369,6 @@ __global__ void __launch_bounds__(K1S_WARPS * 32, 2) k1_scatter(const __grid_con
 
     const double inv_xr = 1.0 / g.x_res, inv_yr = 1.0 / g.y_res;
     const double uv_lo = -g.uv_delta, uv_hi = dadd(1.0, dmul(2.0, g.uv_delta));
-    const float inv_tw = 1.0f / static_cast<float>(g.tile_w), inv_th = 1.0f / static_cast<float>(g.tile_h);
     const int W = static_cast<int>(g.dst_w), R0 = static_cast<int>(g.row_begin), R1 = static_cast<int>(g.row_end);
     const double clamp_hi = static_cast<double>(max(g.dst_w, g.dst_h)) + 8.0;
     // rounding of a pixel coordinate seen through an edge function's gradient, with a factor 8 to
@@ -444,25 +437,22 @@ __global__ void __launch_bounds__(K1S_WARPS * 32, 2) k1_scatter(const __grid_con
                     const double dx3_a = -(fa.dx1 + fa.dx2), dx3_b = -(fb.dx1 + fb.dx2);
                     const uint32_t rej_hi_a = static_cast<uint32_t>(__double2hiint(-2.0 * fa.two_m));
                     const uint32_t rej_hi_b = static_cast<uint32_t>(__double2hiint(-2.0 * fb.two_m));
-                    const int tx_a = fast_div(i_lo, g.tile_w, inv_tw), ty_a = fast_div(j_lo, g.tile_h, inv_th);
-                    const int tx_b = (i_hi < (tx_a + 1) * g.tile_w) ? tx_a : fast_div(i_hi, g.tile_w, inv_tw);
-                    const int ty_b = (j_hi < (ty_a + 1) * g.tile_h) ? ty_a : fast_div(j_hi, g.tile_h, inv_th);
-                    for (int ty = ty_a; ty <= ty_b && !slow; ++ty) {
-                        const int ja = max(j_lo, ty * g.tile_h), jb = min(j_hi, (ty + 1) * g.tile_h - 1);
-                        for (int tx = tx_a; tx <= tx_b; ++tx) {
-                            if (tw.id != ty * g.ntx + tx) load_tile_win(g, ty, tx, tw);
-                            if (!tw.has || qi < tw.qi_lo || qi > tw.qi_hi || qj < tw.qj_lo || qj > tw.qj_hi) continue;
-                            const int ia = max(i_lo, tx * g.tile_w), ib = min(i_hi, (tx + 1) * g.tile_w - 1);
-                            const double ci = static_cast<double>(ia - i_lo);
-                            const double a1c = fma(ci, fa.dx1, fa.e1), a2c = fma(ci, fa.dx2, fa.e2);
-                            const double b1c = fma(ci, fb.dx1, fb.e1), b2c = fma(ci, fb.dx2, fb.e2);
-                            uint32_t *claim_row = g.claims + (static_cast<int64_t>(ja) - g.row_begin) * g.dst_w;
-                            for (int gj = ja; gj <= jb; ++gj, claim_row += g.dst_w) {
+                    // The pixel box of an ordinary quad lies inside ONE reference tile (a box of a few pixels
+                    // against tiles of hundreds); the rare quad that straddles a tile border takes the generic
+                    // kernel, which visits every tile its box touches.
+                    const int tx = static_cast<int>(div_magic(static_cast<uint32_t>(i_lo), g.magic_tw));
+                    const int ty = static_cast<int>(div_magic(static_cast<uint32_t>(j_lo), g.magic_th));
+                    if (i_hi >= (tx + 1) * g.tile_w || j_hi >= (ty + 1) * g.tile_h) slow = true;
+                    if (!slow) {
+                        if (tw.id != ty * g.ntx + tx) load_tile_win(g, ty, tx, tw);
+                        if (tw.has && qi >= tw.qi_lo && qi <= tw.qi_hi && qj >= tw.qj_lo && qj <= tw.qj_hi) {
+                            uint32_t *claim_row = g.claims + (static_cast<int64_t>(j_lo) - g.row_begin) * g.dst_w;
+                            for (int gj = j_lo; gj <= j_hi; ++gj, claim_row += g.dst_w) {
                                 const double rj = static_cast<double>(gj - j_lo);
-                                double a1 = fma(rj, fa.dy1, a1c), a2 = fma(rj, fa.dy2, a2c);
-                                double b1 = fma(rj, fb.dy1, b1c), b2 = fma(rj, fb.dy2, b2c);
+                                double a1 = fma(rj, fa.dy1, fa.e1), a2 = fma(rj, fa.dy2, fa.e2);
+                                double b1 = fma(rj, fb.dy1, fb.e1), b2 = fma(rj, fb.dy2, fb.e2);
                                 double a3 = fa.k3 - (a1 + a2), b3 = fb.k3 - (b1 + b2);  // third condition, stepped too
-                                for (int gi = ia; gi <= ib; ++gi) {
+                                for (int gi = i_lo; gi <= i_hi; ++gi) {
                                     // straight-line decisions (no nested branches): both triangles are
                                     // evaluated, the atomic is the only predicated operation
                                     const uint32_t ha1 = __double2hiint(a1), ha2 = __double2hiint(a2), ha3 = __double2hiint(a3);
@@ -520,16 +510,31 @@ __global__ void __launch_bounds__(256) k1_scatter_slow(IjGeom g) {
 // ---------------------------------------------------------------------------
 // k1_resolve
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(K1R_THREADS) k1_resolve(IjGeom g) {
-    const int64_t c = static_cast<int64_t>(blockIdx.x) * K1R_THREADS + threadIdx.x;
+// One block = K1R_PX * K1R_THREADS consecutive pixels of one target row; a thread resolves K1R_PX of
+// them, K1R_THREADS apart (coalesced), sharing the row context; the claim words are loaded first so
+// that their latency and that of the gathered vertex loads overlap.
+constexpr int K1R_PX = 4;
+__global__ void __launch_bounds__(K1R_THREADS) k1_resolve(const __grid_constant__ IjGeom g) {
+    const int64_t c_first = static_cast<int64_t>(blockIdx.x) * (K1R_THREADS * K1R_PX) + threadIdx.x;
     const int64_t r = g.row_begin + blockIdx.y;
-    if (c >= g.dst_w) return;
     const int64_t n_rows = g.row_end - g.row_begin;
-    const int64_t o = static_cast<int64_t>(blockIdx.y) * g.dst_w + c;
-    double oi, oj;
-    resolve_pixel(g, r, c, __ldcs(g.claims + o), oi, oj);
-    st_stream(g.ij + o, oi);
-    st_stream(g.ij + n_rows * g.dst_w + o, oj);
+    const int64_t row_o = static_cast<int64_t>(blockIdx.y) * g.dst_w;
+    const ResolveRow row = resolve_row(g, r);
+    uint32_t claim[K1R_PX];
+#pragma unroll
+    for (int k = 0; k < K1R_PX; ++k) {
+        const int64_t c = c_first + k * K1R_THREADS;
+        claim[k] = c < g.dst_w ? __ldcs(g.claims + row_o + c) : K1_NOCLAIM;
+    }
+#pragma unroll
+    for (int k = 0; k < K1R_PX; ++k) {
+        const int64_t c = c_first + k * K1R_THREADS;
+        if (c >= g.dst_w) break;
+        double oi, oj;
+        resolve_pixel(g, row, c, claim[k], oi, oj);
+        st_stream(g.ij + row_o + c, oi);
+        st_stream(g.ij + n_rows * g.dst_w + row_o + c, oj);
+    }
 }
 
 static int64_t claims_bytes_of(int64_t rows, int64_t dst_w) {
@@ -562,6 +567,9 @@ int k1_make_geom(const char *who, const double *x, const double *y, int64_t src_
     g.j_up = is_j_axis_up ? 1 : 0; g.uv_delta = uv_delta;
     g.row_begin = row_begin; g.row_end = row_end;
     g.fp_cols = nullptr;
+    g.magic_nqi = div_magic_of(static_cast<uint64_t>(src_w - 1));
+    g.magic_tw = div_magic_of(static_cast<uint64_t>(g.tile_w));
+    g.magic_th = div_magic_of(static_cast<uint64_t>(g.tile_h));
     g.slow_list = reinterpret_cast<uint32_t *>(static_cast<char *>(workspace) + claims_bytes_of(row_end - row_begin, dst_w));
     g.slow_count = reinterpret_cast<unsigned int *>(g.slow_list + (src_h - 1) * (src_w - 1));
     *out = g;
@@ -620,7 +628,7 @@ int xrs_rectify_ij(const double *x, const double *y, int64_t src_h, int64_t src_
     if (int rc = k1_enqueue_claims(g, st)) return rc;
     const int64_t n_rows = row_end - row_begin;
     if (n_rows > 65535) return fail("xrs_rectify_ij: more than 65535 target rows per call");
-    const dim3 rgrid(static_cast<unsigned>(ceil_div(dst_w, K1R_THREADS)), static_cast<unsigned>(n_rows));
+    const dim3 rgrid(static_cast<unsigned>(ceil_div(dst_w, K1R_THREADS * K1R_PX)), static_cast<unsigned>(n_rows));
     XRS_TIMED("k1_resolve", st, k1_resolve<<<rgrid, K1R_THREADS, 0, st>>>(g));
     XRS_LAUNCH_CHECK("k1_resolve");
     return 0;
