@@ -57,7 +57,10 @@ def parse_args():
     ap.add_argument("--fused", action="store_true",
                     help="device-resident leg: one fused xrs_rectify_gather per method (ij in registers, claims "
                          "computed per method) instead of the shared ij image + xrs_gather_ij")
-    ap.add_argument("--chains", type=int, default=2, help="concurrent chains inside the step's CUDA graph")
+    ap.add_argument("--chains", type=int, default=2, help="N > 1: concurrent chains of scenes inside the step's CUDA graph")
+    ap.add_argument("--split-k2", action="store_true",
+                    help="N = 1: run the nearest and the bilinear gather of the scene as two concurrent chains "
+                         "(measured slower than back to back: 3.53 vs 3.46 ms)")
     ap.add_argument("--no-graph", action="store_true", help="take `value` from the eager, sequential region")
     ap.add_argument("--cpu-kind", default="auto", choices=["auto", "reference", "port"],
                     help="CPU baseline: the reference's own numba kernels (oracle/_ref) or the C restatement")
@@ -578,7 +581,7 @@ def ours(args):
 
     def step(record=False, concurrent=False):
         if world == 1:
-            gather_scene(plans[0], 0, record, split=concurrent and n_chains >= 2 and not args.fused)
+            gather_scene(plans[0], 0, record, split=concurrent and args.split_k2 and not args.fused)
             return
         # N > 1: scan 1/N of the coordinates of every scene of the step, ONE all-reduce(MIN) for all
         # their tables, then the band kernels scene after scene (two chains: a rank's band kernels are

@@ -204,6 +204,14 @@ def test_c5_reproject_row_band_full_size(xrs):
             (r0, r1, c0, c1), want = _oracle_tile_block(src, tgt, data, (i0, j0), method, nan, 4326, 3857, band, tx, 256)
             got = out[:, r0 - rows[0]:r1 - rows[0], c0:c1].cpu().numpy()
             _compare_projected(got, want, method, f"C5 {method} tile ({band},{tx})")
+        # the dateline tile columns: their boxes end ON the antimeridian (x = -+pi * a), where the tile
+        # window must not flip to the other side of the globe; the two outermost image columns are left
+        # out (whether their outer tap reads fill is decided by rounding noise, see above)
+        for tx, cols in ((0, slice(2, None)), (7, slice(None, -2))):
+            (r0, r1, c0, c1), want = _oracle_tile_block(src, tgt, data, (i0, j0), method, nan, 4326, 3857, band, tx, 128)
+            got = out[:, r0 - rows[0]:r1 - rows[0], c0:c1].cpu().numpy()
+            assert np.isfinite(got[:, :, cols]).mean() > 0.99, f"C5 {method} dateline tile ({band},{tx}) is mostly fill"
+            _compare_projected(got[:, :, cols], want[:, :, cols], method, f"C5 {method} dateline tile ({band},{tx})")
         del out
 
 

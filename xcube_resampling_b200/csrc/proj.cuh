@@ -82,8 +82,11 @@ __device__ __forceinline__ void clenshaw_complex(const double *c, double sin2xi,
     d_eta = sr * hi1 + si * hr1;
 }
 
+// PROJ's adjlon: longitudes are brought back into [-pi, pi], but a value that overshoots pi by
+// rounding only (x = -20037508.342789244 / a is -pi * (1 + 1 ulp)) is left alone, so that points ON
+// the antimeridian do not flip sign (adjlon.c lets lon overshoot by 1e-12).
 __device__ __forceinline__ double wrap_pi(double lam) {
-    if (fabs(lam) > PROJ_PI) lam -= 2.0 * PROJ_PI * rint(lam / (2.0 * PROJ_PI));
+    if (fabs(lam) > PROJ_PI + 1e-12) lam -= 2.0 * PROJ_PI * rint(lam / (2.0 * PROJ_PI));
     return lam;
 }
 

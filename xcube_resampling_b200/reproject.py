@@ -107,6 +107,13 @@ def transform_bounds(from_crs, to_crs, boxes, densify_pts: int = _DENSIFY_PTS, d
     tx, ty = transform_points(xs, ys, from_crs, to_crs, device)
     if normalize_crs(to_crs).is_geographic:
         tx = _unwrap_longitudes(tx)
+        # the walk is contiguous but may have started on the far side of the antimeridian (its first
+        # sample wrapped): bring every box as a whole back so that its centre lies in [-180, 180]
+        with np.errstate(invalid="ignore"):
+            centre = 0.5 * (np.nanmin(np.where(np.isfinite(tx), tx, np.nan), axis=1)
+                            + np.nanmax(np.where(np.isfinite(tx), tx, np.nan), axis=1))
+        turns = np.where(np.isfinite(centre), np.round(centre / 360.0), 0.0)
+        tx = tx - 360.0 * turns[:, None]
     ok = np.isfinite(tx) & np.isfinite(ty)
     big = np.inf
     out = np.stack([np.where(ok, tx, big).min(axis=1), np.where(ok, ty, big).min(axis=1),
