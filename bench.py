@@ -433,21 +433,19 @@ def ours(args):
             groups = _pipeline.group_by_buffer(
                 [(bands_p, _pipeline.Target(f"bands_{m}", m, np.nan, outs_p[m], row0=r0)) for m in METHODS])
             exchange = multigpu.DistExchange()
-            plan_e2e = xrect.RectifyPlan(target_gm, dev, rows=(r0, r1))
+            plans_e2e = [xrect.RectifyPlan(target_gm, dev, rows=(r0, r1)) for _ in range(2)]
 
             def e2e_step():
-                n = h2d = d2h = 0
-                for _scene in range(world):
-                    st = multigpu.RectifyBandStats()
-                    multigpu.rectify_band(lon_p, lat_p, groups, target_gm, edges_e2e, rank, exchange, device=dev,
-                                          plan=plan_e2e, stats=st)
-                    n += len(METHODS) * nb * (r1 - r0) * W_t
-                    h2d += st.h2d_bytes
-                    d2h += st.d2h_bytes
-                return n, h2d, d2h
+                # the step's N scenes as one stream of band jobs: the prologue of scene s+1 (slab scan, NCCL
+                # all-reduce of the tables, footprint, K1) overlaps the data streaming of scene s
+                stats = multigpu.rectify_band_stream(((lon_p, lat_p, groups) for _ in range(world)), target_gm,
+                                                     edges_e2e, rank, exchange, device=dev, plans=plans_e2e)
+                n = world * len(METHODS) * nb * (r1 - r0) * W_t
+                return n, sum(st.h2d_bytes for st in stats), sum(st.d2h_bytes for st in stats)
 
-            api = ("multigpu.rectify_band per rank (what rectify_dataset(..., devices=range(N)) runs per device): slab "
-                   "scan + NCCL all-reduce(MIN) of the tables + footprint-only uploads + band download")
+            api = ("multigpu.rectify_band_stream per rank (the per-device worker of rectify_dataset(..., devices=range(N)), "
+                   "over the step's N scenes): slab scan + NCCL all-reduce(MIN) of the tables + footprint-only uploads "
+                   "+ band download")
 
         # Warm-up to steady state.  The first step page-locks the output buffers (seconds); for two to
         # three seconds after that, single steps were measured to take 1.5-4x longer at random on
@@ -634,6 +632,7 @@ def ours(args):
     eager_ms = max_over_ranks(a0.elapsed_time(a1))
     e0, e1 = a0, a1
     graph_used = False
+    graph = None
     if use_graph:
         # Region B, the one `value` is computed from: the same step captured once in a CUDA graph and
         # replayed K times (at N > 1 the all-reduce is captured with it).
@@ -785,7 +784,24 @@ def ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear-down: the CUDA graph holds captured NCCL kernels; it must be gone, and every rank idle,
+        # before the communicator is destroyed (destroying it under a live graph was seen to hang the
+        # last rank for the watchdog's 8 minutes).  A timer makes sure a stuck tear-down cannot keep
+        # the GPUs -- the result line is already printed.
+        graph = None  # noqa: F841
+        import gc
+
+        gc.collect()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        killer = threading.Timer(20.0, lambda: os._exit(0))
+        killer.daemon = True
+        killer.start()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        finally:
+            killer.cancel()
 
 
 def spot_check(lon, lat, bands, size, xy_min, res, outs, rows, plan, strip=48):

@@ -246,3 +246,40 @@ def test_unsigned_sum_and_prod_are_uint64(xrs):
         out = affine.resample_dataset(ds, ((2, 0, 0), (0, 2, 0)), ("y", "x"), (6, 4), None, interp_methods=1,
                                       agg_methods=agg)["v"].values
         assert out.dtype == np.uint64, (agg, out.dtype)
+
+
+def test_rectify_band_stream_pipelines_scenes(xrs):
+    """A rank working through a sequence of scenes (prologue of scene s+1 on a side stream while
+    scene s streams its data): every scene's band equals the oracle."""
+    from xcube_resampling_b200._pipeline import Target, group_by_buffer
+
+    n, n_scenes = 2, 3
+    scenes = []
+    for s in range(n_scenes):
+        x, y = swath(420, 330, theta=12.0 + 9.0 * s, seed=20 + s)
+        data = np.random.default_rng(s).random((5, 330, 420)).astype(np.float32)
+        scenes.append((x, y, data))
+    # one target grid for all scenes (the bench's situation: scene after scene onto the same grid)
+    xs = np.concatenate([sc[0].ravel() for sc in scenes])
+    ys = np.concatenate([sc[1].ravel() for sc in scenes])
+    res = 0.0027
+    size, xy_min = covering_grid_args(xs, ys, res)
+    tgt_gm = xrs.GridMapping.regular(size, xy_min, res, "EPSG:4326", tile_size=128)
+    g = ogrid.regular_grid(size, xy_min, res, tile_size=128)
+    edges = xrs.mg.default_band_edges(tgt_gm.height, n)
+    outs = [{m: np.full((5, tgt_gm.height, tgt_gm.width), -5.0, dtype=np.float32) for m in ("nearest", "bilinear")}
+            for _ in range(n_scenes)]
+
+    def worker(k, dev, exchange):
+        jobs = []
+        for s, (x, y, data) in enumerate(scenes):
+            groups = group_by_buffer([(data, Target(m, m, nan, outs[s][m])) for m in ("nearest", "bilinear")])
+            jobs.append((x, y, groups))
+        stats = xrs.mg.rectify_band_stream(jobs, tgt_gm, edges, k, exchange, device=dev)
+        assert len(stats) == n_scenes and all(st.d2h_bytes > 0 for st in stats)
+
+    xrs.mg.run_on_devices([0] * n, worker)
+    for s, (x, y, data) in enumerate(scenes):
+        ij = orect.rectify_ij(x, y, g)
+        for m in ("nearest", "bilinear"):
+            assert_same(outs[s][m], orect.gather(data, ij, m, nan), f"scene {s} {m}")

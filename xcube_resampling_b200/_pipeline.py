@@ -118,13 +118,25 @@ class GatherPipeline:
         self._out_slots: dict = {}
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self._pending = None
+        self._keep = None
 
     def _slots(self, cache, key, shape, dtype):
         if key not in cache:
             cache[key] = [torch.empty(shape, dtype=_dev.torch_dtype(dtype), device=self.dev) for _ in range(2)]
         return cache[key]
 
-    def run(self, groups: list[SourceGroup], process) -> None:
+    def wait(self) -> None:
+        """Block until everything enqueued by :meth:`run` has landed in host memory."""
+        if self._pending is not None:
+            s_out, main = self._pending
+            s_out.synchronize()
+            main.synchronize()
+            self._pending = None
+
+    def run(self, groups: list[SourceGroup], process, wait: bool = True) -> None:
+        """Enqueue uploads, kernels and downloads of every band chunk; ``wait=False`` returns as soon as
+        everything is enqueued (call :meth:`wait` before touching the outputs or dropping the inputs)."""
         dev = self.dev
         main = torch.cuda.current_stream(dev)
         s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
@@ -186,5 +198,7 @@ class GatherPipeline:
                         out_free[oslot].record(s_out)
                 in_free[slot].record(main)
             keep.append(v)
-        s_out.synchronize()
-        main.synchronize()
+        self._keep = keep
+        self._pending = (s_out, main)
+        if wait:
+            self.wait()

@@ -168,93 +168,178 @@ class RectifyBandStats:
         self.window = None
 
 
-def rectify_band(x: np.ndarray, y: np.ndarray, groups: list, target_gm, band_edges, k: int, exchange,
-                 device=None, plan=None, stats: RectifyBandStats | None = None, chunk_bands: int = 4) -> None:
-    """Participant ``k``: rectify target rows ``band_edges[k]:band_edges[k+1]`` of every target in
-    ``groups`` (``_pipeline.SourceGroup`` list; ``Target.out_host`` arrays are (bands, H, W) and rows
-    of the band are filled) from host coordinates ``x``, ``y`` (h, w) float64.
+class RectifyBandJob:
+    """Participant ``k``'s share of ONE scene: target rows ``band_edges[k]:band_edges[k+1]`` of every
+    target in ``groups`` (``_pipeline.SourceGroup`` list; ``Target.out_host`` arrays are (bands, H, W)
+    -- or band-only arrays with ``Target.row0`` -- and the rows of the band are filled) from host
+    coordinates ``x``, ``y`` (h, w) float64.
 
-    Every participant must call this with the same ``x``, ``y``, ``target_gm`` and ``band_edges``;
-    ``exchange`` merges the partial tables.  Blocks until the band's rows are in host memory."""
-    from .rectify import RectifyPlan, gather_ij
+    Three phases, so that a rank working through a sequence of scenes can overlap them
+    (:func:`rectify_band_stream`): :meth:`prologue` -- slab scan, table exchange, footprint, K1, all on
+    ``stream`` (blocks only on that stream: the tiny footprint table has to reach the host);
+    :meth:`enqueue` -- the band-chunk pipeline of all data variables on the current stream;
+    :meth:`wait`.  Every participant must run the same sequence of prologues with the same ``x``,
+    ``y``, ``target_gm`` and ``band_edges``; ``exchange`` merges the partial tables."""
 
-    lib = load()
-    dev = _dev.require_cuda(device)
-    torch.cuda.set_device(dev)
-    stats = stats if stats is not None else RectifyBandStats()
-    n = exchange.n
-    edges = [int(e) for e in band_edges]
-    if len(edges) != n + 1:
-        raise ValueError("band_edges must have one more entry than there are participants")
-    rows = (edges[k], edges[k + 1])
-    h, w = x.shape
-    if x.dtype != np.float64 or y.dtype != np.float64 or y.shape != x.shape:
-        raise TypeError("source coordinates must be float64 arrays of the same shape")
-    if x.strides[1] != 8 or y.strides[1] != 8:
-        x, y = np.ascontiguousarray(x), np.ascontiguousarray(y)
-    group = int(lib.xrs_quad_row_group())
-    n_groups = -(-(h - 1) // group)
-    if plan is None or plan.rows != rows or plan.device != dev:
-        plan = RectifyPlan(target_gm, dev, rows=(rows if rows[1] > rows[0] else (0, 1)))
-    n_tiles = plan.ntx * plan.nty
-    gm = target_gm
-    x_min, y_min, x_max, y_max = gm.xy_bbox
+    def __init__(self, x: np.ndarray, y: np.ndarray, groups: list, target_gm, band_edges, k: int, exchange,
+                 device=None, plan=None, stats: RectifyBandStats | None = None, chunk_bands: int = 4, stream=None):
+        from .rectify import RectifyPlan
 
-    # 1. slab scan: per-tile source windows + band footprints, partial tables in min-form
-    table = _dev.empty((4 * n_tiles + 2 * n * n_groups,), np.int32, dev)
-    check(lib.xrs_minform_init(_dev.ptr(table), table.numel(), _dev.stream_ptr(dev)), "xrs_minform_init")
-    s0, s1 = source_slabs(h, n, group)[k]
-    if s1 > s0:
-        s1v = min(h, s1 + 1)  # first vertex row of the next slab closes this slab's last quad row
-        wp = -(-w // 16) * 16
-        xs = _dev.empty((s1v - s0, wp), np.float64, dev)
-        ys = _dev.empty((s1v - s0, wp), np.float64, dev)
+        self.lib = load()
+        self.dev = _dev.require_cuda(device)
+        self.stats = stats if stats is not None else RectifyBandStats()
+        self.exchange, self.k, self.n = exchange, int(k), exchange.n
+        self.edges = [int(e) for e in band_edges]
+        if len(self.edges) != self.n + 1:
+            raise ValueError("band_edges must have one more entry than there are participants")
+        self.rows = (self.edges[k], self.edges[k + 1])
+        if x.dtype != np.float64 or y.dtype != np.float64 or y.shape != x.shape or x.ndim != 2:
+            raise TypeError("source coordinates must be 2-D float64 arrays of the same shape")
+        if x.strides[1] != 8 or y.strides[1] != 8:
+            x, y = np.ascontiguousarray(x), np.ascontiguousarray(y)
+        self.x, self.y, self.groups, self.gm = x, y, groups, target_gm
+        self.h, self.w = x.shape
+        self.group = int(self.lib.xrs_quad_row_group())
+        self.n_groups = -(-(self.h - 1) // self.group)
+        rows = self.rows
+        if plan is None or plan.rows != (rows if rows[1] > rows[0] else (0, 1)) or plan.device != self.dev:
+            plan = RectifyPlan(target_gm, self.dev, rows=(rows if rows[1] > rows[0] else (0, 1)))
+        self.plan = plan
+        self.chunk_bands = chunk_bands
+        self.stream = stream
+        self.pipe = None
+        self._ij = self._ready = self._window = self._segments = None
+        self._done = False
+
+    def _fill_band(self):
+        r0, r1 = self.rows
+        for grp in self.groups:
+            for tgt in grp.targets:
+                tgt.out_host[:, r0 - tgt.row0:r1 - tgt.row0, :] = np.asarray(tgt.fill).astype(tgt.out_dtype)
+
+    def prologue(self) -> None:
         from ._pipeline import copy2d
 
-        for buf, host in ((xs, x), (ys, y)):
-            copy2d(buf.data_ptr(), wp * 8, 0, host.__array_interface__["data"][0] + s0 * host.strides[0],
-                   host.strides[0], 0, w * 8, s1v - s0, 1, dev)
-        stats.h2d_bytes += 2 * (s1v - s0) * w * 8
-        plan.scan_slab(xs, ys, s0, s1 - s0, h, w, edges, table)
-    # 2. the exchange step
-    table = exchange.merge(k, table)
-    if rows[1] <= rows[0]:
-        return
-    tile_boxes = plan.finalize_windows(table, w, h)
-    fp = _dev.to_host(table[4 * n_tiles:].view(n, n_groups, 2)[k])
-    window, segments, n_px = footprint_segments(fp, h, w, group)
-    stats.window, stats.src_px = window, n_px
-    if window is None:  # no source quad reaches the band: everything is fill
-        for grp in groups:
-            for tgt in grp.targets:
-                tgt.out_host[:, rows[0] - tgt.row0:rows[1] - tgt.row0, :] = np.asarray(tgt.fill).astype(tgt.out_dtype)
-        return
-    # 3. coordinates of the footprint, K1 restricted to it
-    fj0, fj1 = window
-    wp = -(-w // 16) * 16
-    xw = _dev.empty((fj1 - fj0, wp), np.float64, dev)
-    yw = _dev.empty((fj1 - fj0, wp), np.float64, dev)
-    from ._pipeline import copy2d
+        dev, lib, plan, st = self.dev, self.lib, self.plan, self.stats
+        h, w, n, k, group, n_groups = self.h, self.w, self.n, self.k, self.group, self.n_groups
+        torch.cuda.set_device(dev)
+        stream = self.stream if self.stream is not None else torch.cuda.current_stream(dev)
+        with torch.cuda.stream(stream):
+            n_tiles = plan.ntx * plan.nty
+            # 1. slab scan: per-tile source windows + band footprints, partial tables in min-form
+            table = _dev.empty((4 * n_tiles + 2 * n * n_groups,), np.int32, dev)
+            check(lib.xrs_minform_init(_dev.ptr(table), table.numel(), _dev.stream_ptr(dev)), "xrs_minform_init")
+            s0, s1 = source_slabs(h, n, group)[k]
+            wp = -(-w // 16) * 16
+            if s1 > s0:
+                s1v = min(h, s1 + 1)  # first vertex row of the next slab closes this slab's last quad row
+                xs = _dev.empty((s1v - s0, wp), np.float64, dev)
+                ys = _dev.empty((s1v - s0, wp), np.float64, dev)
+                for buf, host in ((xs, self.x), (ys, self.y)):
+                    copy2d(buf.data_ptr(), wp * 8, 0, host.__array_interface__["data"][0] + s0 * host.strides[0],
+                           host.strides[0], 0, w * 8, s1v - s0, 1, dev)
+                st.h2d_bytes += 2 * (s1v - s0) * w * 8
+                plan.scan_slab(xs, ys, s0, s1 - s0, h, w, self.edges, table)
+            # 2. the exchange step
+            table = self.exchange.merge(k, table)
+            if self.rows[1] <= self.rows[0]:
+                self._done = True
+                return
+            tile_boxes = plan.finalize_windows(table, w, h)
+            fp = _dev.to_host(table[4 * n_tiles:].view(n, n_groups, 2)[k])
+            window, segments, n_px = footprint_segments(fp, h, w, group)
+            st.window, st.src_px = window, n_px
+            if window is None:  # no source quad reaches the band: everything is fill
+                self._fill_band()
+                self._done = True
+                return
+            # 3. coordinates of the footprint, K1 restricted to it
+            fj0, fj1 = window
+            xw = _dev.empty((fj1 - fj0, wp), np.float64, dev)
+            yw = _dev.empty((fj1 - fj0, wp), np.float64, dev)
+            for buf, host in ((xw, self.x), (yw, self.y)):
+                for (j0, j1, i0, i1) in segments:
+                    copy2d(buf.data_ptr() + ((j0 - fj0) * wp + i0) * 8, wp * 8, 0,
+                           host.__array_interface__["data"][0] + j0 * host.strides[0] + i0 * 8, host.strides[0], 0,
+                           (i1 - i0) * 8, j1 - j0, 1, dev)
+            st.h2d_bytes += 2 * n_px * 8
+            col_ranges = table[4 * n_tiles:].view(n, n_groups, 2)[k]
+            self._ij = plan.ij_window(xw, yw, fj0, h, w, tile_boxes, col_ranges)
+            self._ready = torch.cuda.Event()
+            self._ready.record(stream)
+            self._window, self._segments = window, segments
+            self._buffers = (xw, yw, table)  # alive until the kernels that read them have run
 
-    for buf, host in ((xw, x), (yw, y)):
-        for (j0, j1, i0, i1) in segments:
-            copy2d(buf.data_ptr() + ((j0 - fj0) * wp + i0) * 8, wp * 8, 0,
-                   host.__array_interface__["data"][0] + j0 * host.strides[0] + i0 * 8, host.strides[0], 0,
-                   (i1 - i0) * 8, j1 - j0, 1, dev)
-    stats.h2d_bytes += 2 * n_px * 8
-    col_ranges = table[4 * n_tiles:].view(n, n_groups, 2)[k]
-    ij = plan.ij_window(xw, yw, fj0, h, w, tile_boxes, col_ranges)
-    # 4. data bands of the footprint through K2, band chunk by band chunk
-    pipe = GatherPipeline(dev, (h, w), gm.width, rows, src_window=window, segments=segments, chunk_bands=chunk_bands)
-    n_rows = rows[1] - rows[0]
+    def enqueue(self) -> None:
+        """The data bands of the footprint through K2, band chunk by band chunk, on the current stream."""
+        from .rectify import gather_ij
 
-    def process(src_view, tgt, out_view, b0):
-        gather_ij(src_view, ij, tgt.method, tgt.fill, out=out_view, window_origin=(0, fj0), full_size=(w, h))
+        if self._done:
+            return
+        dev = self.dev
+        torch.cuda.current_stream(dev).wait_event(self._ready)
+        fj0 = self._window[0]
+        ij, h, w = self._ij, self.h, self.w
+        self.pipe = GatherPipeline(dev, (h, w), self.gm.width, self.rows, src_window=self._window,
+                                   segments=self._segments, chunk_bands=self.chunk_bands)
 
-    pipe.run(groups, process)
-    stats.h2d_bytes += pipe.h2d_bytes
-    stats.d2h_bytes += pipe.d2h_bytes
-    del n_rows
+        def process(src_view, tgt, out_view, b0):
+            gather_ij(src_view, ij, tgt.method, tgt.fill, out=out_view, window_origin=(0, fj0), full_size=(w, h))
+
+        self.pipe.run(self.groups, process, wait=False)
+
+    def wait(self) -> None:
+        if self.pipe is not None:
+            self.pipe.wait()
+            self.stats.h2d_bytes += self.pipe.h2d_bytes
+            self.stats.d2h_bytes += self.pipe.d2h_bytes
+            self.pipe = None
+        self._buffers = None
+        self._done = True
+
+
+def rectify_band(x: np.ndarray, y: np.ndarray, groups: list, target_gm, band_edges, k: int, exchange,
+                 device=None, plan=None, stats: RectifyBandStats | None = None, chunk_bands: int = 4) -> None:
+    """One scene, one participant, start to finish (see :class:`RectifyBandJob`).  Blocks until the
+    band's rows are in host memory."""
+    job = RectifyBandJob(x, y, groups, target_gm, band_edges, k, exchange, device, plan, stats, chunk_bands)
+    job.prologue()
+    job.enqueue()
+    job.wait()
+
+
+def rectify_band_stream(scenes, target_gm, band_edges, k: int, exchange, device=None, plans=None,
+                        chunk_bands: int = 4) -> list:
+    """Participant ``k`` working through a SEQUENCE of scenes (an iterable of ``(x, y, groups)``): while
+    the band-chunk pipeline of scene s streams data through the copy engines, the prologue of scene
+    s + 1 (slab scan, table exchange, footprint, K1) already runs on a second, high-priority stream
+    with its own plan, so the copy engines never wait for it.  Returns one
+    :class:`RectifyBandStats` per scene.  Single host thread: the exchange steps of all participants
+    stay in scene order."""
+    from .rectify import RectifyPlan
+
+    dev = _dev.require_cuda(device)
+    torch.cuda.set_device(dev)
+    edges = [int(e) for e in band_edges]
+    rows = (edges[k], edges[k + 1])
+    rows_p = rows if rows[1] > rows[0] else (0, 1)
+    if plans is None:
+        plans = [RectifyPlan(target_gm, dev, rows=rows_p) for _ in range(2)]
+    side = torch.cuda.Stream(dev, priority=-1)
+    stats, prev = [], None
+    for s, (x, y, groups) in enumerate(scenes):
+        st = RectifyBandStats()
+        stats.append(st)
+        job = RectifyBandJob(x, y, groups, target_gm, edges, k, exchange, dev, plans[s % 2], st, chunk_bands,
+                             stream=side)
+        job.prologue()          # overlaps the previous scene's streaming
+        job.enqueue()
+        if prev is not None:
+            prev.wait()
+        prev = job
+    if prev is not None:
+        prev.wait()
+    return stats
 
 
 def default_band_edges(height: int, n: int, align: int = 32) -> list[int]:
