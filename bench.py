@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--fused", action="store_true",
                     help="device-resident leg: one fused xrs_rectify_gather per method (ij in registers, claims "
                          "computed per method) instead of the shared ij image + xrs_gather_ij")
-    ap.add_argument("--chains", type=int, default=2, help="N > 1: concurrent chains of scenes inside the step's CUDA graph")
+    ap.add_argument("--chains", type=int, default=4, help="N > 1: concurrent chains of scenes inside the step's CUDA graph")
     ap.add_argument("--split-k2", action="store_true",
                     help="N = 1: run the nearest and the bilinear gather of the scene as two concurrent chains "
                          "(measured slower than back to back: 3.53 vs 3.46 ms)")
@@ -525,10 +525,9 @@ def ours(args):
         e.record()
         return e
 
-    def scan_scene(scene):
-        check_rc(lib.xrs_minform_init(_dev.ptr(tables[scene]), table_len, _dev.stream_ptr(dev)))
+    def scan_scene(scene, plan):
         if s1 > s0:
-            plans[0].scan_slab(x_dev[s0:s1v], y_dev[s0:s1v], s0, s1 - s0, h, w, edges, tables[scene])
+            plan.scan_slab(x_dev[s0:s1v], y_dev[s0:s1v], s0, s1 - s0, h, w, edges, tables[scene])
 
     def check_rc(rc):
         _lib.check(rc, "libxrs")
@@ -585,28 +584,36 @@ def ours(args):
         # their tables, then the band kernels scene after scene (two chains: a rank's band kernels are
         # 10-250 us, K0 finalize / K1 scatter latency-bound)
         e0 = mark(record)
-        for scene in range(world):
-            scan_scene(scene)
+        check_rc(lib.xrs_minform_init(_dev.ptr(tables), world * table_len, _dev.stream_ptr(dev)))  # all scenes at once
+        main = torch.cuda.current_stream(dev)
+        multi = concurrent and n_plans > 1
+
+        def on_chains(work):
+            """work(c) on chain c, forked from and joined to the main stream."""
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for c in range(n_plans):
+                chains[c].wait_event(fork)
+                with torch.cuda.stream(chains[c]):
+                    work(c)
+                    joined = torch.cuda.Event()
+                    joined.record(chains[c])
+                main.wait_event(joined)
+
+        if multi:  # the slab scans of the scenes are latency-bound kernels of 40-70 us: side by side
+            on_chains(lambda c: [scan_scene(scene, plans[c]) for scene in range(c, world, n_plans)])
+        else:
+            for scene in range(world):
+                scan_scene(scene, plans[0])
         dist.all_reduce(tables, op=dist.ReduceOp.MIN)
         e1 = mark(record)
         if record:
             pending.append(("scan+allreduce", e0, e1))
-        if not concurrent or n_plans == 1:
+        if multi:
+            on_chains(lambda c: [gather_scene(plans[c], scene, False, outs=outs_c[c]) for scene in range(c, world, n_plans)])
+        else:
             for scene in range(world):
                 gather_scene(plans[0], scene, record)
-            return
-        main = torch.cuda.current_stream(dev)
-        fork = torch.cuda.Event()
-        fork.record(main)
-        for c in range(n_plans):
-            chain = chains[c]
-            chain.wait_event(fork)
-            with torch.cuda.stream(chain):
-                for scene in range(c, world, n_plans):
-                    gather_scene(plans[c], scene, False, outs=outs_c[c])
-                joined = torch.cuda.Event()
-                joined.record(chain)
-            main.wait_event(joined)
 
     for _ in range(args.warmup):
         step()
@@ -637,6 +644,8 @@ def ours(args):
         # Region B, the one `value` is computed from: the same step captured once in a CUDA graph and
         # replayed K times (at N > 1 the all-reduce is captured with it).
         try:
+            step(concurrent=True)  # eagerly once: every chain's plan allocates its workspaces / uploads its tables
+            barrier()
             launches0 = lib.xrs_launch_count()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
@@ -761,6 +770,46 @@ def ours(args):
                                             restore_affinity=all_cpus)
         except Exception as e:
             configs = [{"error": f"{type(e).__name__}: {e}"}]
+
+    # ---- BASELINE.json configs[4] across the N GPUs by target row bands (N > 1) ----------------
+    if world > 1 and not args.no_configs and args.scale == 1.0:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_configs
+
+            barrier()
+            err5 = None
+            try:
+                c5 = bench_configs.c5_across(rank, world, reps=3, e2e=not args.no_e2e)
+            except Exception as e:  # keep the ranks' collectives below in step whatever happened here
+                err5 = f"{type(e).__name__}: {e}"
+                c5 = {"kernel_ms": 1.0, "units": 0, "algorithmic_bytes": 0.0, "per_band_ms": [], "e2e_s": 1.0,
+                      "h2d_bytes": 0, "d2h_bytes": 0}
+                if args.no_e2e:
+                    c5["e2e_s"] = None
+            if max_over_ranks(1.0 if err5 else 0.0) != 0.0:
+                raise RuntimeError(err5 or "C5 failed on another rank")
+            kernel_ms = max_over_ranks(c5["kernel_ms"])
+            units = sum_over_ranks(float(c5["units"]))
+            alg = sum_over_ranks(c5["algorithmic_bytes"])
+            barrier()
+            line5 = {"config": f"C5 reproject global 0.01deg (36000x18000, 8 float32 variables) -> EPSG:3857 36000^2 across "
+                               f"{world} GPUs by target row bands of 4500 rows, bilinear, float32 out",
+                     "ms": kernel_ms, "Mpix_band_per_s": units / kernel_ms / 1e3, "algorithmic_bytes": alg,
+                     "GB_per_s": alg / kernel_ms / 1e6, "frac": alg / kernel_ms / 1e6 / (peak * world),
+                     "timing": "per rank: CUDA events around xrs_reproject of each of its bands (median of 3), summed; "
+                               "max over ranks", "rank0_per_band_ms": c5["per_band_ms"]}
+            if c5["e2e_s"] is not None:
+                e2e_s = max_over_ranks(c5["e2e_s"])
+                line5["e2e"] = {"Mpix_band_per_s": units / e2e_s / 1e6, "seconds": e2e_s,
+                                "h2d_bytes": int(sum_over_ranks(float(c5["h2d_bytes"]))),
+                                "d2h_bytes": int(sum_over_ranks(float(c5["d2h_bytes"]))),
+                                "api": "reproject_groups per rank (the per-device worker of reproject_dataset(..., "
+                                       "devices=range(N))): footprint-only upload from page-locked host arrays, band "
+                                       "download into page-locked host arrays"}
+            configs = [line5]
+        except Exception as e:
+            configs = [{"config": "C5 across GPUs", "error": f"{type(e).__name__}: {e}"}]
 
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------
     cpu = None

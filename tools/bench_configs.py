@@ -265,6 +265,63 @@ def c5(reps, one_shot, cpu, threads):
     return out
 
 
+def c5_across(rank, world, reps=3, e2e=True):
+    """BASELINE.json configs[4]: the global 0.01-deg stack (8 float32 variables) reprojected to EPSG:3857,
+    36000^2, partitioned over ``world`` GPUs by target row bands of 4500 rows (the reference tile rows):
+    rank r computes bands r, r + world, ...  Returns this rank's figures (the caller reduces over
+    ranks): device-resident kernel time per band and, with ``e2e``, the same bands through
+    ``reproject_groups`` from page-locked host arrays (footprint-only upload, band download)."""
+    from xcube_resampling_b200._pipeline import Target, group_by_buffer
+
+    src, tgt = c5_grids()
+    windows = reproject.get_source_windows(src, tgt)
+    nb, n_bands = 8, 8
+    mine = [b for b in range(n_bands) if b % world == rank]
+    out = {"bands": mine, "kernel_ms": 0.0, "units": 0, "algorithmic_bytes": 0.0, "per_band_ms": [],
+           "e2e_s": None, "h2d_bytes": 0, "d2h_bytes": 0}
+    for b in mine:
+        rows = (b * 4500, (b + 1) * 4500)
+        plan = reproject.ReprojectPlan(src, tgt, rows=rows, windows=windows)
+        i0, j0, i1, j1 = plan.footprint()
+        window = rand_dev((nb, j1 - j0, i1 - i0))
+        dst = _dev.empty((nb, 4500, 36000), np.float32)
+        ms = timed(lambda: plan.run(window, "bilinear", float("nan"), out=dst, out_dtype=np.float32,
+                                    window_origin=(i0, j0)), reps, False)
+        out["kernel_ms"] += ms
+        out["per_band_ms"].append(ms)
+        out["units"] += nb * 4500 * 36000
+        out["algorithmic_bytes"] += 4.0 * nb * (j1 - j0) * (i1 - i0) + 4.0 * nb * 4500 * 36000
+        del window, dst
+        torch.cuda.empty_cache()
+    if e2e and mine:
+        # one page-locked source plane shared by the 8 variables (zero band stride: the bytes that move
+        # are real, the host memory stays at 2.6 GB per rank), band-only page-locked outputs
+        plane = _dev.pinned_empty((src.height, src.width), np.float32)
+        rng = np.random.default_rng(rank)
+        for j in range(0, src.height, 1000):
+            plane[j:j + 1000] = rng.random((min(1000, src.height - j), src.width), dtype=np.float32)
+        values = np.lib.stride_tricks.as_strided(plane, shape=(nb,) + plane.shape, strides=(0,) + plane.strides)
+        host_out = _dev.pinned_empty((nb, 4500, 36000), np.float32)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        stats = []
+
+        def run_all_bands():
+            for b in mine:
+                groups = group_by_buffer([(values, Target("v", "bilinear", float("nan"), host_out, row0=b * 4500))])
+                reproject.reproject_groups(groups, src, tgt, [dev], band_edges=[b * 4500, (b + 1) * 4500],
+                                           windows=windows, stats=stats)
+
+        run_all_bands()  # warm-up (page-locking, allocator)
+        stats.clear()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run_all_bands()
+        out["e2e_s"] = time.perf_counter() - t0
+        out["h2d_bytes"] = sum(st["h2d_bytes"] for st in stats)
+        out["d2h_bytes"] = sum(st["d2h_bytes"] for st in stats)
+    return out
+
+
 CASES = {"c1": c1, "c3": c3, "c4": c4, "c5": c5}
 
 

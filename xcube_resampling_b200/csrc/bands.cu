@@ -19,7 +19,9 @@
 namespace xrs {
 
 constexpr int KB_THREADS = 256;
+constexpr int KB_COLS = 64;  // quad columns per block
 constexpr int KB_MAX_BANDS = 64;
+static_assert(K1S_ROWS % (KB_THREADS / KB_COLS) == 0, "row groups must split evenly over the thread rows");
 
 __global__ void kb_fill_i32(int32_t *p, int64_t n, int32_t v) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -32,8 +34,8 @@ struct BandGrid {
     int64_t dst_w, dst_h;
 };
 
-// One block = KB_THREADS quad columns x K1S_ROWS quad rows (one row group); a thread marches down its
-// quad column.  A quad counts for every band its pixel box (grown by a margin that covers the
+// One block = KB_COLS quad columns x K1S_ROWS quad rows (one row group); a thread marches down a
+// quarter of its quad column.  A quad counts for every band its pixel box (grown by a margin that covers the
 // barycentric tolerance and the +-1 px between tile-local and global pixel arithmetic) overlaps.
 // Quads with fewer than three finite vertices cannot accept a pixel (both triangles hold a NaN).
 __global__ void __launch_bounds__(KB_THREADS)
@@ -46,10 +48,15 @@ kb_quad_footprints(const double *__restrict__ x, const double *__restrict__ y, i
     for (int k = threadIdx.x; k < n_bands; k += blockDim.x) { s_tab[k][0] = INT32_MAX; s_tab[k][1] = INT32_MAX; }
     __syncthreads();
     const int64_t nqi = src_w - 1;
-    const int64_t n_col_chunks = ceil_div(nqi, KB_THREADS);
+    const int64_t n_col_chunks = ceil_div(nqi, KB_COLS);
     const int64_t chunk = blockIdx.x % n_col_chunks, row_chunk = blockIdx.x / n_col_chunks;
-    const int64_t qi = chunk * KB_THREADS + threadIdx.x;
-    const int64_t q0 = row_chunk * K1S_ROWS, q1 = min(q0 + K1S_ROWS, slab_h - 1);  // local quad rows
+    const int64_t qi = chunk * KB_COLS + (threadIdx.x % KB_COLS);
+    // the K1S_ROWS quad rows of the group are split over KB_THREADS / KB_COLS thread rows (short
+    // dependent-load chains, four times as many blocks as one thread per column would give)
+    constexpr int ROWS_PER_THREAD = K1S_ROWS / (KB_THREADS / KB_COLS);
+    const int64_t g0 = row_chunk * K1S_ROWS;
+    const int64_t q0 = g0 + (threadIdx.x / KB_COLS) * ROWS_PER_THREAD;
+    const int64_t q1 = min(min(q0 + ROWS_PER_THREAD, g0 + K1S_ROWS), slab_h - 1);  // local quad rows
     if (qi < nqi && q0 < q1) {
         auto px = [&](double vx, double vy, double &fx, double &fy) {
             fx = (vx - g.x_min) * g.inv_xr;
@@ -129,7 +136,7 @@ int xrs_band_quad_footprints(const double *x, const double *y, int64_t slab_h, i
     g.x_min = x_min; g.y_min = y_min; g.y_max = y_max; g.inv_xr = 1.0 / x_res; g.inv_yr = 1.0 / y_res;
     g.j_up = is_j_axis_up ? 1 : 0; g.dst_w = dst_w; g.dst_h = dst_h;
     const int n_groups = static_cast<int>(ceil_div(src_h - 1, K1S_ROWS));
-    const int64_t n_blocks = ceil_div(src_w - 1, KB_THREADS) * ceil_div(slab_h - 1, K1S_ROWS);
+    const int64_t n_blocks = ceil_div(src_w - 1, KB_COLS) * ceil_div(slab_h - 1, K1S_ROWS);
     if (n_blocks > 0x7fffffffLL) return fail("xrs_band_quad_footprints: slab too large");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     XRS_TIMED("kb_quad_footprints", st, kb_quad_footprints<<<static_cast<unsigned>(n_blocks), KB_THREADS, 0, st>>>(x, y, slab_h, src_w, src_pitch, j_offset, g, band_edges, n_bands, n_groups, minform_fp));

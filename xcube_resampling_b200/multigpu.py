@@ -106,7 +106,7 @@ def source_slabs(src_h: int, n: int, group: int) -> list[tuple[int, int]]:
     return [(edges[k], edges[k + 1]) for k in range(n)]
 
 
-def footprint_segments(fp_minform: np.ndarray, src_h: int, src_w: int, group: int, merge_groups: int = 4,
+def footprint_segments(fp_minform: np.ndarray, src_h: int, src_w: int, group: int, merge_groups: int = 1,
                        align: int = 32):
     """Upload plan of one band from its row of the footprint table.
 
