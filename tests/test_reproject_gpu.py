@@ -182,6 +182,10 @@ def test_identity_transform_is_bit_exact(xrs, dtype, method, tile):
     plan = xrs.rep.ReprojectPlan(src_gm, tgt_gm)
     got = xrs.dev.to_host(plan.run(xrs.dev.to_device(data), method, fill))
     assert_same(got, want, f"{np.dtype(dtype).name}/{method}/{tile}")
+    # a 128-byte row pitch lets the TMA-staged kernel run (k3_reproject_staged); border tiles of this
+    # case still take its direct per-pixel path
+    got = xrs.dev.to_host(plan.run(xrs.dev.to_device_pitched(data), method, fill))
+    assert_same(got, want, f"staged {np.dtype(dtype).name}/{method}/{tile}")
 
 
 def test_identity_transform_j_axis_up_target_and_2d(xrs):
@@ -421,3 +425,43 @@ def test_band_pipeline_equals_plain_path(xrs):
         plain = xrs.dev.to_host(plan.run(sd, method, np.nan))
         piped = xrs.reproject_dataset(ds, tgt_gm, source_gm=src_gm, interp_methods=method)["v"].values
         assert_same(piped, plain, method)
+
+
+@pytest.mark.parametrize("tile", [128, (100, 77)])
+@pytest.mark.parametrize("case", ["utm", "webmerc", "laea", "coarse_target"])
+def test_staged_kernel_equals_direct_kernel(xrs, case, tile):
+    """k3_reproject_staged (source box of every band staged through TMA) against the direct per-pixel
+    kernel on the same inputs, bit for bit: real projections, reference tiles that are not multiples
+    of the 32 x 32 CTA tile, float64 and float32 outputs, a row band with a resident window, and a
+    target so coarse that the box does not fit the staging buffers (in-kernel fallback)."""
+    if case == "utm":
+        src_gm, tgt_gm = _case_utm_from_geographic(xrs, n=300, tile=tile)
+    elif case == "webmerc":
+        src_gm = xrs.GridMapping.regular((420, 300), (5.0, 44.0), 0.01, "EPSG:4326")
+        tgt_gm = xrs.GridMapping.regular((400, 380), (570000.0, 5500000.0), 1113.2, "EPSG:3857", tile_size=tile)
+    elif case == "laea":
+        src_gm = xrs.GridMapping.regular((420, 300), (9.0, 47.0), 0.01, "EPSG:4326")
+        tgt_gm = xrs.GridMapping.regular((500, 420), (4180000.0, 2660000.0), 600.0, "EPSG:3035", tile_size=tile)
+    else:
+        src_gm = xrs.GridMapping.regular((900, 700), (9.0, 47.0), 0.002, "EPSG:4326")
+        tgt_gm = xrs.GridMapping.regular((200, 180), (4250000.0, 2700000.0), 700.0, "EPSG:3035", tile_size=tile)
+    rng = np.random.default_rng(5)
+    data = rng.random((5, src_gm.height, src_gm.width)).astype(np.float32)
+    data[1, 40:60, 50:90] = nan
+    plain, pitched = xrs.dev.to_device(data), xrs.dev.to_device_pitched(data)
+    if (plain.stride(1) * 4) % 16 == 0:
+        plain = xrs.dev.to_device(np.pad(data, ((0, 0), (0, 0), (0, 1))))[:, :, :-1]  # force the direct kernel
+    plan = xrs.rep.ReprojectPlan(src_gm, tgt_gm)
+    for method in ("nearest", "bilinear", "triangular"):
+        for out_dtype in ((None, np.float32) if method == "bilinear" else (None,)):
+            want = xrs.dev.to_host(plan.run(plain, method, nan, out_dtype=out_dtype))
+            got = xrs.dev.to_host(plan.run(pitched, method, nan, out_dtype=out_dtype))
+            assert_same(got, want, f"{case} {method} out={out_dtype}")
+            assert np.isfinite(got).mean() > 0.2
+    rows = (64, 230) if tgt_gm.height > 300 else (32, 150)
+    band = xrs.rep.ReprojectPlan(src_gm, tgt_gm, rows=rows)
+    i0, j0, i1, j1 = band.footprint()
+    full = xrs.dev.to_host(plan.run(pitched, "bilinear", nan))
+    part = band.run(xrs.dev.to_device_pitched(np.ascontiguousarray(data[:, j0:j1, i0:i1])), "bilinear", nan,
+                    window_origin=(i0, j0))
+    assert_same(xrs.dev.to_host(part), full[:, rows[0]:rows[1]], f"{case} row band with resident window")

@@ -65,12 +65,21 @@ def line(name, ms, units, bytes_, extra=None, cpu=None):
     return out
 
 
-def rand_dev(shape, dtype=torch.float32, seed=0):
+def rand_dev(shape, dtype=torch.float32, seed=0, pitch_bytes=None):
+    """Random device array; ``pitch_bytes`` pads the rows (a view of the padded buffer is returned) --
+    a 128-byte pitch is what the entry points' upload pipeline produces and what the TMA-staged
+    kernels need."""
     g = torch.Generator(device="cuda")
     g.manual_seed(seed)
+    w = shape[-1]
+    if pitch_bytes:
+        per = max(1, pitch_bytes // torch.empty((), dtype=dtype).element_size())
+        shape = tuple(shape[:-1]) + (-(-w // per) * per,)
     if dtype == torch.uint8:
-        return torch.randint(0, 20, shape, dtype=torch.uint8, device="cuda", generator=g)
-    return torch.rand(shape, dtype=dtype, device="cuda", generator=g)
+        t = torch.randint(0, 20, shape, dtype=torch.uint8, device="cuda", generator=g)
+    else:
+        t = torch.rand(shape, dtype=dtype, device="cuda", generator=g)
+    return t[..., :w]
 
 
 def cpu_timed(fn, units, threads, sample):
@@ -191,7 +200,7 @@ def _reproject_case(name, src_gm, tgt_gm, bands, reps, one_shot, cpu, threads, e
     plan = reproject.ReprojectPlan(src_gm, tgt_gm)
     fp = plan.footprint()
     s_fp = (fp[2] - fp[0]) * (fp[3] - fp[1])
-    src = rand_dev((bands, src_gm.height, src_gm.width))
+    src = rand_dev((bands, src_gm.height, src_gm.width), pitch_bytes=128)
     T = tgt_gm.width * tgt_gm.height
     out = []
     for method in methods:
@@ -249,7 +258,7 @@ def c5(reps, one_shot, cpu, threads):
         plan = reproject.ReprojectPlan(src, tgt, rows=rows, windows=windows)
         i0, j0, i1, j1 = plan.footprint()
         nb = 8
-        window = rand_dev((nb, j1 - j0, i1 - i0))
+        window = rand_dev((nb, j1 - j0, i1 - i0), pitch_bytes=128)
         dst = _dev.empty((nb, 4500, 36000), np.float32)
         ms = timed(lambda: plan.run(window, "bilinear", float("nan"), out=dst, out_dtype=np.float32,
                                     window_origin=(i0, j0)), reps, one_shot)
@@ -283,7 +292,7 @@ def c5_across(rank, world, reps=3, e2e=True):
         rows = (b * 4500, (b + 1) * 4500)
         plan = reproject.ReprojectPlan(src, tgt, rows=rows, windows=windows)
         i0, j0, i1, j1 = plan.footprint()
-        window = rand_dev((nb, j1 - j0, i1 - i0))
+        window = rand_dev((nb, j1 - j0, i1 - i0), pitch_bytes=128)
         dst = _dev.empty((nb, 4500, 36000), np.float32)
         ms = timed(lambda: plan.run(window, "bilinear", float("nan"), out=dst, out_dtype=np.float32,
                                     window_origin=(i0, j0)), reps, False)

@@ -10,9 +10,8 @@
 //     Needs a 16-byte aligned source pitch (TMA global strides); tiles whose box exceeds 64x48
 //     take the direct path inside the same kernel.
 //   * k2_gather_direct: plain per-pixel global loads, for sources whose pitch TMA cannot describe.
-#include <cuda.h>
-
 #include "rectify_common.cuh"
+#include "tma.cuh"
 
 namespace xrs {
 
@@ -65,15 +64,6 @@ __device__ __forceinline__ Taps make_taps(double fi, double fj, int64_t src_w, i
 
 template <typename T>
 __device__ __forceinline__ double ld_f64(const T *p) { return static_cast<double>(__ldg(p)); }
-
-// base + index * sizeof(T) as ONE wide multiply-add (the compiler's shift-and-add pair costs two
-// issue slots per store in the band loop)
-template <typename T>
-__device__ __forceinline__ T *elem_ptr(T *base, uint32_t index) {
-    uint64_t out;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(out) : "r"(index), "n"(sizeof(T)), "l"(reinterpret_cast<uint64_t>(base)));
-    return reinterpret_cast<T *>(out);
-}
 
 // Where a gather kernel gets the fractional source index of a target pixel from: the ij image of
 // xrs_rectify_ij, or -- fused mode (xrs_rectify_gather) -- straight from K1's claim words, running
@@ -155,14 +145,6 @@ struct StagedParams {
     const T *src[K2_MAX_BANDS];
     T *dst[K2_MAX_BANDS];
 };
-
-__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *map, int x, int y, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-            smem_u32(dst_smem)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar))
-        : "memory");
-}
 
 template <typename T, int METHOD, bool FUSED>
 __global__ void __launch_bounds__(K2S_THREADS, (!FUSED && METHOD == XRS_NEAREST) ? 4 : 3)
@@ -361,6 +343,26 @@ static EncodeTiledFn get_encode_tiled() {
     return fn;
 }
 
+bool tma_available() { return get_encode_tiled() != nullptr; }
+
+// 2-D tensor map over a (height, width) plane of `elem_size`-byte elements with row pitch `pitch_bytes`
+// (a multiple of 16) and a (box_h, box_w) box; out-of-bounds elements read as zero.
+bool tma_encode_2d(CUtensorMap *map, int elem_size, const void *base, uint64_t width, uint64_t height,
+                   uint64_t pitch_bytes, uint32_t box_w, uint32_t box_h) {
+    EncodeTiledFn fn = get_encode_tiled();
+    if (!fn) return false;
+    const CUtensorMapDataType dt = elem_size == 1   ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                   : elem_size == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
+                                   : elem_size == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32
+                                                    : CU_TENSOR_MAP_DATA_TYPE_UINT64;
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(height)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch_bytes)};
+    const cuuint32_t box[2] = {box_w, box_h};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <typename T>
 static T cast_fill(double fill) {
     if (std::is_floating_point<T>::value) return static_cast<T>(fill);
@@ -390,7 +392,7 @@ static int launch_gather(const void *const *src_planes, void *const *dst_planes,
     const T fill_t = cast_fill<T>(fill);
     // TMA needs 16-byte aligned plane bases and row strides
     bool tma_ok = (src_pitch * sizeof(T)) % 16 == 0 && win_w < (1ll << 31) && win_h < (1ll << 31) &&
-                  ceil_div(dst_h, K2S_TH) <= 65535 && dst_h * dst_w < (1ll << 32) && get_encode_tiled() != nullptr;
+                  ceil_div(dst_h, K2S_TH) <= 65535 && dst_h * dst_w < (1ll << 32) && tma_available();
     for (int b = 0; b < n_bands && tma_ok; ++b)
         tma_ok = (reinterpret_cast<uintptr_t>(src_planes[b]) & 15) == 0;
 
@@ -399,23 +401,13 @@ static int launch_gather(const void *const *src_planes, void *const *dst_planes,
         if (tma_ok) {
             StagedParams<T> sp;
             memset(&sp, 0, sizeof(sp));
-            const CUtensorMapDataType dt = sizeof(T) == 1   ? CU_TENSOR_MAP_DATA_TYPE_UINT8
-                                           : sizeof(T) == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
-                                           : sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32
-                                                            : CU_TENSOR_MAP_DATA_TYPE_UINT64;
-            const cuuint64_t dims[2] = {static_cast<cuuint64_t>(win_w), static_cast<cuuint64_t>(win_h)};
-            const cuuint64_t strides[1] = {static_cast<cuuint64_t>(src_pitch) * sizeof(T)};
-            const cuuint32_t box[2] = {K2S_BOX_W, K2S_BOX_H};
-            const cuuint32_t estr[2] = {1, 1};
             bool ok = true;
             for (int b = 0; b < nb && ok; ++b) {
                 sp.src[b] = static_cast<const T *>(src_planes[b0 + b]);
                 sp.dst[b] = static_cast<T *>(dst_planes[b0 + b]);
-                const CUresult rc = get_encode_tiled()(&sp.maps[b], dt, 2, const_cast<void *>(src_planes[b0 + b]), dims,
-                                                       strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                ok = rc == CUDA_SUCCESS;
+                ok = tma_encode_2d(&sp.maps[b], sizeof(T), src_planes[b0 + b], static_cast<uint64_t>(win_w),
+                                   static_cast<uint64_t>(win_h), static_cast<uint64_t>(src_pitch) * sizeof(T), K2S_BOX_W,
+                                   K2S_BOX_H);
             }
             if (ok) {
                 int rc;

@@ -12,8 +12,10 @@
 // source dtype, the lerps in float64 -- uses explicit round-to-nearest intrinsics in the
 // reference's operation order.
 #include <cmath>
+#include <cstring>
 
 #include "proj.cuh"
+#include "tma.cuh"
 
 namespace xrs {
 
@@ -234,6 +236,24 @@ __device__ __forceinline__ OUT k3_store_cast(double v) {
     else return cast_like_numpy<OUT>(v);
 }
 
+// reproject.py:301-328: the blend of the four taps.  Differences are taken in the array's own dtype
+// (numpy subtracts before the float64 promotion), the lerps in float64 without contraction.
+template <typename T, typename OUT, int METHOD>
+__device__ __forceinline__ OUT k3_blend(T v00, T v01, T v10, T v11, double u, double v) {
+    double val;
+    if (METHOD == XRS_BILINEAR) {  // reproject.py:325-327
+        const double a = dadd(static_cast<double>(v00), dmul(u, diff_as_f64(v01, v00)));
+        const double bb = dadd(static_cast<double>(v10), dmul(u, diff_as_f64(v11, v10)));
+        val = dadd(a, dmul(v, dsub(bb, a)));
+    } else if (dadd(u, v) < 1.0) {  // reproject.py:301-307
+        val = dadd(dadd(static_cast<double>(v00), dmul(u, diff_as_f64(v01, v00))), dmul(v, diff_as_f64(v10, v00)));
+    } else {                        // reproject.py:309-313
+        val = dadd(dadd(static_cast<double>(v11), dmul(dsub(1.0, u), diff_as_f64(v10, v11))),
+                   dmul(dsub(1.0, v), diff_as_f64(v01, v11)));
+    }
+    return k3_store_cast<T, OUT>(val);
+}
+
 // ---- per-pixel gather (reproject.py:268-335) given the source-CRS coordinates (sx, sy) --------
 constexpr int K3_CHUNK = 4;  // bands whose taps are loaded before any of them is consumed
 
@@ -290,21 +310,7 @@ __device__ __forceinline__ void k3_gather_pixel(const K3Geom &g, const K3Planes<
     const double u = dsub(fx, fx0), v = dsub(fy, fy0);
     const int ix0 = __double2int_rd(fx), ix1 = __double2int_ru(fx);
     const int iy0 = __double2int_rd(fy), iy1 = __double2int_ru(fy);
-    const bool lower = dadd(u, v) < 1.0;                 // reproject.py:301
-    const double u1 = dsub(1.0, u), v1 = dsub(1.0, v);
-    auto blend = [&](T v00, T v01, T v10, T v11) -> OUT {
-        double val;
-        if (METHOD == XRS_BILINEAR) {  // reproject.py:325-327
-            const double a = dadd(static_cast<double>(v00), dmul(u, diff_as_f64(v01, v00)));
-            const double bb = dadd(static_cast<double>(v10), dmul(u, diff_as_f64(v11, v10)));
-            val = dadd(a, dmul(v, dsub(bb, a)));
-        } else if (lower) {            // reproject.py:303-307
-            val = dadd(dadd(static_cast<double>(v00), dmul(u, diff_as_f64(v01, v00))), dmul(v, diff_as_f64(v10, v00)));
-        } else {                       // reproject.py:309-313
-            val = dadd(dadd(static_cast<double>(v11), dmul(u1, diff_as_f64(v10, v11))), dmul(v1, diff_as_f64(v01, v11)));
-        }
-        return k3_store_cast<T, OUT>(val);
-    };
+    auto blend = [&](T v00, T v01, T v10, T v11) -> OUT { return k3_blend<T, OUT, METHOD>(v00, v01, v10, v11, u, v); };
     // common case: the 2 x 2 taps lie inside the tile window and inside the resident source
     const int si0 = i_base + ix0, sj0 = j_base + iy0, si1 = i_base + ix1, sj1 = j_base + iy1;
     if (ix0 >= 0 && iy0 >= 0 && ix1 < ww && iy1 < wh && si0 >= res_i0 && sj0 >= res_j0 && si1 < res_i1 && sj1 < res_j1) {
@@ -364,6 +370,64 @@ __device__ __noinline__ void forward_point(const ProjC &to, double lam, double p
     if (!proj_forward(to, lam, phi, ox, oy)) ox = oy = NAN;
 }
 
+// Source-CRS coordinates of target pixel (r, c) from its row / column terms.
+__device__ __forceinline__ void k3_pixel_source_xy(const K3Geom &g, int plan, const Terms4 &rt, const Terms4 &ct,
+                                                   int64_t c, int64_t r, double &sx, double &sy) {
+    if (plan == K3_PLAN_TMERC_INV) {
+        double lam, phi;
+        if (tmerc_inv_tail(g.from, rt, ct, lam, phi)) {
+            if (g.to.kind == XRS_PROJ_GEOGRAPHIC) {
+                sx = lam * PROJ_RAD2DEG;
+                sy = phi * PROJ_RAD2DEG;
+            } else {
+                forward_point(g.to, lam, phi, sx, sy);
+            }
+        } else {
+            transform_point(g.from, g.to, __ldg(g.dst_x + c), __ldg(g.dst_y + r), sx, sy);
+        }
+    } else if (plan == K3_PLAN_SEPARABLE) {
+        fwd_tail(g.to, rt, ct, sx, sy);
+    } else if (plan == K3_PLAN_IDENTITY) {
+        sx = ct.a;
+        sy = rt.a;
+    } else {
+        transform_point(g.from, g.to, ct.a, rt.a, sx, sy);
+    }
+}
+
+// Row-only / column-only terms of the target -> source transform (one sincos / exp per tile row or
+// column instead of one per pixel).
+__device__ __forceinline__ Terms4 k3_row_terms(const K3Geom &g, int plan, double y) {
+    Terms4 t;
+    t.a = y; t.b = t.c = t.d = 0.0;
+    if (plan == K3_PLAN_TMERC_INV) {
+        t = tmerc_inv_row_terms(g.from, y);
+    } else if (plan == K3_PLAN_SEPARABLE) {
+        double phi;
+        bool ok = true;
+        if (g.from.kind == XRS_PROJ_GEOGRAPHIC) {
+            phi = y * PROJ_DEG2RAD;
+            ok = fabs(y) <= 90.0;
+        } else {
+            phi = atan(sinh((y - g.from.fn) / g.from.a));
+        }
+        t = fwd_row_terms(g.to, phi, ok);
+    }
+    return t;
+}
+__device__ __forceinline__ Terms4 k3_col_terms(const K3Geom &g, int plan, double x) {
+    Terms4 t;
+    t.a = x; t.b = t.c = t.d = 0.0;
+    if (plan == K3_PLAN_TMERC_INV) {
+        t = tmerc_inv_col_terms(g.from, x);
+    } else if (plan == K3_PLAN_SEPARABLE) {
+        const double lam = g.from.kind == XRS_PROJ_GEOGRAPHIC ? x * PROJ_DEG2RAD
+                                                               : wrap_pi(g.from.lon0 + (x - g.from.fe) / g.from.a);
+        t = fwd_col_terms(g.to, lam);
+    }
+    return t;
+}
+
 constexpr int K3T_COLS = 64, K3T_ROWS = 32, K3T_THREADS = 256;
 constexpr int K3T_RPT = K3T_ROWS / (K3T_THREADS / 32 / (K3T_COLS / 32));  // rows per thread (8)
 
@@ -385,40 +449,14 @@ k3_reproject(const __grid_constant__ K3Geom g, const __grid_constant__ K3Planes<
     if (tid < K3T_ROWS) {
         const int64_t r = r0 + tid;
         if (r < g.row_end) {
-            const double y = __ldg(g.dst_y + r);
-            Terms4 t;
-            t.a = y; t.b = t.c = t.d = 0.0;
-            if (plan == K3_PLAN_TMERC_INV) {
-                t = tmerc_inv_row_terms(g.from, y);
-            } else if (plan == K3_PLAN_SEPARABLE) {
-                double phi;
-                bool ok = true;
-                if (g.from.kind == XRS_PROJ_GEOGRAPHIC) {
-                    phi = y * PROJ_DEG2RAD;
-                    ok = fabs(y) <= 90.0;
-                } else {
-                    phi = atan(sinh((y - g.from.fn) / g.from.a));
-                }
-                t = fwd_row_terms(g.to, phi, ok);
-            }
-            s_row[tid] = t;
+            s_row[tid] = k3_row_terms(g, plan, __ldg(g.dst_y + r));
             s_ty[tid] = static_cast<int>(r / g.tile_h);
         }
     } else if (tid < K3T_ROWS + K3T_COLS) {
         const int k = tid - K3T_ROWS;
         const int64_t c = c0 + k;
         if (c < g.dst_w) {
-            const double x = __ldg(g.dst_x + c);
-            Terms4 t;
-            t.a = x; t.b = t.c = t.d = 0.0;
-            if (plan == K3_PLAN_TMERC_INV) {
-                t = tmerc_inv_col_terms(g.from, x);
-            } else if (plan == K3_PLAN_SEPARABLE) {
-                const double lam = g.from.kind == XRS_PROJ_GEOGRAPHIC ? x * PROJ_DEG2RAD
-                                                                       : wrap_pi(g.from.lon0 + (x - g.from.fe) / g.from.a);
-                t = fwd_col_terms(g.to, lam);
-            }
-            s_col[k] = t;
+            s_col[k] = k3_col_terms(g, plan, __ldg(g.dst_x + c));
             s_tx[k] = static_cast<int>(c / g.tile_w);
         }
     }
@@ -437,28 +475,229 @@ k3_reproject(const __grid_constant__ K3Geom g, const __grid_constant__ K3Planes<
         if (r >= g.row_end) break;
         const Terms4 rt = s_row[rl];
         double sx, sy;
-        if (plan == K3_PLAN_TMERC_INV) {
-            double lam, phi;
-            if (tmerc_inv_tail(g.from, rt, ct, lam, phi)) {
-                if (g.to.kind == XRS_PROJ_GEOGRAPHIC) {
-                    sx = lam * PROJ_RAD2DEG;
-                    sy = phi * PROJ_RAD2DEG;
-                } else {
-                    forward_point(g.to, lam, phi, sx, sy);
-                }
-            } else {
-                transform_point(g.from, g.to, __ldg(g.dst_x + c), __ldg(g.dst_y + r), sx, sy);
-            }
-        } else if (plan == K3_PLAN_SEPARABLE) {
-            fwd_tail(g.to, rt, ct, sx, sy);
-        } else if (plan == K3_PLAN_IDENTITY) {
-            sx = ct.a;
-            sy = rt.a;
-        } else {
-            transform_point(g.from, g.to, ct.a, rt.a, sx, sy);
-        }
+        k3_pixel_source_xy(g, plan, rt, ct, c, r, sx, sy);
         k3_gather_pixel<T, OUT, METHOD>(g, planes, n_bands, fill, (r - g.row_begin) * g.dst_w + c,
                                         s_ty[rl] * g.ntx + tx, sx, sy);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K3, staged form: the gather of K2 (gather.cu) under the reprojection's index arithmetic.
+//
+// One CTA per 32 x 32 target tile, 4 pixels per thread (same column, rows 8 apart).  Every thread
+// finishes the transform of its pixels and derives their taps; the CTA reduces the bounding box of
+// the source pixels the tile reaches and pulls that box of every band into shared memory with 2-D TMA
+// tensor copies (4-stage mbarrier ring), so that the 2 x 2 taps are shared-memory reads and each
+// source pixel crosses L2 -> SM once per tile instead of once per tap.  Tiles that touch the source
+// border (padding, numpy's negative-index wrap), whose box does not fit, or whose source pitch TMA
+// cannot describe take the direct per-pixel path (k3_gather_pixel) -- same arithmetic.
+// ---------------------------------------------------------------------------
+constexpr int K3S_TW = 32, K3S_TH = 32, K3S_THREADS = 256, K3S_PX = 4;
+constexpr int K3S_ROW_STEP = K3S_THREADS / K3S_TW;
+constexpr int K3S_BOX_W = 48, K3S_BOX_H = 40, K3S_STAGES = 4;
+
+template <typename T, typename OUT>
+struct K3StagedParams {
+    CUtensorMap maps[K3_MAX_BANDS];
+    K3Planes<T, OUT> planes;
+};
+
+template <typename T, typename OUT, int METHOD>
+__global__ void __launch_bounds__(K3S_THREADS, 2)
+k3_reproject_staged(const __grid_constant__ K3Geom g, const __grid_constant__ K3StagedParams<T, OUT> p, int n_bands,
+                    T fill, int plan) {
+    extern __shared__ unsigned char k3s_smem_raw[];
+    constexpr int STAGE_ELEMS = K3S_BOX_W * K3S_BOX_H;
+    unsigned char *base = k3s_smem_raw + ((128u - (smem_u32(k3s_smem_raw) & 127u)) & 127u);
+    T *stages = reinterpret_cast<T *>(base);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(base + static_cast<size_t>(K3S_STAGES) * STAGE_ELEMS * sizeof(T));
+    Terms4 *s_row = reinterpret_cast<Terms4 *>(full_bar + K3S_STAGES);
+    Terms4 *s_col = s_row + K3S_TH;
+    int *s_ty = reinterpret_cast<int *>(s_col + K3S_TW);
+    int *s_tx = s_ty + K3S_TH;
+    int(*red)[K3S_THREADS / 32] = reinterpret_cast<int(*)[K3S_THREADS / 32]>(s_tx + K3S_TW);  // [5][8]
+
+    const int tid = threadIdx.x;
+    const int64_t c0 = static_cast<int64_t>(blockIdx.x) * K3S_TW;
+    const int64_t r0 = g.row_begin + static_cast<int64_t>(blockIdx.y) * K3S_TH;
+    if (tid < K3S_TH) {
+        const int64_t r = r0 + tid;
+        if (r < g.row_end) {
+            s_row[tid] = k3_row_terms(g, plan, __ldg(g.dst_y + r));
+            s_ty[tid] = static_cast<int>(r / g.tile_h);
+        }
+    } else if (tid < K3S_TH + K3S_TW) {
+        const int k = tid - K3S_TH;
+        const int64_t c = c0 + k;
+        if (c < g.dst_w) {
+            s_col[k] = k3_col_terms(g, plan, __ldg(g.dst_x + c));
+            s_tx[k] = static_cast<int>(c / g.tile_w);
+        }
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < K3S_STAGES; ++s) mbar_init(&full_bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int lx = tid % K3S_TW, ly = tid / K3S_TW;
+    const int64_t c = c0 + lx;
+    const bool col_in = c < g.dst_w;
+    const int res_i0 = static_cast<int>(g.win_i0), res_j0 = static_cast<int>(g.win_j0);
+    const int res_i1 = res_i0 + static_cast<int>(g.win_w), res_j1 = res_j0 + static_cast<int>(g.win_h);
+    const int ww = g.tile_win_w, wh = g.tile_win_h;
+
+    // ---- this thread's pixels: transform, taps, fractions ----------------------------------
+    double us[K3S_PX], vs[K3S_PX];
+    int si0[K3S_PX], sj0[K3S_PX];
+    uint32_t in_mask = 0, fast_mask = 0, d01_mask = 0, d10_mask = 0;  // bit k: pixel k / its right / lower tap is one further
+    int i_lo = INT32_MAX, i_hi = -1, j_lo = INT32_MAX, j_hi = -1;
+    Terms4 ct;
+    int tx_tile = 0;
+    if (col_in) {
+        ct = s_col[lx];
+        tx_tile = s_tx[lx];
+    }
+#pragma unroll
+    for (int k = 0; k < K3S_PX; ++k) {
+        us[k] = vs[k] = 0.0;
+        si0[k] = sj0[k] = 0;
+    }
+    // (the transform code appears once: the loop is not unrolled and its results are moved into the
+    // statically indexed per-pixel registers by predicated copies)
+#pragma unroll 1
+    for (int k = 0; k < K3S_PX; ++k) {
+        const int rl = ly + k * K3S_ROW_STEP;
+        const int64_t r = r0 + rl;
+        if (!(col_in && r < g.row_end)) continue;
+        double sx, sy, u = 0.0, v = 0.0;
+        int a0 = 0, b0 = 0, da = 0, db = 0;
+        bool fast = false;
+        k3_pixel_source_xy(g, plan, s_row[rl], ct, c, r, sx, sy);
+        const int t = s_ty[rl] * g.ntx + tx_tile;
+        // reproject.py:278-279
+        const double fx = ddiv(dsub(sx, __ldg(g.tile_x0 + t)), g.x_res);
+        const double fy = ddiv(dsub(sy, __ldg(g.tile_y0 + t)), -g.y_res);
+        if (fabs(fx) < 1e9 && fabs(fy) < 1e9) {
+            const int i_base = __ldg(g.tile_i0 + t), j_base = __ldg(g.tile_j0 + t);
+            int wx0, wx1, wy0, wy1;
+            if (METHOD == XRS_NEAREST) {
+                wx0 = wx1 = __double2int_rn(fx);
+                wy0 = wy1 = __double2int_rn(fy);
+            } else {
+                wx0 = __double2int_rd(fx); wx1 = __double2int_ru(fx);
+                wy0 = __double2int_rd(fy); wy1 = __double2int_ru(fy);
+                u = dsub(fx, floor(fx));
+                v = dsub(fy, floor(fy));
+            }
+            a0 = i_base + wx0; b0 = j_base + wy0;
+            const int a1 = i_base + wx1, b1 = j_base + wy1;
+            da = a1 - a0; db = b1 - b0;
+            // all taps inside the tile window (no negative-index wrap, no IndexError) and inside the resident source
+            fast = wx0 >= 0 && wy0 >= 0 && wx1 < ww && wy1 < wh && a0 >= res_i0 && b0 >= res_j0 && a1 < res_i1 && b1 < res_j1;
+            if (fast) {
+                i_lo = min(i_lo, a0); i_hi = max(i_hi, a1);
+                j_lo = min(j_lo, b0); j_hi = max(j_hi, b1);
+            }
+        }
+        in_mask |= 1u << k;
+        fast_mask |= fast ? (1u << k) : 0u;
+        d01_mask |= (fast && da) ? (1u << k) : 0u;
+        d10_mask |= (fast && db) ? (1u << k) : 0u;
+#pragma unroll
+        for (int q = 0; q < K3S_PX; ++q)
+            if (q == k) {
+                us[q] = u; vs[q] = v;
+                si0[q] = a0; sj0[q] = b0;
+            }
+    }
+    // ---- CTA-wide: are all pixels on the fast path, and which source box do they reach? ----------
+    int all_fast = (fast_mask == in_mask) ? 1 : 0;
+    all_fast = __reduce_min_sync(0xffffffffu, all_fast);
+    i_lo = __reduce_min_sync(0xffffffffu, i_lo); i_hi = __reduce_max_sync(0xffffffffu, i_hi);
+    j_lo = __reduce_min_sync(0xffffffffu, j_lo); j_hi = __reduce_max_sync(0xffffffffu, j_hi);
+    if ((tid & 31) == 0) {
+        red[0][tid >> 5] = i_lo; red[1][tid >> 5] = i_hi; red[2][tid >> 5] = j_lo; red[3][tid >> 5] = j_hi;
+        red[4][tid >> 5] = all_fast;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < K3S_THREADS / 32; ++w) {
+        i_lo = min(i_lo, red[0][w]); i_hi = max(i_hi, red[1][w]);
+        j_lo = min(j_lo, red[2][w]); j_hi = max(j_hi, red[3][w]);
+        all_fast = min(all_fast, red[4][w]);
+    }
+    constexpr int ALIGN_ELEMS = 16 / sizeof(T) > 0 ? 16 / sizeof(T) : 1;
+    const int box_x = i_hi >= 0 ? ((i_lo - res_i0) / ALIGN_ELEMS) * ALIGN_ELEMS : 0;
+    const int box_y = i_hi >= 0 ? j_lo - res_j0 : 0;
+    const int box_i0 = box_x + res_i0;  // first source column held by the staged box
+    const bool staged = all_fast && i_hi >= 0 && (i_hi - box_i0 + 1 <= K3S_BOX_W) && (j_hi - j_lo + 1 <= K3S_BOX_H);
+
+    if (!staged) {  // CTA-uniform and rare: the direct per-pixel path, same arithmetic (transform redone)
+#pragma unroll 1
+        for (int k = 0; k < K3S_PX; ++k) {
+            if (!(in_mask & (1u << k))) continue;
+            const int rl = ly + k * K3S_ROW_STEP;
+            const int64_t r = r0 + rl;
+            double sx, sy;
+            k3_pixel_source_xy(g, plan, s_row[rl], ct, c, r, sx, sy);
+            k3_gather_pixel<T, OUT, METHOD>(g, p.planes, n_bands, fill, (r - g.row_begin) * g.dst_w + c,
+                                            s_ty[rl] * g.ntx + tx_tile, sx, sy);
+        }
+        return;
+    }
+
+    const T *t00[K3S_PX], *t01[K3S_PX], *t10[K3S_PX], *t11[K3S_PX];
+    uint32_t o32[K3S_PX];
+#pragma unroll
+    for (int k = 0; k < K3S_PX; ++k) {
+        const bool on = in_mask & (1u << k);
+        const int off = on ? (sj0[k] - j_lo) * K3S_BOX_W + (si0[k] - box_i0) : 0;
+        const int d01 = (d01_mask >> k) & 1u, d10 = ((d10_mask >> k) & 1u) * K3S_BOX_W;
+        t00[k] = stages + off;
+        t01[k] = t00[k] + d01;
+        t10[k] = t00[k] + d10;
+        t11[k] = t10[k] + d01;
+        const int64_t r = r0 + ly + k * K3S_ROW_STEP;
+        o32[k] = static_cast<uint32_t>((r - g.row_begin) * g.dst_w + c);
+    }
+    asm volatile("" : "+r"(in_mask));  // keep the store predicate a one-bit test inside the band loop
+    constexpr uint32_t STAGE_BYTES = STAGE_ELEMS * sizeof(T);
+    if (tid == 0) {
+        for (int s = 0; s < K3S_STAGES && s < n_bands; ++s) {
+            mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+            tma_load_2d(stages + s * STAGE_ELEMS, &p.maps[s], box_x, box_y, &full_bar[s]);
+        }
+    }
+    for (int b0 = 0; b0 < n_bands; b0 += K3S_STAGES) {
+        const uint32_t parity = (b0 / K3S_STAGES) & 1;
+#pragma unroll
+        for (int s = 0; s < K3S_STAGES; ++s) {
+            const int b = b0 + s;
+            if (b >= n_bands) break;
+            mbar_wait(&full_bar[s], parity);
+            OUT out[K3S_PX];
+#pragma unroll
+            for (int k = 0; k < K3S_PX; ++k) {
+                if (METHOD == XRS_NEAREST) {
+                    out[k] = static_cast<OUT>(t00[k][s * STAGE_ELEMS]);
+                } else {
+                    out[k] = k3_blend<T, OUT, METHOD>(t00[k][s * STAGE_ELEMS], t01[k][s * STAGE_ELEMS],
+                                                      t10[k][s * STAGE_ELEMS], t11[k][s * STAGE_ELEMS], us[k], vs[k]);
+                }
+            }
+            OUT *dp = p.planes.dst[b];
+#pragma unroll
+            for (int k = 0; k < K3S_PX; ++k)
+                if (in_mask & (1u << k)) st_stream(elem_ptr(dp, o32[k]), out[k]);
+            __syncthreads();  // every thread is done with stage s
+            if (tid == 0 && b + K3S_STAGES < n_bands) {
+                fence_proxy_async();
+                mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                tma_load_2d(stages + s * STAGE_ELEMS, &p.maps[b + K3S_STAGES], box_x, box_y, &full_bar[s]);
+            }
+        }
     }
 }
 
@@ -479,12 +718,37 @@ int launch_reproject(const K3Geom &g, const void *const *src_planes, void *const
     if constexpr (std::is_floating_point<T>::value) fill_t = static_cast<T>(fill);
     else fill_t = static_cast<T>(static_cast<long long>(fill));
     const int plan = choose_plan(g.from, g.to);
+    // TMA needs 16-byte aligned plane bases and row strides; 32-bit output offsets need < 2^32 elements
+    bool tma_ok = tma_available() && (g.src_pitch * sizeof(T)) % 16 == 0 && rows * g.dst_w < (int64_t(1) << 32) &&
+                  ceil_div(rows, K3S_TH) <= 65535;
+    for (int b = 0; b < n_bands && tma_ok; ++b) tma_ok = (reinterpret_cast<uintptr_t>(src_planes[b]) & 15) == 0;
     for (int b0 = 0; b0 < n_bands; b0 += K3_MAX_BANDS) {
         const int nb = std::min(K3_MAX_BANDS, n_bands - b0);
         K3Planes<T, OUT> planes = {};
         for (int b = 0; b < nb; ++b) {
             planes.src[b] = static_cast<const T *>(src_planes[b0 + b]);
             planes.dst[b] = static_cast<OUT *>(dst_planes[b0 + b]);
+        }
+        if (tma_ok) {
+            K3StagedParams<T, OUT> sp;
+            memset(&sp, 0, sizeof(sp));
+            sp.planes = planes;
+            bool ok = true;
+            for (int b = 0; b < nb && ok; ++b)
+                ok = tma_encode_2d(&sp.maps[b], sizeof(T), src_planes[b0 + b], static_cast<uint64_t>(g.win_w),
+                                   static_cast<uint64_t>(g.win_h), static_cast<uint64_t>(g.src_pitch) * sizeof(T),
+                                   K3S_BOX_W, K3S_BOX_H);
+            if (ok) {
+                const size_t smem = static_cast<size_t>(K3S_STAGES) * K3S_BOX_W * K3S_BOX_H * sizeof(T) +
+                                    K3S_STAGES * sizeof(uint64_t) + (K3S_TH + K3S_TW) * (sizeof(Terms4) + sizeof(int)) +
+                                    5 * (K3S_THREADS / 32) * sizeof(int) + 128;
+                XRS_CUDA(cudaFuncSetAttribute(k3_reproject_staged<T, OUT, METHOD>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                const dim3 sgrid(static_cast<unsigned>(ceil_div(g.dst_w, K3S_TW)), static_cast<unsigned>(ceil_div(rows, K3S_TH)));
+                XRS_TIMED(METHOD == XRS_NEAREST ? "k3_reproject_staged<nearest>" : METHOD == XRS_BILINEAR ? "k3_reproject_staged<bilinear>" : "k3_reproject_staged<triangular>", st, k3_reproject_staged<T, OUT, METHOD><<<sgrid, K3S_THREADS, smem, st>>>(g, sp, nb, fill_t, plan));
+                XRS_LAUNCH_CHECK("k3_reproject_staged");
+                continue;
+            }
         }
         XRS_TIMED(METHOD == XRS_NEAREST ? "k3_reproject<nearest>" : METHOD == XRS_BILINEAR ? "k3_reproject<bilinear>" : "k3_reproject<triangular>", st, k3_reproject<T, OUT, METHOD><<<grid, K3T_THREADS, 0, st>>>(g, planes, nb, fill_t, plan));
         XRS_LAUNCH_CHECK("k3_reproject");
