@@ -12,6 +12,7 @@
 // source dtype, the lerps in float64 -- uses explicit round-to-nearest intrinsics in the
 // reference's operation order.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "proj.cuh"
@@ -254,8 +255,58 @@ __device__ __forceinline__ OUT k3_blend(T v00, T v01, T v10, T v11, double u, do
     return k3_store_cast<T, OUT>(val);
 }
 
-// ---- per-pixel gather (reproject.py:268-335) given the source-CRS coordinates (sx, sy) --------
+// ---- band loops of a pixel whose taps all lie inside the resident source ----------------------
 constexpr int K3_CHUNK = 4;  // bands whose taps are loaded before any of them is consumed
+
+template <typename T, typename OUT>
+__device__ __forceinline__ void k3_copy_tap(const K3Planes<T, OUT> &planes, int n_bands, int64_t o, int off) {
+    int b = 0;
+    for (; b + K3_CHUNK <= n_bands; b += K3_CHUNK) {
+        T v[K3_CHUNK];
+#pragma unroll
+        for (int q = 0; q < K3_CHUNK; ++q) v[q] = __ldg(planes.src[b + q] + off);
+#pragma unroll
+        for (int q = 0; q < K3_CHUNK; ++q) st_stream(planes.dst[b + q] + o, static_cast<OUT>(v[q]));
+    }
+    for (; b < n_bands; ++b) st_stream(planes.dst[b] + o, static_cast<OUT>(__ldg(planes.src[b] + off)));
+}
+
+// o00: element offset of tap (0, 0); d01 in {0, 1}: the right-hand tap is the next element or the same;
+// d10 in {0, pitch}: likewise for the lower taps
+template <typename T, typename OUT, int METHOD>
+__device__ __forceinline__ void k3_blend_taps(const K3Planes<T, OUT> &planes, int n_bands, int64_t o, int o00, int d01,
+                                              int d10, int pitch, double u, double v) {
+    const int d11 = d10 + d01;
+    if (d01 == 1 && d10 != 0) {
+        // generic position: the right-hand taps are the next element, so they are addressed with an
+        // immediate offset from the two row pointers (2 address computations per band instead of 4)
+        int b = 0;
+        for (; b + K3_CHUNK <= n_bands; b += K3_CHUNK) {
+            T w[K3_CHUNK][4];
+#pragma unroll
+            for (int q = 0; q < K3_CHUNK; ++q) {
+                const T *p0 = planes.src[b + q] + o00;
+                const T *p1 = p0 + pitch;
+                w[q][0] = __ldg(p0); w[q][1] = __ldg(p0 + 1); w[q][2] = __ldg(p1); w[q][3] = __ldg(p1 + 1);
+            }
+#pragma unroll
+            for (int q = 0; q < K3_CHUNK; ++q)
+                st_stream(planes.dst[b + q] + o, k3_blend<T, OUT, METHOD>(w[q][0], w[q][1], w[q][2], w[q][3], u, v));
+        }
+        for (; b < n_bands; ++b) {
+            const T *p0 = planes.src[b] + o00;
+            const T *p1 = p0 + pitch;
+            st_stream(planes.dst[b] + o, k3_blend<T, OUT, METHOD>(__ldg(p0), __ldg(p0 + 1), __ldg(p1), __ldg(p1 + 1), u, v));
+        }
+        return;
+    }
+    for (int b = 0; b < n_bands; ++b) {  // a coordinate exactly on a pixel centre: ceil == floor
+        const T *sp = planes.src[b] + o00;
+        st_stream(planes.dst[b] + o, k3_blend<T, OUT, METHOD>(__ldg(sp), __ldg(sp + d01), __ldg(sp + d10), __ldg(sp + d11), u, v));
+    }
+}
+
+// ---- per-pixel gather (reproject.py:268-335) given the source-CRS coordinates (sx, sy) --------
 
 template <typename T, typename OUT, int METHOD>
 __device__ __forceinline__ void k3_gather_pixel(const K3Geom &g, const K3Planes<T, OUT> &planes, int n_bands, T fill,
@@ -292,15 +343,7 @@ __device__ __forceinline__ void k3_gather_pixel(const K3Geom &g, const K3Planes<
         int off = tap(__double2int_rn(fy), __double2int_rn(fx), ok);
         if (!ok) off = -1;
         if (off >= 0) {
-            int b = 0;
-            for (; b + K3_CHUNK <= n_bands; b += K3_CHUNK) {
-                T v[K3_CHUNK];
-#pragma unroll
-                for (int q = 0; q < K3_CHUNK; ++q) v[q] = __ldg(planes.src[b + q] + off);
-#pragma unroll
-                for (int q = 0; q < K3_CHUNK; ++q) st_stream(planes.dst[b + q] + o, static_cast<OUT>(v[q]));
-            }
-            for (; b < n_bands; ++b) st_stream(planes.dst[b] + o, static_cast<OUT>(__ldg(planes.src[b] + off)));
+            k3_copy_tap<T, OUT>(planes, n_bands, o, off);
         } else {
             for (int b = 0; b < n_bands; ++b) st_stream(planes.dst[b] + o, fill_out);
         }
@@ -314,34 +357,8 @@ __device__ __forceinline__ void k3_gather_pixel(const K3Geom &g, const K3Planes<
     // common case: the 2 x 2 taps lie inside the tile window and inside the resident source
     const int si0 = i_base + ix0, sj0 = j_base + iy0, si1 = i_base + ix1, sj1 = j_base + iy1;
     if (ix0 >= 0 && iy0 >= 0 && ix1 < ww && iy1 < wh && si0 >= res_i0 && sj0 >= res_j0 && si1 < res_i1 && sj1 < res_j1) {
-        const int o00 = (sj0 - res_j0) * pitch + (si0 - res_i0);
-        const int d01 = ix1 - ix0, d10 = (iy1 - iy0) * pitch, d11 = d10 + d01;
-        if (d01 == 1 && iy1 != iy0) {
-            // generic position: the right-hand taps are the next element, so they are addressed with an
-            // immediate offset from the two row pointers (2 address computations per band instead of 4)
-            int b = 0;
-            for (; b + K3_CHUNK <= n_bands; b += K3_CHUNK) {
-                T w[K3_CHUNK][4];
-#pragma unroll
-                for (int q = 0; q < K3_CHUNK; ++q) {
-                    const T *p0 = planes.src[b + q] + o00;
-                    const T *p1 = p0 + pitch;
-                    w[q][0] = __ldg(p0); w[q][1] = __ldg(p0 + 1); w[q][2] = __ldg(p1); w[q][3] = __ldg(p1 + 1);
-                }
-#pragma unroll
-                for (int q = 0; q < K3_CHUNK; ++q) st_stream(planes.dst[b + q] + o, blend(w[q][0], w[q][1], w[q][2], w[q][3]));
-            }
-            for (; b < n_bands; ++b) {
-                const T *p0 = planes.src[b] + o00;
-                const T *p1 = p0 + pitch;
-                st_stream(planes.dst[b] + o, blend(__ldg(p0), __ldg(p0 + 1), __ldg(p1), __ldg(p1 + 1)));
-            }
-            return;
-        }
-        for (int b = 0; b < n_bands; ++b) {  // a coordinate exactly on a pixel centre: ceil == floor
-            const T *sp = planes.src[b] + o00;
-            st_stream(planes.dst[b] + o, blend(__ldg(sp), __ldg(sp + d01), __ldg(sp + d10), __ldg(sp + d11)));
-        }
+        k3_blend_taps<T, OUT, METHOD>(planes, n_bands, o, (sj0 - res_j0) * pitch + (si0 - res_i0), ix1 - ix0,
+                                      (iy1 - iy0) * pitch, pitch, u, v);
         return;
     }
     bool ok = true;
@@ -428,6 +445,29 @@ __device__ __forceinline__ Terms4 k3_col_terms(const K3Geom &g, int plan, double
     return t;
 }
 
+// One axis of a pixel's taps (separable transforms): source index of tap 0, whether tap 1 is the next
+// element (flags bit 0), whether both taps lie inside the tile window and the resident source
+// (bit 1), and the interpolation fraction.  Same arithmetic as k3_gather_pixel, per axis.
+struct AxisTap {
+    double frac;
+    int idx, flags;
+};
+template <int METHOD>
+__device__ __forceinline__ void axis_tap(double f, int base, int win_n, int res_lo, int res_hi, AxisTap &a) {
+    if (!(fabs(f) < 1e9)) return;  // NaN / inf / absurdly far: the general path writes the fill value
+    int w0, w1;
+    if (METHOD == XRS_NEAREST) {
+        w0 = w1 = __double2int_rn(f);
+    } else {
+        w0 = __double2int_rd(f);
+        w1 = __double2int_ru(f);
+        a.frac = dsub(f, floor(f));
+    }
+    a.idx = base + w0;
+    const bool ok = w0 >= 0 && w1 < win_n && base + w0 >= res_lo && base + w1 < res_hi;
+    a.flags = (w1 - w0) | (ok ? 2 : 0);
+}
+
 constexpr int K3T_COLS = 64, K3T_ROWS = 32, K3T_THREADS = 256;
 constexpr int K3T_RPT = K3T_ROWS / (K3T_THREADS / 32 / (K3T_COLS / 32));  // rows per thread (8)
 
@@ -443,6 +483,8 @@ k3_reproject(const __grid_constant__ K3Geom g, const __grid_constant__ K3Planes<
     __shared__ Terms4 s_col[K3T_COLS];
     __shared__ int s_ty[K3T_ROWS];
     __shared__ int s_tx[K3T_COLS];
+    __shared__ AxisTap s_rowtap[K3T_ROWS][2];
+    __shared__ AxisTap s_coltap[K3T_COLS][2];
     const int tid = threadIdx.x;
     const int64_t c0 = static_cast<int64_t>(blockIdx.x) * K3T_COLS;
     const int64_t r0 = g.row_begin + static_cast<int64_t>(blockIdx.y) * K3T_ROWS;
@@ -461,6 +503,42 @@ k3_reproject(const __grid_constant__ K3Geom g, const __grid_constant__ K3Planes<
         }
     }
     __syncthreads();
+    // Separable transforms (geographic <-> web Mercator, identity): the source x of a pixel depends on
+    // its column only and the source y on its row only, so the whole index arithmetic of
+    // reproject.py:278-300 -- the two divisions, floor / ceil, the fractions, the window and residency
+    // tests -- is done once per tile column and tile row instead of once per pixel.  The window
+    // origins belong to the reference tile, and a CTA tile can straddle a reference-tile border, so
+    // every column gets one entry per reference-tile ROW the CTA touches (at most two) and vice versa.
+    const int ty_a = static_cast<int>(r0 / g.tile_h), tx_a = static_cast<int>(c0 / g.tile_w);
+    const int ty_b = static_cast<int>(min(r0 + K3T_ROWS, g.row_end) - 1) / g.tile_h;
+    const int tx_b = static_cast<int>(min(c0 + K3T_COLS, g.dst_w) - 1) / g.tile_w;
+    const bool sep = (plan == K3_PLAN_IDENTITY || plan == K3_PLAN_SEPARABLE) && ty_b - ty_a <= 1 && tx_b - tx_a <= 1;
+    if (sep) {
+        const int res_i0 = static_cast<int>(g.win_i0), res_j0 = static_cast<int>(g.win_j0);
+        const int res_i1 = res_i0 + static_cast<int>(g.win_w), res_j1 = res_j0 + static_cast<int>(g.win_h);
+        if (tid < 2 * K3T_ROWS) {  // rows: entry [rl][q] for reference-tile column tx_a + q
+            const int rl = tid >> 1, q = tid & 1;
+            AxisTap a;
+            a.frac = 0.0; a.idx = 0; a.flags = 0;
+            if (r0 + rl < g.row_end && tx_a + q <= tx_b) {
+                const int t = s_ty[rl] * g.ntx + tx_a + q;
+                const double f = ddiv(dsub(s_row[rl].a, __ldg(g.tile_y0 + t)), -g.y_res);
+                axis_tap<METHOD>(f, __ldg(g.tile_j0 + t), g.tile_win_h, res_j0, res_j1, a);
+            }
+            s_rowtap[rl][q] = a;
+        } else if (tid < 2 * K3T_ROWS + 2 * K3T_COLS) {  // columns: entry [cl][q] for reference-tile row ty_a + q
+            const int cl = (tid - 2 * K3T_ROWS) >> 1, q = tid & 1;
+            AxisTap a;
+            a.frac = 0.0; a.idx = 0; a.flags = 0;
+            if (c0 + cl < g.dst_w && ty_a + q <= ty_b) {
+                const int t = (ty_a + q) * g.ntx + s_tx[cl];
+                const double f = ddiv(dsub(s_col[cl].a, __ldg(g.tile_x0 + t)), g.x_res);
+                axis_tap<METHOD>(f, __ldg(g.tile_i0 + t), g.tile_win_w, res_i0, res_i1, a);
+            }
+            s_coltap[cl][q] = a;
+        }
+        __syncthreads();
+    }
     const int warp = tid >> 5, lane = tid & 31;
     const int col_l = (warp % (K3T_COLS / 32)) * 32 + lane;
     const int row_l0 = (warp / (K3T_COLS / 32)) * K3T_RPT;
@@ -468,6 +546,30 @@ k3_reproject(const __grid_constant__ K3Geom g, const __grid_constant__ K3Planes<
     if (c >= g.dst_w) return;
     const Terms4 ct = s_col[col_l];
     const int tx = s_tx[col_l];
+    if (sep) {
+        const int pitch = static_cast<int>(g.src_pitch);
+        const int res_i0 = static_cast<int>(g.win_i0), res_j0 = static_cast<int>(g.win_j0);
+        const AxisTap ca0 = s_coltap[col_l][0], ca1 = s_coltap[col_l][1];
+#pragma unroll 1
+        for (int k = 0; k < K3T_RPT; ++k) {
+            const int rl = row_l0 + k;
+            const int64_t r = r0 + rl;
+            if (r >= g.row_end) break;
+            const int ty = s_ty[rl];
+            const AxisTap ca = (ty == ty_a) ? ca0 : ca1;
+            const AxisTap ra = s_rowtap[rl][tx - tx_a];
+            const int64_t o = (r - g.row_begin) * g.dst_w + c;
+            if (ca.flags & ra.flags & 2) {  // every tap inside the tile window and the resident source
+                const int o00 = (ra.idx - res_j0) * pitch + (ca.idx - res_i0);
+                if (METHOD == XRS_NEAREST) k3_copy_tap<T, OUT>(planes, n_bands, o, o00);
+                else k3_blend_taps<T, OUT, METHOD>(planes, n_bands, o, o00, ca.flags & 1, (ra.flags & 1) * pitch, pitch,
+                                                   ca.frac, ra.frac);
+            } else {  // source border, padding, untransformable: the general per-pixel path
+                k3_gather_pixel<T, OUT, METHOD>(g, planes, n_bands, fill, o, ty * g.ntx + tx, ct.a, s_row[rl].a);
+            }
+        }
+        return;
+    }
 #pragma unroll 1
     for (int k = 0; k < K3T_RPT; ++k) {
         const int rl = row_l0 + k;
@@ -495,6 +597,7 @@ k3_reproject(const __grid_constant__ K3Geom g, const __grid_constant__ K3Planes<
 constexpr int K3S_TW = 32, K3S_TH = 32, K3S_THREADS = 256, K3S_PX = 4;
 constexpr int K3S_ROW_STEP = K3S_THREADS / K3S_TW;
 constexpr int K3S_BOX_W = 48, K3S_BOX_H = 40, K3S_STAGES = 4;
+constexpr int K3S_MIN_BANDS = 32;  // direct form below (measured: 13 bands 4.9 ms direct vs 5.8 ms staged on config C3)
 
 template <typename T, typename OUT>
 struct K3StagedParams {
@@ -719,8 +822,12 @@ int launch_reproject(const K3Geom &g, const void *const *src_planes, void *const
     else fill_t = static_cast<T>(static_cast<long long>(fill));
     const int plan = choose_plan(g.from, g.to);
     // TMA needs 16-byte aligned plane bases and row strides; 32-bit output offsets need < 2^32 elements
-    bool tma_ok = tma_available() && (g.src_pitch * sizeof(T)) % 16 == 0 && rows * g.dst_w < (int64_t(1) << 32) &&
-                  ceil_div(rows, K3S_TH) <= 65535;
+    // The staged form pays a fixed price per CTA tile (box reduction, TMA round trip, a barrier per band);
+    // it is amortised by many bands.  XRS_K3_STAGED=0 / 1 forces the choice (measurements, tests).
+    const char *staged_env = getenv("XRS_K3_STAGED");
+    const bool want_staged = staged_env ? staged_env[0] == '1' : n_bands >= K3S_MIN_BANDS;
+    bool tma_ok = want_staged && tma_available() && (g.src_pitch * sizeof(T)) % 16 == 0 &&
+                  rows * g.dst_w < (int64_t(1) << 32) && ceil_div(rows, K3S_TH) <= 65535;
     for (int b = 0; b < n_bands && tma_ok; ++b) tma_ok = (reinterpret_cast<uintptr_t>(src_planes[b]) & 15) == 0;
     for (int b0 = 0; b0 < n_bands; b0 += K3_MAX_BANDS) {
         const int nb = std::min(K3_MAX_BANDS, n_bands - b0);
