@@ -413,7 +413,10 @@ def test_resample_in_space_dispatches_to_reproject(xrs):
 
 @pytest.fixture
 def staged_k3(monkeypatch):
-    """The staged reproject kernel is chosen for many-band variables only (K3S_MIN_BANDS); force it."""
+    """The TMA-staged reproject kernel is an experiment that measured slower than the direct kernel
+    (csrc/reproject.cu); it is compiled only with -DXRS_K3_STAGED_EXPERIMENT and selected by
+    XRS_K3_STAGED=1.  In a default build the switch is ignored and both runs below take the direct
+    kernel (pitched and unpitched sources), which is still a useful comparison."""
     monkeypatch.setenv("XRS_K3_STAGED", "1")
     yield
 
@@ -484,4 +487,6 @@ def _same_up_to_contraction(got, want, method, what):
         frac = float(np.mean(~((got == want) | (np.isnan(got) & np.isnan(want)))))
         assert frac < 1e-4, (what, frac)
     else:
-        np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-12, equal_nan=True, err_msg=what)
+        # float32 outputs: a last-bit difference of the float64 value can cross a float32 rounding boundary
+        rtol = 1e-9 if got.dtype == np.float64 else 2.5e-7
+        np.testing.assert_allclose(got, want, rtol=rtol, atol=1e-12, equal_nan=True, err_msg=what)

@@ -331,21 +331,7 @@ def c5_across(rank, world, reps=3, e2e=True):
     return out
 
 
-def c3x(reps, one_shot, cpu, threads):
-    """C3's geometry with 32 bands, direct and staged kernel (XRS_K3_STAGED): where many bands amortise
-    the staging."""
-    src, tgt = c3_grids()
-    out = []
-    for flag in ("0", "1"):
-        os.environ["XRS_K3_STAGED"] = flag
-        for ln in _reproject_case(f"C3 geometry, 32 bands, XRS_K3_STAGED={flag}", src, tgt, 32, reps, one_shot, False,
-                                  threads, (4326, 32632), methods=("bilinear",)):
-            out.append(ln)
-    os.environ.pop("XRS_K3_STAGED", None)
-    return out
-
-
-CASES = {"c1": c1, "c3": c3, "c4": c4, "c5": c5, "c3x": c3x}
+CASES = {"c1": c1, "c3": c3, "c4": c4, "c5": c5}
 
 
 def run_all(reps=3, cpu=True, cpu_threads=None, restore_affinity=None, names=("c1", "c3", "c4", "c5"), one_shot=False):

@@ -475,7 +475,7 @@ constexpr int K3T_RPT = K3T_ROWS / (K3T_THREADS / 32 / (K3T_COLS / 32));  // row
 // parts of the transform (one sincos / exp each instead of one per pixel) into shared memory.
 // Phase 2: a warp owns 32 columns x 8 rows; each lane keeps its column terms in registers,
 // finishes the transform per pixel and gathers all bands.
-template <typename T, typename OUT, int METHOD>
+template <typename T, typename OUT, int METHOD, bool SEP>
 __global__ void __launch_bounds__(K3T_THREADS)
 k3_reproject(const __grid_constant__ K3Geom g, const __grid_constant__ K3Planes<T, OUT> planes, int n_bands, T fill,
              int plan) {
@@ -483,8 +483,8 @@ k3_reproject(const __grid_constant__ K3Geom g, const __grid_constant__ K3Planes<
     __shared__ Terms4 s_col[K3T_COLS];
     __shared__ int s_ty[K3T_ROWS];
     __shared__ int s_tx[K3T_COLS];
-    __shared__ AxisTap s_rowtap[K3T_ROWS][2];
-    __shared__ AxisTap s_coltap[K3T_COLS][2];
+    __shared__ AxisTap s_rowtap[SEP ? K3T_ROWS : 1][2];
+    __shared__ AxisTap s_coltap[SEP ? K3T_COLS : 1][2];
     const int tid = threadIdx.x;
     const int64_t c0 = static_cast<int64_t>(blockIdx.x) * K3T_COLS;
     const int64_t r0 = g.row_begin + static_cast<int64_t>(blockIdx.y) * K3T_ROWS;
@@ -512,7 +512,9 @@ k3_reproject(const __grid_constant__ K3Geom g, const __grid_constant__ K3Planes<
     const int ty_a = static_cast<int>(r0 / g.tile_h), tx_a = static_cast<int>(c0 / g.tile_w);
     const int ty_b = static_cast<int>(min(r0 + K3T_ROWS, g.row_end) - 1) / g.tile_h;
     const int tx_b = static_cast<int>(min(c0 + K3T_COLS, g.dst_w) - 1) / g.tile_w;
-    const bool sep = (plan == K3_PLAN_IDENTITY || plan == K3_PLAN_SEPARABLE) && ty_b - ty_a <= 1 && tx_b - tx_a <= 1;
+    // (SEP kernels are launched only for transforms whose source x / y depend on the target column / row
+    // alone: both CRSs geographic or web Mercator)
+    const bool sep = SEP && ty_b - ty_a <= 1 && tx_b - tx_a <= 1;
     if (sep) {
         const int res_i0 = static_cast<int>(g.win_i0), res_j0 = static_cast<int>(g.win_j0);
         const int res_i1 = res_i0 + static_cast<int>(g.win_w), res_j1 = res_j0 + static_cast<int>(g.win_h);
@@ -583,6 +585,7 @@ k3_reproject(const __grid_constant__ K3Geom g, const __grid_constant__ K3Planes<
     }
 }
 
+#ifdef XRS_K3_STAGED_EXPERIMENT
 // ---------------------------------------------------------------------------
 // K3, staged form: the gather of K2 (gather.cu) under the reprojection's index arithmetic.
 //
@@ -593,11 +596,16 @@ k3_reproject(const __grid_constant__ K3Geom g, const __grid_constant__ K3Planes<
 // source pixel crosses L2 -> SM once per tile instead of once per tap.  Tiles that touch the source
 // border (padding, numpy's negative-index wrap), whose box does not fit, or whose source pitch TMA
 // cannot describe take the direct per-pixel path (k3_gather_pixel) -- same arithmetic.
+//
+// MEASURED SLOWER than the direct kernel on B200 (config C3, 13 bands: 5.8 vs 4.9 ms; 32 bands: 12.3 vs
+// 10.8 ms; config C5, 8 variables: 4.4 vs 3.2 ms): the reprojection's taps of neighbouring pixels
+// are neighbours in the source, so L1 / L2 already serve them, while the staging adds a box
+// reduction, a TMA round trip per tile and a barrier per band, at half the occupancy.  Kept as a
+// documented experiment: compiled only with -DXRS_K3_STAGED_EXPERIMENT, selected with XRS_K3_STAGED=1.
 // ---------------------------------------------------------------------------
 constexpr int K3S_TW = 32, K3S_TH = 32, K3S_THREADS = 256, K3S_PX = 4;
 constexpr int K3S_ROW_STEP = K3S_THREADS / K3S_TW;
 constexpr int K3S_BOX_W = 48, K3S_BOX_H = 40, K3S_STAGES = 4;
-constexpr int K3S_MIN_BANDS = 32;  // direct form below (measured: 13 bands 4.9 ms direct vs 5.8 ms staged on config C3)
 
 template <typename T, typename OUT>
 struct K3StagedParams {
@@ -804,6 +812,8 @@ k3_reproject_staged(const __grid_constant__ K3Geom g, const __grid_constant__ K3
     }
 }
 
+#endif  // XRS_K3_STAGED_EXPERIMENT
+
 static int choose_plan(const ProjC &from, const ProjC &to) {
     if (from.kind == XRS_PROJ_GEOGRAPHIC && to.kind == XRS_PROJ_GEOGRAPHIC) return K3_PLAN_IDENTITY;
     if (from.kind == XRS_PROJ_GEOGRAPHIC || from.kind == XRS_PROJ_WEBMERC) return K3_PLAN_SEPARABLE;
@@ -822,13 +832,12 @@ int launch_reproject(const K3Geom &g, const void *const *src_planes, void *const
     else fill_t = static_cast<T>(static_cast<long long>(fill));
     const int plan = choose_plan(g.from, g.to);
     // TMA needs 16-byte aligned plane bases and row strides; 32-bit output offsets need < 2^32 elements
-    // The staged form pays a fixed price per CTA tile (box reduction, TMA round trip, a barrier per band);
-    // it is amortised by many bands.  XRS_K3_STAGED=0 / 1 forces the choice (measurements, tests).
+#ifdef XRS_K3_STAGED_EXPERIMENT
     const char *staged_env = getenv("XRS_K3_STAGED");
-    const bool want_staged = staged_env ? staged_env[0] == '1' : n_bands >= K3S_MIN_BANDS;
-    bool tma_ok = want_staged && tma_available() && (g.src_pitch * sizeof(T)) % 16 == 0 &&
+    bool tma_ok = staged_env && staged_env[0] == '1' && tma_available() && (g.src_pitch * sizeof(T)) % 16 == 0 &&
                   rows * g.dst_w < (int64_t(1) << 32) && ceil_div(rows, K3S_TH) <= 65535;
     for (int b = 0; b < n_bands && tma_ok; ++b) tma_ok = (reinterpret_cast<uintptr_t>(src_planes[b]) & 15) == 0;
+#endif
     for (int b0 = 0; b0 < n_bands; b0 += K3_MAX_BANDS) {
         const int nb = std::min(K3_MAX_BANDS, n_bands - b0);
         K3Planes<T, OUT> planes = {};
@@ -836,6 +845,7 @@ int launch_reproject(const K3Geom &g, const void *const *src_planes, void *const
             planes.src[b] = static_cast<const T *>(src_planes[b0 + b]);
             planes.dst[b] = static_cast<OUT *>(dst_planes[b0 + b]);
         }
+#ifdef XRS_K3_STAGED_EXPERIMENT
         if (tma_ok) {
             K3StagedParams<T, OUT> sp;
             memset(&sp, 0, sizeof(sp));
@@ -857,7 +867,14 @@ int launch_reproject(const K3Geom &g, const void *const *src_planes, void *const
                 continue;
             }
         }
-        XRS_TIMED(METHOD == XRS_NEAREST ? "k3_reproject<nearest>" : METHOD == XRS_BILINEAR ? "k3_reproject<bilinear>" : "k3_reproject<triangular>", st, k3_reproject<T, OUT, METHOD><<<grid, K3T_THREADS, 0, st>>>(g, planes, nb, fill_t, plan));
+#endif
+        const bool axis_only = (g.from.kind == XRS_PROJ_GEOGRAPHIC || g.from.kind == XRS_PROJ_WEBMERC) &&
+                               (g.to.kind == XRS_PROJ_GEOGRAPHIC || g.to.kind == XRS_PROJ_WEBMERC);
+        if (axis_only) {
+            XRS_TIMED(METHOD == XRS_NEAREST ? "k3_reproject_sep<nearest>" : METHOD == XRS_BILINEAR ? "k3_reproject_sep<bilinear>" : "k3_reproject_sep<triangular>", st, k3_reproject<T, OUT, METHOD, true><<<grid, K3T_THREADS, 0, st>>>(g, planes, nb, fill_t, plan));
+        } else {
+            XRS_TIMED(METHOD == XRS_NEAREST ? "k3_reproject<nearest>" : METHOD == XRS_BILINEAR ? "k3_reproject<bilinear>" : "k3_reproject<triangular>", st, k3_reproject<T, OUT, METHOD, false><<<grid, K3T_THREADS, 0, st>>>(g, planes, nb, fill_t, plan));
+        }
         XRS_LAUNCH_CHECK("k3_reproject");
     }
     return 0;
