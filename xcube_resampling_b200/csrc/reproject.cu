@@ -257,40 +257,41 @@ __device__ __forceinline__ OUT k3_blend(T v00, T v01, T v10, T v11, double u, do
 
 // ---- band loops of a pixel whose taps all lie inside the resident source ----------------------
 constexpr int K3_CHUNK = 4;  // bands whose taps are loaded before any of them is consumed
+constexpr int K3_SEP_CHUNK = 4;  // ... in the separable kernel
 
-template <typename T, typename OUT>
+template <typename T, typename OUT, int CHUNK = K3_CHUNK>
 __device__ __forceinline__ void k3_copy_tap(const K3Planes<T, OUT> &planes, int n_bands, int64_t o, int off) {
     int b = 0;
-    for (; b + K3_CHUNK <= n_bands; b += K3_CHUNK) {
-        T v[K3_CHUNK];
+    for (; b + CHUNK <= n_bands; b += CHUNK) {
+        T v[CHUNK];
 #pragma unroll
-        for (int q = 0; q < K3_CHUNK; ++q) v[q] = __ldg(planes.src[b + q] + off);
+        for (int q = 0; q < CHUNK; ++q) v[q] = __ldg(planes.src[b + q] + off);
 #pragma unroll
-        for (int q = 0; q < K3_CHUNK; ++q) st_stream(planes.dst[b + q] + o, static_cast<OUT>(v[q]));
+        for (int q = 0; q < CHUNK; ++q) st_stream(planes.dst[b + q] + o, static_cast<OUT>(v[q]));
     }
     for (; b < n_bands; ++b) st_stream(planes.dst[b] + o, static_cast<OUT>(__ldg(planes.src[b] + off)));
 }
 
 // o00: element offset of tap (0, 0); d01 in {0, 1}: the right-hand tap is the next element or the same;
-// d10 in {0, pitch}: likewise for the lower taps
-template <typename T, typename OUT, int METHOD>
+// d10 in {0, pitch}: likewise for the lower taps.  Bands [b_begin, n_bands).
+template <typename T, typename OUT, int METHOD, int CHUNK = K3_CHUNK>
 __device__ __forceinline__ void k3_blend_taps(const K3Planes<T, OUT> &planes, int n_bands, int64_t o, int o00, int d01,
-                                              int d10, int pitch, double u, double v) {
+                                              int d10, int pitch, double u, double v, int b_begin = 0) {
     const int d11 = d10 + d01;
     if (d01 == 1 && d10 != 0) {
         // generic position: the right-hand taps are the next element, so they are addressed with an
         // immediate offset from the two row pointers (2 address computations per band instead of 4)
-        int b = 0;
-        for (; b + K3_CHUNK <= n_bands; b += K3_CHUNK) {
-            T w[K3_CHUNK][4];
+        int b = b_begin;
+        for (; b + CHUNK <= n_bands; b += CHUNK) {
+            T w[CHUNK][4];
 #pragma unroll
-            for (int q = 0; q < K3_CHUNK; ++q) {
+            for (int q = 0; q < CHUNK; ++q) {
                 const T *p0 = planes.src[b + q] + o00;
                 const T *p1 = p0 + pitch;
                 w[q][0] = __ldg(p0); w[q][1] = __ldg(p0 + 1); w[q][2] = __ldg(p1); w[q][3] = __ldg(p1 + 1);
             }
 #pragma unroll
-            for (int q = 0; q < K3_CHUNK; ++q)
+            for (int q = 0; q < CHUNK; ++q)
                 st_stream(planes.dst[b + q] + o, k3_blend<T, OUT, METHOD>(w[q][0], w[q][1], w[q][2], w[q][3], u, v));
         }
         for (; b < n_bands; ++b) {
@@ -300,14 +301,13 @@ __device__ __forceinline__ void k3_blend_taps(const K3Planes<T, OUT> &planes, in
         }
         return;
     }
-    for (int b = 0; b < n_bands; ++b) {  // a coordinate exactly on a pixel centre: ceil == floor
+    for (int b = b_begin; b < n_bands; ++b) {  // a coordinate exactly on a pixel centre: ceil == floor
         const T *sp = planes.src[b] + o00;
         st_stream(planes.dst[b] + o, k3_blend<T, OUT, METHOD>(__ldg(sp), __ldg(sp + d01), __ldg(sp + d10), __ldg(sp + d11), u, v));
     }
 }
 
 // ---- per-pixel gather (reproject.py:268-335) given the source-CRS coordinates (sx, sy) --------
-
 template <typename T, typename OUT, int METHOD>
 __device__ __forceinline__ void k3_gather_pixel(const K3Geom &g, const K3Planes<T, OUT> &planes, int n_bands, T fill,
                                                 int64_t o, int t, double sx, double sy) {
@@ -475,8 +475,11 @@ constexpr int K3T_RPT = K3T_ROWS / (K3T_THREADS / 32 / (K3T_COLS / 32));  // row
 // parts of the transform (one sincos / exp each instead of one per pixel) into shared memory.
 // Phase 2: a warp owns 32 columns x 8 rows; each lane keeps its column terms in registers,
 // finishes the transform per pixel and gathers all bands.
+#ifndef XRS_K3_MINBLOCKS
+#define XRS_K3_MINBLOCKS 4  // 64 registers; 2 and 3 CTAs per SM measured slower (profiles/README.md)
+#endif
 template <typename T, typename OUT, int METHOD, bool SEP>
-__global__ void __launch_bounds__(K3T_THREADS)
+__global__ void __launch_bounds__(K3T_THREADS, XRS_K3_MINBLOCKS)
 k3_reproject(const __grid_constant__ K3Geom g, const __grid_constant__ K3Planes<T, OUT> planes, int n_bands, T fill,
              int plan) {
     __shared__ Terms4 s_row[K3T_ROWS];
@@ -563,15 +566,19 @@ k3_reproject(const __grid_constant__ K3Geom g, const __grid_constant__ K3Planes<
             const int64_t o = (r - g.row_begin) * g.dst_w + c;
             if (ca.flags & ra.flags & 2) {  // every tap inside the tile window and the resident source
                 const int o00 = (ra.idx - res_j0) * pitch + (ca.idx - res_i0);
-                if (METHOD == XRS_NEAREST) k3_copy_tap<T, OUT>(planes, n_bands, o, o00);
-                else k3_blend_taps<T, OUT, METHOD>(planes, n_bands, o, o00, ca.flags & 1, (ra.flags & 1) * pitch, pitch,
-                                                   ca.frac, ra.frac);
+                // (nothing but these loads stands between a pixel and its stores: more of them in flight)
+                if (METHOD == XRS_NEAREST) k3_copy_tap<T, OUT, K3_SEP_CHUNK>(planes, n_bands, o, o00);
+                else k3_blend_taps<T, OUT, METHOD, K3_SEP_CHUNK>(planes, n_bands, o, o00, ca.flags & 1,
+                                                                 (ra.flags & 1) * pitch, pitch, ca.frac, ra.frac);
             } else {  // source border, padding, untransformable: the general per-pixel path
                 k3_gather_pixel<T, OUT, METHOD>(g, planes, n_bands, fill, o, ty * g.ntx + tx, ct.a, s_row[rl].a);
             }
         }
         return;
     }
+    // (Tried and measured slower on config C3, 13 bands: requesting the first bands' taps of pixel k before
+    // transforming pixel k + 1 -- 6.9 ms against 4.9 ms, the extra live registers halve the occupancy; and
+    // eight instead of four bands in flight in the separable kernel -- 2.99 against 2.92 ms on config C5.)
 #pragma unroll 1
     for (int k = 0; k < K3T_RPT; ++k) {
         const int rl = row_l0 + k;
