@@ -1,0 +1,147 @@
+"""CF grid-mapping discovery (xcube_resampling_b200/cfconv.py) against the expectations of the
+reference's tests/gridmapping/test_cfconv.py: which CRS, under which key, with which coordinate
+variables -- and ``add_spatial_ref`` on an uncompressed Zarr-v2 directory store."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+from xcube_resampling_b200 import CRS, CRS_CRS84, CRS_WGS84, DataArray, Dataset, GridMapping
+from xcube_resampling_b200.cfconv import (
+    GridCoords,
+    GridMappingProxy,
+    add_spatial_ref,
+    find_potential_coord_vars,
+    get_dataset_grid_mapping_proxies,
+)
+
+UTM_33N = CRS.from_epsg(32633)
+
+
+def _check(gmp, crs, name, x_name, y_name):
+    assert isinstance(gmp, GridMappingProxy) and isinstance(gmp.coords, GridCoords)
+    assert gmp.crs == crs and gmp.name == name
+    assert gmp.coords.x.name == x_name and gmp.coords.y.name == y_name
+
+
+def test_no_crs_lon_lat_common_names():
+    # test_cfconv.py:58-75
+    ds = Dataset(coords=dict(lon=DataArray(np.linspace(10, 12, 11), dims="lon"),
+                             lat=DataArray(np.linspace(50, 52, 11), dims="lat")))
+    gms = get_dataset_grid_mapping_proxies(ds)
+    assert list(gms) == [None]
+    _check(gms[None], CRS_WGS84, "latitude_longitude", "lon", "lat")
+
+
+def test_no_crs_lon_lat_standard_names():
+    # test_cfconv.py:77-103
+    ds = Dataset(coords=dict(
+        weird_x=DataArray(np.linspace(10, 12, 11), dims="i", attrs=dict(standard_name="longitude")),
+        weird_y=DataArray(np.linspace(50, 52, 11), dims="j", attrs=dict(standard_name="latitude"))))
+    gms = get_dataset_grid_mapping_proxies(ds)
+    assert list(gms) == [None]
+    _check(gms[None], CRS_WGS84, "latitude_longitude", "weird_x", "weird_y")
+
+
+def test_crs_x_y_with_common_and_standard_names():
+    # test_cfconv.py:105-153
+    ds = Dataset(dict(crs=DataArray(np.array(0), dims=(), attrs=UTM_33N.to_cf())),
+                 coords=dict(x=DataArray(np.linspace(1000, 12000, 11), dims="x"),
+                             y=DataArray(np.linspace(5000, 52000, 11), dims="y")))
+    gms = get_dataset_grid_mapping_proxies(ds)
+    assert list(gms) == ["crs"]
+    _check(gms["crs"], UTM_33N, "transverse_mercator", "x", "y")
+    ds = Dataset(dict(crs=DataArray(np.array(0), dims=(), attrs=UTM_33N.to_cf())),
+                 coords=dict(myx=DataArray(np.linspace(1000, 12000, 11), dims="x",
+                                           attrs=dict(standard_name="projection_x_coordinate")),
+                             myy=DataArray(np.linspace(5000, 52000, 11), dims="y",
+                                           attrs=dict(standard_name="projection_y_coordinate"))))
+    gms = get_dataset_grid_mapping_proxies(ds)
+    _check(gms["crs"], UTM_33N, "transverse_mercator", "myx", "myy")
+
+
+def test_latitude_longitude_with_x_y():
+    # test_cfconv.py:155-179: a CRS-84 GeoTIFF opened with rioxarray
+    ds = Dataset(dict(band_1=DataArray(np.zeros((11, 11)), dims=["y", "x"]),
+                      spatial_ref=DataArray(np.array(0), dims=(), attrs=CRS_CRS84.to_cf())),
+                 coords=dict(x=DataArray(np.linspace(10, 20, 11), dims="x"),
+                             y=DataArray(np.linspace(50, 40, 11), dims="y")))
+    gms = get_dataset_grid_mapping_proxies(ds)
+    assert list(gms) == ["spatial_ref"]
+    gmp = gms["spatial_ref"]
+    assert gmp.crs.is_geographic and gmp.name == "latitude_longitude"
+    assert gmp.coords.x.name == "x" and gmp.coords.y.name == "y"
+    gm = GridMapping.from_dataset(ds)
+    assert gm.crs.is_geographic and gm.size == (11, 11) and gm.is_regular and not gm.is_j_axis_up
+
+
+def test_grid_mapping_attribute_and_dataset_attrs():
+    attrs = UTM_33N.to_cf()
+    ds = Dataset(dict(band=DataArray(np.zeros((5, 6)), dims=["y", "x"], attrs=dict(grid_mapping="my_crs")),
+                      my_crs=DataArray(np.array(0), dims=(), attrs=attrs)),
+                 coords=dict(x=DataArray(np.linspace(0, 50, 6), dims="x"), y=DataArray(np.linspace(40, 0, 5), dims="y")))
+    assert list(get_dataset_grid_mapping_proxies(ds)) == ["my_crs"]
+    ds = Dataset(coords=dict(x=DataArray(np.linspace(0, 50, 6), dims="x"), y=DataArray(np.linspace(40, 0, 5), dims="y")),
+                 attrs=attrs)
+    gms = get_dataset_grid_mapping_proxies(ds)
+    assert list(gms) == [None] and gms[None].crs == UTM_33N
+    # projected coordinates without any CRS: only usable with the caller's default
+    ds = Dataset(coords=dict(x=DataArray(np.linspace(0, 50, 6), dims="x"), y=DataArray(np.linspace(40, 0, 5), dims="y")))
+    assert get_dataset_grid_mapping_proxies(ds) == {}
+    assert get_dataset_grid_mapping_proxies(ds, missing_projected_crs=UTM_33N)[None].crs == UTM_33N
+    with pytest.raises(ValueError, match="cannot find any grid mapping in dataset"):
+        GridMapping.from_dataset(ds)
+    assert GridMapping.from_dataset(ds, crs=UTM_33N).crs == UTM_33N
+
+
+def test_2d_lon_lat_and_bounds_are_not_coordinates():
+    # test_cfconv.py (_find_potential_coord_vars): bounds variables are excluded, 2-D coordinates found
+    lon = np.add.outer(np.zeros(4), np.linspace(10, 12, 5))
+    lat = np.add.outer(np.linspace(52, 50, 4), np.zeros(5))
+    ds = Dataset(dict(rad=DataArray(np.zeros((4, 5)), dims=["y", "x"]),
+                      lon_bnds=DataArray(np.zeros((4, 5)), dims=["y", "x"]),
+                      lat_bounds=DataArray(np.zeros((4, 5)), dims=["y", "x"]),
+                      cube=DataArray(np.zeros((2, 4, 5)), dims=["t", "y", "x"])),
+                 coords=dict(lon=DataArray(lon, dims=["y", "x"], attrs=dict(bounds="lon_bnds")),
+                             lat=DataArray(lat, dims=["y", "x"])))
+    names = find_potential_coord_vars(ds)
+    assert "lon" in names and "lat" in names and "rad" in names
+    assert "lon_bnds" not in names and "lat_bounds" not in names and "cube" not in names
+    gms = get_dataset_grid_mapping_proxies(ds)
+    _check(gms[None], CRS_WGS84, "latitude_longitude", "lon", "lat")
+    gm = GridMapping.from_dataset(ds)
+    assert gm.size == (5, 4) and gm.xy_dim_names == ("x", "y")
+
+
+def test_incomplete_coordinates_warn():
+    ds = Dataset(dict(crs=DataArray(np.array(0), dims=(), attrs=UTM_33N.to_cf())),
+                 coords=dict(x=DataArray(np.linspace(1000, 12000, 11), dims="x")))
+    with pytest.warns(UserWarning, match="missing x- and/or y-coordinates"):
+        assert get_dataset_grid_mapping_proxies(ds, emit_warnings=True) == {}
+
+
+def test_add_spatial_ref_to_zarr_directory(tmp_path):
+    # test_cfconv.py (AddSpatialRefTest): a (y, x) array gains grid_mapping, a scalar CRS array appears
+    store = tmp_path / "cube.zarr"
+    os.makedirs(store / "band")
+    json.dump({"zarr_format": 2}, open(store / ".zgroup", "w"))
+    json.dump({"chunks": [2, 3], "compressor": None, "dtype": "<f4", "fill_value": None, "filters": None, "order": "C",
+               "shape": [4, 6], "zarr_format": 2}, open(store / "band" / ".zarray", "w"))
+    json.dump({"_ARRAY_DIMENSIONS": ["y", "x"]}, open(store / "band" / ".zattrs", "w"))
+    os.makedirs(store / "t")
+    json.dump({"chunks": [3], "compressor": None, "dtype": "<i8", "fill_value": None, "filters": None, "order": "C",
+               "shape": [3], "zarr_format": 2}, open(store / "t" / ".zarray", "w"))
+    json.dump({"_ARRAY_DIMENSIONS": ["t"]}, open(store / "t" / ".zattrs", "w"))
+    json.dump({"metadata": {}, "zarr_consolidated_format": 1}, open(store / ".zmetadata", "w"))
+    add_spatial_ref(str(store), UTM_33N)
+    assert json.load(open(store / "band" / ".zattrs"))["grid_mapping"] == "spatial_ref"
+    assert "grid_mapping" not in json.load(open(store / "t" / ".zattrs"))
+    sr = json.load(open(store / "spatial_ref" / ".zattrs"))
+    assert sr["grid_mapping_name"] == "transverse_mercator" and sr["_ARRAY_DIMENSIONS"] == []
+    assert CRS.from_cf(sr) == UTM_33N
+    meta = json.load(open(store / ".zmetadata"))["metadata"]
+    assert "spatial_ref/.zarray" in meta and meta["band/.zattrs"]["grid_mapping"] == "spatial_ref"
+    with pytest.raises(TypeError):
+        add_spatial_ref(42, UTM_33N)

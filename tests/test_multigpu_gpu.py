@@ -283,3 +283,32 @@ def test_rectify_band_stream_pipelines_scenes(xrs):
         ij = orect.rectify_ij(x, y, g)
         for m in ("nearest", "bilinear"):
             assert_same(outs[s][m], orect.gather(data, ij, m, nan), f"scene {s} {m}")
+
+
+def test_lazy_zarr_variables_stream_through_the_pipeline(xrs, tmp_path):
+    """The I/O edge: variables that live in an uncompressed Zarr-v2 store are read band chunk by band
+    chunk into page-locked staging buffers while the previous chunk uploads (io.py); same bytes as the
+    in-memory dataset, on one device and on row bands."""
+    from xcube_resampling_b200.io import LazyDataArray, open_zarr_dataset, write_zarr_array
+
+    x, y, size, xy_min, res, tile = _scene(300, 240, 15.0, 11)
+    h, w = x.shape
+    rng = np.random.default_rng(6)
+    rad = rng.random((7, h, w)).astype(np.float32)
+    cls = rng.integers(0, 30, (h, w)).astype(np.uint8)
+    store = tmp_path / "scene.zarr"
+    write_zarr_array(str(store / "lon"), x, (64, 64), ("y", "x"))
+    write_zarr_array(str(store / "lat"), y, (64, 64), ("y", "x"))
+    write_zarr_array(str(store / "rad"), rad, (2, 100, 128), ("band", "y", "x"))
+    write_zarr_array(str(store / "cls"), cls, (64, 300), ("y", "x"))
+    lazy = open_zarr_dataset(str(store))
+    assert isinstance(lazy["rad"], LazyDataArray) and isinstance(lazy["cls"], LazyDataArray)
+    eager = xrs.Dataset(data_vars=dict(rad=(("band", "y", "x"), rad), cls=(("y", "x"), cls)),
+                        coords=dict(lon=(("y", "x"), x), lat=(("y", "x"), y)))
+    tgt_gm = xrs.GridMapping.regular(size, xy_min, res, "EPSG:4326", tile_size=tile)
+    interp = {"rad": "bilinear", "cls": "nearest"}
+    want = xrs.rectify_dataset(eager, target_gm=tgt_gm, interp_methods=interp)
+    for devices in (None, [0, 0]):
+        got = xrs.rectify_dataset(lazy, target_gm=tgt_gm, interp_methods=interp, devices=devices)
+        for name in interp:
+            assert_same(got[name].values, want[name].values, f"{name} lazy store, devices={devices}")

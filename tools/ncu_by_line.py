@@ -50,14 +50,18 @@ def main():
     match = [blk for blk in blocks if want in blk["name"]]
     b = match[0] if match else blocks[0]
     h = b["hdr"]
-    i_ex, i_s = h.index("Instructions Executed"), h.index("# Samples")
+    i_ex = h.index("Instructions Executed")
+    # the sampling column's name differs between ncu versions / report sections
+    cands = [k for k, name in enumerate(h) if name.strip() in ("# Samples", "Samples", "Warp Stall Sampling (All Samples)")
+             or name.strip().startswith("# Samples")]
+    i_s = cands[0] if cands else None
     if len(b["rows"]) != len(lines):
         print(f"warning: {len(b['rows'])} profiled instructions vs {len(lines)} disassembled", file=sys.stderr)
     agg = defaultdict(lambda: [0, 0])
     tot_i = tot_s = 0
     for k, r in enumerate(b["rows"]):
         key = lines[k] if k < len(lines) else None
-        n, s = int(float(r[i_ex] or 0)), int(float(r[i_s] or 0))
+        n, s = int(float(r[i_ex] or 0)), (int(float(r[i_s] or 0)) if i_s is not None else 0)
         agg[key][0] += n
         agg[key][1] += s
         tot_i += n

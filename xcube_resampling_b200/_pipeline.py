@@ -54,8 +54,11 @@ class SourceGroup:
     targets: list = field(default_factory=list)
 
 
-def as_bands(values: np.ndarray) -> np.ndarray:
-    """(h, w) or (bands, h, w) -> (bands, h, w) view with unit stride along x."""
+def as_bands(values):
+    """(h, w) or (bands, h, w) -> (bands, h, w) view with unit stride along x; lazy sources
+    (``io.LazySource``: bands still in a chunked store) pass through."""
+    if hasattr(values, "read_bands"):
+        return values
     v = values if values.ndim == 3 else values[None]
     if v.strides[-1] != v.itemsize or v.strides[-2] < v.shape[-1] * v.itemsize or not v.flags.aligned:
         v = np.ascontiguousarray(v)
@@ -68,7 +71,8 @@ def group_by_buffer(items) -> list[SourceGroup]:
     groups: dict = {}
     for values, target in items:
         v = as_bands(values)
-        key = (v.__array_interface__["data"][0], v.shape, v.strides, v.dtype.str)
+        key = ("lazy", id(v)) if hasattr(v, "read_bands") else \
+            (v.__array_interface__["data"][0], v.shape, v.strides, v.dtype.str)
         if key not in groups:
             groups[key] = SourceGroup(v)
         groups[key].targets.append(target)
@@ -150,17 +154,41 @@ class GatherPipeline:
         keep = []
         for grp in groups:
             v = grp.values
-            bands, h, w = v.shape
+            lazy = hasattr(v, "read_bands")
+            dtype = np.dtype(v.dtype)
+            bands = (1 if v.ndim == 2 else v.shape[0]) if lazy else v.shape[0]
+            h, w = v.shape[-2:]
             if (h, w) != (self.h, self.w):
                 raise ValueError(f"variable of shape {(h, w)} does not match the source image {(self.h, self.w)}")
-            isz = v.itemsize
+            isz = dtype.itemsize
             per = max(1, self.pitch_bytes // isz)
             wp = -(-w // per) * per
             chunk = max(1, min(self.chunk, bands))
-            in_slots = self._slots(self._in_slots, (v.dtype.str, chunk), (chunk, win_h, wp), v.dtype)
-            base = v.__array_interface__["data"][0]
-            sb, sr = v.strides[0], v.strides[1]
-            for b0, nb in chunk_schedule(bands, chunk):
+            in_slots = self._slots(self._in_slots, (dtype.str, chunk), (chunk, win_h, wp), dtype)
+            schedule = chunk_schedule(bands, chunk)
+            if lazy:
+                # the I/O edge: band chunk k+1 is read from the store into one of two page-locked staging
+                # buffers on a reader thread while chunk k is copied to the device
+                from concurrent.futures import ThreadPoolExecutor
+
+                stage = [_dev.pinned_empty((chunk, h, w), dtype) for _ in range(2)]
+                stage_done = [None, None]
+                reader = ThreadPoolExecutor(max_workers=1)
+                pending = reader.submit(v.read_bands, schedule[0][0], schedule[0][1], stage[0])
+                keep.append(stage)
+            else:
+                base = v.__array_interface__["data"][0]
+                sb, sr = v.strides[0], v.strides[1]
+            for ci, (b0, nb) in enumerate(schedule):
+                if lazy:
+                    pending.result()
+                    base, sb, sr = stage[ci % 2].__array_interface__["data"][0], h * w * isz, w * isz
+                    if ci + 1 < len(schedule):
+                        if stage_done[(ci + 1) % 2] is not None:
+                            stage_done[(ci + 1) % 2].synchronize()  # its previous upload has left the buffer
+                        pending = reader.submit(v.read_bands, schedule[ci + 1][0], schedule[ci + 1][1],
+                                                stage[(ci + 1) % 2])
+                b_off = 0 if lazy else b0
                 slot = k_in % 2
                 k_in += 1
                 src_slot = in_slots[slot]
@@ -168,10 +196,12 @@ class GatherPipeline:
                     s_in.wait_event(in_free[slot])
                     for (j0, j1, i0, i1) in self.segments:
                         copy2d(src_slot.data_ptr() + ((j0 - self.win[0]) * wp + i0) * isz, wp * isz, win_h * wp * isz,
-                               base + b0 * sb + j0 * sr + i0 * isz, sr, sb, (i1 - i0) * isz, j1 - j0, nb, dev)
+                               base + b_off * sb + j0 * sr + i0 * isz, sr, sb, (i1 - i0) * isz, j1 - j0, nb, dev)
                         self.h2d_bytes += (i1 - i0) * isz * (j1 - j0) * nb
                     ready = torch.cuda.Event()
                     ready.record(s_in)
+                if lazy:
+                    stage_done[ci % 2] = ready
                 main.wait_event(ready)
                 src_view = src_slot[:nb, :, :w]
                 for tgt in grp.targets:
@@ -197,6 +227,8 @@ class GatherPipeline:
                         self.d2h_bytes += self.out_w * osz * n_rows * nb
                         out_free[oslot].record(s_out)
                 in_free[slot].record(main)
+            if lazy:
+                reader.shutdown(wait=True)
             keep.append(v)
         self._keep = keep
         self._pending = (s_out, main)

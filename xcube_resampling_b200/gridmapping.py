@@ -4,9 +4,8 @@ A from-scratch host-side restatement of the subset of the reference's
 ``GridMapping`` that the resampling path reads:
 ``gridmapping/base.py:59-913``, ``regular.py:38-166``, ``coords.py:49-337``,
 ``helpers.py:39-255``.  Coordinates are plain numpy on the host; device copies
-are made by the entry points.  CF-convention discovery (``cfconv.py``) is out
-of scope: :meth:`GridMapping.from_dataset` recognises ``lon/lat`` and ``x/y``
-coordinate variables plus a ``spatial_ref`` / ``crs`` variable only.
+are made by the entry points (or stay there: :meth:`GridMapping.from_device_coords`).
+CF-convention discovery lives in ``cfconv.py``.
 """
 
 from __future__ import annotations
@@ -711,55 +710,37 @@ class GridMapping:
     @classmethod
     def from_dataset(cls, dataset: Any, *, crs=None, tile_size=None, prefer_is_regular: bool = True, prefer_crs=None,
                      emit_warnings: bool = False, tolerance: float = DEFAULT_TOLERANCE) -> "GridMapping":
-        """base.py:760-801, reduced: lon/lat or x/y coordinate variables + spatial_ref/crs variable."""
+        """base.py:760-801 -> dataset.py:34-112: CF grid-mapping discovery (``cfconv.py``), one grid
+        mapping per CRS found, then the preference rules when there are several."""
+        from .cfconv import get_dataset_grid_mapping_proxies
+
         ds = from_any(dataset)
-        found_crs = None
-        for gm_name in ("spatial_ref", "crs"):
-            if gm_name in ds and ds[gm_name].attrs:
-                try:
-                    found_crs = CRS.from_cf(ds[gm_name].attrs)
-                except ValueError:
-                    found_crs = None
-                break
-        candidates = []
-        for names in (("x", "y"), ("lon", "lat"), ("transformed_x", "transformed_y")):
-            if names[0] in ds and names[1] in ds:
-                xv, yv = ds[names[0]], ds[names[1]]
-                if xv.ndim == yv.ndim and xv.ndim in (1, 2):
-                    candidates.append((names, xv, yv))
-        if not candidates:
-            raise ValueError("cannot find any grid mapping in dataset")
-        gms = []
-        for names, xv, yv in candidates:
-            geographic_names = names == ("lon", "lat")
-            if crs is not None:
-                c = normalize_crs(crs)
-            elif found_crs is not None and (found_crs.is_geographic == geographic_names):
-                c = found_crs
-            elif geographic_names:
-                c = CRS_WGS84
-            elif found_crs is not None:
-                c = found_crs
-            else:
-                continue
-            gms.append(cls.from_coords(DataArray(xv.values, dims=xv.dims, name=names[0]),
-                                       DataArray(yv.values, dims=yv.dims, name=names[1]), c,
-                                       tile_size=tile_size, tolerance=tolerance))
-        if not gms:
-            raise ValueError("cannot find any grid mapping in dataset")
-        pc = normalize_crs(prefer_crs) if prefer_crs is not None else (normalize_crs(crs) if crs is not None else None)
+        crs = normalize_crs(crs) if crs is not None else None
+        prefer_crs = normalize_crs(prefer_crs) if prefer_crs is not None else crs
+        proxies = get_dataset_grid_mapping_proxies(ds, emit_warnings=emit_warnings, missing_projected_crs=crs,
+                                                   missing_rotated_latitude_longitude_crs=crs,
+                                                   missing_latitude_longitude_crs=crs).values()
+        gms = [cls.from_coords(gmp.coords.x, gmp.coords.y, gmp.crs, tile_size=tile_size or gmp.tile_size,
+                               tolerance=tolerance) for gmp in proxies]
         if len(gms) > 1:
-            if pc is not None:
+            def both_geographic(gm):
+                return gm.crs.is_geographic and prefer_crs.is_geographic
+
+            rules = []
+            if prefer_crs is not None and prefer_is_regular is not None:
+                rules += [lambda gm: gm.crs == prefer_crs and bool(gm.is_regular) == prefer_is_regular,
+                          lambda gm: both_geographic(gm) and bool(gm.is_regular) == prefer_is_regular]
+            if prefer_crs is not None:
+                rules += [lambda gm: gm.crs == prefer_crs, both_geographic]
+            if prefer_is_regular is not None:
+                rules += [lambda gm: bool(gm.is_regular) == prefer_is_regular]
+            for rule in rules:
                 for gm in gms:
-                    if gm.crs == pc and bool(gm.is_regular) == bool(prefer_is_regular):
+                    if rule(gm):
                         return gm
-                for gm in gms:
-                    if gm.crs == pc:
-                        return gm
-            for gm in gms:
-                if bool(gm.is_regular) == bool(prefer_is_regular):
-                    return gm
-        return gms[0]
+        if gms:
+            return gms[0]
+        raise ValueError("cannot find any grid mapping in dataset")
 
     # -- comparisons / assertions --------------------------------------------
     def is_close(self, other: "GridMapping", tolerance: float = DEFAULT_TOLERANCE) -> bool:

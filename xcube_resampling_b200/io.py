@@ -1,0 +1,187 @@
+"""The I/O edge: chunked arrays on disk -> page-locked host staging -> H2D, overlapped.
+
+The reference opens Zarr / NetCDF through xarray + dask and lets the dask chunks flow into its tile
+tasks.  Here a data variable may be a :class:`LazyDataArray` whose bands live in a chunked store;
+the band-chunk pipeline (``_pipeline.GatherPipeline``) then reads band chunk k+1 from the store into
+one of two page-locked staging buffers on a reader thread while chunk k is being copied to the
+device and chunk k-1 is being gathered -- decode / read, PCIe upload, kernels and download all
+overlap, and the host never holds more than two chunks of a variable.
+
+Stores understood without third-party packages:
+
+* :class:`ZarrV2Source` -- an UNCOMPRESSED Zarr-v2 array in a directory store (``.zarray`` with
+  ``"compressor": null``, C order, any chunking): what ``add_spatial_ref`` (``cfconv.py``) and the
+  reference's Zarr helpers operate on.  Compressed stores need the ``zarr`` / ``numcodecs``
+  packages, which this build does not have; open them with xarray and pass the arrays instead.
+* :class:`NpySource` -- a ``.npy`` file, memory-mapped.
+
+:func:`open_zarr_dataset` assembles a :class:`~xcube_resampling_b200.dataset.Dataset` from a
+directory store: coordinate arrays (1-D, or 2-D named like coordinates) are read eagerly, every
+other array becomes a lazy variable.
+"""
+
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+
+from .dataset import DataArray, Dataset
+
+
+class LazySource:
+    """A (bands, h, w) or (h, w) array that can deliver whole bands into a caller's buffer."""
+
+    shape: tuple
+    dtype: np.dtype
+
+    def read_bands(self, b0: int, nb: int, out: np.ndarray) -> None:  # pragma: no cover - interface
+        """Fill ``out[:nb]`` (shape (>= nb, h, w), C-contiguous rows) with bands ``b0 : b0 + nb``."""
+        raise NotImplementedError
+
+    @property
+    def ndim(self) -> int:
+        return len(self.shape)
+
+    @property
+    def nbytes(self) -> int:
+        return int(np.prod(self.shape)) * np.dtype(self.dtype).itemsize
+
+    def read_all(self) -> np.ndarray:
+        bands = 1 if len(self.shape) == 2 else self.shape[0]
+        out = np.empty((bands,) + tuple(self.shape[-2:]), dtype=self.dtype)
+        self.read_bands(0, bands, out)
+        return out[0] if len(self.shape) == 2 else out
+
+
+class NpySource(LazySource):
+    """A ``.npy`` file read through a memory map."""
+
+    def __init__(self, path: str):
+        self._mm = np.load(path, mmap_mode="r")
+        if self._mm.ndim not in (2, 3):
+            raise ValueError(f"{path}: expected a 2-D or 3-D array, got {self._mm.ndim} dimensions")
+        self.shape, self.dtype = tuple(self._mm.shape), self._mm.dtype
+
+    def read_bands(self, b0, nb, out):
+        src = self._mm[None] if self._mm.ndim == 2 else self._mm
+        out[:nb] = src[b0:b0 + nb]
+
+
+class ZarrV2Source(LazySource):
+    """One uncompressed Zarr-v2 array of a directory store (2-D or 3-D, C order)."""
+
+    def __init__(self, path: str):
+        meta = json.load(open(os.path.join(path, ".zarray")))
+        if meta.get("zarr_format") != 2:
+            raise ValueError(f"{path}: not a Zarr v2 array")
+        if meta.get("compressor") is not None or meta.get("filters"):
+            raise NotImplementedError(f"{path}: compressed / filtered Zarr arrays need the zarr package, which this "
+                                      "build does not have; open the store with xarray and pass the arrays instead")
+        if meta.get("order", "C") != "C":
+            raise NotImplementedError(f"{path}: only C-order chunks are supported")
+        self.path = path
+        self.shape = tuple(int(n) for n in meta["shape"])
+        if len(self.shape) not in (2, 3):
+            raise ValueError(f"{path}: expected a 2-D or 3-D array, got shape {self.shape}")
+        self.chunks = tuple(int(n) for n in meta["chunks"])
+        self.dtype = np.dtype(meta["dtype"])
+        self.fill = meta.get("fill_value")
+        self.sep = meta.get("dimension_separator", ".")
+        attrs_path = os.path.join(path, ".zattrs")
+        self.attrs = json.load(open(attrs_path)) if os.path.isfile(attrs_path) else {}
+
+    def _chunk(self, idx):
+        p = os.path.join(self.path, self.sep.join(str(i) for i in idx))
+        if not os.path.isfile(p):  # a missing chunk is all fill value
+            fill = self.fill if self.fill not in (None, "NaN") else (np.nan if self.dtype.kind == "f" else 0)
+            return np.full(self.chunks, fill, dtype=self.dtype)
+        return np.fromfile(p, dtype=self.dtype).reshape(self.chunks)
+
+    def read_bands(self, b0, nb, out):
+        three_d = len(self.shape) == 3
+        cb = self.chunks[0] if three_d else 1
+        ch, cw = self.chunks[-2:]
+        h, w = self.shape[-2:]
+        for kb in range(b0 // cb, -(-(b0 + nb) // cb)):
+            lo, hi = max(b0, kb * cb), min(b0 + nb, (kb + 1) * cb)
+            for kj in range(-(-h // ch)):
+                for ki in range(-(-w // cw)):
+                    block = self._chunk((kb, kj, ki) if three_d else (kj, ki))
+                    if not three_d:
+                        block = block[None]
+                    j0, i0 = kj * ch, ki * cw
+                    j1, i1 = min(h, j0 + ch), min(w, i0 + cw)
+                    out[lo - b0:hi - b0, j0:j1, i0:i1] = block[lo - kb * cb:hi - kb * cb, :j1 - j0, :i1 - i0]
+
+
+class LazyDataArray(DataArray):
+    """A dataset variable whose values stay in a chunked store until a pipeline streams them (``source``);
+    ``values`` materialises the whole array for anything that is not a streaming consumer."""
+
+    __slots__ = ("source",)
+
+    def __init__(self, source: LazySource, dims, attrs=None, name=None):
+        self.source = source
+        stand_in = np.broadcast_to(np.zeros((), dtype=source.dtype), source.shape)  # shape / dtype without memory
+        DataArray.__init__(self, stand_in, dims=dims, attrs=attrs, name=name)
+
+    @property
+    def values(self) -> np.ndarray:
+        return self.source.read_all()
+
+    data = values
+
+
+def open_zarr_dataset(path: str, coord_names=("lon", "lat", "x", "y", "longitude", "latitude",
+                                              "transformed_x", "transformed_y")) -> Dataset:
+    """An uncompressed Zarr-v2 directory store as a :class:`Dataset`: scalar, 1-D and coordinate-named
+    arrays are read now, every other 2-D / 3-D array becomes a :class:`LazyDataArray`."""
+    data_vars, coords = {}, {}
+    for item in sorted(os.listdir(path)):
+        arr_dir = os.path.join(path, item)
+        if not os.path.isfile(os.path.join(arr_dir, ".zarray")):
+            continue
+        meta = json.load(open(os.path.join(arr_dir, ".zarray")))
+        attrs_path = os.path.join(arr_dir, ".zattrs")
+        attrs = json.load(open(attrs_path)) if os.path.isfile(attrs_path) else {}
+        dims = attrs.pop("_ARRAY_DIMENSIONS", None) or [f"dim_{k}" for k in range(len(meta["shape"]))]
+        shape = tuple(meta["shape"])
+        if len(shape) == 0:
+            chunk = os.path.join(arr_dir, "0")
+            value = np.fromfile(chunk, dtype=np.dtype(meta["dtype"]))[0] if os.path.isfile(chunk) else 0
+            coords[item] = DataArray(np.asarray(value), dims=(), attrs=attrs, name=item)
+        elif len(shape) == 1:
+            dt = np.dtype(meta["dtype"])
+            n, c = shape[0], int(meta["chunks"][0])
+            parts = [np.fromfile(os.path.join(arr_dir, str(k)), dtype=dt)[:min(c, n - k * c)] for k in range(-(-n // c))]
+            coords[item] = DataArray(np.concatenate(parts), dims=dims, attrs=attrs, name=item)
+        else:
+            src = ZarrV2Source(arr_dir)
+            if item in coord_names:
+                coords[item] = DataArray(src.read_all(), dims=dims, attrs=attrs, name=item)
+            else:
+                data_vars[item] = LazyDataArray(src, dims=dims, attrs=attrs, name=item)
+    group_attrs = os.path.join(path, ".zattrs")
+    return Dataset(data_vars=data_vars, coords=coords, attrs=json.load(open(group_attrs)) if os.path.isfile(group_attrs) else {})
+
+
+def write_zarr_array(path: str, array: np.ndarray, chunks, dims) -> None:
+    """Write ``array`` as an uncompressed Zarr-v2 array (test fixtures, synthetic benchmark stores)."""
+    os.makedirs(path, exist_ok=True)
+    array = np.asarray(array)
+    chunks = tuple(int(c) for c in chunks)
+    json.dump({"chunks": list(chunks), "compressor": None, "dtype": array.dtype.str, "fill_value": None, "filters": None,
+               "order": "C", "shape": list(array.shape), "zarr_format": 2}, open(os.path.join(path, ".zarray"), "w"))
+    json.dump({"_ARRAY_DIMENSIONS": list(dims)}, open(os.path.join(path, ".zattrs"), "w"))
+    if array.ndim == 0:
+        array.reshape(1).tofile(os.path.join(path, "0"))
+        return
+    grid = [range(-(-n // c)) for n, c in zip(array.shape, chunks)]
+    for idx in np.ndindex(*[len(g) for g in grid]):
+        block = np.zeros(chunks, dtype=array.dtype)
+        sl = tuple(slice(k * c, min(n, (k + 1) * c)) for k, c, n in zip(idx, chunks, array.shape))
+        part = array[sl]
+        block[tuple(slice(0, s) for s in part.shape)] = part
+        block.tofile(os.path.join(path, ".".join(str(k) for k in idx)))

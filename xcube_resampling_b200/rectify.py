@@ -435,7 +435,7 @@ def rectify_dataset(
                     f"interp_methods must be one of 0, 1, 'nearest', 'bilinear', "
                     f"'triangular', was '{interp_method}'."
                 )
-            values = var.values
+            values = getattr(var, "source", None) or var.values  # io.LazyDataArray: streamed from its store
             n_b = 1 if values.ndim == 2 else values.shape[0]
             out = _dev.pinned_empty((n_b, H, W), values.dtype)
             items.append((values, Target(str(var_name), interp_method, fill_value, out)))
@@ -486,7 +486,8 @@ def _rectify_groups_single(source_gm, x_dev, y_dev, groups, target_gm, dev):
         plan = RectifyPlan(target_gm, dev, uv_delta=UV_DELTA)
         H, W = target_gm.height, target_gm.width
         h, w = x_dev.shape
-        if len(groups) == 1 and len(groups[0].targets) == 1 and groups[0].values.nbytes < _PIPELINE_MIN_BYTES:
+        if (len(groups) == 1 and len(groups[0].targets) == 1 and not hasattr(groups[0].values, "read_bands")
+                and groups[0].values.nbytes < _PIPELINE_MIN_BYTES):
             grp = groups[0]
             tgt = grp.targets[0]
             src = _dev.to_device_pitched(grp.values, dev)

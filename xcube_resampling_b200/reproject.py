@@ -303,7 +303,7 @@ def reproject_dataset(
                     f"interp_methods must be one of 0, 1, 'nearest', 'bilinear', "
                     f"'triangular', was '{interp_method}'."
                 )
-            values = var.values
+            values = getattr(var, "source", None) or var.values  # io.LazyDataArray: streamed from its store
             n_b = 1 if values.ndim == 2 else values.shape[0]
             # numpy's promotion in reproject.py:315-328 makes bilinear results float64
             out_dtype = np.float64 if interp_method == "bilinear" else values.dtype

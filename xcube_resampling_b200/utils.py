@@ -200,7 +200,10 @@ def normalize_grid_mapping(ds: Dataset, gm: GridMapping) -> Dataset:
     for name, var in ds.items():
         attrs = dict(var.attrs)
         attrs["grid_mapping"] = "spatial_ref"
-        out[name] = DataArray(var.values, dims=var.dims, attrs=attrs, name=name)
+        if getattr(var, "source", None) is not None:  # io.LazyDataArray: stays in its store
+            out[name] = type(var)(var.source, dims=var.dims, attrs=attrs, name=name)
+        else:
+            out[name] = DataArray(var.values, dims=var.dims, attrs=attrs, name=name)
     return out
 
 
