@@ -291,7 +291,8 @@ def test_lazy_zarr_variables_stream_through_the_pipeline(xrs, tmp_path):
     in-memory dataset, on one device and on row bands."""
     from xcube_resampling_b200.io import LazyDataArray, open_zarr_dataset, write_zarr_array
 
-    x, y, size, xy_min, res, tile = _scene(300, 240, 15.0, 11)
+    x, y, size, xy_min, res, tile = _scene(300, 240, 15.0, 11, holes=False)  # (no source_gm given below: the
+    x[80:83, 75:150] = nan                                                  # resolution estimate must stay finite)
     h, w = x.shape
     rng = np.random.default_rng(6)
     rad = rng.random((7, h, w)).astype(np.float32)
