@@ -308,8 +308,10 @@ def test_lazy_zarr_variables_stream_through_the_pipeline(xrs, tmp_path):
                         coords=dict(lon=(("y", "x"), x), lat=(("y", "x"), y)))
     tgt_gm = xrs.GridMapping.regular(size, xy_min, res, "EPSG:4326", tile_size=tile)
     interp = {"rad": "bilinear", "cls": "nearest"}
-    want = xrs.rectify_dataset(eager, target_gm=tgt_gm, interp_methods=interp)
+    # (explicit source resolution: the estimate from cell areas, 0.0025, would trigger the pre-downscale)
+    src_gm = xrs.GridMapping.from_coords(x, y, "EPSG:4326", xy_res=res, xy_dim_names=("x", "y"))
+    want = xrs.rectify_dataset(eager, target_gm=tgt_gm, source_gm=src_gm, interp_methods=interp)
     for devices in (None, [0, 0]):
-        got = xrs.rectify_dataset(lazy, target_gm=tgt_gm, interp_methods=interp, devices=devices)
+        got = xrs.rectify_dataset(lazy, target_gm=tgt_gm, source_gm=src_gm, interp_methods=interp, devices=devices)
         for name in interp:
             assert_same(got[name].values, want[name].values, f"{name} lazy store, devices={devices}")
