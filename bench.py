@@ -494,11 +494,13 @@ def ours(args):
     else:
         # Row bands of equal WORK, not equal height: a rotated swath leaves the top and bottom rows of
         # the target mostly empty.  The weights come from one full ij image (valid pixels per row plus
-        # a constant for the fill writes); every rank derives the same partition.
+        # a constant for the fill writes: measured at N=1, a valid pixel costs ~103 ps across K1 + both
+        # gathers, a fill pixel ~31 ps, i.e. row cost ~ valid + 0.43 * width); every rank derives the
+        # same partition.
         ij_full = xrect.RectifyPlan(target_gm, dev).ij(x_dev, y_dev)
         valid_per_row = (~torch.isnan(ij_full[0])).sum(dim=1).cpu().numpy().astype(np.float64)
         del ij_full
-        bands_w = xbands.weighted_row_bands(valid_per_row + 0.3 * W_t, world, align=32)
+        bands_w = xbands.weighted_row_bands(valid_per_row + 0.43 * W_t, world, align=8)
         edges = [b[0] for b in bands_w] + [H_t]
     rows = (edges[rank], edges[rank + 1])
     band_px = (rows[1] - rows[0]) * W_t
