@@ -63,14 +63,26 @@ kb_quad_footprints(const double *__restrict__ x, const double *__restrict__ y, i
             fy = g.j_up ? (vy - g.y_min) * g.inv_yr : (g.y_max - vy) * g.inv_yr;
             return fabs(fx) < 1e15 && fabs(fy) < 1e15;  // false for NaN / inf
         };
+        // all vertex rows of the thread's quads are requested before any is used (one memory round trip
+        // instead of one per row: the kernel is latency-bound on slabs of a few hundred rows)
+        double vx[ROWS_PER_THREAD + 1][2], vy[ROWS_PER_THREAD + 1][2];
+#pragma unroll
+        for (int k = 0; k <= ROWS_PER_THREAD; ++k) {
+            const bool in = q0 + k <= q1;
+            const int64_t o = (q0 + k) * pitch + qi;
+            vx[k][0] = in ? __ldg(x + o) : NAN; vx[k][1] = in ? __ldg(x + o + 1) : NAN;
+            vy[k][0] = in ? __ldg(y + o) : NAN; vy[k][1] = in ? __ldg(y + o + 1) : NAN;
+        }
         double ax, ay, bx, by;  // upper vertices of the current quad row
-        bool ok_a = px(__ldg(x + q0 * pitch + qi), __ldg(y + q0 * pitch + qi), ax, ay);
-        bool ok_b = px(__ldg(x + q0 * pitch + qi + 1), __ldg(y + q0 * pitch + qi + 1), bx, by);
+        bool ok_a = px(vx[0][0], vy[0][0], ax, ay);
+        bool ok_b = px(vx[0][1], vy[0][1], bx, by);
         const int ci = static_cast<int>(qi);
-        for (int64_t q = q0; q < q1; ++q) {
+#pragma unroll
+        for (int k = 0; k < ROWS_PER_THREAD; ++k) {
+            if (q0 + k >= q1) break;
             double cx, cy, dx, dy;
-            const bool ok_c = px(__ldg(x + (q + 1) * pitch + qi), __ldg(y + (q + 1) * pitch + qi), cx, cy);
-            const bool ok_d = px(__ldg(x + (q + 1) * pitch + qi + 1), __ldg(y + (q + 1) * pitch + qi + 1), dx, dy);
+            const bool ok_c = px(vx[k + 1][0], vy[k + 1][0], cx, cy);
+            const bool ok_d = px(vx[k + 1][1], vy[k + 1][1], dx, dy);
             if (static_cast<int>(ok_a) + ok_b + ok_c + ok_d >= 3) {
                 double lo_x = INFINITY, hi_x = -INFINITY, lo_y = INFINITY, hi_y = -INFINITY;
                 if (ok_a) { lo_x = fmin(lo_x, ax); hi_x = fmax(hi_x, ax); lo_y = fmin(lo_y, ay); hi_y = fmax(hi_y, ay); }

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(K0_THREADS)
 k0_tile_windows(const double *__restrict__ x, const double *__restrict__ y, int64_t h, int64_t w, int64_t pitch,
                 const double *__restrict__ g_x_lo, const double *__restrict__ g_x_hi, int ntx,
                 const double *__restrict__ g_y_lo, const double *__restrict__ g_y_hi, int nty,
-                int4 *__restrict__ table, int j_offset) {
+                int4 *__restrict__ table, int j_offset, int rows_per_block) {
     extern __shared__ __align__(16) unsigned char k0_smem[];
     double *s_x_lo = reinterpret_cast<double *>(k0_smem);
     double *s_x_hi = s_x_lo + ntx;
@@ -99,7 +99,7 @@ k0_tile_windows(const double *__restrict__ x, const double *__restrict__ y, int6
     const int64_t n_col_chunks = ceil_div(w, K0_THREADS);
     const int64_t chunk = blockIdx.x % n_col_chunks, row_chunk = blockIdx.x / n_col_chunks;
     const int64_t col = chunk * K0_THREADS + threadIdx.x;
-    const int64_t row0 = row_chunk * K0_ROWS, row1 = min(row0 + K0_ROWS, h);
+    const int64_t row0 = row_chunk * rows_per_block, row1 = min(row0 + rows_per_block, h);
     if (col < w) {
         AxisRange rx, ry;
         rx.a = ry.a = 1; rx.b = ry.b = 0;
@@ -235,7 +235,9 @@ static int k0_scan(const char *who, const double *x, const double *y, int64_t sr
     XRS_TIMED("k0_init_table", st, k0_init_table<<<static_cast<unsigned>(ceil_div(n_tiles, 256)), 256, 0, st>>>(table, n_tiles));
     XRS_LAUNCH_CHECK("k0_init_table");
 
-    const int64_t n_blocks = ceil_div(src_w, K0_THREADS) * ceil_div(src_h, K0_ROWS);
+    // a short slab (one GPU's share of the swath) is cut into shorter row chunks: more blocks, shorter chains
+    const int rows_per_block = src_h >= 2048 ? K0_ROWS : 8;
+    const int64_t n_blocks = ceil_div(src_w, K0_THREADS) * ceil_div(src_h, rows_per_block);
     if (n_blocks > 0x7fffffffLL) return fail(w + ": source too large");
     const unsigned grid = static_cast<unsigned>(n_blocks);
     const size_t axis_bytes = static_cast<size_t>(2 * ntx + 2 * nty) * sizeof(double);
@@ -243,11 +245,11 @@ static int k0_scan(const char *who, const double *x, const double *y, int64_t sr
     if (n_tiles <= K0_SMEM_TILES) {
         const size_t smem = axis_bytes + static_cast<size_t>(n_tiles) * sizeof(int4);
         XRS_CUDA(cudaFuncSetAttribute(k0_tile_windows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        XRS_TIMED("k0_tile_windows", st, k0_tile_windows<true><<<grid, K0_THREADS, smem, st>>>(x, y, src_h, src_w, src_pitch, x_lo, x_hi, ntx, y_lo, y_hi, nty, table, joff));
+        XRS_TIMED("k0_tile_windows", st, k0_tile_windows<true><<<grid, K0_THREADS, smem, st>>>(x, y, src_h, src_w, src_pitch, x_lo, x_hi, ntx, y_lo, y_hi, nty, table, joff, rows_per_block));
     } else {
         if (axis_bytes > 200 * 1024) return fail(w + ": too many tile rows/columns");
         XRS_CUDA(cudaFuncSetAttribute(k0_tile_windows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(axis_bytes)));
-        XRS_TIMED("k0_tile_windows", st, k0_tile_windows<false><<<grid, K0_THREADS, axis_bytes, st>>>(x, y, src_h, src_w, src_pitch, x_lo, x_hi, ntx, y_lo, y_hi, nty, table, joff));
+        XRS_TIMED("k0_tile_windows", st, k0_tile_windows<false><<<grid, K0_THREADS, axis_bytes, st>>>(x, y, src_h, src_w, src_pitch, x_lo, x_hi, ntx, y_lo, y_hi, nty, table, joff, rows_per_block));
     }
     XRS_LAUNCH_CHECK("k0_tile_windows");
     return 0;
