@@ -333,19 +333,9 @@ def pin_to_gpu_numa_node(gpu_index):
         original = os.sched_getaffinity(0)
     except (AttributeError, OSError):
         return None
-    try:
-        import pynvml
+    from xcube_resampling_b200._affinity import bind_to_device
 
-        pynvml.nvmlInit()
-        handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
-        n_words = (max(original) // 64) + 1
-        words = pynvml.nvmlDeviceGetCpuAffinity(handle, n_words)
-        local = {64 * k + b for k, word in enumerate(words) for b in range(64) if (word >> b) & 1}
-        local &= original
-        if local:
-            os.sched_setaffinity(0, local)
-    except Exception:  # NVML missing or not permitted: keep the inherited affinity
-        pass
+    bind_to_device(gpu_index)  # best effort: no NVML / nothing local in the cpuset leave the affinity as inherited
     return original
 
 

@@ -126,7 +126,8 @@ int xrs_tile_src_bboxes_finalize(const int32_t *minform_table, int32_t n_tiles, 
  * inside, so K1 restricted to the footprint (src_col_ranges) gives the same claims as K1 on the
  * whole swath.  n_groups = ceil((src_h - 1) / group); the slab is rows [j_offset, j_offset + slab_h)
  * of the image (include the first row of the next slab so that no quad row is lost) and j_offset
- * must be a multiple of the group size.  Tables of different slabs merge with MIN. */
+ * must be a multiple of the group size.  band_edges (device, n_bands + 1 values) must ascend; equal
+ * neighbours make an empty band, which gets no footprint.  Tables of different slabs merge with MIN. */
 int32_t xrs_quad_row_group(void);
 int xrs_band_quad_footprints(const double *x, const double *y, int64_t slab_h, int64_t src_w, int64_t src_pitch,
                              int64_t j_offset, int64_t src_h, int64_t dst_h, int64_t dst_w, double x_min, double y_min,

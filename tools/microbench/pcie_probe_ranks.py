@@ -4,7 +4,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port 29533 tools/microbench/pcie_probe_ranks.py [--mb 1024] [--reps 5]
 
-Every rank page-locks two host buffers on the NUMA node of its GPU and times, with CUDA events
+Every rank page-locks two host buffers (with --bind: after pinning itself to the CPUs NVML lists as
+local to its GPU, so that first touch places them on that NUMA node) and times, with CUDA events
 between barriers: H2D alone, D2H alone, both directions at once (two streams).  Rank 0 prints one
 JSON line with the per-rank minimum / median and the aggregate rates.  This is the ceiling of the
 end-to-end leg of bench.py at N ranks: no kernel runs here.
@@ -23,10 +24,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mb", type=int, default=1024)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--bind", action="store_true", help="bind the rank to its GPU's CPUs before allocating")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
+    from xcube_resampling_b200._affinity import bind_to_device, device_cpus
+    allowed = sorted(os.sched_getaffinity(0))
+    local_cpus = sorted(device_cpus(local))
+    bound = sorted(bind_to_device(local)) if args.bind else []
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -78,7 +86,17 @@ def main():
             vals = [gbs]
         out[name] = {"per_rank_gbs_min": min(vals), "per_rank_gbs_median": float(np.median(vals)),
                      "aggregate_gbs": float(sum(vals))}
+    def span(c):
+        return f"{c[0]}-{c[-1]} ({len(c)})" if c else "none"
+    info = f"rank {rank}: allowed {span(allowed)} device-local {span(local_cpus)} bound {span(bound)}"
+    if world > 1:
+        infos = [None] * world
+        dist.all_gather_object(infos, info)
+    else:
+        infos = [info]
     if rank == 0:
+        out["cpu_sets"] = infos
+        out["bind"] = bool(args.bind)
         print(json.dumps({"probe": "pcie copy-only", "ranks": world, "mb_per_direction": args.mb, **out}), flush=True)
     if world > 1:
         dist.destroy_process_group()

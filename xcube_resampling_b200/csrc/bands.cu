@@ -57,12 +57,9 @@ kb_quad_footprints(const double *__restrict__ x, const double *__restrict__ y, i
     const int64_t g0 = row_chunk * K1S_ROWS;
     const int64_t q0 = g0 + (threadIdx.x / KB_COLS) * ROWS_PER_THREAD;
     const int64_t q1 = min(min(q0 + ROWS_PER_THREAD, g0 + K1S_ROWS), slab_h - 1);  // local quad rows
+    // a thread's quads all lie in ONE column: it only has to remember which bands they touch (bit b)
+    unsigned long long touched = 0;
     if (qi < nqi && q0 < q1) {
-        auto px = [&](double vx, double vy, double &fx, double &fy) {
-            fx = (vx - g.x_min) * g.inv_xr;
-            fy = g.j_up ? (vy - g.y_min) * g.inv_yr : (g.y_max - vy) * g.inv_yr;
-            return fabs(fx) < 1e15 && fabs(fy) < 1e15;  // false for NaN / inf
-        };
         // all vertex rows of the thread's quads are requested before any is used (one memory round trip
         // instead of one per row: the kernel is latency-bound on slabs of a few hundred rows)
         double vx[ROWS_PER_THREAD + 1][2], vy[ROWS_PER_THREAD + 1][2];
@@ -73,22 +70,37 @@ kb_quad_footprints(const double *__restrict__ x, const double *__restrict__ y, i
             vx[k][0] = in ? __ldg(x + o) : NAN; vx[k][1] = in ? __ldg(x + o + 1) : NAN;
             vy[k][0] = in ? __ldg(y + o) : NAN; vy[k][1] = in ? __ldg(y + o + 1) : NAN;
         }
-        double ax, ay, bx, by;  // upper vertices of the current quad row
-        bool ok_a = px(vx[0][0], vy[0][0], ax, ay);
-        bool ok_b = px(vx[0][1], vy[0][1], bx, by);
-        const int ci = static_cast<int>(qi);
+        // One vertex row = the pair (qi, qi + 1): its pixel-space box and its number of usable vertices.
+        // A vertex that is not usable (NaN / inf) becomes NaN, which fmin / fmax skip, so a quad's box is
+        // the box of its two vertex rows and every row box is computed once for the two quads sharing it.
+        struct RowBox { double lo_x, hi_x, lo_y, hi_y; int n_ok; };
+        auto row_box = [&](int k) {
+            double fx0 = (vx[k][0] - g.x_min) * g.inv_xr, fx1 = (vx[k][1] - g.x_min) * g.inv_xr;
+            double fy0 = g.j_up ? (vy[k][0] - g.y_min) * g.inv_yr : (g.y_max - vy[k][0]) * g.inv_yr;
+            double fy1 = g.j_up ? (vy[k][1] - g.y_min) * g.inv_yr : (g.y_max - vy[k][1]) * g.inv_yr;
+            const bool ok0 = fabs(fx0) < 1e15 && fabs(fy0) < 1e15, ok1 = fabs(fx1) < 1e15 && fabs(fy1) < 1e15;
+            if (!ok0) fx0 = fy0 = NAN;
+            if (!ok1) fx1 = fy1 = NAN;
+            RowBox r;
+            r.lo_x = fmin(fx0, fx1); r.hi_x = fmax(fx0, fx1);
+            r.lo_y = fmin(fy0, fy1); r.hi_y = fmax(fy0, fy1);
+            r.n_ok = static_cast<int>(ok0) + static_cast<int>(ok1);
+            return r;
+        };
+        // the bands a row interval [r_lo, r_hi] overlaps are b_lo .. b_hi with
+        //   b_lo = first band whose end edge lies above r_lo,  b_hi = last band whose start edge is <= r_hi
+        // (edges ascend); both stay valid while r_lo / r_hi stay inside the cached edge intervals, which
+        // they do from one quad of a column to the next almost always
+        int b_lo = 0, b_hi = -1;
+        int lo_from = 1, lo_to = 0, hi_from = 1, hi_to = 0;  // empty: the first quad searches
+        RowBox up = row_box(0);
 #pragma unroll
         for (int k = 0; k < ROWS_PER_THREAD; ++k) {
             if (q0 + k >= q1) break;
-            double cx, cy, dx, dy;
-            const bool ok_c = px(vx[k + 1][0], vy[k + 1][0], cx, cy);
-            const bool ok_d = px(vx[k + 1][1], vy[k + 1][1], dx, dy);
-            if (static_cast<int>(ok_a) + ok_b + ok_c + ok_d >= 3) {
-                double lo_x = INFINITY, hi_x = -INFINITY, lo_y = INFINITY, hi_y = -INFINITY;
-                if (ok_a) { lo_x = fmin(lo_x, ax); hi_x = fmax(hi_x, ax); lo_y = fmin(lo_y, ay); hi_y = fmax(hi_y, ay); }
-                if (ok_b) { lo_x = fmin(lo_x, bx); hi_x = fmax(hi_x, bx); lo_y = fmin(lo_y, by); hi_y = fmax(hi_y, by); }
-                if (ok_c) { lo_x = fmin(lo_x, cx); hi_x = fmax(hi_x, cx); lo_y = fmin(lo_y, cy); hi_y = fmax(hi_y, cy); }
-                if (ok_d) { lo_x = fmin(lo_x, dx); hi_x = fmax(hi_x, dx); lo_y = fmin(lo_y, dy); hi_y = fmax(hi_y, dy); }
+            const RowBox dn = row_box(k + 1);
+            if (up.n_ok + dn.n_ok >= 3) {
+                double lo_x = fmin(up.lo_x, dn.lo_x), hi_x = fmax(up.hi_x, dn.hi_x);
+                double lo_y = fmin(up.lo_y, dn.lo_y), hi_y = fmax(up.hi_y, dn.hi_y);
                 const double mrg = 2.0 + 0.01 * fmax(hi_x - lo_x, hi_y - lo_y);
                 lo_x = floor(lo_x) - mrg; hi_x = floor(hi_x) + mrg;
                 lo_y = floor(lo_y) - mrg; hi_y = floor(hi_y) + mrg;
@@ -96,14 +108,40 @@ kb_quad_footprints(const double *__restrict__ x, const double *__restrict__ y, i
                     lo_y < static_cast<double>(g.dst_h)) {
                     const int r_lo = static_cast<int>(fmax(lo_y, 0.0));
                     const int r_hi = static_cast<int>(fmin(hi_y, static_cast<double>(g.dst_h - 1)));
-                    for (int b = 0; b < n_bands; ++b) {
-                        if (s_edges[b + 1] <= r_lo || s_edges[b] > r_hi || s_edges[b] >= s_edges[b + 1]) continue;
-                        atomicMin(&s_tab[b][0], ci);
-                        atomicMin(&s_tab[b][1], -ci);
+                    if (r_lo < lo_from || r_lo >= lo_to) {
+                        b_lo = 0;
+                        while (b_lo < n_bands && s_edges[b_lo + 1] <= r_lo) ++b_lo;
+                        lo_from = b_lo > 0 ? s_edges[b_lo] : INT32_MIN;
+                        lo_to = b_lo < n_bands ? s_edges[b_lo + 1] : INT32_MAX;
                     }
+                    if (r_hi < hi_from || r_hi >= hi_to) {
+                        b_hi = n_bands - 1;
+                        while (b_hi >= 0 && s_edges[b_hi] > r_hi) --b_hi;
+                        hi_from = b_hi >= 0 ? s_edges[b_hi] : INT32_MIN;
+                        hi_to = b_hi + 1 < n_bands ? s_edges[b_hi + 1] : INT32_MAX;
+                    }
+                    if (b_lo <= b_hi) touched |= (~0ull >> (63 - b_hi)) & (~0ull << b_lo);
                 }
             }
-            ax = cx; ay = cy; bx = dx; by = dy; ok_a = ok_c; ok_b = ok_d;
+            up = dn;
+        }
+    }
+    // per band: the warp's lowest and highest touching column (lanes = consecutive columns), one pair of
+    // shared atomics per warp and band instead of one per quad
+    {
+        const int ci = static_cast<int>(qi);
+        unsigned long long any = touched;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) any |= __shfl_xor_sync(0xffffffffu, any, o);
+        while (any) {
+            const int b = __ffsll(static_cast<long long>(any)) - 1;
+            any &= any - 1;
+            if (s_edges[b] >= s_edges[b + 1]) continue;  // an empty band between two others (warp-uniform)
+            const unsigned lanes = __ballot_sync(0xffffffffu, (touched >> b) & 1ull);
+            const int lane = threadIdx.x & 31;
+            const int first = __ffs(lanes) - 1, last = 31 - __clz(lanes);
+            if (lane == first) atomicMin(&s_tab[b][0], ci);
+            if (lane == last) atomicMin(&s_tab[b][1], -ci);
         }
     }
     __syncthreads();

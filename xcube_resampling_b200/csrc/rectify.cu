@@ -6,6 +6,7 @@
 //
 // Compiled with -fmad=false; the parity-critical expressions additionally use
 // explicit round-to-nearest intrinsics so they round like numba's LLVM code.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace xrs {
@@ -69,7 +70,10 @@ __device__ __forceinline__ AxisRange locate(const double *lo, const double *hi, 
 // x axis arrays ascend with tx; the y arrays may descend with ty (j-axis-down grids).
 // Block = K0_THREADS consecutive source columns x K0_ROWS consecutive rows; each thread marches
 // down its column, accumulating the row span per cached tile range in registers.
-template <bool SMEM_TABLE>
+// MINFORM (shared-memory table only): the block's entries go straight into a min-form exchange table
+// (maxima negated, see below) that the caller initialised to INT32_MAX -- no table of its own to
+// initialise and fold afterwards.
+template <bool SMEM_TABLE, bool MINFORM = false>
 __global__ void __launch_bounds__(K0_THREADS)
 k0_tile_windows(const double *__restrict__ x, const double *__restrict__ y, int64_t h, int64_t w, int64_t pitch,
                 const double *__restrict__ g_x_lo, const double *__restrict__ g_x_hi, int ntx,
@@ -100,12 +104,12 @@ k0_tile_windows(const double *__restrict__ x, const double *__restrict__ y, int6
     const int64_t chunk = blockIdx.x % n_col_chunks, row_chunk = blockIdx.x / n_col_chunks;
     const int64_t col = chunk * K0_THREADS + threadIdx.x;
     const int64_t row0 = row_chunk * rows_per_block, row1 = min(row0 + rows_per_block, h);
+    AxisRange rx, ry;
+    rx.a = ry.a = 1; rx.b = ry.b = 0;
+    rx.lower = ry.lower = INFINITY; rx.upper = ry.upper = -INFINITY;  // nothing cached yet
+    int j_first = -1, j_last = -1;
+    const int ci = static_cast<int>(col);
     if (col < w) {
-        AxisRange rx, ry;
-        rx.a = ry.a = 1; rx.b = ry.b = 0;
-        rx.lower = ry.lower = INFINITY; rx.upper = ry.upper = -INFINITY;  // nothing cached yet
-        int j_first = -1, j_last = -1;
-        const int ci = static_cast<int>(col);
         auto flush = [&]() {
             if (j_first < 0 || rx.a > rx.b || ry.a > ry.b) return;
             for (int ky = ry.a; ky <= ry.b; ++ky) {
@@ -143,7 +147,33 @@ k0_tile_windows(const double *__restrict__ x, const double *__restrict__ y, int6
                 }
             }
         }
-        flush();
+    }
+    // The last span of every thread: neighbouring columns nearly always sit in the same tile range with
+    // the same row span, so the lanes of a warp that agree on the range combine their spans and ONE of them
+    // updates the table (the per-thread version serialises 4 same-address atomics per lane and tile).
+    {
+        const bool have = col < w && j_first >= 0 && rx.a <= rx.b && ry.a <= ry.b;
+        const unsigned long long key = !have ? ~0ull
+            : static_cast<unsigned long long>(rx.a) | static_cast<unsigned long long>(rx.b) << 16 |
+              static_cast<unsigned long long>(ry.a) << 32 | static_cast<unsigned long long>(ry.b) << 48;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (have) {
+            const int c_lo = __reduce_min_sync(peers, ci), c_hi = __reduce_max_sync(peers, ci + 1);
+            const int j_lo = __reduce_min_sync(peers, j_first + j_offset);
+            const int j_hi = __reduce_max_sync(peers, j_last + 1 + j_offset);
+            if ((threadIdx.x & 31) == __ffs(peers) - 1) {
+                for (int ky = ry.a; ky <= ry.b; ++ky) {
+                    const int ty = y_desc ? nty - 1 - ky : ky;
+                    for (int tx = rx.a; tx <= rx.b; ++tx) {
+                        int *e = reinterpret_cast<int *>(tab + ty * ntx + tx);
+                        atomicMin(e + 0, c_lo);
+                        atomicMin(e + 1, j_lo);
+                        atomicMax(e + 2, c_hi);
+                        atomicMax(e + 3, j_hi);
+                    }
+                }
+            }
+        }
     }
     if (SMEM_TABLE) {
         __syncthreads();
@@ -153,8 +183,13 @@ k0_tile_windows(const double *__restrict__ x, const double *__restrict__ y, int6
                 int *g = reinterpret_cast<int *>(table + k);
                 atomicMin(g + 0, e.x);
                 atomicMin(g + 1, e.y);
-                atomicMax(g + 2, e.z);
-                atomicMax(g + 3, e.w);
+                if (MINFORM) {
+                    atomicMin(g + 2, -e.z);
+                    atomicMin(g + 3, -e.w);
+                } else {
+                    atomicMax(g + 2, e.z);
+                    atomicMax(g + 3, e.w);
+                }
             }
         }
     }
@@ -225,13 +260,23 @@ int64_t xrs_tile_src_bboxes_workspace_bytes(int32_t ntx, int32_t nty) {
 
 static int k0_scan(const char *who, const double *x, const double *y, int64_t src_h, int64_t src_w, int64_t src_pitch,
                    int64_t j_offset, const double *x_lo, const double *x_hi, int32_t ntx, const double *y_lo,
-                   const double *y_hi, int32_t nty, int4 *table, cudaStream_t st) {
+                   const double *y_hi, int32_t nty, int4 *table, cudaStream_t st, int32_t *minform = nullptr) {
     const std::string w(who);
     if (!x || !y || !x_lo || !x_hi || !y_lo || !y_hi || !table) return fail(w + ": null pointer");
     if (src_h < 1 || src_w < 1 || src_pitch < src_w) return fail(w + ": bad source shape");
     if (ntx < 1 || nty < 1 || ntx > 65535 || nty > 65535) return fail(w + ": tile counts must be in [1, 65535]");
     if (src_w > INT32_MAX - 1 || src_h + j_offset > INT32_MAX - 1 || j_offset < 0) return fail(w + ": source too large");
     const int n_tiles = ntx * nty;
+    if (minform && n_tiles <= K0_SMEM_TILES) {  // straight into the caller's (initialised) exchange table
+        const int rows = src_h >= 2048 ? K0_ROWS : 8;
+        const int64_t blocks = ceil_div(src_w, K0_THREADS) * ceil_div(src_h, rows);
+        if (blocks > 0x7fffffffLL) return fail(w + ": source too large");
+        const size_t smem = static_cast<size_t>(2 * ntx + 2 * nty) * sizeof(double) + static_cast<size_t>(n_tiles) * sizeof(int4);
+        XRS_CUDA(cudaFuncSetAttribute(k0_tile_windows<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        XRS_TIMED("k0_tile_windows", st, (k0_tile_windows<true, true><<<static_cast<unsigned>(blocks), K0_THREADS, smem, st>>>(x, y, src_h, src_w, src_pitch, x_lo, x_hi, ntx, y_lo, y_hi, nty, reinterpret_cast<int4 *>(minform), static_cast<int>(j_offset), rows)));
+        XRS_LAUNCH_CHECK("k0_tile_windows");
+        return 1 << 30;  // done, nothing to fold (positive: not an error code)
+    }
     XRS_TIMED("k0_init_table", st, k0_init_table<<<static_cast<unsigned>(ceil_div(n_tiles, 256)), 256, 0, st>>>(table, n_tiles));
     XRS_LAUNCH_CHECK("k0_init_table");
 
@@ -278,8 +323,8 @@ int xrs_tile_src_bboxes_partial(const double *x, const double *y, int64_t slab_h
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int4 *table = static_cast<int4 *>(workspace);
     if (int rc = k0_scan("xrs_tile_src_bboxes_partial", x, y, slab_h, src_w, src_pitch, j_offset, x_lo, x_hi, ntx, y_lo,
-                         y_hi, nty, table, st))
-        return rc;
+                         y_hi, nty, table, st, minform_table))
+        return rc == 1 << 30 ? 0 : rc;
     const int n_tiles = ntx * nty;
     XRS_TIMED("k0_fold_minform", st, k0_fold_minform<<<static_cast<unsigned>(ceil_div(n_tiles, 256)), 256, 0, st>>>(table, n_tiles, minform_table));
     XRS_LAUNCH_CHECK("k0_fold_minform");

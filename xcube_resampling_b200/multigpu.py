@@ -32,6 +32,7 @@ import threading
 import numpy as np
 import torch
 
+from ._affinity import bind_to_device
 from . import _dev
 from ._lib import check, load
 from ._pipeline import GatherPipeline, SourceGroup  # noqa: F401
@@ -362,6 +363,7 @@ def run_on_devices(devices, worker) -> None:
     def run(k):
         try:
             torch.cuda.set_device(devs[k])
+            bind_to_device(devs[k].index or 0)  # this thread page-locks the band's staging buffers: keep them local
             worker(k, devs[k], exchange)
         except BaseException as e:  # noqa: BLE001 - reported to the caller below
             errors[k] = e
