@@ -280,6 +280,7 @@ __device__ __forceinline__ void scatter_quad_generic(const IjGeom &g, const Scat
 // (quads larger than K1_MAX_EXTENT pixels take the generic path).
 // ---------------------------------------------------------------------------
 constexpr double K1_MAX_EXTENT = 64.0;
+constexpr double K1_TIGHT_EXTENT = 8.0;  // quads up to this many pixels get the centre-tight candidate box
 
 struct TileWin {
     int id;                          // ty * ntx + tx, -1 = nothing cached
@@ -325,8 +326,19 @@ __device__ __forceinline__ PxEdges make_px_edges(double ax, double ay, double bx
     f.e2 = s * nv - lo * ad - m;
     f.k3 = (hi - 2.0 * lo) * ad - 3.0 * m;
     f.two_m = 2.0 * m;
-    f.degenerate = !(ad > 1e-6);  // (nearly) collapsed triangle: the generic kernel decides
+    // (nearly) collapsed triangle, in absolute terms or as a sliver of its own edges: the reference's
+    // u = nu / det is then dominated by rounding, so the generic kernel (the reference's arithmetic) decides
+    const double edge_sum = fabs(acy) + fabs(acx) + fabs(aby) + fabs(abx);
+    f.degenerate = !(ad > 1e-6) || ad < 1e-4 * edge_sum * edge_sum;
     return f;
+}
+
+// The same verdict from the vertices alone (quads that need no edge functions).
+__device__ __forceinline__ bool px_degenerate(double ax, double ay, double bx, double by, double cx, double cy) {
+    const double abx = ax - bx, aby = ay - by, acx = ax - cx, acy = ay - cy;
+    const double ad = fabs(abx * acy - acx * aby);
+    const double edge_sum = fabs(acy) + fabs(acx) + fabs(aby) + fabs(abx);
+    return !(ad > 1e-6) || ad < 1e-4 * edge_sum * edge_sum;
 }
 
 // The per-pixel decisions read only the SIGN / high word of the three condition values
@@ -386,13 +398,30 @@ __global__ void __launch_bounds__(K1S_WARPS * 32, XRS_K1_MINBLOCKS) k1_scatter(c
     tw.id = -1;
     // A vertex in pixel space: fractional coordinates and their floors (pixel indices, clamped to a
     // band around the image so that they fit an int).  `ok` is false for non-finite coordinates.
+    // Besides the floor, a vertex carries two flags per axis (packed below the index: (floor << 2) | up << 1 | dn):
+    // `up`: its fraction lies above 0.5 + t, so no pixel CENTRE of column `floor` is at or beyond it;
+    // `dn`: its fraction lies below 0.5 - t, the same towards the other side.  A pixel is accepted only if
+    // its centre lies inside the triangle grown by the uv tolerance, i.e. within t = 3 * uv_delta * extent
+    // (+ rounding) pixels of the quad's coordinate box, so the centres worth testing are columns
+    //   min over vertices (floor + up) ... max over vertices (floor - dn)
+    // -- about extent^2 instead of (extent + 1)^2 candidates.  t is taken for quads of up to K1_TIGHT_EXTENT
+    // pixels; larger quads (and tolerances too large for t < 0.45) keep the plain floor box.
+    const double tight_t = 3.0 * g.uv_delta * (K1_TIGHT_EXTENT + 2.0) + 1e-5;
+    const bool tight = tight_t < 0.45;
+    const double frac_up = tight ? 0.5 + tight_t : 2.0, frac_dn = tight ? 0.5 - tight_t : -2.0;
     auto to_px = [&](double vx, double vy, double &fx, double &fy, int &pi, int &pj) {
         fx = (vx - g.x_min) * inv_xr;
         fy = g.j_up ? (vy - g.y_min) * inv_yr : (g.y_max - vy) * inv_yr;
-        pi = __double2int_rd(fmin(fmax(fx, -8.0), clamp_hi));
-        pj = __double2int_rd(fmin(fmax(fy, -8.0), clamp_hi));
+        const double cx = fmin(fmax(fx, -8.0), clamp_hi), cy = fmin(fmax(fy, -8.0), clamp_hi);
+        const int ix = __double2int_rd(cx), iy = __double2int_rd(cy);
+        const double rx = cx - static_cast<double>(ix), ry = cy - static_cast<double>(iy);
+        pi = (ix << 2) | (rx > frac_up ? 2 : 0) | (rx < frac_dn ? 1 : 0);
+        pj = (iy << 2) | (ry > frac_up ? 2 : 0) | (ry < frac_dn ? 1 : 0);
         return fabs(fx) < 1e9 && fabs(fy) < 1e9;  // false for NaN / inf
     };
+    auto px_floor = [](int packed) { return packed >> 2; };
+    auto px_first = [](int packed) { return (packed >> 2) + ((packed >> 1) & 1); };  // first column whose centre can count
+    auto px_last = [](int packed) { return (packed >> 2) - (packed & 1); };          // last such column
     double fx0, fy0;
     int pi0, pj0;
     bool ok0 = to_px(col_ok ? __ldg(g.x + j_begin * g.src_pitch + col) : NAN,
@@ -418,55 +447,69 @@ __global__ void __launch_bounds__(K1S_WARPS * 32, XRS_K1_MINBLOCKS) k1_scatter(c
         const bool ok3 = (__ballot_sync(0xffffffffu, ok2) >> ((lane + 1) & 31)) & 1u;
         bool slow = false;
         if (quad_lane) {
-            const int bi_lo = min(min(pi0, pi1), min(pi2, pi3)), bi_hi = max(max(pi0, pi1), max(pi2, pi3));
-            const int bj_lo = min(min(pj0, pj1), min(pj2, pj3)), bj_hi = max(max(pj0, pj1), max(pj2, pj3));
+            // (the packed values order like their floors, so min / max commute with the unpacking)
+            const int ni_lo = min(min(pi0, pi1), min(pi2, pi3)), ni_hi = max(max(pi0, pi1), max(pi2, pi3));
+            const int nj_lo = min(min(pj0, pj1), min(pj2, pj3)), nj_hi = max(max(pj0, pj1), max(pj2, pj3));
+            const int bi_lo = px_floor(ni_lo), bi_hi = px_floor(ni_hi), bj_lo = px_floor(nj_lo), bj_hi = px_floor(nj_hi);
             if (!(ok0 && ok1 && ok2 && ok3) || !small_tolerance) {
                 slow = true;  // non-finite vertices: generic path (it also rejects far-away quads)
             } else if (!(bi_hi < 0 || bi_lo >= W || bj_hi < R0 || bj_lo >= R1)) {
                 if (bi_hi - bi_lo >= static_cast<int>(K1_MAX_EXTENT) || bj_hi - bj_lo >= static_cast<int>(K1_MAX_EXTENT)) {
                     slow = true;
                 } else {
-                    const int i_lo = max(bi_lo, 0), i_hi = min(bi_hi, W - 1), j_lo = max(bj_lo, R0), j_hi = min(bj_hi, R1 - 1);
-                    const uint32_t qkey = static_cast<uint32_t>(j * nqi + col);
-                    const int qj = static_cast<int>(j);
-                    const double pcx = static_cast<double>(i_lo) + 0.5, pcy = static_cast<double>(j_lo) + 0.5;
-                    // triangle A: origin p0, u towards p1, v towards p2; triangle B: origin p3, u towards p2, v towards p1
-                    const PxEdges fa = make_px_edges(fx0, fy0, fx1, fy1, fx2, fy2, pcx, pcy, uv_lo, uv_hi, coord_bound);
-                    const PxEdges fb = make_px_edges(fx3, fy3, fx2, fy2, fx1, fy1, pcx, pcy, uv_lo, uv_hi, coord_bound);
-                    if (fa.degenerate || fb.degenerate) slow = true;
-                    const double dx3_a = -(fa.dx1 + fa.dx2), dx3_b = -(fb.dx1 + fb.dx2);
-                    const uint32_t rej_hi_a = static_cast<uint32_t>(__double2hiint(-2.0 * fa.two_m));
-                    const uint32_t rej_hi_b = static_cast<uint32_t>(__double2hiint(-2.0 * fb.two_m));
-                    // The pixel box of an ordinary quad lies inside ONE reference tile (a box of a few pixels
-                    // against tiles of hundreds); the rare quad that straddles a tile border takes the generic
-                    // kernel, which visits every tile its box touches.
-                    const int tx = static_cast<int>(div_magic(static_cast<uint32_t>(i_lo), g.magic_tw));
-                    const int ty = static_cast<int>(div_magic(static_cast<uint32_t>(j_lo), g.magic_th));
-                    if (i_hi >= (tx + 1) * g.tile_w || j_hi >= (ty + 1) * g.tile_h) slow = true;
-                    if (!slow) {
-                        if (tw.id != ty * g.ntx + tx) load_tile_win(g, ty, tx, tw);
-                        if (tw.has && qi >= tw.qi_lo && qi <= tw.qi_hi && qj >= tw.qj_lo && qj <= tw.qj_hi) {
-                            uint32_t *claim_row = g.claims + (static_cast<int64_t>(j_lo) - g.row_begin) * g.dst_w;
-                            for (int gj = j_lo; gj <= j_hi; ++gj, claim_row += g.dst_w) {
-                                const double rj = static_cast<double>(gj - j_lo);
-                                double a1 = fma(rj, fa.dy1, fa.e1), a2 = fma(rj, fa.dy2, fa.e2);
-                                double b1 = fma(rj, fb.dy1, fb.e1), b2 = fma(rj, fb.dy2, fb.e2);
-                                double a3 = fa.k3 - (a1 + a2), b3 = fb.k3 - (b1 + b2);  // third condition, stepped too
-                                for (int gi = i_lo; gi <= i_hi; ++gi) {
-                                    // straight-line decisions (no nested branches): both triangles are
-                                    // evaluated, the atomic is the only predicated operation
-                                    const uint32_t ha1 = __double2hiint(a1), ha2 = __double2hiint(a2), ha3 = __double2hiint(a3);
-                                    const uint32_t hb1 = __double2hiint(b1), hb2 = __double2hiint(b2), hb3 = __double2hiint(b3);
-                                    const bool acc_a = static_cast<int>(ha1 | ha2 | ha3) >= 0;
-                                    const bool rej_a = max(max(ha1, ha2), ha3) > rej_hi_a;
-                                    const bool acc_b = !acc_a && rej_a && static_cast<int>(hb1 | hb2 | hb3) >= 0;
-                                    const bool rej_b = max(max(hb1, hb2), hb3) > rej_hi_b;
-                                    // within the margin of an edge: the whole quad is redone by the generic
-                                    // kernel with the reference's arithmetic (atomicMin is idempotent)
-                                    slow = slow || (!acc_a && !acc_b && !(rej_a && rej_b));
-                                    if (acc_a || acc_b) atomicMin(claim_row + gi, (qkey << 1) | (acc_b ? 1u : 0u));
-                                    a1 += fa.dx1; a2 += fa.dx2; a3 += dx3_a;
-                                    b1 += fb.dx1; b2 += fb.dx2; b3 += dx3_b;
+                    int i_lo = max(bi_lo, 0), i_hi = min(bi_hi, W - 1), j_lo = max(bj_lo, R0), j_hi = min(bj_hi, R1 - 1);
+                    if (bi_hi - bi_lo < static_cast<int>(K1_TIGHT_EXTENT) && bj_hi - bj_lo < static_cast<int>(K1_TIGHT_EXTENT)) {
+                        i_lo = max(i_lo, min(min(px_first(pi0), px_first(pi1)), min(px_first(pi2), px_first(pi3))));
+                        i_hi = min(i_hi, max(max(px_last(pi0), px_last(pi1)), max(px_last(pi2), px_last(pi3))));
+                        j_lo = max(j_lo, min(min(px_first(pj0), px_first(pj1)), min(px_first(pj2), px_first(pj3))));
+                        j_hi = min(j_hi, max(max(px_last(pj0), px_last(pj1)), max(px_last(pj2), px_last(pj3))));
+                    }
+                    if (i_lo > i_hi || j_lo > j_hi) {
+                        // no pixel centre inside the grown quad: nothing to claim -- unless a collapsed triangle
+                        // lets rounding noise accept something, which the generic kernel finds out
+                        slow = px_degenerate(fx0, fy0, fx1, fy1, fx2, fy2) || px_degenerate(fx3, fy3, fx2, fy2, fx1, fy1);
+                    } else {
+                        const uint32_t qkey = static_cast<uint32_t>(j * nqi + col);
+                        const int qj = static_cast<int>(j);
+                        const double pcx = static_cast<double>(i_lo) + 0.5, pcy = static_cast<double>(j_lo) + 0.5;
+                        // triangle A: origin p0, u towards p1, v towards p2; triangle B: origin p3, u towards p2, v towards p1
+                        const PxEdges fa = make_px_edges(fx0, fy0, fx1, fy1, fx2, fy2, pcx, pcy, uv_lo, uv_hi, coord_bound);
+                        const PxEdges fb = make_px_edges(fx3, fy3, fx2, fy2, fx1, fy1, pcx, pcy, uv_lo, uv_hi, coord_bound);
+                        if (fa.degenerate || fb.degenerate) slow = true;
+                        const double dx3_a = -(fa.dx1 + fa.dx2), dx3_b = -(fb.dx1 + fb.dx2);
+                        const uint32_t rej_hi_a = static_cast<uint32_t>(__double2hiint(-2.0 * fa.two_m));
+                        const uint32_t rej_hi_b = static_cast<uint32_t>(__double2hiint(-2.0 * fb.two_m));
+                        // The pixel box of an ordinary quad lies inside ONE reference tile (a box of a few pixels
+                        // against tiles of hundreds); the rare quad that straddles a tile border takes the generic
+                        // kernel, which visits every tile its box touches.
+                        const int tx = static_cast<int>(div_magic(static_cast<uint32_t>(i_lo), g.magic_tw));
+                        const int ty = static_cast<int>(div_magic(static_cast<uint32_t>(j_lo), g.magic_th));
+                        if (i_hi >= (tx + 1) * g.tile_w || j_hi >= (ty + 1) * g.tile_h) slow = true;
+                        if (!slow) {
+                            if (tw.id != ty * g.ntx + tx) load_tile_win(g, ty, tx, tw);
+                            if (tw.has && qi >= tw.qi_lo && qi <= tw.qi_hi && qj >= tw.qj_lo && qj <= tw.qj_hi) {
+                                uint32_t *claim_row = g.claims + (static_cast<int64_t>(j_lo) - g.row_begin) * g.dst_w;
+                                for (int gj = j_lo; gj <= j_hi; ++gj, claim_row += g.dst_w) {
+                                    const double rj = static_cast<double>(gj - j_lo);
+                                    double a1 = fma(rj, fa.dy1, fa.e1), a2 = fma(rj, fa.dy2, fa.e2);
+                                    double b1 = fma(rj, fb.dy1, fb.e1), b2 = fma(rj, fb.dy2, fb.e2);
+                                    double a3 = fa.k3 - (a1 + a2), b3 = fb.k3 - (b1 + b2);  // third condition, stepped too
+                                    for (int gi = i_lo; gi <= i_hi; ++gi) {
+                                        // straight-line decisions (no nested branches): both triangles are
+                                        // evaluated, the atomic is the only predicated operation
+                                        const uint32_t ha1 = __double2hiint(a1), ha2 = __double2hiint(a2), ha3 = __double2hiint(a3);
+                                        const uint32_t hb1 = __double2hiint(b1), hb2 = __double2hiint(b2), hb3 = __double2hiint(b3);
+                                        const bool acc_a = static_cast<int>(ha1 | ha2 | ha3) >= 0;
+                                        const bool rej_a = max(max(ha1, ha2), ha3) > rej_hi_a;
+                                        const bool acc_b = !acc_a && rej_a && static_cast<int>(hb1 | hb2 | hb3) >= 0;
+                                        const bool rej_b = max(max(hb1, hb2), hb3) > rej_hi_b;
+                                        // within the margin of an edge: the whole quad is redone by the generic
+                                        // kernel with the reference's arithmetic (atomicMin is idempotent)
+                                        slow = slow || (!acc_a && !acc_b && !(rej_a && rej_b));
+                                        if (acc_a || acc_b) atomicMin(claim_row + gi, (qkey << 1) | (acc_b ? 1u : 0u));
+                                        a1 += fa.dx1; a2 += fa.dx2; a3 += dx3_a;
+                                        b1 += fb.dx1; b2 += fb.dx2; b3 += dx3_b;
+                                    }
                                 }
                             }
                         }
