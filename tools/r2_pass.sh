@@ -16,6 +16,8 @@ timeout 300 $B --impl reference --steps 3 --warmup 1 > "$OUT/bench_reference.jso
 timeout 400 $B --steps 10 --warmup 3 > "$OUT/bench.json" 2> "$OUT/bench.err"; echo "bench rc=$?" | tee -a "$OUT/status.txt"
 timeout 200 $B --steps 10 --warmup 3 --fused --no-e2e --no-cpu --no-configs > "$OUT/bench_fused.json" 2> "$OUT/bench_fused.err"
 
+timeout 100 python tools/microbench/scan_slab_bench.py > "$OUT/scan_slab_n8.json" 2> "$OUT/scan_slab_n8.err"
+
 SHORT="$B --steps 1 --warmup 1 --no-e2e --no-cpu --no-configs --no-graph"
 timeout 200 $SHORT > "$OUT/short_plain.log" 2>&1 || { echo "short bench failed"; exit 1; }
 # launch list (per-launch gpu__time_duration.sum; cold-cache, serialised: compare shares)
