@@ -47,8 +47,13 @@ def main():
         elif cur_b is not None and cur_b["hdr"] and len(r) == len(cur_b["hdr"]):
             cur_b["rows"].append(r)
     want = sys.argv[5] if len(sys.argv) > 5 else kernel.split("EN")[0].lstrip("_Z0123456789N").replace("3xrs", "")
-    match = [blk for blk in blocks if want in blk["name"]]
-    b = match[0] if match else blocks[0]
+    def norm(name):  # ncu prints template arguments as "(int)1, (bool)0" and prefixes "void xrs::"
+        return re.sub(r"\((?:int|bool|long|unsigned int)\)|\s+|xrs::|^void", "", name)
+
+    match = [blk for blk in blocks if norm(want) in norm(blk["name"])]
+    if not match:
+        sys.exit(f"no kernel matching {want!r} in the report; kernels: {sorted({blk['name'] for blk in blocks})}")
+    b = match[0]
     h = b["hdr"]
     i_ex = h.index("Instructions Executed")
     # the sampling column's name differs between ncu versions / report sections
