@@ -490,3 +490,75 @@ def _same_up_to_contraction(got, want, method, what):
         # float32 outputs: a last-bit difference of the float64 value can cross a float32 rounding boundary
         rtol = 1e-9 if got.dtype == np.float64 else 2.5e-7
         np.testing.assert_allclose(got, want, rtol=rtol, atol=1e-12, equal_nan=True, err_msg=what)
+
+
+# ---------------------------------------------------------------------------
+# lattice form of the transform (csrc/reproject.cu: k3_lattice_setup) against the per-pixel formulas
+# ---------------------------------------------------------------------------
+def _lattice_case(xrs, case):
+    if case == "utm":  # scaled-down C3
+        return _case_utm_from_geographic(xrs, n=300, tile=128)
+    if case == "laea":  # target LAEA: the generic per-pixel plan
+        src_gm = xrs.GridMapping.regular((700, 500), (9.0, 47.0), 0.0005, "EPSG:4326")
+        tgt_gm = xrs.GridMapping.regular((500, 420), (4250000.0, 2660000.0), 30.0, "EPSG:3035", tile_size=(100, 77))
+        return src_gm, tgt_gm
+    if case == "utm_source":  # geographic target, projected source: forward projection per pixel
+        tgt_gm = xrs.GridMapping.regular((400, 300), (9.02, 48.01), 0.0002, "EPSG:4326", tile_size=128)
+        box = oproj.transform_bounds(oproj.from_epsg(4326), oproj.from_epsg(32632), *tgt_gm.xy_bbox)
+        src_gm = xrs.GridMapping.regular((int((box[2] - box[0]) / 20.0) + 8, int((box[3] - box[1]) / 20.0) + 8),
+                                         (box[0] - 60.0, box[1] - 60.0), 20.0, "EPSG:32632")
+        return src_gm, tgt_gm
+    raise AssertionError(case)
+
+
+@pytest.mark.parametrize("case", ["utm", "laea", "utm_source"])
+def test_lattice_transform_equals_exact_transform(xrs, case, monkeypatch):
+    """The CTA-level bicubic interpolation of the transform against XRS_K3_EXACT=1 (full formulas per
+    pixel): coordinates agree to ~1e-9 px, so float64 bilinear outputs agree to 1e-7 of the data range
+    -- and differ somewhere in the last bits, which shows that the lattice path is the one that ran."""
+    src_gm, tgt_gm = _lattice_case(xrs, case)
+    rng = np.random.default_rng(11)
+    data = rng.random((3, src_gm.height, src_gm.width)).astype(np.float32)
+    sd = xrs.dev.to_device(data)
+    plan = xrs.rep.ReprojectPlan(src_gm, tgt_gm)
+    out = {}
+    for exact in ("1", "0"):
+        monkeypatch.setenv("XRS_K3_EXACT", exact)
+        out[exact] = {m: xrs.dev.to_host(plan.run(sd, m, nan)) for m in ("nearest", "bilinear")}
+    got, want = out["0"], out["1"]
+    assert np.isfinite(want["bilinear"]).mean() > 0.5
+    assert got["bilinear"].dtype == np.float64
+    np.testing.assert_allclose(got["bilinear"], want["bilinear"], rtol=0, atol=1e-7, equal_nan=True)
+    assert np.any(got["bilinear"] != want["bilinear"]), "lattice path did not run"
+    frac = float(np.mean(~((got["nearest"] == want["nearest"]) | (np.isnan(got["nearest"]) & np.isnan(want["nearest"])))))
+    assert frac < 1e-4, frac
+
+
+def test_lattice_falls_back_to_exact_on_coarse_grids(xrs, monkeypatch):
+    """5 km pixels: the cubic through a 320 km tile misses the exact centre by far more than 1e-8 px,
+    so every CTA takes the per-pixel formulas -- bit-identical to XRS_K3_EXACT=1."""
+    src_gm = xrs.GridMapping.regular((900, 700), (-10.0, 30.0), 0.05, "EPSG:4326")
+    tgt_gm = xrs.GridMapping.regular((300, 280), (3200000.0, 1700000.0), 5000.0, "EPSG:3035", tile_size=128)
+    rng = np.random.default_rng(12)
+    data = rng.random((2, src_gm.height, src_gm.width)).astype(np.float32)
+    sd = xrs.dev.to_device(data)
+    plan = xrs.rep.ReprojectPlan(src_gm, tgt_gm)
+    monkeypatch.setenv("XRS_K3_EXACT", "1")
+    want = xrs.dev.to_host(plan.run(sd, "bilinear", nan))
+    monkeypatch.setenv("XRS_K3_EXACT", "0")
+    got = xrs.dev.to_host(plan.run(sd, "bilinear", nan))
+    assert np.isfinite(want).mean() > 0.5
+    assert_same(got, want, "coarse grid: exact path")
+
+
+def test_lattice_is_independent_of_the_row_band(xrs):
+    """CTA tiles are anchored at absolute target rows, so a row band that does not start at a multiple
+    of the tile height gives the same bits as the whole image."""
+    src_gm, tgt_gm = _case_utm_from_geographic(xrs, n=300, tile=128)
+    rng = np.random.default_rng(13)
+    data = rng.random((4, src_gm.height, src_gm.width)).astype(np.float32)
+    sd = xrs.dev.to_device(data)
+    full = xrs.dev.to_host(xrs.rep.ReprojectPlan(src_gm, tgt_gm).run(sd, "bilinear", nan))
+    for rows in ((45, 211), (1, 33), (290, 300)):
+        part = xrs.dev.to_host(xrs.rep.ReprojectPlan(src_gm, tgt_gm, rows=rows).run(sd, "bilinear", nan))
+        assert_same(part, full[:, rows[0]:rows[1]], f"rows {rows}")
