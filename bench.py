@@ -57,6 +57,11 @@ def parse_args():
     ap.add_argument("--fused", action="store_true",
                     help="device-resident leg: one fused xrs_rectify_gather per method (ij in registers, claims "
                          "computed per method) instead of the shared ij image + xrs_gather_ij")
+    ap.add_argument("--dual", dest="dual", action="store_true", default=None,
+                    help="device-resident leg: nearest + bilinear of the scene in ONE gather launch (xrs_gather_ij2); "
+                         "default: what rectify_dataset does (rectify.DUAL_GATHER)")
+    ap.add_argument("--no-dual", dest="dual", action="store_false",
+                    help="one xrs_gather_ij launch per method (the round-1/early round-2 form)")
     ap.add_argument("--chains", type=int, default=4, help="N > 1: concurrent chains of scenes inside the step's CUDA graph")
     ap.add_argument("--split-k2", action="store_true",
                     help="N = 1: run the nearest and the bilinear gather of the scene as two concurrent chains "
@@ -88,7 +93,7 @@ def workload_config(w, h, nb, size, n_gpus):
         "source": f"{w}x{h} lon/lat float64, {nb} float32 bands",
         "target": f"{size[0]}x{size[1]} @0.0027deg, reference tile_size {TILE}",
         "scene_pass": "ONE rectify_dataset call giving the 21 bands with nearest and with bilinear interpolation: "
-                      "K0 tile windows + K1 ij image once (shared by both, as in the reference), K2 gather per method",
+                      "K0 tile windows + K1 ij image once (shared by both, as in the reference), K2 gather of both methods",
         "scenes_per_step": n_gpus,
         "partition": "target row bands, rank r = band r of every scene; exchange step: one NCCL all-reduce(MIN) of "
                      "the partial tile/footprint tables (each rank scans 1/N of the swath coordinates)",
@@ -369,6 +374,8 @@ def ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     notes = []
+    dual = (xrect.DUAL_GATHER if args.dual is None else args.dual) and not args.fused
+    xrect.DUAL_GATHER = dual  # the end-to-end leg (rectify_dataset / rectify_band_stream) takes the same form
 
     def barrier():
         if world > 1:
@@ -554,6 +561,13 @@ def ours(args):
             xrect.gather_ij(src_dev, ij, METHODS[1], np.nan, out=outs[METHODS[1]])
             main.wait_event(joined)
             return
+        if dual:  # both methods of the scene from ONE pass over ij and the source
+            xrect.gather_ij_pair(src_dev, ij, METHODS[1], np.nan, np.nan, outs[METHODS[1]], outs[METHODS[0]])
+            if record:
+                pending.append(("k0", e0, e1))
+                pending.append(("k1", e1, e2))
+                pending.append(("k2_nearest+bilinear", e2, mark(record)))
+            return
         for k, m in enumerate(METHODS):
             if world == 1 and args.fused:
                 plans[k].rectify_gather(x_dev, y_dev, src_dev, m, np.nan, out=outs[m], tile_boxes=boxes)
@@ -570,7 +584,7 @@ def ours(args):
 
     def step(record=False, concurrent=False):
         if world == 1:
-            gather_scene(plans[0], 0, record, split=concurrent and args.split_k2 and not args.fused)
+            gather_scene(plans[0], 0, record, split=concurrent and args.split_k2 and not args.fused and not dual)
             return
         # N > 1: scan 1/N of the coordinates of every scene of the step, ONE all-reduce(MIN) for all
         # their tables, then the band kernels scene after scene (two chains: a rank's band kernels are
@@ -714,16 +728,19 @@ def ours(args):
         "k1_resolve": (4.0 * T + 16.0 * T + 16.0 * s_used, "4*T (claims) + 16*T (ij fp64 out) + 16*S_used (winning quads' vertices)"),
         "k2_gather_staged<nearest>": (k2_index_bytes + 4.0 * nb * s_used + 4.0 * nb * T, k2_model),
         "k2_gather_staged<bilinear>": (k2_index_bytes + 4.0 * nb * s_used + 4.0 * nb * T, k2_model),
+        "k2_gather_dual<nearest+bilinear>": (16.0 * T + 4.0 * nb * s_used + 8.0 * nb * T,
+                                             "16*T (ij) + 4*B*S_used (source once) + 8*B*T (nearest and bilinear output once each)"),
     }
     traffic_table = load_traffic_table() if (world == 1 and args.scale == 1.0) else {}
-    traffic_key = "fused" if fused else "two_step"
+    traffic_key = "fused" if fused else "dual" if dual else "two_step"
     total_kernel_ms = sum(v[0] for v in kernel_times.values()) or 1.0
     kernels = []
     for name, (ms_total, n_launch) in sorted(kernel_times.items(), key=lambda kv: -kv[1][0]):
         ms_launch = ms_total / max(n_launch, 1)
         nbytes, model = models.get(name, (0.0, "n/a"))
         gbs = nbytes / (ms_launch * 1e-3) / 1e9 if ms_launch > 0 else 0.0
-        traffic = (traffic_table.get(traffic_key, {}).get(name) or {}).get("dram_bytes_per_launch")
+        traffic = (traffic_table.get(traffic_key, {}).get(name) or traffic_table.get("two_step", {}).get(name)
+                   or {}).get("dram_bytes_per_launch")
         kernels.append({"kernel": name, "launches": int(n_launch), "ms_per_launch": ms_launch,
                         "share_of_kernel_time": ms_total / total_kernel_ms, "algorithmic_bytes_per_launch": nbytes,
                         "achieved_gbs": gbs, "frac": gbs / peak, "bytes_model": model, "traffic": traffic})
@@ -820,7 +837,8 @@ def ours(args):
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(w, h, nb, size, world), "clocks": clocks, "e2e": e2e,
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity,
+            "gpu_launches": int(launches), "k2_form": "fused" if fused else "dual" if dual else "per-method",
+            "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity,
             "configs": configs, "notes": notes,
         }
         print(json.dumps(line), flush=True)

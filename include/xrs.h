@@ -201,6 +201,24 @@ int xrs_gather_ij(const void *const *src_planes_host, void *const *dst_planes_ho
                   int64_t win_w, int64_t win_h, const double *ij, int64_t dst_h, int64_t dst_w, int32_t method,
                   double fill, void *stream);
 
+/* K2, two methods in one pass -- nearest AND bilinear (or triangular) samples of the same bands.
+ * Replaces two _compute_var_image passes over the same ij image: the reference calls
+ * _rectify_data_array once per output variable (rectify.py:160-176, 263-309), so a dataset that
+ * wants the same source bands with both methods walks ij and the source twice.  The nearest sample
+ * is always one of the four taps of the bilinear / triangular one (rectify.py:689-698), so one
+ * launch reads ij and the source once and writes both results.
+ *   dst_interp_planes_host   HOST array of n_bands device pointers: planes for `method`
+ *                            (XRS_BILINEAR or XRS_TRIANGULAR)
+ *   dst_nearest_planes_host  the same for the nearest-neighbour result
+ *   fill_interp, fill_nearest  fill value of either result
+ * Everything else as in xrs_gather_ij; results are bit-identical to two xrs_gather_ij calls (which
+ * is what runs when the source layout rules out the TMA-staged kernel). */
+int xrs_gather_ij2(const void *const *src_planes_host, void *const *dst_interp_planes_host,
+                   void *const *dst_nearest_planes_host, int32_t n_bands, int32_t dtype, int64_t src_h,
+                   int64_t src_w, int64_t src_pitch, int64_t win_i0, int64_t win_j0, int64_t win_w, int64_t win_h,
+                   const double *ij, int64_t dst_h, int64_t dst_w, int32_t method, double fill_interp,
+                   double fill_nearest, void *stream);
+
 /* K1 + K2 fused -- xrs_rectify_ij followed by xrs_gather_ij without materialising the ij image:
  * the claim stage of K1 runs as usual, then the gather kernel resolves each pixel's fractional
  * source index in registers (same arithmetic, same results) and gathers all bands.  Saves the

@@ -86,12 +86,18 @@ def test_c2_rectify_full_size(xrs):
     bands[1, np.random.default_rng(3).random((h, w)) < 0.01] = nan
     sd = xrs.dev.to_device_pitched(bands)
     ij_np = xrs.dev.to_host(ij)
+    kept = {}
     for method in ("nearest", "bilinear"):
         two = xrs.rect.gather_ij(sd, ij, method, nan)
         fused = plan.rectify_gather(xd, yd, sd, method, nan, tile_boxes=windows)
         assert torch.equal(_bits(two), _bits(fused)), f"C2 {method}: fused form differs from the two-step form"
         assert_same(xrs.dev.to_host(two), orect.gather(bands, ij_np, method, nan), f"C2 K2 {method}")
+        kept[method] = two
         del two, fused
+    # both methods from one pass over ij and the source (xrs_gather_ij2)
+    pair_bilinear, pair_nearest = xrs.rect.gather_ij_pair(sd, ij, "bilinear", nan, nan)
+    assert torch.equal(_bits(pair_bilinear), _bits(kept["bilinear"])), "C2 two-method gather: bilinear differs"
+    assert torch.equal(_bits(pair_nearest), _bits(kept["nearest"])), "C2 two-method gather: nearest differs"
 
 
 # ---------------------------------------------------------------------------

@@ -21,6 +21,9 @@ def short_name(full: str) -> str:
     m = re.search(r"(k2_gather_staged|k2_gather_direct)<\w+, \(?(?:int\))?(\d)", full)
     if m:
         return f"{m.group(1)}<{METHODS.get(m.group(2), m.group(2))}>" if m.group(1) == "k2_gather_staged" else m.group(1)
+    m = re.search(r"k2_gather_dual<\w+, \(?(?:int\))?(\d)", full)
+    if m:
+        return f"k2_gather_dual<nearest+{METHODS.get(m.group(1), m.group(1))}>"
     m = re.search(r"(k3_reproject)<\w+, \w+, \(?(?:int\))?(\d), \(?(?:bool\))?(\d)", full)
     if m:
         return f"k3_reproject{'_sep' if m.group(3) == '1' else ''}<{METHODS.get(m.group(2), m.group(2))}>"

@@ -53,6 +53,8 @@ SIGNATURES = {
                                c_f64, c_f64, c_f64, c_i32, c_f64, c_i64, c_i64, c_p, c_p, c_p]),
     "xrs_gather_ij": (c_int, [c_p, c_p, c_i32, c_i32, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_p, c_i64,
                               c_i64, c_i32, c_f64, c_p]),
+    "xrs_gather_ij2": (c_int, [c_p, c_p, c_p, c_i32, c_i32, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_p, c_i64,
+                               c_i64, c_i32, c_f64, c_f64, c_p]),
     "xrs_rectify_gather": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, c_p, c_i64, c_i64, c_i32, c_i32, c_f64, c_f64, c_f64,
                                    c_f64, c_f64, c_i32, c_f64, c_i64, c_i64, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i64, c_i64,
                                    c_i64, c_i64, c_i64, c_i32, c_f64, c_p]),

@@ -79,6 +79,31 @@ def group_by_buffer(items) -> list[SourceGroup]:
     return list(groups.values())
 
 
+def pair_targets(targets: list, src_dtype) -> list[tuple]:
+    """Jobs of one source group: ``(interp_target, nearest_target)`` pairs where a bilinear / triangular
+    target and a nearest target share the group's bands and dtype (one launch gives both,
+    ``xrs_gather_ij2``), single-target jobs ``(target,)`` for the rest; the order of first appearance is kept."""
+    src_dtype = np.dtype(src_dtype)
+    same = [t for t in targets if t.out_dtype == src_dtype]
+    near = [t for t in same if t.method == "nearest"]
+    interp = [t for t in same if t.method in ("bilinear", "triangular")]
+    partner = {id(a): b for a, b in zip(interp, near)}
+    partner.update({id(b): a for a, b in zip(interp, near)})
+    jobs, seen = [], set()
+    for t in targets:
+        if id(t) in seen:
+            continue
+        other = partner.get(id(t))
+        if other is None:
+            jobs.append((t,))
+            seen.add(id(t))
+        else:
+            a, b = (t, other) if t.method != "nearest" else (other, t)
+            jobs.append((a, b))
+            seen.update((id(a), id(b)))
+    return jobs
+
+
 def chunk_schedule(bands: int, chunk: int) -> list[tuple[int, int]]:
     """Band chunks 1, 2, 4, ..., chunk, chunk, ...: a short first chunk starts the download early."""
     out, b0, size = [], 0, 1
@@ -125,9 +150,9 @@ class GatherPipeline:
         self._pending = None
         self._keep = None
 
-    def _slots(self, cache, key, shape, dtype):
-        if key not in cache:
-            cache[key] = [torch.empty(shape, dtype=_dev.torch_dtype(dtype), device=self.dev) for _ in range(2)]
+    def _slots(self, cache, key, shape, dtype, n=2):
+        if key not in cache or len(cache[key]) < n:
+            cache[key] = [torch.empty(shape, dtype=_dev.torch_dtype(dtype), device=self.dev) for _ in range(n)]
         return cache[key]
 
     def wait(self) -> None:
@@ -138,9 +163,13 @@ class GatherPipeline:
             main.synchronize()
             self._pending = None
 
-    def run(self, groups: list[SourceGroup], process, wait: bool = True) -> None:
+    def run(self, groups: list[SourceGroup], process, wait: bool = True, process_pair=None) -> None:
         """Enqueue uploads, kernels and downloads of every band chunk; ``wait=False`` returns as soon as
-        everything is enqueued (call :meth:`wait` before touching the outputs or dropping the inputs)."""
+        everything is enqueued (call :meth:`wait` before touching the outputs or dropping the inputs).
+
+        ``process_pair(src_view, target_interp, target_nearest, out_interp, out_nearest, b0)``, when given,
+        computes a bilinear / triangular target and a nearest target of the same group in one launch
+        (:func:`pair_targets` decides which); everything else goes through ``process``."""
         dev = self.dev
         main = torch.cuda.current_stream(dev)
         s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
@@ -148,7 +177,10 @@ class GatherPipeline:
         win_h = self.win[1] - self.win[0]
         k_in = k_out = 0
         in_free = [torch.cuda.Event() for _ in range(2)]
-        out_free = [torch.cuda.Event() for _ in range(2)]
+        # output slots: double-buffered per target of a job, so that the kernels of chunk k+1 never wait for
+        # the downloads of chunk k (a pair job fills two slots at once)
+        n_out = 4 if process_pair is not None else 2
+        out_free = [torch.cuda.Event() for _ in range(n_out)]
         for e in in_free + out_free:
             e.record(main)
         keep = []
@@ -204,28 +236,37 @@ class GatherPipeline:
                     stage_done[ci % 2] = ready
                 main.wait_event(ready)
                 src_view = src_slot[:nb, :, :w]
-                for tgt in grp.targets:
-                    oslot = k_out % 2
-                    k_out += 1
-                    out_slots = self._slots(self._out_slots, (tgt.out_dtype.str, chunk), (chunk, n_rows, self.out_w),
-                                            tgt.out_dtype)
-                    out_view = out_slots[oslot][:nb]
-                    main.wait_event(out_free[oslot])
-                    process(src_view, tgt, out_view, b0)
+                for job in (pair_targets(grp.targets, dtype) if process_pair is not None
+                            else [(t,) for t in grp.targets]):
+                    # one output slot per target of the job (a pair takes both slots of its dtype)
+                    views, oslots = [], []
+                    for tgt in job:
+                        oslot = k_out % n_out
+                        k_out += 1
+                        out_slots = self._slots(self._out_slots, (tgt.out_dtype.str, chunk),
+                                                (chunk, n_rows, self.out_w), tgt.out_dtype, n_out)
+                        main.wait_event(out_free[oslot])
+                        views.append(out_slots[oslot][:nb])
+                        oslots.append(oslot)
+                    if len(job) == 2:
+                        process_pair(src_view, job[0], job[1], views[0], views[1], b0)
+                    else:
+                        process(src_view, job[0], views[0], b0)
                     done = torch.cuda.Event()
                     done.record(main)
-                    oh = tgt.out_host
-                    osz = oh.itemsize
-                    if oh.ndim != 3 or oh.shape[2] != self.out_w or oh.strides[2] != osz:
-                        raise ValueError("output arrays must be (bands, rows, width) with unit x stride")
-                    with torch.cuda.stream(s_out):
-                        s_out.wait_event(done)
-                        copy2d(oh.__array_interface__["data"][0] + b0 * oh.strides[0]
-                               + (self.rows[0] - tgt.row0) * oh.strides[1],
-                               oh.strides[1], oh.strides[0], out_view.data_ptr(), self.out_w * osz,
-                               n_rows * self.out_w * osz, self.out_w * osz, n_rows, nb, dev)
-                        self.d2h_bytes += self.out_w * osz * n_rows * nb
-                        out_free[oslot].record(s_out)
+                    for tgt, out_view, oslot in zip(job, views, oslots):
+                        oh = tgt.out_host
+                        osz = oh.itemsize
+                        if oh.ndim != 3 or oh.shape[2] != self.out_w or oh.strides[2] != osz:
+                            raise ValueError("output arrays must be (bands, rows, width) with unit x stride")
+                        with torch.cuda.stream(s_out):
+                            s_out.wait_event(done)
+                            copy2d(oh.__array_interface__["data"][0] + b0 * oh.strides[0]
+                                   + (self.rows[0] - tgt.row0) * oh.strides[1],
+                                   oh.strides[1], oh.strides[0], out_view.data_ptr(), self.out_w * osz,
+                                   n_rows * self.out_w * osz, self.out_w * osz, n_rows, nb, dev)
+                            self.d2h_bytes += self.out_w * osz * n_rows * nb
+                            out_free[oslot].record(s_out)
                 in_free[slot].record(main)
             if lazy:
                 reader.shutdown(wait=True)

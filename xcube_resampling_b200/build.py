@@ -32,6 +32,7 @@ SOURCES = {
     "bands.cu": ["-fmad=false"],
     "coords.cu": ["-fmad=false"],
     "gather.cu": ["-fmad=false"],
+    "gather_dual.cu": ["-fmad=false"],
     "resample.cu": ["-fmad=false"],
     "resample_fast.cu": ["-fmad=false"],
     "reproject.cu": [],  # projection math may contract; the numpy-parity part uses _rn intrinsics

@@ -273,6 +273,7 @@ class RectifyBandJob:
 
     def enqueue(self) -> None:
         """The data bands of the footprint through K2, band chunk by band chunk, on the current stream."""
+        from . import rectify as xrect
         from .rectify import gather_ij
 
         if self._done:
@@ -287,7 +288,11 @@ class RectifyBandJob:
         def process(src_view, tgt, out_view, b0):
             gather_ij(src_view, ij, tgt.method, tgt.fill, out=out_view, window_origin=(0, fj0), full_size=(w, h))
 
-        self.pipe.run(self.groups, process, wait=False)
+        def process_pair(src_view, tgt_interp, tgt_near, out_interp, out_near, b0):
+            xrect.gather_ij_pair(src_view, ij, tgt_interp.method, tgt_interp.fill, tgt_near.fill, out_interp, out_near,
+                                 window_origin=(0, fj0), full_size=(w, h))
+
+        self.pipe.run(self.groups, process, wait=False, process_pair=process_pair if xrect.DUAL_GATHER else None)
 
     def wait(self) -> None:
         if self.pipe is not None:

@@ -326,6 +326,47 @@ def gather_ij(src: torch.Tensor, ij: torch.Tensor, interp_method: str, fill_valu
     return out[0] if squeeze else out
 
 
+# Two output variables computed from the same source bands, one with nearest and one with bilinear /
+# triangular interpolation, come out of ONE pass over ij and the source (xrs_gather_ij2).  Module
+# switch so that both forms can be compared in one session (tests, bench.py --no-dual).
+DUAL_GATHER = True
+
+
+def gather_ij_pair(src: torch.Tensor, ij: torch.Tensor, interp_method: str, fill_interp, fill_nearest,
+                   out_interp: torch.Tensor | None = None, out_nearest: torch.Tensor | None = None,
+                   window_origin: tuple[int, int] = (0, 0), full_size: tuple[int, int] | None = None):
+    """Two ``_compute_var_image`` passes (rectify.py:579-734) over the same ij image in one launch:
+    the bands of ``src`` with ``interp_method`` ('bilinear' or 'triangular') AND with 'nearest'.
+
+    Returns ``(out_interp, out_nearest)``, bit-identical to two :func:`gather_ij` calls.  Arguments as
+    in :func:`gather_ij`.
+    """
+    lib = load()
+    if interp_method not in ("bilinear", "triangular"):
+        raise NotImplementedError(
+            f"gather_ij_pair: the method beside 'nearest' must be 'bilinear' or 'triangular', was '{interp_method}'."
+        )
+    squeeze = src.dim() == 2
+    src3 = src.unsqueeze(0) if squeeze else src
+    if src3.stride(2) != 1 or (src3.shape[0] > 1 and src3.stride(0) < src3.stride(1) * src3.shape[1]):
+        src3 = src3.contiguous()
+    np_dtype = np.dtype(str(src3.dtype).replace("torch.", ""))
+    bands, win_h, win_w = src3.shape
+    w, h = (win_w, win_h) if full_size is None else (int(full_size[0]), int(full_size[1]))
+    _, H, W = ij.shape
+    if out_interp is None:
+        out_interp = torch.empty((bands, H, W), dtype=src3.dtype, device=src3.device)
+    if out_nearest is None:
+        out_nearest = torch.empty((bands, H, W), dtype=src3.dtype, device=src3.device)
+    check(lib.xrs_gather_ij2(_dev.plane_ptr_array(src3), _dev.plane_ptr_array(out_interp),
+                             _dev.plane_ptr_array(out_nearest), bands, DTYPE_CODES[np_dtype], h, w, src3.stride(1),
+                             int(window_origin[0]), int(window_origin[1]), win_w, win_h, _dev.ptr(ij), H, W,
+                             INTERP_CODES[interp_method], float(fill_interp), float(fill_nearest),
+                             _dev.stream_ptr(src3.device)),
+          "xrs_gather_ij2")
+    return (out_interp[0], out_nearest[0]) if squeeze else (out_interp, out_nearest)
+
+
 def rectify_band_host(x: np.ndarray, y: np.ndarray, src_window: np.ndarray, window_origin: tuple[int, int],
                       full_size: tuple[int, int], target_gm: GridMapping, rows: tuple[int, int], interp_method: str,
                       fill_value, device=None) -> np.ndarray:
@@ -500,7 +541,10 @@ def _rectify_groups_single(source_gm, x_dev, y_dev, groups, target_gm, dev):
         def process(src_view, tgt, out_view, b0):
             gather_ij(src_view, ij, tgt.method, tgt.fill, out=out_view)
 
-        pipe.run(groups, process)
+        def process_pair(src_view, tgt_interp, tgt_near, out_interp, out_near, b0):
+            gather_ij_pair(src_view, ij, tgt_interp.method, tgt_interp.fill, tgt_near.fill, out_interp, out_near)
+
+        pipe.run(groups, process, process_pair=process_pair if DUAL_GATHER else None)
 
 
 def _rectify_groups_multi(source_gm, x_dev, y_dev, groups, target_gm, devices):
