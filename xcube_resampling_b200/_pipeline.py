@@ -22,6 +22,7 @@ streams, events and device buffers.
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -179,7 +180,7 @@ class GatherPipeline:
         in_free = [torch.cuda.Event() for _ in range(2)]
         # output slots: double-buffered per target of a job, so that the kernels of chunk k+1 never wait for
         # the downloads of chunk k (a pair job fills two slots at once)
-        n_out = 4 if process_pair is not None else 2
+        n_out = int(os.environ.get("XRS_PIPE_OUT_SLOTS", 4 if process_pair is not None else 2))
         out_free = [torch.cuda.Event() for _ in range(n_out)]
         for e in in_free + out_free:
             e.record(main)
