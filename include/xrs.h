@@ -203,7 +203,7 @@ int xrs_gather_ij(const void *const *src_planes_host, void *const *dst_planes_ho
 
 /* K2, two methods in one pass -- nearest AND bilinear (or triangular) samples of the same bands.
  * Replaces two _compute_var_image passes over the same ij image: the reference calls
- * _rectify_data_array once per output variable (rectify.py:160-176, 263-309), so a dataset that
+ * _rectify_data_array once per output variable (rectify.py:159-174, 263-309), so a dataset that
  * wants the same source bands with both methods walks ij and the source twice.  The nearest sample
  * is always one of the four taps of the bilinear / triangular one (rectify.py:689-698), so one
  * launch reads ij and the source once and writes both results.

@@ -1,7 +1,7 @@
 // gather_dual.cu -- K2d: the same bands gathered with TWO interpolation methods in one launch.
 //
 //   xrs_gather_ij2   rectify.py:579-734 (_compute_var_image*), called by the reference once per
-//                    output variable (rectify.py:160-176): when a call wants the same source bands
+//                    output variable (rectify.py:159-174): when a call wants the same source bands
 //                    with nearest AND with bilinear / triangular interpolation, both passes walk the
 //                    same ij image and read the same source pixels.
 //

@@ -557,7 +557,10 @@ __global__ void __launch_bounds__(256) k1_scatter_slow(IjGeom g) {
 // them, K1R_THREADS apart (coalesced), sharing the row context; the claim words are loaded first so
 // that their latency and that of the gathered vertex loads overlap.
 constexpr int K1R_PX = 4;
-__global__ void __launch_bounds__(K1R_THREADS) k1_resolve(const __grid_constant__ IjGeom g) {
+#ifndef XRS_K1R_MINBLOCKS
+#define XRS_K1R_MINBLOCKS 1  // build variants k1r5 / k1r6 (tools/r2f_pass.sh): resident CTAs per SM asked of ptxas
+#endif
+__global__ void __launch_bounds__(K1R_THREADS, XRS_K1R_MINBLOCKS) k1_resolve(const __grid_constant__ IjGeom g) {
     const int64_t c_first = static_cast<int64_t>(blockIdx.x) * (K1R_THREADS * K1R_PX) + threadIdx.x;
     const int64_t r = g.row_begin + blockIdx.y;
     const int64_t n_rows = g.row_end - g.row_begin;
