@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(256) k1_scatter_slow(IjGeom g) {
 // that their latency and that of the gathered vertex loads overlap.
 constexpr int K1R_PX = 4;
 #ifndef XRS_K1R_MINBLOCKS
-#define XRS_K1R_MINBLOCKS 1  // build variants k1r5 / k1r6 (tools/r2f_pass.sh): resident CTAs per SM asked of ptxas
+#define XRS_K1R_MINBLOCKS 5  // 48 registers: 0.317 -> 0.292 ms on C2 (variants 1 / 5 / 6: tools/r2f_pass.sh, profiles/r02c_k1_resolve_variants.txt)
 #endif
 __global__ void __launch_bounds__(K1R_THREADS, XRS_K1R_MINBLOCKS) k1_resolve(const __grid_constant__ IjGeom g) {
     const int64_t c_first = static_cast<int64_t>(blockIdx.x) * (K1R_THREADS * K1R_PX) + threadIdx.x;
