@@ -11,7 +11,7 @@ import pytest
 from oracle import grid as ogrid
 from oracle import rectify as orect
 
-from .helpers import assert_same, covering_grid_args, swath
+from .helpers import assert_same, covering_grid_args, hand_made_ij, swath
 
 pytestmark = pytest.mark.gpu
 nan = np.nan
@@ -107,39 +107,11 @@ def test_pair_coarse_target_takes_the_global_tap_path(xrs, ratio):
         assert_same(xrs.dev.to_host(got_n), orect.gather(data, ij_ref, "nearest", -1.0), f"pair/nearest ratio={ratio}")
 
 
-def _hand_made_ij(smooth: bool, h, w, H, W):
-    """ij planes with exact half-pixel fractions (ties keep the lower index, rectify.py:693-698), the
-    last row / column (neighbour taps clamp at the image edge), zeros, NaN in one plane only.
-    ``smooth``: neighbouring target pixels reach neighbouring source pixels (every tile's box fits the
-    staging buffers); otherwise random positions (every tile takes the global-tap branch)."""
-    rng = np.random.default_rng(4)
-    if smooth:
-        fi = np.clip(np.arange(W)[None, :] * 0.7 + rng.random((H, W)), 0, w - 1)
-        fj = np.clip(np.arange(H)[:, None] * 0.6 + rng.random((H, W)), 0, h - 1)
-    else:
-        fi = rng.random((H, W)) * (w - 1)
-        fj = rng.random((H, W)) * (h - 1)
-    fi[::3, ::2] = np.minimum(np.floor(fi[::3, ::2]) + 0.5, w - 1)      # ties in i
-    fj[1::3, ::2] = np.minimum(np.floor(fj[1::3, ::2]) + 0.5, h - 1)    # ties in j
-    fi[:, W - 2:] = w - 1                                 # last column: i1 == i0
-    fj[H - 2:, :] = h - 1                                 # last row: j1 == j0
-    fi[40, W - 6:] = w - 1 - 0.25
-    fj[H - 5, 10:20] = h - 1 - 0.75
-    fi[:, :2] = 0.0
-    fj[:2, :] = 0.0
-    fi[20:24, 30:40] = nan
-    fj[20:24, 30:40] = nan
-    fi[30, 50] = nan                                      # NaN in one plane only: still "no source"
-    fj[31, 51] = nan
-    fi[32:64, 64:96] = nan                                # one whole 32x32 tile without a source (CTA early out)
-    return np.stack([fi, fj])
-
-
 @pytest.mark.parametrize("smooth", [True, False])
 @pytest.mark.parametrize("dtype", [np.float32, np.uint16])
 def test_pair_image_edges_and_half_pixel_ties(xrs, smooth, dtype):
     h, w = 40, 70
-    ij_ref = _hand_made_ij(smooth, h, w, 64, 96)
+    ij_ref = hand_made_ij(smooth, h, w, 64, 96)
     data = (np.random.default_rng(6).random((6, h, w)) * 100).astype(dtype)
     sd = xrs.dev.to_device_pitched(data)
     ij = xrs.dev.to_device(ij_ref)
