@@ -11,7 +11,7 @@ import pytest
 from oracle import grid as ogrid
 from oracle import rectify as orect
 
-from .helpers import assert_same, covering_grid_args, hand_made_ij, swath
+from .helpers import assert_same, covering_grid_args, hand_made_ij, load_golden, swath
 
 pytestmark = pytest.mark.gpu
 nan = np.nan
@@ -38,6 +38,24 @@ def _scene(w, h, theta, seed, res, tile):
     x[h // 3:h // 3 + 3, w // 4:w // 2] = nan  # a hole: pixels without a source inside covered tiles
     size, xy_min = covering_grid_args(x, y, res)
     return x, y, size, xy_min, ogrid.regular_grid(size, xy_min, res, tile_size=tile)
+
+
+def _golden_cases():
+    return [str(c) for c in load_golden("rectify.npz")["cases"]]
+
+
+@pytest.mark.parametrize("case", _golden_cases())
+def test_pair_against_the_reference_goldens(xrs, case):
+    """Outputs of the reference's own kernels (tests/golden/rectify.npz): one launch gives the nearest AND
+    the bilinear / triangular golden of every variable from the golden ij image."""
+    z = load_golden("rectify.npz")
+    ij = xrs.dev.to_device(np.ascontiguousarray(z[f"{case}/ij"]))
+    for vname, fill in (("f32", nan), ("u8", 255), ("i16", -1), ("f64", nan)):
+        src = xrs.dev.to_device_pitched(z[f"{case}/src_{vname}"])
+        for method in ("bilinear", "triangular"):
+            got_i, got_n = xrs.rect.gather_ij_pair(src, ij, method, fill, fill)
+            assert_same(xrs.dev.to_host(got_i), z[f"{case}/out_{vname}_{method}"], f"{case} {vname}/{method}")
+            assert_same(xrs.dev.to_host(got_n), z[f"{case}/out_{vname}_nearest"], f"{case} {vname}/nearest")
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.uint8, np.int16, np.int64])

@@ -74,3 +74,28 @@ def test_picked_tap_equals_the_reference_kernels():
         assert_same(_apply_fill(interp, valid, nan), ref[method], f"{method} vs reference kernel")
         assert_same(_apply_fill(near, valid, nan), ref["nearest"], "nearest vs reference kernel")
     assert valid.mean() > 0.3
+
+
+def _golden_cases():
+    from .helpers import load_golden
+
+    return [str(c) for c in load_golden("rectify.npz")["cases"]]
+
+
+@pytest.mark.parametrize("case", _golden_cases())
+def test_picked_tap_equals_the_reference_goldens(case):
+    """The committed outputs of the reference's own kernels (tests/golden/rectify.npz): the two-method
+    logic reproduces the nearest AND the bilinear / triangular golden of every variable from the golden ij."""
+    from .helpers import load_golden
+
+    z = load_golden("rectify.npz")
+    ij = z[f"{case}/ij"]
+    for vname, fill in (("f32", nan), ("u8", 255), ("i16", -1), ("f64", nan)):
+        src = z[f"{case}/src_{vname}"]
+        for method in ("bilinear", "triangular"):
+            interp, near, valid = two_method_gather_np(src, ij, method)
+            interp, near = _apply_fill(interp, valid, fill), _apply_fill(near, valid, fill)
+            if src.ndim == 2:
+                interp, near = interp[0], near[0]
+            assert_same(interp, z[f"{case}/out_{vname}_{method}"], f"{case} {vname}/{method}")
+            assert_same(near, z[f"{case}/out_{vname}_nearest"], f"{case} {vname}/nearest")
