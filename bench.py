@@ -753,7 +753,9 @@ def ours(args):
         "peak_kind": peak_kind, "unit": "GB/s", "frac": top["frac"],
         "traffic": top["traffic"],
         "traffic_source": ("profiles/kernel_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch from "
-                           + str(traffic_table.get("source"))) if top["traffic"] else None,
+                           + str(traffic_table.get(traffic_key + "_source") if top["kernel"] in traffic_table.get(traffic_key, {})
+                                 and traffic_table.get(traffic_key + "_source") else traffic_table.get("source")))
+        if top["traffic"] else None,
         "algorithmic_bytes_per_launch": top["algorithmic_bytes_per_launch"], "bytes_model": top["bytes_model"],
         "ms_per_launch": top["ms_per_launch"], "share_of_kernel_time": top["share_of_kernel_time"],
         "timing": "CUDA events recorded by libxrs around every launch on the launching stream over K eager, "
