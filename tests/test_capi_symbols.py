@@ -58,3 +58,46 @@ def test_no_cpu_fallback_without_gpu():
     gm = xrs.GridMapping.regular((4, 4), (-1, 49), 2, "EPSG:4326")
     with pytest.raises(XrsError):
         xrs.rectify_dataset(ds, target_gm=gm, interp_methods=0)
+
+
+C_CLIENT = r"""
+#include <stdio.h>
+#include <string.h>
+#include "xrs.h"
+
+/* A plain C99 client of the boundary: argument checks run on the host, so these calls need no GPU. */
+int main(void) {
+    if (xrs_version() != 100) return 1;
+    if (xrs_quad_row_group() < 1) return 2;
+    if (xrs_rectify_ij_workspace_bytes(100, 200, 50, 60) <= 0) return 3;
+    if (xrs_rectify_ij_workspace_bytes(1, 1, 0, 0) != 0) return 4;
+    /* null plane tables are rejected with an error message instead of a crash */
+    if (xrs_gather_ij(NULL, NULL, 1, XRS_F32, 4, 4, 4, 0, 0, 4, 4, NULL, 4, 4, XRS_NEAREST, 0.0, NULL) == 0) return 5;
+    if (strstr(xrs_last_error(), "null") == NULL) return 6;
+    if (xrs_gather_ij2(NULL, NULL, NULL, 1, XRS_F32, 4, 4, 4, 0, 0, 4, 4, NULL, 4, 4, XRS_BILINEAR, 0.0, 0.0, NULL) == 0)
+        return 7;
+    printf("ok %d\n", xrs_version());
+    return 0;
+}
+"""
+
+
+def test_header_is_c99_and_a_c_client_links(lib_path, tmp_path):
+    """include/xrs.h is a C header (no C++ in the signatures): a C99 translation unit compiles with
+    -pedantic, links against libxrs.so and gets host-side argument errors through xrs_last_error()."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "client.c"
+    src.write_text(C_CLIENT)
+    exe = tmp_path / "client"
+    lib_dir = os.path.dirname(lib_path)
+    cmd = [gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", f"-I{os.path.join(ROOT, 'include')}", str(src), "-o", str(exe),
+           f"-L{lib_dir}", f"-l:{os.path.basename(lib_path)}", f"-Wl,-rpath,{lib_dir}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0 and run.stdout.strip() == "ok 100", (run.returncode, run.stdout, run.stderr)
