@@ -99,3 +99,20 @@ def test_picked_tap_equals_the_reference_goldens(case):
                 interp, near = interp[0], near[0]
             assert_same(interp, z[f"{case}/out_{vname}_{method}"], f"{case} {vname}/{method}")
             assert_same(near, z[f"{case}/out_{vname}_nearest"], f"{case} {vname}/nearest")
+
+
+def test_picked_tap_at_the_full_size_of_config_c2():
+    """BASELINE config C2 at full size (4865 x 4091 swath -> 7992 x 5013, 28 M valid target pixels): the
+    picked tap equals the oracle's nearest gather and the shared taps its bilinear gather, one band."""
+    from xcube_resampling_b200 import synthetic as syn
+
+    w, h, res = syn.OLCI_WIDTH, syn.OLCI_HEIGHT, syn.OLCI_RES_DEG
+    lon, lat = syn.swath(w, h, res=res, theta=12.0, seed=0)
+    size, xy_min = syn.covering_grid_args(lon, lat, res)
+    g = ogrid.regular_grid(size, xy_min, res, tile_size=512)
+    ij = orect.rectify_ij(lon, lat, g)
+    band = syn.band_stack(1, h, w, seed=0)
+    interp, near, valid = two_method_gather_np(band, ij, "bilinear")
+    assert 0.6 < valid.mean() < 0.8
+    assert_same(_apply_fill(interp, valid, nan), orect.gather(band, ij, "bilinear", nan), "C2 bilinear")
+    assert_same(_apply_fill(near, valid, nan), orect.gather(band, ij, "nearest", nan), "C2 nearest")
