@@ -180,6 +180,8 @@ class GatherPipeline:
         in_free = [torch.cuda.Event() for _ in range(2)]
         # output slots: double-buffered per target of a job, so that the kernels of chunk k+1 never wait for
         # the downloads of chunk k (a pair job fills two slots at once)
+        # (XRS_PIPE_OUT_SLOTS overrides the count for measurements: with two slots a pair's kernel waits for
+        # both downloads of the previous chunk, 147 vs 141 ms per C2 call, profiles/r02c_e2e_ab_same_box.json)
         n_out = int(os.environ.get("XRS_PIPE_OUT_SLOTS", 4 if process_pair is not None else 2))
         out_free = [torch.cuda.Event() for _ in range(n_out)]
         for e in in_free + out_free:
