@@ -1,0 +1,195 @@
+"""Host tests (no GPU) of the boundary's small containers: the CRS descriptor that stands in for
+``pyproj.CRS`` (``gridmapping/helpers.py:59-63`` ``_normalize_crs``; CF attributes as ``pyproj.CRS.to_cf``
+emits them, ``cfconv.py``) and the numpy-backed Dataset / DataArray that stand in for xarray's, incl. the
+xarray bridge exercised with a stand-in module (xarray itself is not installed in the build image)."""
+
+import types
+
+import numpy as np
+import pytest
+
+from xcube_resampling_b200 import dataset as xds
+from xcube_resampling_b200.crs import CRS, CRS_CRS84, CRS_WGS84, KIND_GEOGRAPHIC, KIND_LAEA, KIND_TMERC, KIND_WEBMERC, \
+    normalize_crs
+from xcube_resampling_b200.dataset import DataArray, Dataset
+
+
+# ---------------------------------------------------------------------------
+# CRS
+# ---------------------------------------------------------------------------
+def test_epsg_families():
+    assert CRS.from_epsg(4326).kind == KIND_GEOGRAPHIC and CRS.from_epsg(4326).is_geographic
+    utm32n, utm32s = CRS.from_epsg(32632), CRS.from_epsg(32732)
+    assert utm32n.kind == KIND_TMERC and utm32n.is_projected
+    assert (utm32n.lon0, utm32n.k0, utm32n.fe, utm32n.fn) == (9.0, 0.9996, 500000.0, 0.0)
+    assert utm32s.fn == 10000000.0 and utm32s.lon0 == 9.0
+    assert CRS.from_epsg(32601).lon0 == -177.0 and CRS.from_epsg(32660).lon0 == 177.0
+    etrs = CRS.from_epsg(25832)
+    assert etrs.kind == KIND_TMERC and etrs.inv_f == 298.257222101 and etrs.lon0 == 9.0
+    assert CRS.from_epsg(3857).kind == KIND_WEBMERC
+    laea = CRS.from_epsg(3035)
+    assert laea.kind == KIND_LAEA and (laea.lon0, laea.lat0, laea.fe, laea.fn) == (10.0, 52.0, 4321000.0, 3210000.0)
+    for bad in (2154, 32661, 32700, 25839, 0):
+        with pytest.raises(ValueError, match="not supported"):
+            CRS.from_epsg(bad)
+
+
+def test_strings_and_normalize():
+    assert CRS.from_string("epsg:4326") == CRS_WGS84 and CRS.from_string(" EPSG:4326 ") == CRS_WGS84
+    assert CRS.from_string("urn:ogc:def:crs:EPSG::32632") == CRS.from_epsg(32632)
+    for s in ("OGC:CRS84", "crs84", "CRS:84"):
+        assert CRS.from_string(s) == CRS_CRS84
+    with pytest.raises(ValueError):
+        CRS.from_string("+proj=longlat")
+    assert normalize_crs(CRS_WGS84) is CRS_WGS84
+    assert normalize_crs(3857) == CRS.from_epsg(3857) and normalize_crs("EPSG:3035") == CRS.from_epsg(3035)
+    with pytest.raises(TypeError):
+        normalize_crs(4326.0)
+
+
+def test_equality_follows_axis_order_and_parameters_not_names():
+    # EPSG:4326 (lat, lon) and OGC:CRS84 (lon, lat) are different CRSs for pyproj too (rectify.py:126)
+    assert CRS_WGS84 != CRS_CRS84 and not CRS_WGS84.equals("OGC:CRS84")
+    assert CRS_WGS84 == "EPSG:4326" and CRS_WGS84 == 4326
+    assert CRS.from_epsg(32632) != CRS.from_epsg(32633) and CRS.from_epsg(32632) != CRS.from_epsg(25832)
+    assert (CRS_WGS84 == object()) is False
+    a = CRS(KIND_TMERC, "mine", lon0=9.0, k0=0.9996, fe=500000.0)
+    assert a == CRS.from_epsg(32632) and hash(a) == hash(CRS.from_epsg(32632))
+    assert len({CRS_WGS84, CRS.from_epsg(4326), CRS_CRS84}) == 2
+
+
+@pytest.mark.parametrize("code", [4326, 4258, 32632, 32733, 25833, 3857, 3035])
+def test_cf_round_trip(code):
+    crs = CRS.from_epsg(code)
+    cf = crs.to_cf()
+    assert cf["epsg_code"] == f"EPSG:{code}" and cf["semi_major_axis"] == 6378137.0
+    assert CRS.from_cf(cf) == crs
+    # without the EPSG code the projection parameters alone rebuild an equal CRS (web Mercator aside:
+    # CF has no parameter set that identifies the spherical pseudo-Mercator)
+    cf.pop("epsg_code")
+    if code != 3857:
+        assert CRS.from_cf(cf) == crs
+    else:
+        with pytest.raises(ValueError):
+            CRS.from_cf(cf)
+    assert CRS_CRS84.to_cf()["epsg_code"] == "OGC:CRS84" and CRS.from_cf(CRS_CRS84.to_cf()) == CRS_CRS84
+
+
+def test_duck_typed_pyproj_objects():
+    class WithEpsg:
+        def to_epsg(self):
+            return 32632
+
+    class WithCfOnly:
+        def to_epsg(self):
+            return None
+
+        def to_cf(self):
+            return CRS.from_epsg(3035).to_cf() | {"epsg_code": "EPSG:3035"}
+
+    assert normalize_crs(WithEpsg()) == CRS.from_epsg(32632)
+    assert normalize_crs(WithCfOnly()) == CRS.from_epsg(3035)
+    assert CRS.from_epsg(32632).proj_params() == (KIND_TMERC, 6378137.0, 298.257223563, 9.0, 0.0, 0.9996, 500000.0, 0.0)
+
+
+# ---------------------------------------------------------------------------
+# DataArray / Dataset
+# ---------------------------------------------------------------------------
+def test_dataarray_surface_and_indexing():
+    a = DataArray(np.arange(24, dtype=np.int16).reshape(2, 3, 4), dims=("band", "y", "x"), attrs={"units": "1"}, name="v")
+    assert a.dims == ("band", "y", "x") and a.shape == (2, 3, 4) and a.dtype == np.int16 and a.ndim == 3 and a.size == 24
+    assert a.sizes == {"band": 2, "y": 3, "x": 4} and a.chunks is None and a.values is a.data
+    assert a[0].dims == ("y", "x") and a[:, 1].dims == ("band", "x") and a[1, 2, 3].dims == ()
+    assert a[0].attrs == {"units": "1"} and a[0].name == "v"
+    assert np.asarray(a, dtype=np.float32).dtype == np.float32
+    with pytest.raises(NotImplementedError):
+        a[..., 0]
+    with pytest.raises(ValueError, match="do not match"):
+        DataArray(np.zeros((2, 2)), dims=("x",))
+    assert DataArray(np.zeros((2, 3))).dims == ("dim_0", "dim_1") and DataArray(np.zeros(3), dims="t").dims == ("t",)
+    b = DataArray(a, name="w")
+    assert b.dims == a.dims and b.attrs == a.attrs and b.name == "w" and b.values is a.values
+
+
+def test_dataset_variables_coords_and_mapping_surface():
+    x, y = np.arange(4.0), np.arange(3.0)
+    ds = Dataset(data_vars=dict(rad=(("y", "x"), np.ones((3, 4))), flag=(("y", "x"), np.zeros((3, 4), np.uint8), {"m": 1}),
+                                scalar=np.array(5)),
+                 coords=dict(x=x, y=y, spatial_ref=np.array(0)), attrs={"title": "t"})
+    assert list(ds) == ["rad", "flag", "scalar"] and [n for n, _ in ds.items()] == ["rad", "flag", "scalar"]
+    assert set(ds.coords) == {"x", "y", "spatial_ref"} and len(ds.data_vars) == 3
+    assert ds["x"].dims == ("x",) and ds["spatial_ref"].dims == () and ds["flag"].attrs == {"m": 1}
+    assert ds.sizes == {"x": 4, "y": 3} and ds.dims == ds.sizes and ds.rad is ds["rad"] and "rad" in ds
+    with pytest.raises(AttributeError):
+        ds.nope
+    with pytest.raises(KeyError):
+        ds.data_vars["x"]
+    with pytest.raises(ValueError, match="give a DataArray"):
+        Dataset(data_vars=dict(bad=np.zeros((2, 2))))
+    sub = ds[["rad"]]
+    assert list(sub) == ["rad"] and set(sub.coords) == {"x", "y", "spatial_ref"} and sub.attrs == {"title": "t"}
+    dropped = ds.drop_vars(["flag", "y"])
+    assert list(dropped) == ["rad", "scalar"] and set(dropped.coords) == {"x", "spatial_ref"}
+    assert list(ds.drop_vars("rad")) == ["flag", "scalar"] and list(ds) == ["rad", "flag", "scalar"]
+    ds2 = ds.assign_coords(lon=(("y", "x"), np.zeros((3, 4))))
+    assert "lon" in ds2.coords and "lon" not in ds.coords
+    ds2["rad"] = (("y", "x"), np.full((3, 4), 2.0))
+    assert ds["rad"].values[0, 0] == 1.0 and ds2["rad"].values[0, 0] == 2.0
+    assert list(ds.coords.to_dataset().coords) == list(ds.coords) and "Dataset" in repr(ds)
+
+
+def test_dataarray_subclasses_are_kept_as_they_are():
+    class Lazy(DataArray):
+        __slots__ = ()
+
+    lazy = Lazy(np.zeros((2, 2)), dims=("y", "x"))
+    ds = Dataset(coords=dict(lon=lazy))
+    assert ds["lon"] is lazy and lazy.name == "lon"
+
+
+# ---------------------------------------------------------------------------
+# xarray bridge, with a stand-in for the xarray module
+# ---------------------------------------------------------------------------
+def _fake_xarray():
+    class XDataArray:
+        def __init__(self, values, dims=(), attrs=None):
+            self.values, self.dims, self.attrs = np.asarray(values), tuple(dims), dict(attrs or {})
+            assert len(self.dims) == self.values.ndim
+
+    class XDataset:
+        def __init__(self, data_vars=None, coords=None, attrs=None):
+            self.data_vars, self.coords, self.attrs = dict(data_vars or {}), dict(coords or {}), dict(attrs or {})
+            sizes = {}
+            for name, v in {**self.coords, **self.data_vars}.items():  # what xarray checks on construction
+                for d, n in zip(v.dims, v.values.shape):
+                    if sizes.setdefault(d, n) != n:
+                        raise ValueError(f"conflicting sizes for dimension {d!r} ({name})")
+
+    return types.SimpleNamespace(Dataset=XDataset, DataArray=XDataArray)
+
+
+def test_xarray_bridge_round_trip(monkeypatch):
+    xr = _fake_xarray()
+    monkeypatch.setattr(xds, "_xr", xr)
+    user = xr.Dataset(data_vars=dict(rad=xr.DataArray(np.ones((3, 4), np.float32), ("y", "x"), {"units": "W"})),
+                      coords=dict(lon=xr.DataArray(np.zeros((3, 4)), ("y", "x")), lat=xr.DataArray(np.zeros((3, 4)), ("y", "x"))),
+                      attrs={"title": "scene"})
+    assert xds.is_xarray(user) and not xds.is_xarray(Dataset())
+    ours = xds.from_any(user)
+    assert isinstance(ours, Dataset) and list(ours) == ["rad"] and set(ours.coords) == {"lon", "lat"}
+    assert ours["rad"].attrs == {"units": "W"} and ours.attrs == {"title": "scene"} and ours["rad"].dtype == np.float32
+    assert xds.from_any(ours) is ours
+    with pytest.raises(TypeError):
+        xds.from_any({"rad": 1})
+    # a rectified result: target-sized variable on (y, x), 1-D target coordinates, no source-shaped lon/lat
+    result = Dataset(data_vars=dict(rad=(("y", "x"), np.zeros((6, 9), np.float32), {"units": "W"})),
+                     coords=dict(x=np.arange(9.0), y=np.arange(6.0), spatial_ref=np.array(0)), attrs=ours.attrs)
+    back = xds.to_like(result, user)
+    assert isinstance(back, xr.Dataset) and back.data_vars["rad"].values.shape == (6, 9)
+    assert back.data_vars["rad"].attrs == {"units": "W"} and set(back.coords) == {"x", "y", "spatial_ref"}
+    assert xds.to_like(result, ours) is result
+    # what ADVICE r1 described: source-shaped 2-D coordinates carried into a target-sized result on the
+    # same dimension names cannot become an xarray.Dataset -- rectify_dataset therefore drops them
+    stale = result.assign_coords(lon=(("y", "x"), np.zeros((3, 4))))
+    with pytest.raises(ValueError, match="conflicting sizes"):
+        xds.to_like(stale, user)
