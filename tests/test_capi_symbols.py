@@ -101,3 +101,26 @@ def test_header_is_c99_and_a_c_client_links(lib_path, tmp_path):
     assert res.returncode == 0, res.stderr
     run = subprocess.run([str(exe)], capture_output=True, text=True)
     assert run.returncode == 0 and run.stdout.strip() == "ok 100", (run.returncode, run.stdout, run.stderr)
+
+
+def test_integration_md_stub_binds_and_matches_the_binding_table(lib_path, monkeypatch):
+    """The ctypes stub INTEGRATION.md shows a reference maintainer is real code: it is executed here
+    against libxrs.so, and every function it binds has exactly the argument and result types of the
+    package's own binding table (``_lib.SIGNATURES``), i.e. of include/xrs.h."""
+    from xcube_resampling_b200 import _lib
+
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = next(b for b in blocks if "_bind(" in b)
+    monkeypatch.setenv("XRS_LIBRARY", lib_path)
+    ns: dict = {}
+    exec(compile(stub, "INTEGRATION.md", "exec"), ns)
+    bound = {v.__name__: v for v in ns.values() if isinstance(v, ctypes._CFuncPtr)}
+    assert {"xrs_rectify_ij", "xrs_gather_ij", "xrs_gather_ij2", "xrs_reproject", "xrs_affine", "xrs_coarsen",
+            "xrs_tile_src_bboxes", "xrs_transform_points"} <= set(bound)
+    for name, fn in bound.items():
+        restype, argtypes = _lib.SIGNATURES[name]
+        assert list(fn.argtypes) == list(argtypes), f"{name}: INTEGRATION.md stub and the binding table disagree"
+        assert fn.restype == restype, name
+    with pytest.raises(RuntimeError, match="null"):
+        ns["check"](bound["xrs_gather_ij"](None, None, 1, 0, 4, 4, 4, 0, 0, 4, 4, None, 4, 4, 0, 0.0, None))
