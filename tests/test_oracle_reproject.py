@@ -95,6 +95,26 @@ def test_transform_bounds_webmerc_tile_at_the_antimeridian():
     assert abs(west[0] + 180.0) < 1e-9 and abs(west[2] + 135.0) < 1e-9
 
 
+# IOGP Guidance Note 7-2, Transverse Mercator worked example (OSGB 1936 / British National Grid): Airy 1830
+# ellipsoid, a NON-ZERO latitude of origin, scale factor and false origin -- every parameter of the
+# family that the UTM known-answer vector of the reference (test_transform.py:46-65) leaves at its default.
+GN7_2_TM = dict(a=6377563.396, inv_f=299.32496, lon0=-2.0, lat0=49.0, k0=0.9996012717, fe=400000.0, fn=-100000.0)
+GN7_2_TM_LON, GN7_2_TM_LAT = 0.5, 50.5
+GN7_2_TM_E, GN7_2_TM_N = 577274.99, 69740.50
+
+
+def test_tmerc_guidance_note_7_2_example():
+    p = oproj.Proj(oproj.TMERC, **GN7_2_TM)
+    e, n = oproj.tmerc_forward(p, np.array([GN7_2_TM_LON]), np.array([GN7_2_TM_LAT]))
+    # published to the centimetre from the USGS series; the Krueger series (PROJ's etmerc) lands within 1 cm
+    assert abs(e[0] - GN7_2_TM_E) < 0.011 and abs(n[0] - GN7_2_TM_N) < 0.011
+    lon, lat = oproj.tmerc_inverse(p, np.array([GN7_2_TM_E]), np.array([GN7_2_TM_N]))
+    assert abs(lon[0] - GN7_2_TM_LON) < 2e-7 and abs(lat[0] - GN7_2_TM_LAT) < 2e-7  # 1 cm on the ground
+    # and the round trip is exact to the nanodegree
+    lon2, lat2 = oproj.tmerc_inverse(p, e, n)
+    assert abs(lon2[0] - GN7_2_TM_LON) < 1e-11 and abs(lat2[0] - GN7_2_TM_LAT) < 1e-11
+
+
 # ---------------------------------------------------------------------------
 # _reproject_block
 # ---------------------------------------------------------------------------
