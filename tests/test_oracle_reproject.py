@@ -115,6 +115,26 @@ def test_tmerc_guidance_note_7_2_example():
     assert abs(lon2[0] - GN7_2_TM_LON) < 1e-11 and abs(lat2[0] - GN7_2_TM_LAT) < 1e-11
 
 
+# Snyder, "Map Projections -- A Working Manual" (USGS Professional Paper 1395, 1987), numerical examples on
+# the Clarke 1866 ellipsoid, published to 0.1 m: Transverse Mercator (phi0 = 0, lambda0 = 75 W, k0 = 0.9996;
+# 40 30' N, 73 30' W) and Lambert Azimuthal Equal-Area, ellipsoidal oblique form (phi1 = 40 N, lambda0 = 100 W;
+# 30 N, 110 W).
+CLARKE_1866 = dict(a=6378206.4, inv_f=294.978698214)
+
+
+def test_snyder_worked_examples_on_the_clarke_1866_ellipsoid():
+    tm = oproj.Proj(oproj.TMERC, lon0=-75.0, lat0=0.0, k0=0.9996, **CLARKE_1866)
+    x, y = oproj.tmerc_forward(tm, np.array([-73.5]), np.array([40.5]))
+    assert abs(x[0] - 127106.5) < 0.06 and abs(y[0] - 4484124.4) < 0.06
+    lon, lat = oproj.tmerc_inverse(tm, x, y)
+    assert abs(lon[0] + 73.5) < 1e-11 and abs(lat[0] - 40.5) < 1e-11
+    laea = oproj.Proj(oproj.LAEA, lon0=-100.0, lat0=40.0, **CLARKE_1866)
+    x, y = oproj.laea_forward(laea, np.array([-110.0]), np.array([30.0]))
+    assert abs(x[0] + 965932.1) < 0.06 and abs(y[0] + 1056814.9) < 0.06
+    lon, lat = oproj.laea_inverse(laea, x, y)
+    assert abs(lon[0] + 110.0) < 1e-10 and abs(lat[0] - 30.0) < 1e-10
+
+
 # ---------------------------------------------------------------------------
 # _reproject_block
 # ---------------------------------------------------------------------------
