@@ -1,0 +1,196 @@
+"""The projection math of the CUDA kernels, compiled for the HOST (test infrastructure, no GPU needed).
+
+``csrc/proj.cuh`` holds the fp64 formulas the reprojection kernels evaluate on the device (``proj_forward``,
+``proj_inverse``, ``proj_transform``).  They are plain C++ apart from the ``__device__`` qualifiers, so the
+very same text can be compiled by g++: :func:`build` writes a translation unit that defines the CUDA
+qualifiers away, includes the text of proj.cuh and exports one C function, and links it against
+``libxrs.so`` for ``make_proj_consts`` (the host routine that derives the series coefficients).  CPU tests can
+then hold the product's own formulas -- not a restatement -- against published known-answer vectors and
+against the oracle, for any ellipsoid and projection parameters.  Differences to the device build are
+confined to libm vs CUDA math-library rounding and FMA contraction (~1e-9 m).
+"""
+
+import ctypes
+import os
+import re
+import shutil
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+CSRC = os.path.join(ROOT, "xcube_resampling_b200", "csrc")
+
+SHIM = r"""
+#define _GNU_SOURCE 1
+#include <cmath>
+#include <cstdint>
+#include <math.h>
+#include "xrs.h"
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __constant__ const
+using std::fabs; using std::sqrt; using std::sin; using std::cos; using std::tan; using std::atan; using std::atan2;
+using std::asin; using std::sinh; using std::asinh; using std::exp; using std::log; using std::rint; using std::fmin;
+using std::fmax;
+"""
+
+EXPORT = r"""
+extern "C" int xrsh_transform_points(const xrs_proj *from, const xrs_proj *to, const double *x, const double *y,
+                                     double *ox, double *oy, long n) {
+    xrs::ProjC f, t;
+    if (int rc = xrs::make_proj_consts(from, &f)) return rc;
+    if (int rc = xrs::make_proj_consts(to, &t)) return rc;
+    for (long i = 0; i < n; ++i) xrs::proj_transform(f, t, x[i], y[i], ox[i], oy[i]);
+    return 0;
+}
+
+// The separable forms the reprojection kernel uses on regular grids: row-only and column-only terms once
+// per row / column, a tail per pixel, the exact per-pixel path where the tail declines (as the kernel does).
+extern "C" int xrsh_tmerc_inverse_grid(const xrs_proj *crs, const double *xs, long nx, const double *ys, long ny,
+                                       double *lam, double *phi, unsigned char *declined) {
+    xrs::ProjC P;
+    if (int rc = xrs::make_proj_consts(crs, &P)) return rc;
+    for (long j = 0; j < ny; ++j) {
+        const xrs::Terms4 r = xrs::tmerc_inv_row_terms(P, ys[j]);
+        for (long i = 0; i < nx; ++i) {
+            const xrs::Terms4 c = xrs::tmerc_inv_col_terms(P, xs[i]);
+            double l, p;
+            const bool ok = xrs::tmerc_inv_tail(P, r, c, l, p);
+            declined[j * nx + i] = ok ? 0 : 1;
+            if (!ok && !xrs::proj_inverse(P, xs[i], ys[j], l, p)) l = p = NAN;
+            lam[j * nx + i] = l;
+            phi[j * nx + i] = p;
+        }
+    }
+    return 0;
+}
+
+extern "C" int xrsh_forward_grid(const xrs_proj *crs, const double *lam, long nx, const double *phi, long ny, double *x,
+                                 double *y) {
+    xrs::ProjC P;
+    if (int rc = xrs::make_proj_consts(crs, &P)) return rc;
+    for (long j = 0; j < ny; ++j) {
+        const xrs::Terms4 r = xrs::fwd_row_terms(P, phi[j], true);
+        for (long i = 0; i < nx; ++i) xrs::fwd_tail(P, r, xrs::fwd_col_terms(P, lam[i]), x[j * nx + i], y[j * nx + i]);
+    }
+    return 0;
+}
+
+extern "C" int xrsh_inverse_points(const xrs_proj *crs, const double *x, const double *y, double *lam, double *phi, long n) {
+    xrs::ProjC P;
+    if (int rc = xrs::make_proj_consts(crs, &P)) return rc;
+    for (long i = 0; i < n; ++i)
+        if (!xrs::proj_inverse(P, x[i], y[i], lam[i], phi[i])) lam[i] = phi[i] = NAN;
+    return 0;
+}
+
+extern "C" int xrsh_forward_points(const xrs_proj *crs, const double *lam, const double *phi, double *x, double *y, long n) {
+    xrs::ProjC P;
+    if (int rc = xrs::make_proj_consts(crs, &P)) return rc;
+    for (long i = 0; i < n; ++i)
+        if (!xrs::proj_forward(P, lam[i], phi[i], x[i], y[i])) x[i] = y[i] = NAN;
+    return 0;
+}
+"""
+
+
+class XrsProj(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("_pad", ctypes.c_int32), ("a", ctypes.c_double), ("inv_f", ctypes.c_double),
+                ("lon0", ctypes.c_double), ("lat0", ctypes.c_double), ("k0", ctypes.c_double), ("fe", ctypes.c_double),
+                ("fn", ctypes.c_double)]
+
+
+def build(out_dir: str, lib_path: str) -> str:
+    """Compile the host build of proj.cuh into ``out_dir`` and return the path of the shared object."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not available")
+    text = open(os.path.join(CSRC, "proj.cuh")).read()
+    text, n = re.subn(r'#include "common.cuh"\n', "", text)
+    assert n == 1, "proj.cuh no longer includes common.cuh exactly once"
+    text = text.replace("#pragma once\n", "").replace("#pragma unroll\n", "")
+    src = os.path.join(out_dir, "proj_host.cpp")
+    with open(src, "w") as fh:
+        fh.write(SHIM + text + EXPORT)
+    so = os.path.join(out_dir, "libxrs_projhost.so")
+    lib_dir = os.path.dirname(lib_path)
+    cmd = [gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", f"-I{os.path.join(ROOT, 'include')}", src,
+           "-o", so, f"-L{lib_dir}", f"-l:{os.path.basename(lib_path)}", f"-Wl,-rpath,{lib_dir}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("host build of proj.cuh failed:\n" + res.stderr[-3000:])
+    return so
+
+
+class HostProj:
+    """``transform(from, to, x, y)`` through the product's formulas on the CPU; CRSs as (kind, a, inv_f,
+    lon0, lat0, k0, fe, fn) tuples -- what ``CRS.proj_params()`` returns."""
+
+    def __init__(self, so_path: str):
+        self.lib = ctypes.CDLL(so_path)
+        self.lib.xrsh_transform_points.restype = ctypes.c_int
+        self.lib.xrsh_transform_points.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_long]
+
+    @staticmethod
+    def _proj(params) -> XrsProj:
+        kind, a, inv_f, lon0, lat0, k0, fe, fn = params
+        return XrsProj(int(kind), 0, a, inv_f, lon0, lat0, k0, fe, fn)
+
+    def transform(self, src, dst, x, y):
+        x = np.ascontiguousarray(np.atleast_1d(x), dtype=np.float64)
+        y = np.ascontiguousarray(np.atleast_1d(y), dtype=np.float64)
+        ox, oy = np.empty_like(x), np.empty_like(y)
+        f, t = self._proj(src), self._proj(dst)
+        rc = self.lib.xrsh_transform_points(ctypes.byref(f), ctypes.byref(t), x.ctypes.data, y.ctypes.data,
+                                            ox.ctypes.data, oy.ctypes.data, x.size)
+        if rc:
+            raise RuntimeError(f"xrsh_transform_points failed ({rc})")
+        return ox, oy
+
+    def _call(self, name, *args):
+        fn = getattr(self.lib, name)
+        fn.restype = ctypes.c_int
+        rc = fn(*args)
+        if rc:
+            raise RuntimeError(f"{name} failed ({rc})")
+
+    def tmerc_inverse_grid(self, crs, xs, ys):
+        """(lam, phi) in radians on the grid ys x xs through the separable row / column terms + tail, and the
+        mask of pixels where the tail declined (the exact per-pixel inverse was used instead)."""
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        ys = np.ascontiguousarray(ys, dtype=np.float64)
+        lam, phi = np.empty((ys.size, xs.size)), np.empty((ys.size, xs.size))
+        declined = np.zeros((ys.size, xs.size), dtype=np.uint8)
+        p = self._proj(crs)
+        self._call("xrsh_tmerc_inverse_grid", ctypes.byref(p), ctypes.c_void_p(xs.ctypes.data), ctypes.c_long(xs.size),
+                   ctypes.c_void_p(ys.ctypes.data), ctypes.c_long(ys.size), ctypes.c_void_p(lam.ctypes.data),
+                   ctypes.c_void_p(phi.ctypes.data), ctypes.c_void_p(declined.ctypes.data))
+        return lam, phi, declined.astype(bool)
+
+    def forward_grid(self, crs, lam, phi):
+        """CRS coordinates on the grid phi (rows) x lam (columns), radians in, through the separable forms."""
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        phi = np.ascontiguousarray(phi, dtype=np.float64)
+        x, y = np.empty((phi.size, lam.size)), np.empty((phi.size, lam.size))
+        p = self._proj(crs)
+        self._call("xrsh_forward_grid", ctypes.byref(p), ctypes.c_void_p(lam.ctypes.data), ctypes.c_long(lam.size),
+                   ctypes.c_void_p(phi.ctypes.data), ctypes.c_long(phi.size), ctypes.c_void_p(x.ctypes.data),
+                   ctypes.c_void_p(y.ctypes.data))
+        return x, y
+
+    def _points(self, name, crs, a, b):
+        a = np.ascontiguousarray(a, dtype=np.float64).ravel()
+        b = np.ascontiguousarray(b, dtype=np.float64).ravel()
+        oa, ob = np.empty_like(a), np.empty_like(b)
+        p = self._proj(crs)
+        self._call(name, ctypes.byref(p), ctypes.c_void_p(a.ctypes.data), ctypes.c_void_p(b.ctypes.data),
+                   ctypes.c_void_p(oa.ctypes.data), ctypes.c_void_p(ob.ctypes.data), ctypes.c_long(a.size))
+        return oa, ob
+
+    def inverse_points(self, crs, x, y):
+        return self._points("xrsh_inverse_points", crs, x, y)
+
+    def forward_points(self, crs, lam, phi):
+        return self._points("xrsh_forward_points", crs, lam, phi)

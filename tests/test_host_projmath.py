@@ -1,0 +1,217 @@
+"""The projection formulas of the CUDA kernels (csrc/proj.cuh + make_proj_consts) compiled for the HOST
+(tests/hostmath) and held, without a GPU, against
+
+* published known-answer vectors: the reference's CRS84 -> UTM 32N table (tests/gridmapping/test_transform.py:46-65),
+  IOGP Guidance Note 7-2 worked examples (pseudo-Mercator 3.5.1, Transverse Mercator / OSGB National Grid, Lambert
+  Azimuthal Equal-Area / ETRS89-LAEA), Snyder's (USGS PP 1395) Transverse Mercator and LAEA examples on Clarke 1866;
+* the oracle (oracle/proj.py) on random points of every projection family and on projected-to-projected pairs.
+
+The GPU suite compares the DEVICE build of the same text with the oracle (test_reproject_gpu.py); this file pins
+the formulas themselves -- incl. non-default ellipsoids and origins -- where no GPU is at hand.
+"""
+
+import numpy as np
+import pytest
+
+from oracle import proj as oproj
+from xcube_resampling_b200.crs import CRS, KIND_GEOGRAPHIC, KIND_LAEA, KIND_TMERC
+
+nan = np.nan
+EPSG = {"utm32": 32632, "utm33s": 32733, "laea": 3035, "webmerc": 3857, "etrs_utm32": 25832}
+
+
+@pytest.fixture(scope="module")
+def hp(tmp_path_factory):
+    from xcube_resampling_b200 import build as xbuild
+
+    from . import hostmath
+
+    try:
+        so = hostmath.build(str(tmp_path_factory.mktemp("projhost")), xbuild.build())
+    except RuntimeError as e:
+        if "g++ not available" in str(e):
+            pytest.skip(str(e))
+        raise
+    return hostmath.HostProj(so)
+
+
+def _p(code_or_crs):
+    return (CRS.from_epsg(code_or_crs) if isinstance(code_or_crs, int) else code_or_crs).proj_params()
+
+
+GEO = _p(4326)
+
+
+# ---------------------------------------------------------------------------
+# published vectors
+# ---------------------------------------------------------------------------
+def test_reference_crs84_to_utm32_table(hp):
+    lon = 10.0 + 0.1 * (np.arange(3) + 0.5)
+    lat = 53.3 - 0.1 * (np.arange(3) + 0.5)
+    xx, yy = np.meshgrid(lon, lat)
+    x, y = hp.transform(_p(CRS.from_string("OGC:CRS84")), _p(32632), xx.ravel(), yy.ravel())
+    np.testing.assert_almost_equal(x.reshape(3, 3), np.array([
+        [570057.076286, 576728.9360228, 583400.7295284],
+        [570220.3304187, 576907.7404859, 583595.0849538],
+        [570383.3684844, 577086.3083212, 583789.1831954]]), decimal=7)
+    np.testing.assert_almost_equal(y.reshape(3, 3), np.array([
+        [5900595.928991, 5900698.5746648, 5900810.5532744],
+        [5889471.9033896, 5889574.6540572, 5889686.7472201],
+        [5878348.0594403, 5878450.9138481, 5878563.1201969]]), decimal=7)
+
+
+def test_guidance_note_7_2_pseudo_mercator(hp):
+    lon, lat = -(100 + 20 / 60), 24 + 22 / 60 + 54.433 / 3600
+    x, y = hp.transform(GEO, _p(3857), [lon], [lat])
+    assert abs(x[0] + 11169055.58) < 0.005 and abs(y[0] - 2800000.00) < 0.005
+    lon2, lat2 = hp.transform(_p(3857), GEO, [-11169055.58], [2810000.00])
+    assert abs(lon2[0] - lon) < 5e-8 and abs(lat2[0] - (24 + 27 / 60 + 48.889 / 3600)) < 5e-8
+    world = 20037508.342789244
+    x, y = hp.transform(GEO, _p(3857), [180.0, -180.0], [85.0511287798066, -85.0511287798066])
+    np.testing.assert_allclose(x, [world, -world], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(y, [world, -world], rtol=0, atol=2e-6)
+
+
+def test_guidance_note_7_2_transverse_mercator_osgb(hp):
+    airy = dict(a=6377563.396, inv_f=299.32496)
+    osgb = _p(CRS(KIND_TMERC, "OSGB 1936 / British National Grid", lon0=-2.0, lat0=49.0, k0=0.9996012717, fe=400000.0,
+                  fn=-100000.0, **airy))
+    geo = _p(CRS(KIND_GEOGRAPHIC, "OSGB 1936", **airy))
+    e, n = hp.transform(geo, osgb, [0.5], [50.5])
+    assert abs(e[0] - 577274.99) < 0.011 and abs(n[0] - 69740.50) < 0.011
+    lon, lat = hp.transform(osgb, geo, [577274.99], [69740.50])
+    assert abs(lon[0] - 0.5) < 2e-7 and abs(lat[0] - 50.5) < 2e-7
+    lon, lat = hp.transform(osgb, geo, e, n)
+    assert abs(lon[0] - 0.5) < 1e-11 and abs(lat[0] - 50.5) < 1e-11
+
+
+def test_guidance_note_7_2_lambert_azimuthal_equal_area(hp):
+    """ETRS89-extended / LAEA Europe (EPSG:3035): 50 N, 5 E -> E 3962799.45, N 2999718.85."""
+    e, n = hp.transform(_p(4258), _p(3035), [5.0], [50.0])
+    assert abs(e[0] - 3962799.45) < 0.006 and abs(n[0] - 2999718.85) < 0.006
+    lon, lat = hp.transform(_p(3035), _p(4258), [3962799.45], [2999718.85])
+    assert abs(lon[0] - 5.0) < 1e-7 and abs(lat[0] - 50.0) < 1e-7
+
+
+def test_snyder_examples_on_clarke_1866(hp):
+    clarke = dict(a=6378206.4, inv_f=294.978698214)
+    geo = _p(CRS(KIND_GEOGRAPHIC, "Clarke 1866", **clarke))
+    tm = _p(CRS(KIND_TMERC, "Snyder TM", lon0=-75.0, k0=0.9996, **clarke))
+    x, y = hp.transform(geo, tm, [-73.5], [40.5])
+    assert abs(x[0] - 127106.5) < 0.06 and abs(y[0] - 4484124.4) < 0.06
+    laea = _p(CRS(KIND_LAEA, "Snyder LAEA", lon0=-100.0, lat0=40.0, **clarke))
+    x, y = hp.transform(geo, laea, [-110.0], [30.0])
+    assert abs(x[0] + 965932.1) < 0.06 and abs(y[0] + 1056814.9) < 0.06
+    lon, lat = hp.transform(laea, geo, x, y)
+    assert abs(lon[0] + 110.0) < 1e-10 and abs(lat[0] - 30.0) < 1e-10
+
+
+# ---------------------------------------------------------------------------
+# against the oracle
+# ---------------------------------------------------------------------------
+def _lonlat(kind, n=20000, seed=0):
+    rng = np.random.default_rng(seed)
+    p = oproj.from_epsg(EPSG[kind])
+    lon0 = 0.0 if p.kind in (oproj.WEBMERC, oproj.GEOGRAPHIC) else p.lon0
+    span = 170.0 if p.kind == oproj.WEBMERC else 20.0
+    lon = lon0 + rng.uniform(-span, span, n)
+    lat = rng.uniform(25, 75, n) if p.kind == oproj.LAEA else rng.uniform(-84, 84, n)
+    return p, lon, lat
+
+
+@pytest.mark.parametrize("kind", sorted(EPSG))
+def test_forward_and_inverse_match_the_oracle(hp, kind):
+    p, lon, lat = _lonlat(kind)
+    x, y = hp.transform(GEO, _p(EPSG[kind]), lon, lat)
+    ex, ey = oproj.forward(p, lon, lat)
+    assert np.abs(x - ex).max() < 1e-7 and np.abs(y - ey).max() < 1e-7, (np.abs(x - ex).max(), np.abs(y - ey).max())
+    lon2, lat2 = hp.transform(_p(EPSG[kind]), GEO, ex, ey)
+    elon, elat = oproj.inverse(p, ex, ey)
+    assert np.abs(lon2 - elon).max() < 1e-12 and np.abs(lat2 - elat).max() < 1e-12
+    assert np.abs(lon2 - lon).max() < 1e-11 and np.abs(lat2 - lat).max() < 1e-11  # round trip
+
+
+@pytest.mark.parametrize("pair", [("utm32", "laea"), ("laea", "utm32"), ("webmerc", "utm32"), ("utm32", "webmerc"),
+                                  ("utm32", "utm33s")])
+def test_projected_to_projected_matches_the_oracle(hp, pair):
+    a, b = pair
+    pa, lon, lat = _lonlat(a, seed=5)
+    if "laea" in pair:
+        lat = np.clip(lat, 30, 72)
+    lon = np.clip(lon, 0, 18)
+    x, y = oproj.forward(pa, lon, lat)
+    ex, ey = oproj.transform(pa, oproj.from_epsg(EPSG[b]), x, y)
+    gx, gy = hp.transform(_p(EPSG[a]), _p(EPSG[b]), x, y)
+    assert np.abs(gx - ex).max() < 1e-6 and np.abs(gy - ey).max() < 1e-6
+
+
+def test_random_ellipsoids_and_origins_match_the_oracle(hp):
+    """make_proj_consts derives its series coefficients numerically for ANY ellipsoid: transverse Mercator
+    and LAEA with random flattening, origin, scale and false origin against the oracle's closed forms."""
+    rng = np.random.default_rng(11)
+    for _ in range(25):
+        a = rng.uniform(6.3e6, 6.4e6)
+        inv_f = rng.uniform(250.0, 350.0)
+        lon0, lat0 = rng.uniform(-170, 170), rng.uniform(-60, 60)
+        k0, fe, fn = rng.uniform(0.99, 1.0), rng.uniform(-1e6, 1e6), rng.uniform(-1e6, 1e6)
+        lon = lon0 + rng.uniform(-15, 15, 500)
+        geo = _p(CRS(KIND_GEOGRAPHIC, "g", a=a, inv_f=inv_f))
+        tm = CRS(KIND_TMERC, "t", a=a, inv_f=inv_f, lon0=lon0, lat0=lat0, k0=k0, fe=fe, fn=fn)
+        lat = rng.uniform(-80, 80, 500)
+        x, y = hp.transform(geo, _p(tm), lon, lat)
+        ex, ey = oproj.forward(oproj.Proj(oproj.TMERC, a, inv_f, lon0, lat0, k0, fe, fn), lon, lat)
+        assert np.abs(x - ex).max() < 1e-6 and np.abs(y - ey).max() < 1e-6
+        la = CRS(KIND_LAEA, "l", a=a, inv_f=inv_f, lon0=lon0, lat0=lat0, fe=fe, fn=fn)
+        lat = np.clip(lat0 + rng.uniform(-30, 30, 500), -89, 89)
+        x, y = hp.transform(geo, _p(la), lon, lat)
+        ex, ey = oproj.forward(oproj.Proj(oproj.LAEA, a, inv_f, lon0, lat0, 1.0, fe, fn), lon, lat)
+        assert np.abs(x - ex).max() < 1e-6 and np.abs(y - ey).max() < 1e-6
+        lon2, lat2 = hp.transform(_p(la), geo, x, y)
+        dlon = (lon2 - lon + 180.0) % 360.0 - 180.0  # the inverse brings longitudes back into [-180, 180]
+        assert np.abs(dlon).max() < 1e-10 and np.abs(lat2 - lat).max() < 1e-10
+
+
+def test_untransformable_points_are_nan(hp):
+    x, y = hp.transform(GEO, _p(32632), [0.0, 10.0, nan], [95.0, 50.0, 1.0])
+    assert np.isnan(x[0]) and np.isnan(y[0]) and np.isfinite(x[1]) and np.isnan(x[2])
+    x, y = hp.transform(_p(32632), GEO, [5e8], [0.0])  # beyond the transverse Mercator domain
+    assert np.isnan(x[0]) and np.isnan(y[0])
+    # two geographic CRSs pass the coordinates through (PROJ's ballpark identity)
+    x, y = hp.transform(GEO, _p(4258), [12.25], [47.5])
+    assert x[0] == 12.25 and y[0] == 47.5
+
+
+# ---------------------------------------------------------------------------
+# separable forms (what the reprojection kernel evaluates once per tile row / column)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("code,x0,y0,res", [(32632, 399960.0, 5890200.0, 10.0), (32733, 166000.0, 1000000.0, 1000.0),
+                                             (25832, 250000.0, 6500000.0, 250.0), (32632, -2.0e6, 0.0, 20000.0)])
+def test_tmerc_separable_inverse_equals_the_per_pixel_inverse(hp, code, x0, y0, res):
+    """Sentinel-2 tile of config C3, a southern-hemisphere zone, a high-latitude ETRS tile, and a grid far
+    wider than the zone (where the tail must decline and the exact path takes over)."""
+    xs = x0 + res * (np.arange(400) + 0.5)
+    ys = y0 + res * (300 - np.arange(300) - 0.5)
+    lam, phi, declined = hp.tmerc_inverse_grid(_p(code), xs, ys)
+    xx, yy = np.meshgrid(xs, ys)
+    elam, ephi = hp.inverse_points(_p(code), xx, yy)
+    ok = ~np.isnan(elam)
+    assert np.array_equal(np.isnan(lam.ravel()), ~ok)
+    assert np.abs(lam.ravel()[ok] - elam[ok]).max() < 2e-15 * 50 and np.abs(phi.ravel()[ok] - ephi[ok]).max() < 2e-15 * 50
+    if res <= 1000.0:
+        assert not declined.any()  # inside a zone the small-angle tail always applies
+    olon, olat = oproj.inverse(oproj.from_epsg(code), xx.ravel(), yy.ravel())
+    assert np.nanmax(np.abs(np.degrees(lam.ravel()) - olon)) < 1e-11 and np.nanmax(np.abs(np.degrees(phi.ravel()) - olat)) < 1e-11
+
+
+@pytest.mark.parametrize("code", [4326, 3857, 32632, 3035])
+def test_separable_forward_equals_the_per_pixel_forward(hp, code):
+    lon = np.radians(np.linspace(-4.0, 24.0, 300))
+    lat = np.radians(np.linspace(71.0, 33.0, 200))
+    x, y = hp.forward_grid(_p(code), lon, lat)
+    ll, pp = np.meshgrid(lon, lat)
+    ex, ey = hp.forward_points(_p(code), ll, pp)
+    scale = 1.0 if code == 4326 else 1e7
+    assert np.abs(x.ravel() - ex).max() <= 4e-16 * scale and np.abs(y.ravel() - ey).max() <= 4e-16 * scale
+    ox, oy = oproj.forward(oproj.from_epsg(code), np.degrees(ll.ravel()), np.degrees(pp.ravel()))
+    tol = 1e-11 if code == 4326 else 1e-7
+    assert np.abs(x.ravel() - ox).max() < tol and np.abs(y.ravel() - oy).max() < tol
