@@ -215,3 +215,61 @@ def test_separable_forward_equals_the_per_pixel_forward(hp, code):
     ox, oy = oproj.forward(oproj.from_epsg(code), np.degrees(ll.ravel()), np.degrees(pp.ravel()))
     tol = 1e-11 if code == 4326 else 1e-7
     assert np.abs(x.ravel() - ox).max() < tol and np.abs(y.ravel() - oy).max() < tol
+
+
+# ---------------------------------------------------------------------------
+# the lattice form of non-separable transforms (csrc/reproject.cu: k3_lattice_*): error-bound claim
+# ---------------------------------------------------------------------------
+def _lagrange4(t):
+    b, c, d = t - 1.0, t - 2.0, t - 3.0
+    return np.stack([b * c * d * (-1.0 / 6.0), t * c * d * 0.5, t * b * d * -0.5, t * b * c * (1.0 / 6.0)])
+
+
+def _lattice_tile_errors(hp, src, dst, x0, y0, step_x, step_y, src_res, cols=64, rows=32):
+    """numpy restatement of k3_lattice_point / k3_lattice_setup for ONE CTA tile whose first pixel centre is
+    (x0, y0): exact transform (the product's formulas, host build) at the 4 x 4 lattice and the centre, bicubic
+    Lagrange interpolation at every pixel centre.  Returns (max interpolation error over the tile, error at the
+    tile centre), both in source pixels."""
+    hx, hy = step_x * ((cols - 1) / 3.0), step_y * ((rows - 1) / 3.0)
+    ti, tj = np.meshgrid(np.arange(4.0), np.arange(4.0))
+    nx, ny = hp.transform(dst, src, (x0 + ti * hx).ravel(), (y0 + tj * hy).ravel())
+    nx, ny = nx.reshape(4, 4), ny.reshape(4, 4)
+    wc = _lagrange4((np.arange(cols) * step_x) / hx)   # (4, cols)
+    wr = _lagrange4((np.arange(rows) * step_y) / hy)   # (4, rows)
+    ix = np.einsum("jr,jk,kc->rc", wr, nx, wc)
+    iy = np.einsum("jr,jk,kc->rc", wr, ny, wc)
+    xx, yy = np.meshgrid(x0 + np.arange(cols) * step_x, y0 + np.arange(rows) * step_y)
+    ex, ey = hp.transform(dst, src, xx.ravel(), yy.ravel())
+    err = max(np.abs(ix.ravel() - ex).max(), np.abs(iy.ravel() - ey).max()) / src_res
+    w15 = np.array([-0.0625, 0.5625, 0.5625, -0.0625])
+    cx, cy = hp.transform(dst, src, [x0 + 1.5 * hx], [y0 + 1.5 * hy])
+    centre = max(abs(w15 @ nx @ w15 - cx[0]), abs(w15 @ ny @ w15 - cy[0])) / src_res
+    return err, centre
+
+
+@pytest.mark.parametrize("x0,y0", [(399965.0, 1099995.0), (509755.0, 990245.0), (199985.0, 6800005.0),
+                                   (799995.0, 4000005.0)])
+def test_lattice_interpolation_error_on_sentinel_2_grids(hp, x0, y0):
+    """10 m UTM pixels -> 0.0001 deg geographic source (config C3, a Nordic tile, a zone edge): the bicubic
+    interpolant through 4 x 4 exactly transformed points of a 64 x 32 tile stays within 1e-8 source pixels of
+    the exact transform everywhere on the tile -- a hundredth of the 1e-6 px ij tolerance -- and the kernel's
+    acceptance test (the tile centre) sees an error of the same order."""
+    err, centre = _lattice_tile_errors(hp, GEO, _p(32632), x0, y0, 10.0, -10.0, 1e-4)
+    assert err < 1e-8 and centre < 1e-8, (err, centre)
+
+
+def test_lattice_is_rejected_where_the_transform_bends_inside_a_tile(hp):
+    """5 km pixels (a 320 km x 160 km tile): the interpolation error reaches whole source pixels, and the
+    centre test -- error at the centre against 1e-8 px -- rejects the tile, so the kernel's CTA falls back
+    to the exact per-pixel transform.  The centre error is a fair proxy of the tile maximum (cubic
+    interpolation: |w(t)| peaks at 1.0 near t = 0.38 against 0.5625 at the centre, per axis)."""
+    err, centre = _lattice_tile_errors(hp, GEO, _p(32632), 200000.0, 6000000.0, 5000.0, -5000.0, 0.05)
+    assert centre > 1e-8 and err > 1e-8
+    assert err < 10.0 * centre
+    # LAEA Europe at 1 km (64 km x 32 km tiles): 1e-7 px -- harmless, but above the kernel's 1e-8 px bar, so
+    # rejected as well; the centre error tracks the tile maximum (factor ~1.8) ...
+    err, centre = _lattice_tile_errors(hp, _p(4258), _p(3035), 4000000.0, 3000000.0, 1000.0, -1000.0, 0.01)
+    assert 1e-8 < centre < 1e-6 and centre < err < 2.5 * centre, (err, centre)
+    # ... and at 100 m the fourth-power law has taken it four orders of magnitude down
+    err, centre = _lattice_tile_errors(hp, _p(4258), _p(3035), 4000000.0, 3000000.0, 100.0, -100.0, 0.001)
+    assert err < 1e-9 and centre < 1e-9, (err, centre)
