@@ -194,3 +194,95 @@ class HostProj:
 
     def forward_points(self, crs, lam, phi):
         return self._points("xrsh_forward_points", crs, lam, phi)
+
+
+# ---------------------------------------------------------------------------
+# K1's resolve step (csrc/rectify_common.cuh: resolve_row / resolve_pixel, div_magic)
+# ---------------------------------------------------------------------------
+RESOLVE_SHIM = r"""
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include "xrs.h"
+#define __device__
+#define __host__
+#define __forceinline__ inline
+typedef void *cudaStream_t;
+namespace xrs {
+// common.cuh's _rn wrappers: plain IEEE operations (this unit is compiled with -ffp-contract=off)
+static inline double dadd(double a, double b) { return a + b; }
+static inline double dsub(double a, double b) { return a - b; }
+static inline double dmul(double a, double b) { return a * b; }
+static inline double ddiv(double a, double b) { return a / b; }
+}
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) {
+    return static_cast<unsigned long long>((static_cast<unsigned __int128>(a) * b) >> 64);
+}
+"""
+
+RESOLVE_EXPORT = r"""
+extern "C" void xrsh_resolve(const double *x, const double *y, long src_h, long src_w, long src_pitch,
+                             const int64_t *tile_boxes, const uint32_t *claims, double *ij, long dst_h, long dst_w,
+                             int tile_h, int tile_w, double x_min, double y_min, double y_max, double x_res,
+                             double y_res, int j_up) {
+    xrs::IjGeom g = {};
+    g.x = x; g.y = y; g.src_h = src_h; g.src_w = src_w; g.src_pitch = src_pitch;
+    g.tile_boxes = tile_boxes; g.ij = ij; g.claims = const_cast<uint32_t *>(claims);
+    g.dst_h = dst_h; g.dst_w = dst_w;
+    g.tile_h = tile_h < dst_h ? tile_h : static_cast<int>(dst_h);   // as k1_make_geom
+    g.tile_w = tile_w < dst_w ? tile_w : static_cast<int>(dst_w);
+    g.ntx = static_cast<int>((dst_w + g.tile_w - 1) / g.tile_w);
+    g.nty = static_cast<int>((dst_h + g.tile_h - 1) / g.tile_h);
+    g.x_min = x_min; g.y_min = y_min; g.y_max = y_max; g.x_res = x_res; g.y_res = y_res;
+    g.j_up = j_up ? 1 : 0;
+    g.row_begin = 0; g.row_end = dst_h;
+    g.magic_nqi = xrs::div_magic_of(static_cast<uint64_t>(src_w - 1));
+    g.magic_tw = xrs::div_magic_of(static_cast<uint64_t>(g.tile_w));
+    g.magic_th = xrs::div_magic_of(static_cast<uint64_t>(g.tile_h));
+    for (long r = 0; r < dst_h; ++r) {
+        const xrs::ResolveRow row = xrs::resolve_row(g, r);
+        for (long c = 0; c < dst_w; ++c)
+            xrs::resolve_pixel(g, row, c, claims[r * dst_w + c], ij[r * dst_w + c], ij[dst_h * dst_w + r * dst_w + c]);
+    }
+}
+"""
+
+
+def build_resolve(out_dir: str) -> str:
+    """Host build of rectify_common.cuh (K1's resolve step); no library needed."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not available")
+    text = open(os.path.join(CSRC, "rectify_common.cuh")).read()
+    text, n = re.subn(r'#include "common.cuh"\n', "", text)
+    assert n == 1, "rectify_common.cuh no longer includes common.cuh exactly once"
+    text = text.replace("#pragma once\n", "")
+    src = os.path.join(out_dir, "resolve_host.cpp")
+    with open(src, "w") as fh:
+        fh.write(RESOLVE_SHIM + text + RESOLVE_EXPORT)
+    so = os.path.join(out_dir, "libxrs_resolvehost.so")
+    cmd = [gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", f"-I{os.path.join(ROOT, 'include')}", src,
+           "-o", so]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("host build of rectify_common.cuh failed:\n" + res.stderr[-3000:])
+    return so
+
+
+def resolve(so_path: str, x, y, tile_boxes, claims, g) -> np.ndarray:
+    """(2, H, W) ij image from claim words through the product's resolve_pixel; ``g``: oracle RegularGrid."""
+    lib = ctypes.CDLL(so_path)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    boxes = np.ascontiguousarray(tile_boxes, dtype=np.int64)
+    claims = np.ascontiguousarray(claims, dtype=np.uint32)
+    ij = np.empty((2, g.height, g.width), dtype=np.float64)
+    h, w = x.shape
+    c_d, c_l, c_i, c_p = ctypes.c_double, ctypes.c_long, ctypes.c_int, ctypes.c_void_p
+    lib.xrsh_resolve.restype = None
+    lib.xrsh_resolve.argtypes = [c_p, c_p, c_l, c_l, c_l, c_p, c_p, c_p, c_l, c_l, c_i, c_i, c_d, c_d, c_d, c_d, c_d, c_i]
+    lib.xrsh_resolve(x.ctypes.data, y.ctypes.data, h, w, w, boxes.ctypes.data, claims.ctypes.data, ij.ctypes.data,
+                     g.height, g.width, g.tile_h, g.tile_w, float(g.x_min), float(g.y_min), float(g.y_max),
+                     float(g.x_res), float(g.y_res), int(g.is_j_axis_up))
+    return ij
