@@ -286,3 +286,115 @@ def resolve(so_path: str, x, y, tile_boxes, claims, g) -> np.ndarray:
                      g.height, g.width, g.tile_h, g.tile_w, float(g.x_min), float(g.y_min), float(g.y_max),
                      float(g.x_res), float(g.y_res), int(g.is_j_axis_up))
     return ij
+
+
+# ---------------------------------------------------------------------------
+# K2's per-pixel arithmetic (csrc/gather_common.cuh: make_taps / interp_value)
+# ---------------------------------------------------------------------------
+GATHER_SHIM = r"""
+#include <algorithm>
+#include <type_traits>
+using std::min; using std::max;
+namespace xrs {
+// common.cuh: float64 -> T with a C cast (what numba emits for `out[...] = float64_value`)
+template <typename T> static inline T cast_from_f64(double v) {
+    if constexpr (std::is_floating_point<T>::value) return static_cast<T>(v);
+    else return static_cast<T>(static_cast<long long>(v));
+}
+}
+"""
+
+GATHER_EXPORT = r"""
+template <typename T, int METHOD>
+static void gather_one(const T *src, long n_bands, long src_h, long src_w, const double *ij, T *dst, long dst_h, long dst_w,
+                       T fill) {
+    for (long r = 0; r < dst_h; ++r)
+        for (long c = 0; c < dst_w; ++c) {
+            const long o = r * dst_w + c;
+            const xrs::Taps t = xrs::make_taps<METHOD>(ij[o], ij[dst_h * dst_w + o], src_w, src_h);
+            for (long b = 0; b < n_bands; ++b) {
+                const T *sp = src + b * src_h * src_w;
+                T out = fill;
+                if (t.valid) {
+                    if (METHOD == XRS_NEAREST) out = sp[t.j0 * src_w + t.i0];
+                    else out = xrs::cast_from_f64<T>(xrs::interp_value<METHOD>(
+                        static_cast<double>(sp[t.j0 * src_w + t.i0]), static_cast<double>(sp[t.j0 * src_w + t.i1]),
+                        static_cast<double>(sp[t.j1 * src_w + t.i0]), static_cast<double>(sp[t.j1 * src_w + t.i1]), t.u, t.v));
+                }
+                dst[b * dst_h * dst_w + o] = out;
+            }
+        }
+}
+template <typename T>
+static int gather_t(const void *src, long n_bands, long src_h, long src_w, const double *ij, void *dst, long dst_h,
+                    long dst_w, int method, double fill) {
+    const T f = xrs::cast_fill<T>(fill);
+    const T *s = static_cast<const T *>(src);
+    T *d = static_cast<T *>(dst);
+    switch (method) {
+    case XRS_NEAREST: gather_one<T, XRS_NEAREST>(s, n_bands, src_h, src_w, ij, d, dst_h, dst_w, f); return 0;
+    case XRS_BILINEAR: gather_one<T, XRS_BILINEAR>(s, n_bands, src_h, src_w, ij, d, dst_h, dst_w, f); return 0;
+    case XRS_TRIANGULAR: gather_one<T, XRS_TRIANGULAR>(s, n_bands, src_h, src_w, ij, d, dst_h, dst_w, f); return 0;
+    }
+    return 1;
+}
+extern "C" int xrsh_gather(const void *src, int dtype, long n_bands, long src_h, long src_w, const double *ij, void *dst,
+                           long dst_h, long dst_w, int method, double fill) {
+    switch (dtype) {
+    case XRS_F32: return gather_t<float>(src, n_bands, src_h, src_w, ij, dst, dst_h, dst_w, method, fill);
+    case XRS_F64: return gather_t<double>(src, n_bands, src_h, src_w, ij, dst, dst_h, dst_w, method, fill);
+    case XRS_U8: return gather_t<uint8_t>(src, n_bands, src_h, src_w, ij, dst, dst_h, dst_w, method, fill);
+    case XRS_I16: return gather_t<int16_t>(src, n_bands, src_h, src_w, ij, dst, dst_h, dst_w, method, fill);
+    case XRS_U16: return gather_t<uint16_t>(src, n_bands, src_h, src_w, ij, dst, dst_h, dst_w, method, fill);
+    case XRS_I32: return gather_t<int32_t>(src, n_bands, src_h, src_w, ij, dst, dst_h, dst_w, method, fill);
+    case XRS_I64: return gather_t<int64_t>(src, n_bands, src_h, src_w, ij, dst, dst_h, dst_w, method, fill);
+    }
+    return 2;
+}
+"""
+
+
+def build_gather(out_dir: str) -> str:
+    """Host build of gather_common.cuh (on top of rectify_common.cuh, which it includes)."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not available")
+    rc = open(os.path.join(CSRC, "rectify_common.cuh")).read()
+    rc, n = re.subn(r'#include "common.cuh"\n', "", rc)
+    assert n == 1
+    gc = open(os.path.join(CSRC, "gather_common.cuh")).read()
+    gc, n = re.subn(r'#include "rectify_common.cuh"\n#include "tma.cuh"\n', "", gc)
+    assert n == 1, "gather_common.cuh no longer includes rectify_common.cuh and tma.cuh"
+    text = (rc + gc).replace("#pragma once\n", "")
+    src = os.path.join(out_dir, "gather_host.cpp")
+    with open(src, "w") as fh:
+        fh.write(RESOLVE_SHIM + GATHER_SHIM + text + GATHER_EXPORT)
+    so = os.path.join(out_dir, "libxrs_gatherhost.so")
+    cmd = [gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", f"-I{os.path.join(ROOT, 'include')}", src,
+           "-o", so]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("host build of gather_common.cuh failed:\n" + res.stderr[-3000:])
+    return so
+
+
+def gather(so_path: str, src, ij, method: str, fill) -> np.ndarray:
+    """``_compute_var_image`` through the product's make_taps / interp_value on the CPU."""
+    from xcube_resampling_b200.constants import DTYPE_CODES, INTERP_CODES
+
+    lib = ctypes.CDLL(so_path)
+    src = np.asarray(src)
+    squeeze = src.ndim == 2
+    src3 = np.ascontiguousarray(src[None] if squeeze else src)
+    ij = np.ascontiguousarray(ij, dtype=np.float64)
+    bands, sh, sw = src3.shape
+    _, dh, dw = ij.shape
+    out = np.empty((bands, dh, dw), dtype=src3.dtype)
+    c_l, c_i, c_p = ctypes.c_long, ctypes.c_int, ctypes.c_void_p
+    lib.xrsh_gather.restype = c_i
+    lib.xrsh_gather.argtypes = [c_p, c_i, c_l, c_l, c_l, c_p, c_p, c_l, c_l, c_i, ctypes.c_double]
+    rc = lib.xrsh_gather(src3.ctypes.data, DTYPE_CODES[src3.dtype], bands, sh, sw, ij.ctypes.data, out.ctypes.data, dh,
+                         dw, INTERP_CODES[method], float(fill))
+    if rc:
+        raise RuntimeError(f"xrsh_gather failed ({rc})")
+    return out[0] if squeeze else out
