@@ -61,3 +61,31 @@ def test_helpers_without_nvml():
     assert os.sched_getaffinity(0) == before  # no NVML here: affinity untouched
     cfg = bench.workload_config(4865, 4091, 21, (7992, 5013), 8)
     assert cfg["scenes_per_step"] == 8 and "rectify_dataset" in cfg["workload"]
+
+
+def test_traffic_source_expression_of_the_bench_line():
+    """The `roofline.traffic_source` expression of bench.py, lifted from the source by its AST and evaluated
+    with the committed profiles/kernel_traffic.json: names the capture a kernel's DRAM bytes come from, and is
+    None when there is no traffic figure (N > 1, scaled scenes, kernels without a capture)."""
+    import ast
+    import json
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tree = ast.parse(open(os.path.join(root, "bench.py")).read())
+    found = [v for node in ast.walk(tree) if isinstance(node, ast.Dict)
+             for k, v in zip(node.keys, node.values) if isinstance(k, ast.Constant) and k.value == "traffic_source"]
+    assert len(found) == 1
+    expr = ast.Expression(found[0])
+    ast.fix_missing_locations(expr)
+    code = compile(expr, "bench.py", "eval")
+    table = json.load(open(os.path.join(root, "profiles", "kernel_traffic.json")))
+    assert "k2_gather_dual<nearest+bilinear>" in table["dual"] and "k1_scatter" in table["two_step"]
+
+    def ev(key, kernel, traffic, tab=table):
+        return eval(code, dict(traffic_table=tab, traffic_key=key, top={"kernel": kernel, "traffic": traffic}))
+
+    assert "regex:k2_gather_dual" in ev("dual", "k2_gather_dual<nearest+bilinear>", 9.1e9)
+    assert "regex:k2_gather_dual" not in ev("dual", "k1_scatter", 5e8) and "ncu --set full" in ev("dual", "k1_scatter", 5e8)
+    assert "ncu --set full" in ev("two_step", "k2_gather_staged<bilinear>", 5.6e9)
+    assert ev("dual", "k2_gather_dual<nearest+bilinear>", None) is None
+    assert ev("dual", "k2_gather_dual<nearest+bilinear>", None, tab={}) is None
