@@ -398,3 +398,61 @@ def gather(so_path: str, src, ij, method: str, fill) -> np.ndarray:
     if rc:
         raise RuntimeError(f"xrsh_gather failed ({rc})")
     return out[0] if squeeze else out
+
+
+# ---------------------------------------------------------------------------
+# K4 / K5 shared pieces (csrc/resample_common.cuh: numpy's summation order, scipy's output cast, order-1 taps)
+# ---------------------------------------------------------------------------
+RESAMPLE_SHIM = r"""
+#include <limits>
+#include <type_traits>
+using std::isfinite; using std::floor;
+"""
+
+RESAMPLE_EXPORT = r"""
+template <typename A>
+static void window_sums(const A *win, int f_j, int f_i, long n, A *out) {
+    for (long k = 0; k < n; ++k) {
+        const A *w = win + k * f_j * f_i;
+        out[k] = xrs::numpy_window_sum<A>(f_j, f_i, [&](int i) { return w[i]; });
+    }
+}
+extern "C" void xrsh_window_sums_f32(const float *win, int f_j, int f_i, long n, float *out) { window_sums<float>(win, f_j, f_i, n, out); }
+extern "C" void xrsh_window_sums_f64(const double *win, int f_j, int f_i, long n, double *out) { window_sums<double>(win, f_j, f_i, n, out); }
+extern "C" void xrsh_scipy_cast(const double *v, long n, uint8_t *u8, int16_t *i16, int32_t *i32, uint16_t *u16) {
+    for (long k = 0; k < n; ++k) {
+        u8[k] = xrs::scipy_cast<uint8_t>(v[k]);
+        i16[k] = xrs::scipy_cast<int16_t>(v[k]);
+        i32[k] = xrs::scipy_cast<int32_t>(v[k]);
+        u16[k] = xrs::scipy_cast<uint16_t>(v[k]);
+    }
+}
+extern "C" void xrsh_axis_order1(const double *c, long n, long len, long *k0, long *k1, double *w0, double *w1,
+                                 unsigned char *inside) {
+    for (long k = 0; k < n; ++k) {
+        const xrs::Axis1 a = xrs::axis_order1(c[k], len);
+        k0[k] = a.k0; k1[k] = a.k1; w0[k] = a.w0; w1[k] = a.w1; inside[k] = a.inside ? 1 : 0;
+    }
+}
+"""
+
+
+def build_resample(out_dir: str) -> str:
+    """Host build of resample_common.cuh."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not available")
+    text = open(os.path.join(CSRC, "resample_common.cuh")).read()
+    text, n = re.subn(r'#include "common.cuh"\n', "", text)
+    assert n == 1
+    text = text.replace("#pragma once\n", "").replace("#pragma unroll\n", "")
+    src = os.path.join(out_dir, "resample_host.cpp")
+    with open(src, "w") as fh:
+        fh.write(RESOLVE_SHIM + RESAMPLE_SHIM + text + RESAMPLE_EXPORT)
+    so = os.path.join(out_dir, "libxrs_resamplehost.so")
+    cmd = [gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", f"-I{os.path.join(ROOT, 'include')}", src,
+           "-o", so]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("host build of resample_common.cuh failed:\n" + res.stderr[-3000:])
+    return so
