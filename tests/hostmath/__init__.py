@@ -456,3 +456,101 @@ def build_resample(out_dir: str) -> str:
     if res.returncode != 0:
         raise RuntimeError("host build of resample_common.cuh failed:\n" + res.stderr[-3000:])
     return so
+
+
+# ---------------------------------------------------------------------------
+# K4: scipy's affine sample + the 13 numpy reducers (csrc/resample.cu, everything above the kernels)
+# ---------------------------------------------------------------------------
+K4_EXPORT = r"""
+// what k4_affine_generic does per output pixel, as a loop nest (one slice)
+template <typename T, typename OutT>
+static void affine_host(const T *src, OutT *dst, const xrs::AffineGeom &g) {
+    const int n = g.f_j * g.f_i;
+    for (int64_t oj = 0; oj < g.dst_h; ++oj)
+        for (int64_t oi = 0; oi < g.dst_w; ++oi) {
+            OutT *out = dst + oj * g.dst_w + oi;
+            if (n == 1) {
+                *out = static_cast<OutT>(xrs::affine_sample<T>(src, nullptr, oj, oi, g));
+                continue;
+            }
+            T w[xrs::RS_MAX_WINDOW];
+            for (int a = 0; a < g.f_j; ++a)
+                for (int b = 0; b < g.f_i; ++b)
+                    w[a * g.f_i + b] = xrs::affine_sample<T>(src, nullptr, oj * g.f_j + a, oi * g.f_i + b, g);
+            *out = xrs::reduce_window<T, OutT>(w, g.f_j, g.f_i, g.agg);
+        }
+}
+template <typename T>
+static int affine_t(const void *src, void *dst, const xrs::AffineGeom &g, int out_i64) {
+    if (out_i64) affine_host<T, int64_t>(static_cast<const T *>(src), static_cast<int64_t *>(dst), g);
+    else affine_host<T, T>(static_cast<const T *>(src), static_cast<T *>(dst), g);
+    return 0;
+}
+extern "C" int xrsh_affine(const void *src, void *dst, int dtype, long src_h, long src_w, long dst_h, long dst_w,
+                           double j_scale, double j_off, double i_scale, double i_off, int order, double cval, int agg,
+                           int f_j, int f_i, int out_i64) {
+    if (f_j * f_i > xrs::RS_MAX_WINDOW) return 3;
+    xrs::AffineGeom g = {};
+    g.n_slices = 1; g.src_h = src_h; g.src_w = src_w; g.src_pitch = src_w; g.src_slice_stride = src_h * src_w;
+    g.dst_h = dst_h; g.dst_w = dst_w; g.j_scale = j_scale; g.j_off = j_off; g.i_scale = i_scale; g.i_off = i_off;
+    g.cval = cval; g.order = order; g.agg = agg; g.f_j = f_j; g.f_i = f_i; g.slice_blend = 0;
+    switch (dtype) {
+    case XRS_F32: return affine_t<float>(src, dst, g, out_i64);
+    case XRS_F64: return affine_t<double>(src, dst, g, out_i64);
+    case XRS_U8: return affine_t<uint8_t>(src, dst, g, out_i64);
+    case XRS_I16: return affine_t<int16_t>(src, dst, g, out_i64);
+    case XRS_U16: return affine_t<uint16_t>(src, dst, g, out_i64);
+    case XRS_I32: return affine_t<int32_t>(src, dst, g, out_i64);
+    }
+    return 2;
+}
+"""
+
+
+def build_k4(out_dir: str) -> str:
+    """Host build of resample_common.cuh + the device helpers of resample.cu (affine_sample, reduce_window)."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not available")
+    common = open(os.path.join(CSRC, "resample_common.cuh")).read()
+    common, n = re.subn(r'#include "common.cuh"\n', "", common)
+    assert n == 1
+    cu = open(os.path.join(CSRC, "resample.cu")).read()
+    start = cu.index('#include "resample_common.cuh"\n') + len('#include "resample_common.cuh"\n')
+    end = cu.index("// generic kernel: one thread per output pixel and slice")
+    end = cu.rindex("// ----", 0, end)  # the rule above the section title
+    helpers = cu[start:end] + "\n}  // namespace xrs\n"
+    text = (common + helpers).replace("#pragma once\n", "").replace("#pragma unroll\n", "").replace("__restrict__", "")
+    src = os.path.join(out_dir, "k4_host.cpp")
+    with open(src, "w") as fh:
+        fh.write(RESOLVE_SHIM + RESAMPLE_SHIM + "using std::fabs; using std::sqrt; using std::rint;\n" + text + K4_EXPORT)
+    so = os.path.join(out_dir, "libxrs_k4host.so")
+    cmd = [gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", f"-I{os.path.join(ROOT, 'include')}", src,
+           "-o", so]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("host build of resample.cu's helpers failed:\n" + res.stderr[-4000:])
+    return so
+
+
+def affine(so_path: str, src, out_hw, scale_ji=(1.0, 1.0), offset_ji=(0.0, 0.0), order=0, cval=0.0, agg="mean",
+           factors=(1, 1)) -> np.ndarray:
+    """One (h, w) image through the product's affine_sample + reduce_window on the CPU (the loop nest of
+    k4_affine_generic); output dtype as the library chooses it (int64 for mode / count / integer sum, prod)."""
+    from xcube_resampling_b200.constants import AGG_CODES, DTYPE_CODES
+
+    lib = ctypes.CDLL(so_path)
+    src = np.ascontiguousarray(src)
+    is_float = src.dtype.kind == "f"
+    f_j, f_i = int(factors[0]), int(factors[1])
+    i64 = f_j * f_i > 1 and (agg in ("mode", "count") or (not is_float and agg in ("sum", "prod")))
+    out = np.empty((int(out_hw[0]), int(out_hw[1])), dtype=np.int64 if i64 else src.dtype)
+    c_d, c_l, c_i, c_p = ctypes.c_double, ctypes.c_long, ctypes.c_int, ctypes.c_void_p
+    lib.xrsh_affine.restype = c_i
+    lib.xrsh_affine.argtypes = [c_p, c_p, c_i, c_l, c_l, c_l, c_l, c_d, c_d, c_d, c_d, c_i, c_d, c_i, c_i, c_i, c_i]
+    rc = lib.xrsh_affine(src.ctypes.data, out.ctypes.data, DTYPE_CODES[src.dtype], src.shape[0], src.shape[1], out.shape[0],
+                         out.shape[1], float(scale_ji[0]), float(offset_ji[0]), float(scale_ji[1]), float(offset_ji[1]),
+                         int(order), float(cval), AGG_CODES[agg], f_j, f_i, int(i64))
+    if rc:
+        raise RuntimeError(f"xrsh_affine failed ({rc})")
+    return out
