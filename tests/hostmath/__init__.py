@@ -554,3 +554,92 @@ def affine(so_path: str, src, out_hw, scale_ji=(1.0, 1.0), offset_ji=(0.0, 0.0),
     if rc:
         raise RuntimeError(f"xrsh_affine failed ({rc})")
     return out
+
+
+# ---------------------------------------------------------------------------
+# K5: the reducers of the streaming kernels on register windows (csrc/resample_fast.cu: bitonic network,
+# reduce_simple, reduce_sort)
+# ---------------------------------------------------------------------------
+K5_EXPORT = r"""
+template <typename T, typename OutT, int F>
+static void fast_host(const T *src, long src_w, OutT *dst, long dst_h, long dst_w, int agg) {
+    const bool sort = agg == XRS_AGG_MEDIAN || agg == XRS_AGG_MODE;   // CLASS_SORT of k5_window_reduce
+    for (long oj = 0; oj < dst_h; ++oj)
+        for (long oi = 0; oi < dst_w; ++oi) {
+            T w[F * F];
+            for (int a = 0; a < F; ++a)
+                for (int b = 0; b < F; ++b) w[a * F + b] = src[(oj * F + a) * src_w + oi * F + b];
+            dst[oj * dst_w + oi] = sort ? xrs::reduce_sort<T, OutT, F>(w, agg) : xrs::reduce_simple<T, OutT, F>(w, agg);
+        }
+}
+template <typename T, int F>
+static void fast_f(const void *src, long src_w, void *dst, long dst_h, long dst_w, int agg, int out_i64) {
+    if (out_i64) fast_host<T, int64_t, F>(static_cast<const T *>(src), src_w, static_cast<int64_t *>(dst), dst_h, dst_w, agg);
+    else fast_host<T, T, F>(static_cast<const T *>(src), src_w, static_cast<T *>(dst), dst_h, dst_w, agg);
+}
+template <typename T>
+static int fast_t(const void *src, long src_w, void *dst, long dst_h, long dst_w, int f, int agg, int out_i64) {
+    switch (f) {
+    case 2: fast_f<T, 2>(src, src_w, dst, dst_h, dst_w, agg, out_i64); return 0;
+    case 4: fast_f<T, 4>(src, src_w, dst, dst_h, dst_w, agg, out_i64); return 0;
+    case 8: fast_f<T, 8>(src, src_w, dst, dst_h, dst_w, agg, out_i64); return 0;
+    }
+    return 3;
+}
+extern "C" int xrsh_fast_reduce(const void *src, int dtype, long src_w, void *dst, long dst_h, long dst_w, int f, int agg,
+                                int out_i64) {
+    switch (dtype) {
+    case XRS_F32: return fast_t<float>(src, src_w, dst, dst_h, dst_w, f, agg, out_i64);
+    case XRS_F64: return fast_t<double>(src, src_w, dst, dst_h, dst_w, f, agg, out_i64);
+    case XRS_U8: return fast_t<uint8_t>(src, src_w, dst, dst_h, dst_w, f, agg, out_i64);
+    case XRS_I16: return fast_t<int16_t>(src, src_w, dst, dst_h, dst_w, f, agg, out_i64);
+    case XRS_U16: return fast_t<uint16_t>(src, src_w, dst, dst_h, dst_w, f, agg, out_i64);
+    case XRS_I32: return fast_t<int32_t>(src, src_w, dst, dst_h, dst_w, f, agg, out_i64);
+    }
+    return 2;
+}
+"""
+
+
+def build_k5(out_dir: str) -> str:
+    """Host build of resample_common.cuh + the register-window reducers of resample_fast.cu."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not available")
+    common = open(os.path.join(CSRC, "resample_common.cuh")).read()
+    common, n = re.subn(r'#include "common.cuh"\n', "", common)
+    assert n == 1
+    cu = open(os.path.join(CSRC, "resample_fast.cu")).read()
+    start = cu.index("// ---- sorting network")
+    end = cu.index("// tap k+1 of scipy's order-1 filter")
+    helpers = "namespace xrs {\n" + cu[start:end] + "\n}  // namespace xrs\n"
+    text = (common + helpers).replace("#pragma once\n", "").replace("#pragma unroll\n", "")
+    src = os.path.join(out_dir, "k5_host.cpp")
+    with open(src, "w") as fh:
+        fh.write(RESOLVE_SHIM + RESAMPLE_SHIM + "using std::fabs; using std::sqrt; using std::rint;\n" + text + K5_EXPORT)
+    so = os.path.join(out_dir, "libxrs_k5host.so")
+    cmd = [gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", f"-I{os.path.join(ROOT, 'include')}", src,
+           "-o", so]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("host build of resample_fast.cu's reducers failed:\n" + res.stderr[-4000:])
+    return so
+
+
+def fast_reduce(so_path: str, src, f: int, agg: str) -> np.ndarray:
+    """Block aggregation of one (h, w) image by f x f through the streaming kernels' reducers on the CPU."""
+    from xcube_resampling_b200.constants import AGG_CODES, DTYPE_CODES
+
+    lib = ctypes.CDLL(so_path)
+    src = np.ascontiguousarray(src)
+    is_float = src.dtype.kind == "f"
+    i64 = agg in ("mode", "count") or (not is_float and agg in ("sum", "prod"))
+    out = np.empty((src.shape[0] // f, src.shape[1] // f), dtype=np.int64 if i64 else src.dtype)
+    c_l, c_i, c_p = ctypes.c_long, ctypes.c_int, ctypes.c_void_p
+    lib.xrsh_fast_reduce.restype = c_i
+    lib.xrsh_fast_reduce.argtypes = [c_p, c_i, c_l, c_p, c_l, c_l, c_i, c_i, c_i]
+    rc = lib.xrsh_fast_reduce(src.ctypes.data, DTYPE_CODES[src.dtype], src.shape[1], out.ctypes.data, out.shape[0],
+                              out.shape[1], int(f), AGG_CODES[agg], int(i64))
+    if rc:
+        raise RuntimeError(f"xrsh_fast_reduce failed ({rc})")
+    return out
