@@ -643,3 +643,93 @@ def fast_reduce(so_path: str, src, f: int, agg: str) -> np.ndarray:
     if rc:
         raise RuntimeError(f"xrsh_fast_reduce failed ({rc})")
     return out
+
+
+# ---------------------------------------------------------------------------
+# K3: numpy's dtype semantics in the blend of _reproject_block (csrc/reproject.cu: window_index,
+# diff_as_f64, cast_like_numpy, k3_blend)
+# ---------------------------------------------------------------------------
+K3_SHIM = r"""
+#include <type_traits>
+static inline float __fsub_rn(float a, float b) { return a - b; }
+"""
+
+K3_EXPORT = r"""
+template <typename T, typename OUT>
+static void blend_host(int method, long n, const T *v00, const T *v01, const T *v10, const T *v11, const double *u,
+                       const double *v, OUT *out) {
+    for (long k = 0; k < n; ++k)
+        out[k] = method == XRS_BILINEAR ? xrs::k3_blend<T, OUT, XRS_BILINEAR>(v00[k], v01[k], v10[k], v11[k], u[k], v[k])
+                                        : xrs::k3_blend<T, OUT, XRS_TRIANGULAR>(v00[k], v01[k], v10[k], v11[k], u[k], v[k]);
+}
+template <typename T>
+static int blend_t(int out_f64, int method, long n, const void *a, const void *b, const void *c, const void *d,
+                   const double *u, const double *v, void *out) {
+    const T *p = static_cast<const T *>(a), *q = static_cast<const T *>(b), *r = static_cast<const T *>(c),
+            *s = static_cast<const T *>(d);
+    if (out_f64) blend_host<T, double>(method, n, p, q, r, s, u, v, static_cast<double *>(out));
+    else blend_host<T, T>(method, n, p, q, r, s, u, v, static_cast<T *>(out));
+    return 0;
+}
+extern "C" int xrsh_k3_blend(int dtype, int out_f64, int method, long n, const void *v00, const void *v01, const void *v10,
+                             const void *v11, const double *u, const double *v, void *out) {
+    switch (dtype) {
+    case XRS_F32: return blend_t<float>(out_f64, method, n, v00, v01, v10, v11, u, v, out);
+    case XRS_F64: return blend_t<double>(out_f64, method, n, v00, v01, v10, v11, u, v, out);
+    case XRS_U8: return blend_t<uint8_t>(out_f64, method, n, v00, v01, v10, v11, u, v, out);
+    case XRS_I8: return blend_t<int8_t>(out_f64, method, n, v00, v01, v10, v11, u, v, out);
+    case XRS_U16: return blend_t<uint16_t>(out_f64, method, n, v00, v01, v10, v11, u, v, out);
+    case XRS_I16: return blend_t<int16_t>(out_f64, method, n, v00, v01, v10, v11, u, v, out);
+    case XRS_I32: return blend_t<int32_t>(out_f64, method, n, v00, v01, v10, v11, u, v, out);
+    case XRS_U32: return blend_t<uint32_t>(out_f64, method, n, v00, v01, v10, v11, u, v, out);
+    case XRS_I64: return blend_t<int64_t>(out_f64, method, n, v00, v01, v10, v11, u, v, out);
+    }
+    return 2;
+}
+extern "C" int xrsh_window_index(long k, int n, long *out) {
+    int64_t kk = k;
+    const bool ok = xrs::window_index(kk, n);
+    *out = kk;
+    return ok ? 1 : 0;
+}
+"""
+
+
+def build_k3_blend(out_dir: str) -> str:
+    """Host build of the blend helpers of reproject.cu."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not available")
+    cu = open(os.path.join(CSRC, "reproject.cu")).read()
+    start = cu.index("// numpy index semantics inside the reference window")
+    end = cu.index("// A source tap.")
+    helpers = "namespace xrs {\n" + cu[start:end] + "\n}  // namespace xrs\n"
+    src = os.path.join(out_dir, "k3_blend_host.cpp")
+    with open(src, "w") as fh:
+        fh.write(RESOLVE_SHIM + K3_SHIM + helpers + K3_EXPORT)
+    so = os.path.join(out_dir, "libxrs_k3blendhost.so")
+    cmd = [gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", f"-I{os.path.join(ROOT, 'include')}", src,
+           "-o", so]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("host build of reproject.cu's blend helpers failed:\n" + res.stderr[-4000:])
+    return so
+
+
+def k3_blend(so_path: str, v00, v01, v10, v11, u, v, method: str, out_f64: bool) -> np.ndarray:
+    from xcube_resampling_b200.constants import DTYPE_CODES, INTERP_CODES
+
+    lib = ctypes.CDLL(so_path)
+    taps = [np.ascontiguousarray(t) for t in (v00, v01, v10, v11)]
+    dt = taps[0].dtype
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    out = np.empty(u.shape, dtype=np.float64 if out_f64 else dt)
+    c_l, c_i, c_p = ctypes.c_long, ctypes.c_int, ctypes.c_void_p
+    lib.xrsh_k3_blend.restype = c_i
+    lib.xrsh_k3_blend.argtypes = [c_i, c_i, c_i, c_l] + [c_p] * 7
+    rc = lib.xrsh_k3_blend(DTYPE_CODES[dt], int(out_f64), INTERP_CODES[method], u.size, *(t.ctypes.data for t in taps),
+                           u.ctypes.data, v.ctypes.data, out.ctypes.data)
+    if rc:
+        raise RuntimeError(f"xrsh_k3_blend failed ({rc})")
+    return out
