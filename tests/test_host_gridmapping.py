@@ -172,3 +172,64 @@ def test_from_coords_validation():
         GM.from_coords(np.zeros((2, 3)), np.zeros((3, 2)), WGS84)
     with pytest.raises(ValueError):
         GM.from_coords(np.array([1.0]), np.array([1.0]), WGS84)
+
+
+# ---- tests/gridmapping/test_base.py:90-172, 514-end ---------------------------------------------------
+_BASE = dict(size=(720, 360), tile_size=(360, 180), xy_bbox=(-180.0, -90.0, 180.0, 90.0), xy_res=(0.5, 0.5),
+             crs=WGS84, xy_var_names=("x", "y"), xy_dim_names=("x", "y"), is_regular=True, is_lon_360=False,
+             is_j_axis_up=False)
+
+
+def test_constructor_properties_and_tile_boxes():
+    gm = GM(**_BASE)
+    assert (gm.size, gm.width, gm.height) == ((720, 360), 720, 360)
+    assert (gm.is_tiled, gm.tile_size, gm.tile_width, gm.tile_height) == (True, (360, 180), 360, 180)
+    assert gm.ij_bbox == (0, 0, 720, 360) and gm.xy_bbox == (-180.0, -90.0, 180.0, 90.0)
+    assert (gm.x_min, gm.y_min, gm.x_max, gm.y_max) == (-180.0, -90.0, 180.0, 90.0)
+    assert (gm.xy_res, gm.x_res, gm.y_res) == ((0.5, 0.5), 0.5, 0.5)
+    assert gm.crs == WGS84 and gm.spatial_unit_name == "degree"
+    assert GM.regular((10, 10), (0, 0), 10, UTM).spatial_unit_name == "metre"
+    np.testing.assert_array_equal(gm.ij_bboxes, [[0, 0, 360, 180], [360, 0, 720, 180], [0, 180, 360, 360],
+                                                 [360, 180, 720, 360]])
+    np.testing.assert_array_equal(gm.xy_bboxes, [[-180.0, 0.0, 0.0, 90.0], [0.0, 0.0, 180.0, 90.0],
+                                                 [-180.0, -90.0, 0.0, 0.0], [0.0, -90.0, 180.0, 0.0]])
+
+
+@pytest.mark.parametrize("override, message", [
+    (dict(size=(360, 1)), "invalid size"),
+    (dict(size=(360,)), "not enough values to unpack (expected 2, got 1)"),
+    (dict(size=None), "size must be an int or a sequence of two ints"),
+    (dict(tile_size=0), "invalid tile_size"),
+    (dict(xy_res=-0.1), "invalid xy_res")])
+def test_constructor_rejects(override, message):
+    with pytest.raises(ValueError) as e:
+        GM(**dict(_BASE, **override))
+    assert str(e.value) == message
+
+
+def test_constructor_scalars_and_untiled():
+    gm = GM(**dict(_BASE, size=360, tile_size=180, xy_res=0.1))
+    assert (gm.size, gm.tile_size, gm.xy_res) == ((360, 360), (180, 180), (0.1, 0.1))
+    gm = GM(**dict(_BASE, tile_size=None))
+    assert gm.tile_size == (720, 360) and gm.is_tiled is False
+
+
+def test_non_regular_guards():
+    gm = GM(**dict(_BASE, is_regular=False))
+    with pytest.raises(ValueError, match="must be a regular grid mapping"):
+        GM.assert_regular(gm)
+    with pytest.raises(NotImplementedError, match="Operation not implemented for non-regular grid mappings"):
+        gm._assert_regular()
+
+
+def test_repr_markdown():
+    md = GM(**_BASE)._repr_markdown_()
+    for line in ("class: **GridMapping**", "* is_regular: True", "* is_j_axis_up: False", "* is_lon_360: False",
+                 "* crs: EPSG:4326", "* xy_res: (0.5, 0.5)", "* xy_bbox: (-180.0, -90.0, 180.0, 90.0)",
+                 "* ij_bbox: (0, 0, 720, 360)", "* xy_dim_names: ('x', 'y')", "* xy_var_names: ('x', 'y')",
+                 "* size: (720, 360)", "* tile_size: (360, 180)"):
+        assert line in md.split("\n")
+    md = GM(**dict(_BASE, is_regular=None, is_j_axis_up=None, is_lon_360=None))._repr_markdown_()
+    assert "* is_regular: _unknown_" in md and "* is_j_axis_up: _unknown_" in md and "* is_lon_360: _unknown_" in md
+    assert "* xy_res: (0.5, 0.5)  _estimated_" in md
+    assert str(xrs.CRS_CRS84) == "OGC:CRS84" and str(xrs.CRS.from_epsg(32633)) == "EPSG:32633"

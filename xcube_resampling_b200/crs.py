@@ -107,6 +107,19 @@ class CRS:
     def is_projected(self) -> bool:
         return self.kind != KIND_GEOGRAPHIC
 
+    @property
+    def unit_name(self) -> str:
+        """Unit of the first axis, as ``pyproj.CRS.axis_info[0].unit_name`` names it (gridmapping/base.py:402-404)."""
+        return "degree" if self.kind == KIND_GEOGRAPHIC else "metre"
+
+    def __str__(self) -> str:
+        """Authority string where there is one (what ``str(pyproj.CRS)`` prints for these), else the name."""
+        if self.epsg is not None:
+            return f"EPSG:{self.epsg}"
+        if self.kind == KIND_GEOGRAPHIC and not self.lat_first and self.a == WGS84_A and self.inv_f == WGS84_INV_F:
+            return "OGC:CRS84"
+        return self.name
+
     def _key(self):
         return (self.kind, self.a, self.inv_f, self.lon0, self.lat0, self.k0, self.fe, self.fn, self.lat_first)
 

@@ -258,6 +258,7 @@ class GridMapping:
     x_res = property(lambda self: self._xy_res[0])
     y_res = property(lambda self: self._xy_res[1])
     crs = property(lambda self: self._crs)
+    spatial_unit_name = property(lambda self: self._crs.unit_name)  # base.py:402-404 (axis_info[0].unit_name)
     is_lon_360 = property(lambda self: self._is_lon_360)
     is_regular = property(lambda self: self._is_regular)
     is_j_axis_up = property(lambda self: self._is_j_axis_up)
@@ -766,6 +767,19 @@ class GridMapping:
     def _assert_regular(self):
         if not self.is_regular:
             raise NotImplementedError("Operation not implemented for non-regular grid mappings")
+
+    def _repr_markdown_(self) -> str:
+        """Notebook representation, base.py:890-913: one bullet per property; unknown flags say so and the
+        resolution of a non-regular mapping is marked as an estimate."""
+        def flag(v):
+            return "_unknown_" if v is None else v
+
+        rows = [("is_regular", flag(self.is_regular)), ("is_j_axis_up", flag(self.is_j_axis_up)),
+                ("is_lon_360", flag(self.is_lon_360)), ("crs", self.crs),
+                ("xy_res", repr(self.xy_res) + ("" if self.is_regular else "  _estimated_")),
+                ("xy_bbox", self.xy_bbox), ("ij_bbox", self.ij_bbox), ("xy_dim_names", self.xy_dim_names),
+                ("xy_var_names", self.xy_var_names), ("size", self.size), ("tile_size", self.tile_size)]
+        return "\n".join([f"class: **{type(self).__name__}**"] + [f"* {k}: {v}" for k, v in rows])
 
     def __repr__(self):
         return (f"GridMapping(size={self.size}, tile_size={self.tile_size}, xy_bbox={self.xy_bbox}, "
