@@ -145,3 +145,65 @@ def test_add_spatial_ref_to_zarr_directory(tmp_path):
     assert "spatial_ref/.zarray" in meta and meta["band/.zattrs"]["grid_mapping"] == "spatial_ref"
     with pytest.raises(TypeError):
         add_spatial_ref(42, UTM_33N)
+
+
+def test_crs_in_dataset_attrs_with_wkt():
+    # test_cfconv.py:181-224: the CF attributes of EPSG:4326 (crs_wkt included) as DATASET attributes
+    wkt = ('GEOGCRS["WGS 84",ENSEMBLE["World Geodetic System 1984 ensemble",MEMBER["World Geodetic System 1984 '
+           '(Transit)"],ELLIPSOID["WGS 84",6378137,298.257223563,LENGTHUNIT["metre",1]],ENSEMBLEACCURACY[2.0]],'
+           'PRIMEM["Greenwich",0,ANGLEUNIT["degree",0.0174532925199433]],CS[ellipsoidal,2],AXIS["geodetic latitude '
+           '(Lat)",north,ORDER[1],ANGLEUNIT["degree",0.0174532925199433]],AXIS["geodetic longitude (Lon)",east,'
+           'ORDER[2],ANGLEUNIT["degree",0.0174532925199433]],ID["EPSG",4326]]')
+    ds = Dataset(coords=dict(lon=DataArray(np.linspace(10, 12, 11), dims="lon"),
+                             lat=DataArray(np.linspace(50, 52, 11), dims="lat")),
+                 attrs={"crs_wkt": wkt, "semi_major_axis": 6378137.0, "semi_minor_axis": 6356752.314245179,
+                        "inverse_flattening": 298.257223563, "reference_ellipsoid_name": "WGS 84",
+                        "longitude_of_prime_meridian": 0.0, "prime_meridian_name": "Greenwich",
+                        "geographic_crs_name": "WGS 84",
+                        "horizontal_datum_name": "World Geodetic System 1984 ensemble",
+                        "grid_mapping_name": "latitude_longitude"})
+    gms = get_dataset_grid_mapping_proxies(ds)
+    assert list(gms) == [None]
+    _check(gms[None], CRS_WGS84, "latitude_longitude", "lon", "lat")
+
+
+def test_single_point_coordinates_warn_once():
+    # test_cfconv.py:226-237: one-element coordinates are no grid
+    import warnings
+
+    ds = Dataset(coords=dict(lon=DataArray(np.array([10]), dims="lon"), lat=DataArray(np.array([50]), dims="lat")))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        get_dataset_grid_mapping_proxies(ds, emit_warnings=True)
+    assert len(w) == 1 and "missing x- and/or y-coordinates" in str(w[0].message)
+
+
+def test_bounds_detection_and_coordinates_attribute():
+    # test_cfconv.py:287-320
+    ds = Dataset(coords={"lon": DataArray(np.linspace(0, 10, 5), dims="lon"),
+                         "lat": DataArray(np.linspace(0, 5, 5), dims="lat"),
+                         "lon_bnds": DataArray(np.linspace(0, 10, 10), dims="bnds"),
+                         "lat_bounds": DataArray(np.linspace(0, 5, 10), dims="bnds"),
+                         "alt": DataArray(np.linspace(0, 100, 5), dims="alt")})
+    ds["lat"].attrs["bounds"] = "lat_bounds"
+    names = find_potential_coord_vars(ds)
+    assert {"lon", "lat", "alt"} <= set(names) and "lon_bnds" not in names and "lat_bounds" not in names
+    ds = Dataset({"x": DataArray(np.array([0, 1]), dims="dim_0"), "y": DataArray(np.array([0, 1]), dims="dim_0")},
+                 attrs={"coordinates": "x y"})
+    names = find_potential_coord_vars(ds)
+    assert "x" in names and "y" in names
+
+
+def test_add_spatial_ref_custom_variable_name(tmp_path):
+    # test_cfconv.py:430-470 (TestAddSpatialRef) on a directory store
+    store = tmp_path / "c.zarr"
+    os.makedirs(store / "data")
+    json.dump({"zarr_format": 2}, open(store / ".zgroup", "w"))
+    json.dump({"chunks": [3, 3], "compressor": None, "dtype": "<f4", "fill_value": 0.0, "filters": None, "order": "C",
+               "shape": [3, 3], "zarr_format": 2}, open(store / "data" / ".zarray", "w"))
+    json.dump({"_ARRAY_DIMENSIONS": ["y", "x"]}, open(store / "data" / ".zattrs", "w"))
+    add_spatial_ref(str(store), CRS_WGS84, crs_var_name="spatial_ref_test", xy_dim_names=("x", "y"))
+    sr = json.load(open(store / "spatial_ref_test" / ".zattrs"))
+    assert json.load(open(store / "spatial_ref_test" / ".zarray"))["shape"] == []
+    assert sr["_ARRAY_DIMENSIONS"] == [] and len(sr) > 1
+    assert json.load(open(store / "data" / ".zattrs"))["grid_mapping"] == "spatial_ref_test"
