@@ -6,6 +6,7 @@ passes none (rectify.py:112-118)."""
 import numpy as np
 import pytest
 
+import xcube_resampling_b200 as xrs
 from xcube_resampling_b200.crs import CRS
 from xcube_resampling_b200.dataset import DataArray
 from xcube_resampling_b200.gridmapping import GridMapping
@@ -146,3 +147,50 @@ def test_from_coords_skips_nan_in_the_edge_rows_and_columns():
         assert gm.size == clean.size
         for a, b in zip(gm.xy_bbox, clean.xy_bbox):
             assert abs(a - b) < 0.01
+
+
+def _s2plus_dataset():
+    """The two-grid-mapping Sentinel-2 sample of the reference's tests/sampledata.py:211-290: regular UTM x / y
+    (CF transverse_mercator variable) AND irregular 2-D lon / lat of the same 5x5 pixels."""
+    x = xrs.DataArray(310005.0 + 10.0 * np.arange(5), dims=["x"],
+                      attrs=dict(units="m", standard_name="projection_x_coordinate"))
+    y = xrs.DataArray(5689995.0 - 10.0 * np.arange(5), dims=["y"],
+                      attrs=dict(units="m", standard_name="projection_y_coordinate"))
+    lon = xrs.DataArray(np.array([[0.272763, 0.272906, 0.273050, 0.273193, 0.273336],
+                                  [0.272768, 0.272911, 0.273055, 0.273198, 0.273342],
+                                  [0.272773, 0.272917, 0.273060, 0.273204, 0.273347],
+                                  [0.272779, 0.272922, 0.273066, 0.273209, 0.273352],
+                                  [0.272784, 0.272927, 0.273071, 0.273214, 0.273358]]), dims=["y", "x"],
+                        attrs=dict(units="degrees_east", standard_name="longitude"))
+    lat = xrs.DataArray(np.array([[51.329464, 51.329464, 51.329468, 51.32947, 51.329475],
+                                  [51.329372, 51.329376, 51.32938, 51.329384, 51.329388],
+                                  [51.329285, 51.329285, 51.32929, 51.329292, 51.329296],
+                                  [51.329193, 51.329197, 51.32920, 51.329205, 51.329205],
+                                  [51.329100, 51.329105, 51.32911, 51.329113, 51.329117]]), dims=["y", "x"],
+                        attrs=dict(units="degrees_north", standard_name="latitude"))
+    rrs = xrs.DataArray(np.full((5, 5), 0.014), dims=["y", "x"],
+                        attrs=dict(units="sr-1", grid_mapping="transverse_mercator"))
+    tm = xrs.DataArray(np.array([0xFFFFFFFF], dtype=np.uint32), dims=["dim_0"], attrs=dict(
+        grid_mapping_name="transverse_mercator", scale_factor_at_central_meridian=0.9996,
+        longitude_of_central_meridian=3.0, latitude_of_projection_origin=0.0, false_easting=500000.0,
+        false_northing=0.0, semi_major_axis=6378137.0, inverse_flattening=298.257223563))
+    return xrs.Dataset(dict(rrs_443=rrs, rrs_665=rrs, transverse_mercator=tm), coords=dict(x=x, y=y, lon=lon, lat=lat))
+
+
+@pytest.mark.parametrize("prefer, projected, regular", [
+    ({}, True, True), (dict(prefer_is_regular=True), True, True), (dict(prefer_is_regular=False), False, False),
+    (dict(prefer_crs=GEO), False, False), (dict(prefer_crs=GEO, prefer_is_regular=True), False, False)])
+def test_from_dataset_picks_among_two_grid_mappings(prefer, projected, regular):
+    # tests/gridmapping/test_dataset.py:111-141
+    gm = xrs.GridMapping.from_dataset(_s2plus_dataset(), tolerance=1e-6, **prefer)
+    assert gm.crs.is_projected is projected and gm.is_regular is regular and gm.size == (5, 5)
+    if projected:
+        assert gm.xy_res == (10, 10) and gm.xy_bbox == (310000, 5689950, 310050, 5690000)
+        assert gm.crs == xrs.CRS.from_epsg(32631)  # found from the CF parameters alone
+
+
+def test_from_dataset_without_any_grid_mapping():
+    # tests/gridmapping/test_dataset.py:143-146
+    with pytest.raises(ValueError) as e:
+        xrs.GridMapping.from_dataset(xrs.Dataset())
+    assert str(e.value) == "cannot find any grid mapping in dataset"
