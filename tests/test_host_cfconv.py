@@ -207,3 +207,20 @@ def test_add_spatial_ref_custom_variable_name(tmp_path):
     assert json.load(open(store / "spatial_ref_test" / ".zarray"))["shape"] == []
     assert sr["_ARRAY_DIMENSIONS"] == [] and len(sr) > 1
     assert json.load(open(store / "data" / ".zattrs"))["grid_mapping"] == "spatial_ref_test"
+
+
+@pytest.mark.parametrize("coords, x_name, y_name", [
+    (dict(rlon=("rlon", {}), rlat=("rlat", {})), "rlon", "rlat"),
+    (dict(u=("u", dict(standard_name="grid_longitude")), v=("v", dict(standard_name="grid_latitude"))), "u", "v")])
+def test_rotated_pole_is_discovered(coords, x_name, y_name):
+    # test_cfconv.py:239-285: a grid mapping this build cannot transform is still found with its coordinates
+    pole = dict(grid_mapping_name="rotated_latitude_longitude", grid_north_pole_latitude=32.5,
+                grid_north_pole_longitude=170.0)
+    values = {x_name: np.linspace(-180, 180, 11), y_name: np.linspace(0, 90, 11)}
+    ds = Dataset(dict(rotated_pole=DataArray(np.array(0), dims=(), attrs=pole)),
+                 coords={n: DataArray(values[n], dims=d, attrs=a) for n, (d, a) in coords.items()})
+    gms = get_dataset_grid_mapping_proxies(ds)
+    assert list(gms) == ["rotated_pole"]
+    gmp = gms["rotated_pole"]
+    assert gmp.crs.is_geographic and not gmp.crs.has_device_formulas and gmp.name == "rotated_latitude_longitude"
+    assert gmp.coords.x.name == x_name and gmp.coords.y.name == y_name

@@ -29,9 +29,57 @@ def test_epsg_families():
     assert CRS.from_epsg(3857).kind == KIND_WEBMERC
     laea = CRS.from_epsg(3035)
     assert laea.kind == KIND_LAEA and (laea.lon0, laea.lat0, laea.fe, laea.fn) == (10.0, 52.0, 4321000.0, 3210000.0)
-    for bad in (2154, 32661, 32700, 25839, 0):
-        with pytest.raises(ValueError, match="not supported"):
-            CRS.from_epsg(bad)
+    with pytest.raises(ValueError, match="not a CRS code"):
+        CRS.from_epsg(0)
+
+
+def test_crs_without_device_formulas():
+    """Codes and CF grid mappings this build has no formulas for (the reference's own tests use EPSG:5243, a
+    Lambert conformal conic, as "some projected CRS"): usable wherever no transform is needed, compared by
+    code, and a clear error when projection parameters are asked for."""
+    from xcube_resampling_b200.crs import KIND_OPAQUE
+
+    for code in (2154, 5243, 27700, 3031, 32661, 25839):
+        crs = CRS.from_epsg(code)
+        assert crs.kind == KIND_OPAQUE and crs.is_projected and not crs.is_geographic and not crs.has_device_formulas
+        assert crs == CRS.from_string(f"EPSG:{code}") and crs == code and str(crs) == f"EPSG:{code}"
+        assert crs != CRS.from_epsg(32632) and crs != CRS.from_epsg(code + 1) and crs.unit_name == "metre"
+        assert CRS.from_cf(crs.to_cf()) == crs and hash(CRS.from_cf(crs.to_cf())) == hash(crs)
+        with pytest.raises(ValueError, match="no projection formulas"):
+            crs.proj_params()
+    nad83 = CRS.from_epsg(4269)
+    assert nad83.kind == KIND_OPAQUE and nad83.is_geographic and nad83.unit_name == "degree" and nad83 != CRS_WGS84
+    assert CRS.from_epsg(32632).has_device_formulas and CRS_WGS84.has_device_formulas
+    # CF attributes of an unknown grid mapping: kept verbatim, compared by content
+    lcc = dict(grid_mapping_name="lambert_conformal_conic", standard_parallel=[48.0, 54.0],
+               longitude_of_central_meridian=10.5, latitude_of_projection_origin=51.0, false_easting=0.0,
+               false_northing=0.0)
+    a, b = CRS.from_cf(lcc), CRS.from_cf(dict(lcc))
+    assert a.kind == KIND_OPAQUE and a.is_projected and a == b and hash(a) == hash(b) and a.to_cf()["grid_mapping_name"] \
+        == "lambert_conformal_conic"
+    assert a != CRS.from_cf(dict(lcc, longitude_of_central_meridian=11.0))
+    pole = CRS.from_cf(dict(grid_mapping_name="rotated_latitude_longitude", grid_north_pole_latitude=32.5,
+                            grid_north_pole_longitude=170.0))
+    assert pole.kind == KIND_OPAQUE and pole.is_geographic  # pyproj: "Derived Geographic 2D CRS"
+    # the EPSG identifier a WKT string closes with wins over an unknown grid mapping name (rioxarray's spatial_ref)
+    wkt = ('PROJCRS["ETRS89 / LCC Germany (N-E)",BASEGEOGCRS["ETRS89",DATUM["x",ELLIPSOID["GRS 1980",6378137,298.257222101]],'
+           'ID["EPSG",4258]],CONVERSION["LCC Germany",METHOD["Lambert Conic Conformal (2SP)",ID["EPSG",9802]]],'
+           'CS[Cartesian,2],ID["EPSG",5243]]')
+    assert CRS.from_cf(dict(grid_mapping_name="lambert_conformal_conic", crs_wkt=wkt)) == CRS.from_epsg(5243)
+    assert CRS.from_cf(dict(grid_mapping_name="mercator", crs_wkt='PROJCRS["WGS 84 / Pseudo-Mercator",ID["EPSG",3857]]')) \
+        == CRS.from_epsg(3857)
+    wkt1 = 'PROJCS["OSGB 1936 / British National Grid",GEOGCS["OSGB 1936",AUTHORITY["EPSG","4277"]],AUTHORITY["EPSG","27700"]]'
+    assert CRS.from_cf(dict(grid_mapping_name="transverse_mercator_x", spatial_ref=wkt1)) == CRS.from_epsg(27700)
+    with pytest.raises(ValueError):  # no grid mapping at all: still not a CRS
+        CRS.from_cf(dict(units="m", long_name="reflectance"))
+
+    class Pyproj:  # a duck-typed pyproj.CRS knows whether it is geographic
+        is_geographic = True
+
+        def to_epsg(self):
+            return 4170
+
+    assert normalize_crs(Pyproj()).is_geographic and normalize_crs(Pyproj()) == CRS.from_epsg(4170)
 
 
 def test_strings_and_normalize():

@@ -19,7 +19,17 @@ WGS84_INV_F = 298.257223563
 GRS80_INV_F = 298.257222101
 
 KIND_GEOGRAPHIC, KIND_TMERC, KIND_WEBMERC, KIND_LAEA = 0, 1, 2, 3
+# A CRS this build holds no device formulas for (Lambert conformal conic, polar stereographic, national
+# grids, rotated poles ...).  It can name the grid of a dataset and be compared -- everything the same-CRS
+# paths need (affine_transform_dataset, rectify within one CRS, utils.py:186-189) -- but asking for its
+# projection parameters, i.e. for a transform from or to it, is an error.
+KIND_OPAQUE = -1
 _KIND_NAMES = {0: "latitude_longitude", 1: "transverse_mercator", 2: "mercator", 3: "lambert_azimuthal_equal_area"}
+# EPSG codes of geographic CRSs that are met in Earth-observation products; any other code without device
+# formulas is taken as projected (there is no EPSG database in this build)
+_GEOGRAPHIC_EPSG = frozenset({4019, 4030, 4035, 4047, 4148, 4167, 4171, 4173, 4230, 4267, 4269, 4272, 4283, 4289, 4312,
+                              4313, 4314, 4322, 4490, 4612, 4617, 4619, 4674, 4937, 4979, 6318, 6668, 7844, 9057})
+_GEOGRAPHIC_CF_NAMES = ("latitude_longitude", "rotated_latitude_longitude")
 
 
 @dataclasses.dataclass(frozen=True)
@@ -39,6 +49,9 @@ class CRS:
     # EPSG:4326 has (lat, lon) axis order, OGC:CRS84 (lon, lat).  Transforms always
     # run always_xy=True (reproject.py:124-126) so this only affects equality.
     lat_first: bool = False
+    # KIND_OPAQUE only: is it geographic, and the CF attributes it was read from (sorted items)
+    opaque_geographic: bool = False
+    cf: tuple = ()
 
     # -- construction ------------------------------------------------------
     @staticmethod
@@ -62,8 +75,9 @@ class CRS:
         if code == 3035:
             return CRS(KIND_LAEA, "ETRS89-extended / LAEA Europe", inv_f=GRS80_INV_F, lon0=10.0, lat0=52.0,
                        fe=4321000.0, fn=3210000.0, epsg=3035)
-        raise ValueError(f"EPSG:{code} is not supported by the B200 resampling path "
-                         "(supported: 4326, 4258, 326xx/327xx, 258xx, 3857, 3035)")
+        if not 1024 <= code <= 32767:
+            raise ValueError(f"EPSG:{code} is not a CRS code")
+        return CRS(KIND_OPAQUE, f"EPSG:{code}", epsg=code, opaque_geographic=code in _GEOGRAPHIC_EPSG)
 
     @staticmethod
     def from_string(text: str) -> "CRS":
@@ -81,6 +95,15 @@ class CRS:
         if "epsg_code" in attrs:
             return CRS.from_string(str(attrs["epsg_code"]))
         name = attrs.get("grid_mapping_name")
+        if name not in _KIND_NAMES.values() or (name == "mercator" and "crs_wkt" in attrs):
+            code = _epsg_of_wkt(attrs.get("crs_wkt") or attrs.get("spatial_ref"))
+            if code is not None:
+                return CRS.from_epsg(code)
+            if isinstance(name, str) and name and name != "mercator":
+                items = tuple(sorted((str(k), v if isinstance(v, (str, int, float, bool)) else repr(v))
+                                     for k, v in attrs.items()))
+                return CRS(KIND_OPAQUE, str(attrs.get("crs_name") or attrs.get("projected_crs_name") or name),
+                           opaque_geographic=name in _GEOGRAPHIC_CF_NAMES, cf=items)
         a = float(attrs.get("semi_major_axis", WGS84_A))
         inv_f = float(attrs.get("inverse_flattening", WGS84_INV_F))
         if name == "latitude_longitude":
@@ -101,16 +124,21 @@ class CRS:
     # -- pyproj-like surface used by the hot path --------------------------
     @property
     def is_geographic(self) -> bool:
-        return self.kind == KIND_GEOGRAPHIC
+        return self.kind == KIND_GEOGRAPHIC or (self.kind == KIND_OPAQUE and self.opaque_geographic)
 
     @property
     def is_projected(self) -> bool:
-        return self.kind != KIND_GEOGRAPHIC
+        return not self.is_geographic
+
+    @property
+    def has_device_formulas(self) -> bool:
+        """False for a CRS that can only take part in same-CRS operations."""
+        return self.kind != KIND_OPAQUE
 
     @property
     def unit_name(self) -> str:
         """Unit of the first axis, as ``pyproj.CRS.axis_info[0].unit_name`` names it (gridmapping/base.py:402-404)."""
-        return "degree" if self.kind == KIND_GEOGRAPHIC else "metre"
+        return "degree" if self.is_geographic else "metre"
 
     def __str__(self) -> str:
         """Authority string where there is one (what ``str(pyproj.CRS)`` prints for these), else the name."""
@@ -121,6 +149,8 @@ class CRS:
         return self.name
 
     def _key(self):
+        if self.kind == KIND_OPAQUE:
+            return (KIND_OPAQUE, self.epsg, self.cf if self.epsg is None else ())
         return (self.kind, self.a, self.inv_f, self.lon0, self.lat0, self.k0, self.fe, self.fn, self.lat_first)
 
     def equals(self, other: Any) -> bool:
@@ -138,6 +168,8 @@ class CRS:
 
     def to_cf(self) -> dict:
         """CF grid-mapping attributes (subset of what ``pyproj.CRS.to_cf`` emits)."""
+        if self.kind == KIND_OPAQUE:
+            return dict(self.cf) if self.epsg is None else {"crs_name": self.name, "epsg_code": f"EPSG:{self.epsg}"}
         cf = {
             "grid_mapping_name": _KIND_NAMES[self.kind],
             "semi_major_axis": self.a,
@@ -158,11 +190,24 @@ class CRS:
 
     def proj_params(self) -> tuple:
         """(kind, a, inv_f, lon0, lat0, k0, fe, fn) for ``struct xrs_proj``."""
+        if self.kind == KIND_OPAQUE:
+            raise ValueError(f"{self} has no projection formulas in the B200 resampling path: it can be resampled "
+                             "within itself, but not transformed (supported: EPSG 4326, 4258, 326xx/327xx, 258xx, "
+                             "3857, 3035 and CF transverse_mercator / lambert_azimuthal_equal_area parameters)")
         return (self.kind, self.a, self.inv_f, self.lon0, self.lat0, self.k0, self.fe, self.fn)
 
 
 CRS_WGS84 = CRS.from_epsg(4326)
 CRS_CRS84 = CRS.from_string("OGC:CRS84")
+
+
+def _epsg_of_wkt(wkt) -> int | None:
+    """The EPSG code a WKT string closes with (WKT2 ``ID["EPSG",n]]`` / WKT1 ``AUTHORITY["EPSG","n"]]``): the
+    identifier of the CRS itself, not of one of its components."""
+    if not isinstance(wkt, str):
+        return None
+    m = re.search(r'(?:ID|AUTHORITY)\[\s*"EPSG"\s*,\s*"?(\d+)"?\s*\]\s*\]\s*$', wkt.strip())
+    return int(m.group(1)) if m else None
 
 
 def normalize_crs(crs: Any) -> CRS:
@@ -177,9 +222,10 @@ def normalize_crs(crs: Any) -> CRS:
     to_epsg = getattr(crs, "to_epsg", None)
     if callable(to_epsg):
         code = to_epsg()
-        if code is not None:
-            return CRS.from_epsg(code)
         to_cf = getattr(crs, "to_cf", None)
-        if callable(to_cf):
-            return CRS.from_cf(to_cf())
+        out = CRS.from_epsg(code) if code is not None else CRS.from_cf(to_cf()) if callable(to_cf) else None
+        if out is not None:
+            if out.kind == KIND_OPAQUE and isinstance(getattr(crs, "is_geographic", None), bool):
+                out = dataclasses.replace(out, opaque_geographic=crs.is_geographic)  # the object knows better
+            return out
     raise TypeError(f"crs must be a CRS, an EPSG code or a CRS string, was {type(crs)}")
