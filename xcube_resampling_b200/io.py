@@ -9,10 +9,13 @@ overlap, and the host never holds more than two chunks of a variable.
 
 Stores understood without third-party packages:
 
-* :class:`ZarrV2Source` -- an UNCOMPRESSED Zarr-v2 array in a directory store (``.zarray`` with
-  ``"compressor": null``, C order, any chunking): what ``add_spatial_ref`` (``cfconv.py``) and the
-  reference's Zarr helpers operate on.  Compressed stores need the ``zarr`` / ``numcodecs``
-  packages, which this build does not have; open them with xarray and pass the arrays instead.
+* :class:`ZarrV2Source` -- a Zarr-v2 array in a directory store (C order, any chunking): what
+  ``add_spatial_ref`` (``cfconv.py``) and the reference's Zarr helpers operate on.  Chunks may be
+  uncompressed (``"compressor": null``: read straight into the staging buffer) or compressed with a
+  codec whose stream format the standard library or pyarrow decodes (numcodecs ids ``zlib``, ``gzip``,
+  ``bz2``, ``lzma``, ``zstd``, ``lz4``), decoded on the reader thread.  Blosc frames and filters need
+  the ``zarr`` / ``numcodecs`` packages, which this build does not have; open such stores with xarray
+  and pass the arrays instead.
 * :class:`NpySource` -- a ``.npy`` file, memory-mapped.
 
 :func:`open_zarr_dataset` assembles a :class:`~xcube_resampling_b200.dataset.Dataset` from a
@@ -28,6 +31,73 @@ import os
 import numpy as np
 
 from .dataset import DataArray, Dataset
+
+
+def _pyarrow_codec(name: str):
+    try:
+        import pyarrow as pa
+    except ImportError as e:  # pragma: no cover - pyarrow is part of the image
+        raise NotImplementedError(f"{name}-compressed Zarr chunks need pyarrow (or the zarr package)") from e
+    return pa.Codec(name)
+
+
+def chunk_decoder(compressor: dict | None):
+    """``bytes -> bytes`` for a Zarr-v2 ``compressor`` entry (numcodecs configuration), ``None`` for
+    uncompressed chunks; ``NotImplementedError`` for codecs this build cannot decode."""
+    if compressor is None:
+        return None
+    cid = compressor.get("id")
+    if cid == "zlib":
+        import zlib
+
+        return zlib.decompress
+    if cid == "gzip":
+        import gzip
+
+        return gzip.decompress
+    if cid == "bz2":
+        import bz2
+
+        return bz2.decompress
+    if cid == "lzma":
+        import lzma
+
+        fmt, filters = compressor.get("format", lzma.FORMAT_XZ), compressor.get("filters")
+        return lambda raw: lzma.decompress(raw, format=fmt, filters=filters)
+    if cid == "zstd":
+        codec = _pyarrow_codec("zstd")
+
+        def zstd(raw):  # a standard frame; its header carries the decoded size
+            size = _zstd_content_size(raw)
+            if size is None:
+                raise NotImplementedError("zstd frame without a content size")
+            return codec.decompress(raw, decompressed_size=size).to_pybytes()
+
+        return zstd
+    if cid == "lz4":
+        codec = _pyarrow_codec("lz4_raw")
+
+        def lz4(raw):  # numcodecs: little-endian int32 decoded size, then one raw LZ4 block
+            size = int.from_bytes(raw[:4], "little", signed=True)
+            return codec.decompress(raw[4:], decompressed_size=size).to_pybytes()
+
+        return lz4
+    raise NotImplementedError(f"Zarr chunks compressed with {cid!r} need the zarr package, which this build does not "
+                              "have; open the store with xarray and pass the arrays instead")
+
+
+def _zstd_content_size(raw: bytes) -> int | None:
+    """Frame_Content_Size of a zstd frame header (RFC 8878, 3.1.1.1), ``None`` if the frame omits it."""
+    if len(raw) < 6 or raw[:4] != b"\x28\xb5\x2f\xfd":
+        raise ValueError("not a zstd frame")
+    desc = raw[4]
+    fcs_flag, single_segment, dict_flag = desc >> 6, (desc >> 5) & 1, desc & 3
+    pos = 5 + (0 if single_segment else 1) + (0, 1, 2, 4)[dict_flag]
+    n = (1 if single_segment else 0, 2, 4, 8)[fcs_flag]
+    if n == 0:
+        return None
+    value = int.from_bytes(raw[pos:pos + n], "little")
+    return value + 256 if n == 2 else value
 
 
 class LazySource:
@@ -70,15 +140,20 @@ class NpySource(LazySource):
 
 
 class ZarrV2Source(LazySource):
-    """One uncompressed Zarr-v2 array of a directory store (2-D or 3-D, C order)."""
+    """One Zarr-v2 array of a directory store (2-D or 3-D, C order; uncompressed or with a codec of
+    :func:`chunk_decoder`)."""
 
     def __init__(self, path: str):
         meta = json.load(open(os.path.join(path, ".zarray")))
         if meta.get("zarr_format") != 2:
             raise ValueError(f"{path}: not a Zarr v2 array")
-        if meta.get("compressor") is not None or meta.get("filters"):
-            raise NotImplementedError(f"{path}: compressed / filtered Zarr arrays need the zarr package, which this "
+        if meta.get("filters"):
+            raise NotImplementedError(f"{path}: filtered Zarr arrays need the zarr package, which this "
                                       "build does not have; open the store with xarray and pass the arrays instead")
+        try:
+            self._decode = chunk_decoder(meta.get("compressor"))
+        except NotImplementedError as e:
+            raise NotImplementedError(f"{path}: {e}") from None
         if meta.get("order", "C") != "C":
             raise NotImplementedError(f"{path}: only C-order chunks are supported")
         self.path = path
@@ -97,7 +172,10 @@ class ZarrV2Source(LazySource):
         if not os.path.isfile(p):  # a missing chunk is all fill value
             fill = self.fill if self.fill not in (None, "NaN") else (np.nan if self.dtype.kind == "f" else 0)
             return np.full(self.chunks, fill, dtype=self.dtype)
-        return np.fromfile(p, dtype=self.dtype).reshape(self.chunks)
+        if self._decode is None:
+            return np.fromfile(p, dtype=self.dtype).reshape(self.chunks)
+        with open(p, "rb") as fh:
+            return np.frombuffer(self._decode(fh.read()), dtype=self.dtype).reshape(self.chunks)
 
     def read_bands(self, b0, nb, out):
         three_d = len(self.shape) == 3
