@@ -733,3 +733,224 @@ def k3_blend(so_path: str, v00, v01, v10, v11, u, v, method: str, out_f64: bool)
     if rc:
         raise RuntimeError(f"xrsh_k3_blend failed ({rc})")
     return out
+
+
+# ---------------------------------------------------------------------------
+# K1 as a whole (csrc/rectify_ij.cu: k1_init_claims, k1_scatter, k1_scatter_slow, k1_resolve)
+# ---------------------------------------------------------------------------
+# The kernels' text is compiled unchanged.  CUDA's execution model is supplied by the shim: threadIdx /
+# blockIdx are thread-local variables, a WARP is 32 host threads that run the kernel body for the same
+# (block, warp) in lock step -- __shfl_down_sync / __shfl_sync / __ballot_sync exchange through a shared
+# array between two barrier waits -- and atomics are GCC atomics.  k1_scatter's early returns are
+# warp-uniform, so every lane meets the same sequence of collectives.
+K1_SHIM = r"""
+#include <pthread.h>
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "xrs.h"
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __grid_constant__
+typedef void *cudaStream_t;
+using std::min; using std::max; using std::isfinite;
+struct xrsh_dim3 { unsigned x = 0, y = 0, z = 0; };
+static thread_local xrsh_dim3 threadIdx, blockIdx, blockDim, gridDim;
+namespace xrs {
+static inline double dadd(double a, double b) { return a + b; }
+static inline double dsub(double a, double b) { return a - b; }
+static inline double dmul(double a, double b) { return a * b; }
+static inline double ddiv(double a, double b) { return a / b; }
+template <typename T> static inline void st_stream(T *p, T v) { *p = v; }
+}
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+template <typename T> static inline T __ldcs(const T *p) { return *p; }
+static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) {
+    return static_cast<unsigned long long>((static_cast<unsigned __int128>(a) * b) >> 64);
+}
+static inline int __double2hiint(double d) { uint64_t b; std::memcpy(&b, &d, 8); return static_cast<int>(static_cast<uint32_t>(b >> 32)); }
+static inline int __double2int_rd(double d) { return static_cast<int>(std::floor(d)); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline void __syncthreads() {}
+struct uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+template <typename T> static inline T atomicMin(T *p, T v) {
+    T old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+template <typename T> static inline T atomicMax(T *p, T v) {
+    T old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v > old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+// one warp = 32 host threads in lock step
+struct XrshWarp { pthread_barrier_t bar; double d[32]; long long i[32]; };
+static XrshWarp xrsh_warp;
+static thread_local int xrsh_lane = 0;
+static thread_local bool xrsh_in_warp = false;
+static inline void xrsh_sync() { pthread_barrier_wait(&xrsh_warp.bar); }
+static inline double __shfl_down_sync(unsigned, double v, int delta) {
+    xrsh_warp.d[xrsh_lane] = v; xrsh_sync();
+    const double r = xrsh_lane + delta < 32 ? xrsh_warp.d[xrsh_lane + delta] : v; xrsh_sync();
+    return r;
+}
+static inline int __shfl_down_sync(unsigned, int v, int delta) {
+    xrsh_warp.i[xrsh_lane] = v; xrsh_sync();
+    const int r = xrsh_lane + delta < 32 ? static_cast<int>(xrsh_warp.i[xrsh_lane + delta]) : v; xrsh_sync();
+    return r;
+}
+static inline unsigned __shfl_sync(unsigned, unsigned v, int src) {
+    xrsh_warp.i[xrsh_lane] = v; xrsh_sync();
+    const unsigned r = static_cast<unsigned>(xrsh_warp.i[src]); xrsh_sync();
+    return r;
+}
+static inline unsigned __ballot_sync(unsigned, bool p) {
+    xrsh_warp.i[xrsh_lane] = p ? 1 : 0; xrsh_sync();
+    unsigned m = 0;
+    for (int k = 0; k < 32; ++k) m |= static_cast<unsigned>(xrsh_warp.i[k]) << k;
+    xrsh_sync();
+    return m;
+}
+"""
+
+K1_EXPORT = r"""
+namespace {
+struct XrshJob { xrs::IjGeom g; unsigned gx, gy; };
+struct XrshLane { int lane; const XrshJob *job; };
+void *xrsh_lane_main(void *p) {
+    const XrshLane *a = static_cast<const XrshLane *>(p);
+    xrsh_lane = a->lane;
+    blockDim.x = xrs::K1S_WARPS * 32; blockDim.y = blockDim.z = 1;
+    gridDim.x = a->job->gx; gridDim.y = a->job->gy; gridDim.z = 1;
+    for (unsigned by = 0; by < a->job->gy; ++by)
+        for (unsigned bx = 0; bx < a->job->gx; ++bx)
+            for (int w = 0; w < xrs::K1S_WARPS; ++w) {
+                blockIdx.x = bx; blockIdx.y = by; threadIdx.x = static_cast<unsigned>(w * 32 + a->lane);
+                xrs::k1_scatter(a->job->g);
+            }
+    return nullptr;
+}
+}
+
+// xrs_rectify_ij (csrc/rectify_ij.cu) on the host: the geometry of k1_make_geom, then the four kernels in
+// launch order with the launch shapes of k1_enqueue_claims / xrs_rectify_ij.  ij: (2, row_end - row_begin, dst_w);
+// claims_out: (row_end - row_begin, dst_w); counts: [queued quads]
+extern "C" int xrsh_k1(const double *x, const double *y, long src_h, long src_w, long src_pitch, const int64_t *tile_boxes,
+                       double *ij, long dst_h, long dst_w, int tile_h, int tile_w, double x_min, double y_min,
+                       double y_max, double x_res, double y_res, int j_up, double uv_delta, long row_begin, long row_end,
+                       const int32_t *fp_cols, uint32_t *claims_out, unsigned *counts) {
+    using namespace xrs;
+    const long n_rows = row_end - row_begin, n_quads = (src_h - 1) * (src_w - 1);
+    const long n_rb = (src_h - 1 + K1S_ROWS - 1) / K1S_ROWS;
+    std::vector<uint32_t> claims(static_cast<size_t>(n_rows * dst_w), K1_NOCLAIM);
+    std::vector<uint32_t> queue(static_cast<size_t>(n_quads + 4 + 2 * n_rb), 0u);
+    IjGeom g = {};
+    g.x = x; g.y = y; g.src_h = src_h; g.src_w = src_w; g.src_pitch = src_pitch;
+    g.tile_boxes = tile_boxes; g.ij = ij; g.claims = claims.data();
+    g.dst_h = dst_h; g.dst_w = dst_w;
+    g.tile_h = tile_h < dst_h ? tile_h : static_cast<int>(dst_h);
+    g.tile_w = tile_w < dst_w ? tile_w : static_cast<int>(dst_w);
+    g.ntx = static_cast<int>((dst_w + g.tile_w - 1) / g.tile_w);
+    g.nty = static_cast<int>((dst_h + g.tile_h - 1) / g.tile_h);
+    g.x_min = x_min; g.y_min = y_min; g.y_max = y_max; g.x_res = x_res; g.y_res = y_res;
+    g.j_up = j_up ? 1 : 0; g.uv_delta = uv_delta;
+    g.row_begin = row_begin; g.row_end = row_end;
+    g.fp_cols = fp_cols;
+    g.magic_nqi = div_magic_of(static_cast<uint64_t>(src_w - 1));
+    g.magic_tw = div_magic_of(static_cast<uint64_t>(g.tile_w));
+    g.magic_th = div_magic_of(static_cast<uint64_t>(g.tile_h));
+    g.slow_list = queue.data();
+    g.slow_count = queue.data() + n_quads;
+    // k1_init_claims: the claim words are set above; block 0 (one thread) derives the quad row / column ranges
+    blockIdx = xrsh_dim3(); threadIdx = xrsh_dim3(); blockDim = xrsh_dim3(); blockDim.x = 1; gridDim = xrsh_dim3(); gridDim.x = 1;
+    k1_init_claims(reinterpret_cast<uint4 *>(claims.data()), 0, g.slow_count, g);
+    // k1_scatter: 32 lanes in lock step over every (block, warp)
+    XrshJob job{g, static_cast<unsigned>(((src_w - 1 + 30) / 31 + K1S_WARPS - 1) / K1S_WARPS), static_cast<unsigned>(n_rb)};
+    pthread_barrier_init(&xrsh_warp.bar, nullptr, 32);
+    pthread_t th[32];
+    XrshLane lanes[32];
+    for (int l = 0; l < 32; ++l) {
+        lanes[l] = XrshLane{l, &job};
+        if (pthread_create(&th[l], nullptr, xrsh_lane_main, &lanes[l]) != 0) return 1;
+    }
+    for (int l = 0; l < 32; ++l) pthread_join(th[l], nullptr);
+    pthread_barrier_destroy(&xrsh_warp.bar);
+    counts[0] = *g.slow_count;
+    // k1_scatter_slow: one thread strides over the queue
+    blockIdx = xrsh_dim3(); threadIdx = xrsh_dim3(); blockDim.x = 1; gridDim.x = 1;
+    k1_scatter_slow(g);
+    std::memcpy(claims_out, claims.data(), claims.size() * sizeof(uint32_t));
+    // k1_resolve: grid (ceil(dst_w / (K1R_THREADS * K1R_PX)), n_rows) x K1R_THREADS
+    blockDim.x = K1R_THREADS;
+    gridDim.x = static_cast<unsigned>((dst_w + K1R_THREADS * K1R_PX - 1) / (K1R_THREADS * K1R_PX));
+    gridDim.y = static_cast<unsigned>(n_rows);
+    for (unsigned by = 0; by < gridDim.y; ++by)
+        for (unsigned bx = 0; bx < gridDim.x; ++bx)
+            for (unsigned t = 0; t < static_cast<unsigned>(K1R_THREADS); ++t) {
+                blockIdx.x = bx; blockIdx.y = by; threadIdx.x = t;
+                k1_resolve(g);
+            }
+    return 0;
+}
+"""
+
+
+def build_k1(out_dir: str) -> str:
+    """Host build of rectify_common.cuh + the kernels of rectify_ij.cu (everything above its host launch code)."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not available")
+    common = open(os.path.join(CSRC, "rectify_common.cuh")).read()
+    common, n = re.subn(r'#include "common.cuh"\n', "", common)
+    assert n == 1, "rectify_common.cuh no longer includes common.cuh exactly once"
+    common = common.replace("#pragma once\n", "")
+    text = open(os.path.join(CSRC, "rectify_ij.cu")).read()
+    text, n = re.subn(r'#include "rectify_common.cuh"\n', "", text)
+    assert n == 1, "rectify_ij.cu no longer includes rectify_common.cuh exactly once"
+    cut = text.find("static int64_t claims_bytes_of")
+    assert cut > 0 and "<<<" not in text[:cut] and "k1_resolve(const" in text[:cut], "layout of rectify_ij.cu changed"
+    kernels = text[:cut] + "\n}  // namespace xrs\n"
+    src = os.path.join(out_dir, "k1_host.cpp")
+    with open(src, "w") as fh:
+        fh.write(K1_SHIM + common + kernels + K1_EXPORT)
+    so = os.path.join(out_dir, "libxrs_k1host.so")
+    cmd = [gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-ffp-contract=off",
+           f"-I{os.path.join(ROOT, 'include')}", src, "-o", so]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("host build of rectify_ij.cu failed:\n" + res.stderr[-4000:])
+    return so
+
+
+def k1(so_path: str, x, y, tile_boxes, g, uv_delta: float = 1e-3, rows=None, fp_cols=None):
+    """``xrs_rectify_ij`` through the host build: ``(ij (2, rows, W), claims (rows, W) uint32, queued quads)``;
+    ``g``: oracle RegularGrid, ``rows``: target row range (default all)."""
+    lib = ctypes.CDLL(so_path)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    boxes = np.ascontiguousarray(tile_boxes, dtype=np.int64)
+    r0, r1 = rows if rows is not None else (0, g.height)
+    ij = np.empty((2, r1 - r0, g.width), dtype=np.float64)
+    claims = np.empty((r1 - r0, g.width), dtype=np.uint32)
+    counts = np.zeros(1, dtype=np.uint32)
+    fp = None if fp_cols is None else np.ascontiguousarray(fp_cols, dtype=np.int32)
+    h, w = x.shape
+    c_d, c_l, c_i, c_p = ctypes.c_double, ctypes.c_long, ctypes.c_int, ctypes.c_void_p
+    lib.xrsh_k1.restype = c_i
+    lib.xrsh_k1.argtypes = [c_p, c_p, c_l, c_l, c_l, c_p, c_p, c_l, c_l, c_i, c_i, c_d, c_d, c_d, c_d, c_d, c_i, c_d, c_l,
+                            c_l, c_p, c_p, c_p]
+    rc = lib.xrsh_k1(x.ctypes.data, y.ctypes.data, h, w, w, boxes.ctypes.data, ij.ctypes.data, g.height, g.width,
+                     g.tile_h, g.tile_w, float(g.x_min), float(g.y_min), float(g.y_max), float(g.x_res), float(g.y_res),
+                     int(g.is_j_axis_up), float(uv_delta), r0, r1, None if fp is None else fp.ctypes.data,
+                     claims.ctypes.data, counts.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"xrsh_k1 failed ({rc})")
+    return ij, claims, int(counts[0])
