@@ -954,3 +954,211 @@ def k1(so_path: str, x, y, tile_boxes, g, uv_delta: float = 1e-3, rows=None, fp_
     if rc != 0:
         raise RuntimeError(f"xrsh_k1 failed ({rc})")
     return ij, claims, int(counts[0])
+
+
+# ---------------------------------------------------------------------------
+# K0 (csrc/rectify.cu: k0_tile_windows in its three forms, k0_init_table, k0_finalize, k0_fold_minform,
+# k0_finalize_minform)
+# ---------------------------------------------------------------------------
+# A thread BLOCK is K0_THREADS host threads: __syncthreads is a barrier over all of them, dynamic shared
+# memory a static array, __match_any_sync a full-warp exchange (two barrier waits of the warp's 32 threads),
+# and the __reduce_*_sync calls that only the lanes of a peer group execute are group collectives built on
+# per-lane generation counters (a lane publishes its value under generation n, readers wait until every peer
+# of the mask has reached n; values are double-buffered by the generation's parity, and a lane cannot get two
+# generations ahead of a peer that is still reading).
+K0_SHIM = r"""
+#include <pthread.h>
+#include <sched.h>
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "xrs.h"
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__
+#define __align__(n) __attribute__((aligned(n)))
+typedef void *cudaStream_t;
+using std::min; using std::max;
+struct xrsh_dim3 { unsigned x = 0, y = 0, z = 0; };
+static thread_local xrsh_dim3 threadIdx, blockIdx, blockDim, gridDim;
+struct int4 { int x, y, z, w; };
+static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+namespace xrs {
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+template <typename T> static inline T ld_stream(const T *p) { return *p; }
+alignas(16) unsigned char k0_smem[1 << 18];
+}
+template <typename T> static inline T atomicMin(T *p, T v) {
+    T old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+template <typename T> static inline T atomicMax(T *p, T v) {
+    T old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v > old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+static inline int __ffs(unsigned v) { return __builtin_ffs(static_cast<int>(v)); }
+constexpr int XRSH_MAX_WARPS = 32;
+struct XrshWarp { pthread_barrier_t bar; unsigned long long u[32]; int val[2][32]; unsigned gen[32]; };
+static XrshWarp xrsh_warps[XRSH_MAX_WARPS];
+static pthread_barrier_t xrsh_block_bar;
+static thread_local unsigned xrsh_gen = 0;
+static inline XrshWarp &xrsh_w() { return xrsh_warps[threadIdx.x >> 5]; }
+static inline int xrsh_l() { return static_cast<int>(threadIdx.x & 31); }
+static inline void __syncthreads() { pthread_barrier_wait(&xrsh_block_bar); }
+static inline unsigned __match_any_sync(unsigned, unsigned long long key) {
+    XrshWarp &w = xrsh_w();
+    const int l = xrsh_l();
+    w.u[l] = key;
+    pthread_barrier_wait(&w.bar);
+    unsigned m = 0;
+    for (int k = 0; k < 32; ++k) m |= (w.u[k] == key ? 1u : 0u) << k;
+    __atomic_store_n(&w.gen[l], 0u, __ATOMIC_RELEASE);  // a new round of group collectives starts at generation 0
+    xrsh_gen = 0;
+    pthread_barrier_wait(&w.bar);
+    return m;
+}
+template <typename Op> static inline int xrsh_group_reduce(unsigned mask, int v, Op op) {
+    XrshWarp &w = xrsh_w();
+    const int l = xrsh_l();
+    const unsigned my = ++xrsh_gen;
+    w.val[my & 1][l] = v;
+    __atomic_store_n(&w.gen[l], my, __ATOMIC_RELEASE);
+    int r = v;
+    for (int k = 0; k < 32; ++k) {
+        if (!((mask >> k) & 1u) || k == l) continue;
+        while (__atomic_load_n(&w.gen[k], __ATOMIC_ACQUIRE) < my) sched_yield();
+        r = op(r, w.val[my & 1][k]);
+    }
+    return r;
+}
+static inline int __reduce_min_sync(unsigned mask, int v) { return xrsh_group_reduce(mask, v, [](int a, int b) { return a < b ? a : b; }); }
+static inline int __reduce_max_sync(unsigned mask, int v) { return xrsh_group_reduce(mask, v, [](int a, int b) { return a > b ? a : b; }); }
+"""
+
+K0_EXPORT = r"""
+namespace {
+struct XrshK0Job {
+    const double *x, *y; int64_t h, w, pitch; const double *x_lo, *x_hi; int ntx; const double *y_lo, *y_hi; int nty;
+    int4 *table; int j_offset, rows_per_block, form; unsigned blocks;
+};
+struct XrshK0Thread { unsigned tid; const XrshK0Job *job; };
+void *xrsh_k0_thread(void *p) {
+    const XrshK0Thread *a = static_cast<const XrshK0Thread *>(p);
+    const XrshK0Job &j = *a->job;
+    threadIdx.x = a->tid; blockDim.x = xrs::K0_THREADS; gridDim.x = j.blocks;
+    for (unsigned b = 0; b < j.blocks; ++b) {
+        blockIdx.x = b;
+        if (j.form == 0) xrs::k0_tile_windows<true, false>(j.x, j.y, j.h, j.w, j.pitch, j.x_lo, j.x_hi, j.ntx, j.y_lo, j.y_hi, j.nty, j.table, j.j_offset, j.rows_per_block);
+        else if (j.form == 1) xrs::k0_tile_windows<false, false>(j.x, j.y, j.h, j.w, j.pitch, j.x_lo, j.x_hi, j.ntx, j.y_lo, j.y_hi, j.nty, j.table, j.j_offset, j.rows_per_block);
+        else xrs::k0_tile_windows<true, true>(j.x, j.y, j.h, j.w, j.pitch, j.x_lo, j.x_hi, j.ntx, j.y_lo, j.y_hi, j.nty, j.table, j.j_offset, j.rows_per_block);
+        __syncthreads();  // the next block re-initialises the shared table
+    }
+    return nullptr;
+}
+template <typename F> void xrsh_per_thread(int n, F f) {  // <<<ceil(n / 256), 256>>> of a kernel without collectives
+    blockDim.x = 256; gridDim.x = static_cast<unsigned>((n + 255) / 256);
+    for (unsigned b = 0; b < gridDim.x; ++b)
+        for (unsigned t = 0; t < 256; ++t) { blockIdx.x = b; threadIdx.x = t; f(); }
+}
+}
+
+// form 0: xrs_tile_src_bboxes with the table in shared memory; 1: table in global memory; 2: the slab scan
+// of xrs_tile_src_bboxes_partial (slabs of `slab_rows` rows straight into a min-form table) followed by
+// xrs_tile_src_bboxes_finalize; 3: slabs through the global-table kernel + k0_fold_minform, then finalize
+extern "C" int xrsh_k0(const double *x, const double *y, long h, long w, long pitch, const double *x_lo,
+                       const double *x_hi, int ntx, const double *y_lo, const double *y_hi, int nty, int ij_border,
+                       int form, long slab_rows, int64_t *out_boxes) {
+    using namespace xrs;
+    const int n_tiles = ntx * nty;
+    std::vector<int4> table(static_cast<size_t>(n_tiles));
+    std::vector<int32_t> minform(static_cast<size_t>(4 * n_tiles), INT32_MAX);
+    pthread_barrier_init(&xrsh_block_bar, nullptr, K0_THREADS);
+    for (int k = 0; k < K0_THREADS / 32; ++k) pthread_barrier_init(&xrsh_warps[k].bar, nullptr, 32);
+    auto scan = [&](const double *sx, const double *sy, long sh, long joff, int kform, int4 *tab) {
+        const int rows = sh >= 2048 ? K0_ROWS : 8;
+        XrshK0Job job{sx, sy, sh, w, pitch, x_lo, x_hi, ntx, y_lo, y_hi, nty, tab, static_cast<int>(joff), rows, kform,
+                      static_cast<unsigned>(ceil_div(w, K0_THREADS) * ceil_div(sh, rows))};
+        std::vector<pthread_t> th(K0_THREADS);
+        std::vector<XrshK0Thread> args(K0_THREADS);
+        for (int t = 0; t < K0_THREADS; ++t) {
+            args[t] = XrshK0Thread{static_cast<unsigned>(t), &job};
+            pthread_create(&th[t], nullptr, xrsh_k0_thread, &args[t]);
+        }
+        for (int t = 0; t < K0_THREADS; ++t) pthread_join(th[t], nullptr);
+    };
+    if (form == 0 || form == 1) {
+        int4 *tab = table.data();
+        xrsh_per_thread(n_tiles, [&] { k0_init_table(tab, n_tiles); });
+        scan(x, y, h, 0, form, tab);
+        xrsh_per_thread(n_tiles, [&] { k0_finalize(tab, n_tiles, ij_border, w, h, out_boxes); });
+    } else {
+        for (long j0 = 0; j0 < h; j0 += slab_rows) {
+            const long sh = std::min(slab_rows, h - j0);
+            if (form == 2) {
+                scan(x + j0 * pitch, y + j0 * pitch, sh, j0, 2, reinterpret_cast<int4 *>(minform.data()));
+            } else {
+                int4 *tab = table.data();
+                xrsh_per_thread(n_tiles, [&] { k0_init_table(tab, n_tiles); });
+                scan(x + j0 * pitch, y + j0 * pitch, sh, j0, 1, tab);
+                int32_t *mf = minform.data();
+                xrsh_per_thread(n_tiles, [&] { k0_fold_minform(tab, n_tiles, mf); });
+            }
+        }
+        const int32_t *mf = minform.data();
+        xrsh_per_thread(n_tiles, [&] { k0_finalize_minform(mf, n_tiles, ij_border, w, h, out_boxes); });
+    }
+    pthread_barrier_destroy(&xrsh_block_bar);
+    for (int k = 0; k < K0_THREADS / 32; ++k) pthread_barrier_destroy(&xrsh_warps[k].bar);
+    return 0;
+}
+"""
+
+
+def build_k0(out_dir: str) -> str:
+    """Host build of the kernels of rectify.cu (everything above its host launch code)."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not available")
+    text = open(os.path.join(CSRC, "rectify.cu")).read()
+    text, n = re.subn(r'#include "common.cuh"\n', "", text)
+    assert n == 1, "rectify.cu no longer includes common.cuh exactly once"
+    cut = text.find("using namespace xrs;")
+    assert cut > 0 and "<<<" not in text[:cut] and "k0_finalize_minform(const" in text[:cut], "layout of rectify.cu changed"
+    src = os.path.join(out_dir, "k0_host.cpp")
+    with open(src, "w") as fh:
+        fh.write(K0_SHIM + text[:cut] + K0_EXPORT)
+    so = os.path.join(out_dir, "libxrs_k0host.so")
+    cmd = [gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-ffp-contract=off",
+           f"-I{os.path.join(ROOT, 'include')}", src, "-o", so]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("host build of rectify.cu failed:\n" + res.stderr[-4000:])
+    return so
+
+
+def k0(so_path: str, x, y, x_lo, x_hi, y_lo, y_hi, ij_border: int = 1, form: int = 0, slab_rows: int = 0) -> np.ndarray:
+    """(n_tiles, 4) int64 source windows through the host build of K0; ``form`` as in ``xrsh_k0``."""
+    lib = ctypes.CDLL(so_path)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    axes = [np.ascontiguousarray(a, dtype=np.float64) for a in (x_lo, x_hi, y_lo, y_hi)]
+    ntx, nty = len(axes[0]), len(axes[2])
+    out = np.empty((ntx * nty, 4), dtype=np.int64)
+    h, w = x.shape
+    c_l, c_i, c_p = ctypes.c_long, ctypes.c_int, ctypes.c_void_p
+    lib.xrsh_k0.restype = c_i
+    lib.xrsh_k0.argtypes = [c_p, c_p, c_l, c_l, c_l, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_l, c_p]
+    rc = lib.xrsh_k0(x.ctypes.data, y.ctypes.data, h, w, w, axes[0].ctypes.data, axes[1].ctypes.data, ntx,
+                     axes[2].ctypes.data, axes[3].ctypes.data, nty, int(ij_border), int(form), int(slab_rows or h),
+                     out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"xrsh_k0 failed ({rc})")
+    return out
