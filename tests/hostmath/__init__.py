@@ -1162,3 +1162,153 @@ def k0(so_path: str, x, y, x_lo, x_hi, y_lo, y_hi, ij_border: int = 1, form: int
     if rc != 0:
         raise RuntimeError(f"xrsh_k0 failed ({rc})")
     return out
+
+
+# ---------------------------------------------------------------------------
+# KB (csrc/bands.cu: kb_fill_i32, kb_quad_footprints) -- the row bands' ragged quad footprints
+# ---------------------------------------------------------------------------
+KB_SHIM = K0_SHIM.replace("#define __shared__\n", "#define __shared__ static\n") + r"""
+namespace xrs {
+static inline double dadd(double a, double b) { return a + b; }
+static inline double dsub(double a, double b) { return a - b; }
+static inline double dmul(double a, double b) { return a * b; }
+static inline double ddiv(double a, double b) { return a / b; }
+}
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) {
+    return static_cast<unsigned long long>((static_cast<unsigned __int128>(a) * b) >> 64);
+}
+static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
+static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+static inline unsigned long long __shfl_xor_sync(unsigned, unsigned long long v, int lane_mask) {
+    XrshWarp &w = xrsh_w();
+    const int l = xrsh_l();
+    w.u[l] = v;
+    pthread_barrier_wait(&w.bar);
+    const unsigned long long r = w.u[l ^ lane_mask];
+    pthread_barrier_wait(&w.bar);
+    return r;
+}
+static inline unsigned __ballot_sync(unsigned, bool p) {
+    XrshWarp &w = xrsh_w();
+    const int l = xrsh_l();
+    w.u[l] = p ? 1ull : 0ull;
+    pthread_barrier_wait(&w.bar);
+    unsigned m = 0;
+    for (int k = 0; k < 32; ++k) m |= static_cast<unsigned>(w.u[k]) << k;
+    pthread_barrier_wait(&w.bar);
+    return m;
+}
+"""
+assert "#define __shared__ static\n" in KB_SHIM
+
+KB_EXPORT = r"""
+namespace {
+struct XrshKbJob {
+    const double *x, *y; int64_t slab_h, src_w, pitch, j_offset; xrs::BandGrid g; const int32_t *edges; int n_bands, n_groups;
+    int32_t *fp; unsigned blocks;
+};
+struct XrshKbThread { unsigned tid; const XrshKbJob *job; };
+void *xrsh_kb_thread(void *p) {
+    const XrshKbThread *a = static_cast<const XrshKbThread *>(p);
+    const XrshKbJob &j = *a->job;
+    threadIdx.x = a->tid; blockDim.x = xrs::KB_THREADS; gridDim.x = j.blocks;
+    for (unsigned b = 0; b < j.blocks; ++b) {
+        blockIdx.x = b;
+        xrs::kb_quad_footprints(j.x, j.y, j.slab_h, j.src_w, j.pitch, j.j_offset, j.g, j.edges, j.n_bands, j.n_groups, j.fp);
+        __syncthreads();  // the next block re-initialises the shared tables
+    }
+    return nullptr;
+}
+}
+
+extern "C" int xrsh_quad_row_group(void) { return xrs::K1S_ROWS; }
+
+extern "C" void xrsh_minform_init(int32_t *table, long n) {  // xrs_minform_init
+    blockDim.x = 256; gridDim.x = static_cast<unsigned>((n + 255) / 256);
+    for (unsigned b = 0; b < gridDim.x; ++b)
+        for (unsigned t = 0; t < 256; ++t) { blockIdx.x = b; threadIdx.x = t; xrs::kb_fill_i32(table, n, INT32_MAX); }
+}
+
+// xrs_band_quad_footprints on the host (same geometry set-up and launch shape)
+extern "C" int xrsh_band_quad_footprints(const double *x, const double *y, long slab_h, long src_w, long pitch, long j_offset,
+                                         long src_h, long dst_h, long dst_w, double x_min, double y_min, double y_max,
+                                         double x_res, double y_res, int j_up, const int32_t *band_edges, int n_bands,
+                                         int32_t *fp) {
+    using namespace xrs;
+    if (slab_h < 2 || src_w < 2 || j_offset % K1S_ROWS != 0 || j_offset + slab_h > src_h || n_bands < 1 || n_bands > KB_MAX_BANDS) return 1;
+    BandGrid g;
+    g.x_min = x_min; g.y_min = y_min; g.y_max = y_max; g.inv_xr = 1.0 / x_res; g.inv_yr = 1.0 / y_res;
+    g.j_up = j_up ? 1 : 0; g.dst_w = dst_w; g.dst_h = dst_h;
+    XrshKbJob job{x, y, slab_h, src_w, pitch, j_offset, g, band_edges, n_bands, static_cast<int>(ceil_div(src_h - 1, K1S_ROWS)), fp,
+                  static_cast<unsigned>(ceil_div(src_w - 1, KB_COLS) * ceil_div(slab_h - 1, K1S_ROWS))};
+    pthread_barrier_init(&xrsh_block_bar, nullptr, KB_THREADS);
+    for (int k = 0; k < KB_THREADS / 32; ++k) pthread_barrier_init(&xrsh_warps[k].bar, nullptr, 32);
+    std::vector<pthread_t> th(KB_THREADS);
+    std::vector<XrshKbThread> args(KB_THREADS);
+    for (int t = 0; t < KB_THREADS; ++t) {
+        args[t] = XrshKbThread{static_cast<unsigned>(t), &job};
+        pthread_create(&th[t], nullptr, xrsh_kb_thread, &args[t]);
+    }
+    for (int t = 0; t < KB_THREADS; ++t) pthread_join(th[t], nullptr);
+    pthread_barrier_destroy(&xrsh_block_bar);
+    for (int k = 0; k < KB_THREADS / 32; ++k) pthread_barrier_destroy(&xrsh_warps[k].bar);
+    return 0;
+}
+"""
+
+
+def build_kb(out_dir: str) -> str:
+    """Host build of rectify_common.cuh + the kernels of bands.cu."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not available")
+    common = open(os.path.join(CSRC, "rectify_common.cuh")).read()
+    common, n = re.subn(r'#include "common.cuh"\n', "", common)
+    assert n == 1, "rectify_common.cuh no longer includes common.cuh exactly once"
+    common = common.replace("#pragma once\n", "")
+    text = open(os.path.join(CSRC, "bands.cu")).read()
+    text, n = re.subn(r'#include "rectify_common.cuh"\n', "", text)
+    assert n == 1, "bands.cu no longer includes rectify_common.cuh exactly once"
+    cut = text.find("using namespace xrs;")
+    assert cut > 0 and "<<<" not in text[:cut] and "kb_quad_footprints(const" in text[:cut], "layout of bands.cu changed"
+    src = os.path.join(out_dir, "kb_host.cpp")
+    with open(src, "w") as fh:
+        fh.write(KB_SHIM + common + text[:cut] + KB_EXPORT)
+    so = os.path.join(out_dir, "libxrs_kbhost.so")
+    cmd = [gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-ffp-contract=off",
+           f"-I{os.path.join(ROOT, 'include')}", src, "-o", so]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("host build of bands.cu failed:\n" + res.stderr[-4000:])
+    return so
+
+
+def band_quad_footprints(so_path: str, x, y, g, band_edges, slabs=None) -> np.ndarray:
+    """(n_bands, n_groups, 2) int32 min-form footprints through the host build of ``kb_quad_footprints``:
+    ``slabs`` = list of (first vertex row, end vertex row) scanned one after the other into the same table
+    (what the participants' partial scans + the MIN exchange produce); default: the whole image at once."""
+    lib = ctypes.CDLL(so_path)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    h, w = x.shape
+    group = lib.xrsh_quad_row_group()
+    edges = np.ascontiguousarray(band_edges, dtype=np.int32)
+    n_bands, n_groups = len(edges) - 1, -(-(h - 1) // group)
+    fp = np.empty((n_bands, n_groups, 2), dtype=np.int32)
+    c_d, c_l, c_i, c_p = ctypes.c_double, ctypes.c_long, ctypes.c_int, ctypes.c_void_p
+    lib.xrsh_minform_init.restype = None
+    lib.xrsh_minform_init.argtypes = [c_p, c_l]
+    lib.xrsh_minform_init(fp.ctypes.data, fp.size)
+    lib.xrsh_band_quad_footprints.restype = c_i
+    lib.xrsh_band_quad_footprints.argtypes = [c_p, c_p, c_l, c_l, c_l, c_l, c_l, c_l, c_l, c_d, c_d, c_d, c_d, c_d, c_i,
+                                              c_p, c_i, c_p]
+    for j0, j1 in (slabs or [(0, h)]):
+        assert j0 % group == 0
+        rc = lib.xrsh_band_quad_footprints(x.ctypes.data + j0 * w * 8, y.ctypes.data + j0 * w * 8, j1 - j0, w, w, j0, h,
+                                           g.height, g.width, float(g.x_min), float(g.y_min), float(g.y_max),
+                                           float(g.x_res), float(g.y_res), int(g.is_j_axis_up), edges.ctypes.data, n_bands,
+                                           fp.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"xrsh_band_quad_footprints refused the slab ({j0}, {j1})")
+    return fp
