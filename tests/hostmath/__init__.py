@@ -1312,3 +1312,107 @@ def band_quad_footprints(so_path: str, x, y, g, band_edges, slabs=None) -> np.nd
         if rc != 0:
             raise RuntimeError(f"xrsh_band_quad_footprints refused the slab ({j0}, {j1})")
     return fp
+
+
+# ---------------------------------------------------------------------------
+# KC (csrc/coords.cu: kc_stats_init, kc_coords_stats, kc_lon_360)
+# ---------------------------------------------------------------------------
+KC_SHIM = K0_SHIM.replace("#define __shared__\n", "#define __shared__ static\n") + r"""
+namespace xrs {
+static inline double dadd(double a, double b) { return a + b; }
+static inline double dsub(double a, double b) { return a - b; }
+static inline double dmul(double a, double b) { return a * b; }
+}
+static inline long long __double_as_longlong(double d) { long long b; std::memcpy(&b, &d, 8); return b; }
+template <typename T> static inline T atomicOr(T *p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+"""
+
+KC_EXPORT = r"""
+namespace {
+struct XrshKcJob { const double *x, *y; int64_t h, w, pitch; int geographic; unsigned long long *out; unsigned blocks; };
+struct XrshKcThread { unsigned tid; const XrshKcJob *job; };
+void *xrsh_kc_thread(void *p) {
+    const XrshKcThread *a = static_cast<const XrshKcThread *>(p);
+    const XrshKcJob &j = *a->job;
+    threadIdx.x = a->tid; blockDim.x = xrs::KC_THREADS; gridDim.x = j.blocks;
+    for (unsigned b = 0; b < j.blocks; ++b) {
+        blockIdx.x = b;
+        xrs::kc_coords_stats(j.x, j.y, j.h, j.w, j.pitch, j.geographic, j.out);
+        __syncthreads();
+    }
+    return nullptr;
+}
+}
+
+// xrs_coords_stats with `blocks` thread blocks (the device launch takes min(ceil(h * w / 256), 148 * 8))
+extern "C" int xrsh_coords_stats(const double *x, const double *y, long h, long w, long pitch, int geographic,
+                                 unsigned long long *out4, int blocks) {
+    using namespace xrs;
+    kc_stats_init(out4);
+    XrshKcJob job{x, y, h, w, pitch, geographic ? 1 : 0, out4, static_cast<unsigned>(blocks)};
+    pthread_barrier_init(&xrsh_block_bar, nullptr, KC_THREADS);
+    std::vector<pthread_t> th(KC_THREADS);
+    std::vector<XrshKcThread> args(KC_THREADS);
+    for (int t = 0; t < KC_THREADS; ++t) {
+        args[t] = XrshKcThread{static_cast<unsigned>(t), &job};
+        pthread_create(&th[t], nullptr, xrsh_kc_thread, &args[t]);
+    }
+    for (int t = 0; t < KC_THREADS; ++t) pthread_join(th[t], nullptr);
+    pthread_barrier_destroy(&xrsh_block_bar);
+    return 0;
+}
+
+extern "C" void xrsh_lon_360(double *x, long h, long w, long pitch, int blocks) {
+    blockDim.x = 256; gridDim.x = static_cast<unsigned>(blocks);
+    for (unsigned b = 0; b < gridDim.x; ++b)
+        for (unsigned t = 0; t < 256; ++t) { blockIdx.x = b; threadIdx.x = t; xrs::kc_lon_360(x, h, w, pitch); }
+}
+"""
+
+
+def build_kc(out_dir: str) -> str:
+    """Host build of the kernels of coords.cu."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not available")
+    text = open(os.path.join(CSRC, "coords.cu")).read()
+    text, n = re.subn(r'#include "common.cuh"\n', "", text)
+    assert n == 1, "coords.cu no longer includes common.cuh exactly once"
+    cut = text.find("using namespace xrs;")
+    assert cut > 0 and "<<<" not in text[:cut] and "kc_lon_360(double" in text[:cut], "layout of coords.cu changed"
+    src = os.path.join(out_dir, "kc_host.cpp")
+    with open(src, "w") as fh:
+        fh.write(KC_SHIM + text[:cut] + KC_EXPORT)
+    so = os.path.join(out_dir, "libxrs_kchost.so")
+    cmd = [gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-ffp-contract=off",
+           f"-I{os.path.join(ROOT, 'include')}", src, "-o", so]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("host build of coords.cu failed:\n" + res.stderr[-4000:])
+    return so
+
+
+def coords_stats(so_path: str, x, y, geographic: bool, blocks: int = 3):
+    """``(any(x > 180), smallest positive cell area, largest)`` through the host build of ``kc_coords_stats``
+    (areas ``nan`` when no cell has a positive area)."""
+    lib = ctypes.CDLL(so_path)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    h, w = x.shape
+    out = np.zeros(4, dtype=np.uint64)
+    c_l, c_i, c_p = ctypes.c_long, ctypes.c_int, ctypes.c_void_p
+    lib.xrsh_coords_stats.restype = c_i
+    lib.xrsh_coords_stats.argtypes = [c_p, c_p, c_l, c_l, c_l, c_i, c_p, c_i]
+    lib.xrsh_coords_stats(x.ctypes.data, y.ctypes.data, h, w, w, int(bool(geographic)), out.ctypes.data, int(blocks))
+    areas = out[1:3].copy().view(np.float64)
+    return (bool(out[0]), float(areas[0]) if out[1] != np.uint64(0xFFFFFFFFFFFFFFFF) else float("nan"),
+            float(areas[1]) if out[2] != 0 else float("nan"))
+
+
+def lon_360(so_path: str, x, blocks: int = 2) -> np.ndarray:
+    lib = ctypes.CDLL(so_path)
+    x = np.array(x, dtype=np.float64, order="C")
+    lib.xrsh_lon_360.restype = None
+    lib.xrsh_lon_360.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_int]
+    lib.xrsh_lon_360(x.ctypes.data, x.shape[0], x.shape[1], x.shape[1], int(blocks))
+    return x
