@@ -1416,3 +1416,316 @@ def lon_360(so_path: str, x, blocks: int = 2) -> np.ndarray:
     lib.xrsh_lon_360.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_int]
     lib.xrsh_lon_360(x.ctypes.data, x.shape[0], x.shape[1], x.shape[1], int(blocks))
     return x
+
+
+# ---------------------------------------------------------------------------
+# K2 as kernels (csrc/gather.cu: k2_gather_staged / k2_gather_direct; csrc/gather_dual.cu: k2_gather_dual)
+# ---------------------------------------------------------------------------
+# The kernels' text is compiled unchanged.  What the hardware supplies is written out in the shim: a
+# CUtensorMap is a plain descriptor (base, extents, pitch, box), `tma_load_2d` copies the box into "shared
+# memory" (elements outside the tensor read as zero, as the TMA unit fills them) and then completes the
+# mbarrier's phase; an mbarrier is a counter of completed phases whose parity `mbar_wait` polls; the fences are
+# no-ops; `elem_ptr` is pointer arithmetic.  A CTA is K2S_THREADS host threads.
+K2_SHIM = K0_SHIM + GATHER_SHIM.replace("#include <algorithm>\n", "").replace("using std::min; using std::max;\n", "") + r"""
+#include <functional>
+#define __grid_constant__
+namespace xrs {
+static inline double dadd(double a, double b) { return a + b; }
+static inline double dsub(double a, double b) { return a - b; }
+static inline double dmul(double a, double b) { return a * b; }
+static inline double ddiv(double a, double b) { return a / b; }
+template <typename T> static inline void st_stream(T *p, T v) { *p = v; }
+unsigned char k2s_smem_raw[1 << 18];
+unsigned char k2d_smem_raw[1 << 18];
+}
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+template <typename T> static inline T __ldcs(const T *p) { return *p; }
+static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) {
+    return static_cast<unsigned long long>((static_cast<unsigned __int128>(a) * b) >> 64);
+}
+struct CUtensorMap { const void *base; uint64_t width, height, pitch_bytes; uint32_t box_w, box_h; int elem_size; };
+namespace xrs {
+static inline uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p)); }
+static inline void mbar_init(uint64_t *bar, uint32_t) { __atomic_store_n(bar, 0ull, __ATOMIC_RELEASE); }
+static inline void mbar_fence_init() {}
+static inline void fence_proxy_async() {}
+static inline void mbar_arrive_expect_tx(uint64_t *, uint32_t) {}
+static inline void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while ((__atomic_load_n(bar, __ATOMIC_ACQUIRE) & 1ull) == parity) sched_yield();
+}
+static long xrsh_tma_boxes = 0, xrsh_tma_oob = 0;  // statistics for the tests
+static inline void tma_load_2d(void *dst_smem, const CUtensorMap *map, int x, int y, uint64_t *bar) {
+    unsigned char *d = static_cast<unsigned char *>(dst_smem);
+    const unsigned char *s = static_cast<const unsigned char *>(map->base);
+    const int e = map->elem_size;
+    bool oob = false;
+    for (uint32_t r = 0; r < map->box_h; ++r)
+        for (uint32_t c = 0; c < map->box_w; ++c) {
+            const int64_t yy = static_cast<int64_t>(y) + r, xx = static_cast<int64_t>(x) + c;
+            unsigned char *o = d + (static_cast<size_t>(r) * map->box_w + c) * e;
+            if (yy >= 0 && xx >= 0 && yy < static_cast<int64_t>(map->height) && xx < static_cast<int64_t>(map->width))
+                std::memcpy(o, s + yy * map->pitch_bytes + xx * e, e);
+            else { std::memset(o, 0, e); oob = true; }
+        }
+    ++xrsh_tma_boxes;
+    if (oob) ++xrsh_tma_oob;
+    __atomic_fetch_add(bar, 1ull, __ATOMIC_RELEASE);  // the phase completes: its parity flips
+}
+template <typename T> static inline T *elem_ptr(T *base, uint32_t index) { return base + index; }
+}
+"""
+
+K2_EXPORT = r"""
+namespace {
+struct XrshLaunch { unsigned gx, gy; int threads; bool block2d; const std::function<void()> *body; };
+struct XrshLaunchThread { unsigned tid; const XrshLaunch *l; };
+void *xrsh_launch_thread(void *p) {
+    const XrshLaunchThread *a = static_cast<const XrshLaunchThread *>(p);
+    const XrshLaunch &l = *a->l;
+    if (l.block2d) { threadIdx.x = a->tid % 32; threadIdx.y = a->tid / 32; blockDim.x = 32; blockDim.y = l.threads / 32; }
+    else { threadIdx.x = a->tid; threadIdx.y = 0; blockDim.x = l.threads; blockDim.y = 1; }
+    gridDim.x = l.gx; gridDim.y = l.gy;
+    for (unsigned by = 0; by < l.gy; ++by)
+        for (unsigned bx = 0; bx < l.gx; ++bx) {
+            blockIdx.x = bx; blockIdx.y = by;
+            (*l.body)();
+            __syncthreads();  // the next CTA reuses the staging buffers and the barriers
+        }
+    return nullptr;
+}
+void xrsh_launch(unsigned gx, unsigned gy, int threads, bool block2d, const std::function<void()> &body) {
+    XrshLaunch l{gx, gy, threads, block2d, &body};
+    pthread_barrier_init(&xrsh_block_bar, nullptr, threads);
+    for (int k = 0; k < threads / 32; ++k) {
+        pthread_barrier_init(&xrsh_warps[k].bar, nullptr, 32);
+        std::memset(xrsh_warps[k].gen, 0, sizeof(xrsh_warps[k].gen));
+    }
+    std::vector<pthread_t> th(threads);
+    std::vector<XrshLaunchThread> args(threads);
+    for (int t = 0; t < threads; ++t) {
+        args[t] = XrshLaunchThread{static_cast<unsigned>(t), &l};
+        pthread_create(&th[t], nullptr, xrsh_launch_thread, &args[t]);
+    }
+    for (int t = 0; t < threads; ++t) pthread_join(th[t], nullptr);
+    pthread_barrier_destroy(&xrsh_block_bar);
+    for (int k = 0; k < threads / 32; ++k) pthread_barrier_destroy(&xrsh_warps[k].bar);
+}
+CUtensorMap xrsh_map(const void *base, int elem, int64_t win_w, int64_t win_h, int64_t pitch_elems) {
+    return CUtensorMap{base, static_cast<uint64_t>(win_w), static_cast<uint64_t>(win_h), static_cast<uint64_t>(pitch_elems) * elem,
+                       static_cast<uint32_t>(xrs::K2S_BOX_W), static_cast<uint32_t>(xrs::K2S_BOX_H), elem};
+}
+
+// launch_gather of gather.cu: bands in chunks of K2_MAX_BANDS, staged kernel when `staged`, else the direct one
+template <typename T, int METHOD>
+void xrsh_gather_tm(const T *src, int64_t band_stride, int n_bands, int64_t src_h, int64_t src_w, int64_t src_pitch,
+                    int64_t win_i0, int64_t win_j0, int64_t win_w, int64_t win_h, const double *ij, T *dst, int64_t dst_h,
+                    int64_t dst_w, double fill, bool staged) {
+    using namespace xrs;
+    const T fill_t = cast_fill<T>(fill);
+    IjSource ijs = {};
+    ijs.ij = ij;
+    for (int b0 = 0; b0 < n_bands; b0 += K2_MAX_BANDS) {
+        const int nb = std::min(K2_MAX_BANDS, n_bands - b0);
+        if (staged) {
+            StagedParams<T> sp;
+            std::memset(static_cast<void *>(&sp), 0, sizeof(sp));
+            for (int b = 0; b < nb; ++b) {
+                sp.src[b] = src + (b0 + b) * band_stride;
+                sp.dst[b] = dst + (b0 + b) * dst_h * dst_w;
+                sp.maps[b] = xrsh_map(sp.src[b], sizeof(T), win_w, win_h, src_pitch);
+            }
+            xrsh_launch(static_cast<unsigned>(ceil_div(dst_w, K2S_TW)), static_cast<unsigned>(ceil_div(dst_h, K2S_TH)), K2S_THREADS,
+                        false, [&] { k2_gather_staged<T, METHOD, false>(sp, nb, src_h, src_w, src_pitch, win_i0, win_j0, ijs, dst_h, dst_w, fill_t); });
+        } else {
+            PlaneTable<T> pt;
+            for (int b = 0; b < K2_MAX_BANDS; ++b) {
+                pt.src[b] = b < nb ? src + (b0 + b) * band_stride : nullptr;
+                pt.dst[b] = b < nb ? dst + (b0 + b) * dst_h * dst_w : nullptr;
+            }
+            xrsh_launch(static_cast<unsigned>(ceil_div(dst_w, K2_BX)), static_cast<unsigned>(ceil_div(dst_h, K2_BY)), K2_BX * K2_BY, true,
+                        [&] { k2_gather_direct<T, METHOD, false>(pt, nb, src_h, src_w, src_pitch, win_i0, win_j0, ijs, dst_h, dst_w, fill_t); });
+        }
+    }
+}
+template <typename T>
+int xrsh_gather_t(const void *src, int64_t band_stride, int n_bands, int64_t src_h, int64_t src_w, int64_t src_pitch,
+                  int64_t win_i0, int64_t win_j0, int64_t win_w, int64_t win_h, const double *ij, void *dst, int64_t dst_h,
+                  int64_t dst_w, int method, double fill, bool staged) {
+    const T *s = static_cast<const T *>(src);
+    T *d = static_cast<T *>(dst);
+    switch (method) {
+    case XRS_NEAREST: xrsh_gather_tm<T, XRS_NEAREST>(s, band_stride, n_bands, src_h, src_w, src_pitch, win_i0, win_j0, win_w, win_h, ij, d, dst_h, dst_w, fill, staged); return 0;
+    case XRS_BILINEAR: xrsh_gather_tm<T, XRS_BILINEAR>(s, band_stride, n_bands, src_h, src_w, src_pitch, win_i0, win_j0, win_w, win_h, ij, d, dst_h, dst_w, fill, staged); return 0;
+    case XRS_TRIANGULAR: xrsh_gather_tm<T, XRS_TRIANGULAR>(s, band_stride, n_bands, src_h, src_w, src_pitch, win_i0, win_j0, win_w, win_h, ij, d, dst_h, dst_w, fill, staged); return 0;
+    }
+    return 1;
+}
+
+// launch_dual of gather_dual.cu
+template <typename T, int METHOD>
+void xrsh_dual_tm(const T *src, int64_t band_stride, int n_bands, int64_t src_h, int64_t src_w, int64_t src_pitch, int64_t win_i0,
+                  int64_t win_j0, int64_t win_w, int64_t win_h, const double *ij, T *dst_interp, T *dst_near, int64_t dst_h,
+                  int64_t dst_w, double fill_interp, double fill_near) {
+    using namespace xrs;
+    const T fi = cast_fill<T>(fill_interp), fn = cast_fill<T>(fill_near);
+    for (int b0 = 0; b0 < n_bands; b0 += K2_MAX_BANDS) {
+        const int nb = std::min(K2_MAX_BANDS, n_bands - b0);
+        DualParams<T> dp;
+        std::memset(static_cast<void *>(&dp), 0, sizeof(dp));
+        for (int b = 0; b < nb; ++b) {
+            dp.src[b] = src + (b0 + b) * band_stride;
+            dp.dst_interp[b] = dst_interp + (b0 + b) * dst_h * dst_w;
+            dp.dst_near[b] = dst_near + (b0 + b) * dst_h * dst_w;
+            dp.maps[b] = xrsh_map(dp.src[b], sizeof(T), win_w, win_h, src_pitch);
+        }
+        xrsh_launch(static_cast<unsigned>(ceil_div(dst_w, K2S_TW)), static_cast<unsigned>(ceil_div(dst_h, K2S_TH)), K2S_THREADS, false,
+                    [&] { k2_gather_dual<T, METHOD>(dp, nb, src_h, src_w, src_pitch, win_i0, win_j0, ij, dst_h, dst_w, fi, fn); });
+    }
+}
+template <typename T>
+int xrsh_dual_t(const void *src, int64_t band_stride, int n_bands, int64_t src_h, int64_t src_w, int64_t src_pitch, int64_t win_i0,
+                int64_t win_j0, int64_t win_w, int64_t win_h, const double *ij, void *di, void *dn, int64_t dst_h, int64_t dst_w,
+                int method, double fill_interp, double fill_near) {
+    const T *s = static_cast<const T *>(src);
+    if (method == XRS_BILINEAR) xrsh_dual_tm<T, XRS_BILINEAR>(s, band_stride, n_bands, src_h, src_w, src_pitch, win_i0, win_j0, win_w, win_h, ij, static_cast<T *>(di), static_cast<T *>(dn), dst_h, dst_w, fill_interp, fill_near);
+    else if (method == XRS_TRIANGULAR) xrsh_dual_tm<T, XRS_TRIANGULAR>(s, band_stride, n_bands, src_h, src_w, src_pitch, win_i0, win_j0, win_w, win_h, ij, static_cast<T *>(di), static_cast<T *>(dn), dst_h, dst_w, fill_interp, fill_near);
+    else return 1;
+    return 0;
+}
+}
+
+// src points at the window origin (win_i0, win_j0) of band 0; src_h / src_w are the FULL image's (tap clamping)
+extern "C" int xrsh_k2_gather(const void *src, int dtype, long band_stride, int n_bands, long src_h, long src_w, long src_pitch,
+                              long win_i0, long win_j0, long win_w, long win_h, const double *ij, void *dst, long dst_h, long dst_w,
+                              int method, double fill, int staged, long *stats) {
+    xrs::xrsh_tma_boxes = xrs::xrsh_tma_oob = 0;
+    int rc = 2;
+    switch (dtype) {
+    case XRS_F32: rc = xrsh_gather_t<float>(src, band_stride, n_bands, src_h, src_w, src_pitch, win_i0, win_j0, win_w, win_h, ij, dst, dst_h, dst_w, method, fill, staged != 0); break;
+    case XRS_F64: rc = xrsh_gather_t<double>(src, band_stride, n_bands, src_h, src_w, src_pitch, win_i0, win_j0, win_w, win_h, ij, dst, dst_h, dst_w, method, fill, staged != 0); break;
+    case XRS_U8: rc = xrsh_gather_t<uint8_t>(src, band_stride, n_bands, src_h, src_w, src_pitch, win_i0, win_j0, win_w, win_h, ij, dst, dst_h, dst_w, method, fill, staged != 0); break;
+    case XRS_I16: rc = xrsh_gather_t<int16_t>(src, band_stride, n_bands, src_h, src_w, src_pitch, win_i0, win_j0, win_w, win_h, ij, dst, dst_h, dst_w, method, fill, staged != 0); break;
+    }
+    stats[0] = xrs::xrsh_tma_boxes; stats[1] = xrs::xrsh_tma_oob;
+    return rc;
+}
+extern "C" int xrsh_k2_gather_dual(const void *src, int dtype, long band_stride, int n_bands, long src_h, long src_w, long src_pitch,
+                                   long win_i0, long win_j0, long win_w, long win_h, const double *ij, void *dst_interp,
+                                   void *dst_near, long dst_h, long dst_w, int method, double fill_interp, double fill_near,
+                                   long *stats) {
+    xrs::xrsh_tma_boxes = xrs::xrsh_tma_oob = 0;
+    int rc = 2;
+    switch (dtype) {
+    case XRS_F32: rc = xrsh_dual_t<float>(src, band_stride, n_bands, src_h, src_w, src_pitch, win_i0, win_j0, win_w, win_h, ij, dst_interp, dst_near, dst_h, dst_w, method, fill_interp, fill_near); break;
+    case XRS_F64: rc = xrsh_dual_t<double>(src, band_stride, n_bands, src_h, src_w, src_pitch, win_i0, win_j0, win_w, win_h, ij, dst_interp, dst_near, dst_h, dst_w, method, fill_interp, fill_near); break;
+    case XRS_U8: rc = xrsh_dual_t<uint8_t>(src, band_stride, n_bands, src_h, src_w, src_pitch, win_i0, win_j0, win_w, win_h, ij, dst_interp, dst_near, dst_h, dst_w, method, fill_interp, fill_near); break;
+    case XRS_I16: rc = xrsh_dual_t<int16_t>(src, band_stride, n_bands, src_h, src_w, src_pitch, win_i0, win_j0, win_w, win_h, ij, dst_interp, dst_near, dst_h, dst_w, method, fill_interp, fill_near); break;
+    }
+    stats[0] = xrs::xrsh_tma_boxes; stats[1] = xrs::xrsh_tma_oob;
+    return rc;
+}
+"""
+
+
+def _kernel_text(name: str, cut_marker: str, drop_includes) -> str:
+    text = open(os.path.join(CSRC, name)).read()
+    for inc in drop_includes:
+        text, n = re.subn(r"#include " + re.escape(inc) + r"\n", "", text)
+        assert n == 1, f"{name} no longer includes {inc} exactly once"
+    text = text.replace("#pragma once\n", "")
+    if cut_marker:
+        cut = text.find(cut_marker)
+        assert cut > 0 and "<<<" not in text[:cut], f"layout of {name} changed"
+        text = text[:cut] + "\n}  // namespace xrs\n"
+    return text
+
+
+def build_k2(out_dir: str) -> str:
+    """Host build of rectify_common.cuh + gather_common.cuh + the kernels of gather.cu and gather_dual.cu."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not available")
+    parts = [
+        _kernel_text("rectify_common.cuh", "", ['"common.cuh"']),
+        _kernel_text("gather_common.cuh", "", ['"rectify_common.cuh"', '"tma.cuh"']),
+        _kernel_text("gather.cu", "// ---------------------------------------------------------------------------\n// host side",
+                     ['"gather_common.cuh"']),
+        _kernel_text("gather_dual.cu", "template <typename T>\nstatic int launch_dual", ['"gather_common.cuh"']),
+    ]
+    src = os.path.join(out_dir, "k2_host.cpp")
+    with open(src, "w") as fh:
+        fh.write(K2_SHIM + "".join(parts) + K2_EXPORT)
+    so = os.path.join(out_dir, "libxrs_k2host.so")
+    cmd = [gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-ffp-contract=off",
+           f"-I{os.path.join(ROOT, 'include')}", src, "-o", so]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("host build of gather.cu / gather_dual.cu failed:\n" + res.stderr[-6000:])
+    return so
+
+
+def _k2_codes():
+    """dtype / method codes from include/xrs.h (the enums the C ABI uses)."""
+    hdr = open(os.path.join(ROOT, "include", "xrs.h")).read()
+    def code(name):
+        m = re.search(r"\b" + name + r"\s*=\s*(\d+)", hdr)
+        assert m, name
+        return int(m.group(1))
+    dt = {np.dtype(np.float32): code("XRS_F32"), np.dtype(np.float64): code("XRS_F64"), np.dtype(np.uint8): code("XRS_U8"),
+          np.dtype(np.int16): code("XRS_I16")}
+    me = {"nearest": code("XRS_NEAREST"), "bilinear": code("XRS_BILINEAR"), "triangular": code("XRS_TRIANGULAR")}
+    return dt, me
+
+
+def _k2_window(src, window):
+    """(pointer to the window origin of band 0, band stride, pitch, win_i0, win_j0, win_w, win_h)."""
+    nb, h, w = src.shape
+    i0, j0, i1, j1 = window if window is not None else (0, 0, w, h)
+    return src.ctypes.data + (j0 * w + i0) * src.itemsize, h * w, w, i0, j0, i1 - i0, j1 - j0
+
+
+def k2_gather(so_path: str, src, ij, method: str, fill, staged: bool = True, window=None):
+    """``xrs_gather_ij`` through the host build of ``k2_gather_staged`` (or ``k2_gather_direct``): ``(out, stats)``
+    with stats = (boxes copied by the TMA stand-in, boxes that reached outside the tensor).  ``window`` =
+    (i0, j0, i1, j1): only that part of the source is addressable (the kernels get a pointer to its origin)."""
+    lib = ctypes.CDLL(so_path)
+    dt, me = _k2_codes()
+    src = np.ascontiguousarray(src)
+    ij = np.ascontiguousarray(ij, dtype=np.float64)
+    nb, h, w = src.shape
+    _, dh, dw = ij.shape
+    out = np.empty((nb, dh, dw), dtype=src.dtype)
+    stats = np.zeros(2, dtype=np.int64)
+    base, bstride, pitch, i0, j0, ww, wh = _k2_window(src, window)
+    c_d, c_l, c_i, c_p = ctypes.c_double, ctypes.c_long, ctypes.c_int, ctypes.c_void_p
+    lib.xrsh_k2_gather.restype = c_i
+    lib.xrsh_k2_gather.argtypes = [c_p, c_i, c_l, c_i, c_l, c_l, c_l, c_l, c_l, c_l, c_l, c_p, c_p, c_l, c_l, c_i, c_d, c_i, c_p]
+    rc = lib.xrsh_k2_gather(base, dt[src.dtype], bstride, nb, h, w, pitch, i0, j0, ww, wh, ij.ctypes.data, out.ctypes.data, dh,
+                            dw, me[method], float(fill), int(staged), stats.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"xrsh_k2_gather failed ({rc})")
+    return out, (int(stats[0]), int(stats[1]))
+
+
+def k2_gather_dual(so_path: str, src, ij, method: str, fill_interp, fill_near, window=None):
+    """``xrs_gather_ij2`` through the host build of ``k2_gather_dual``: ``(interp, nearest, stats)``."""
+    lib = ctypes.CDLL(so_path)
+    dt, me = _k2_codes()
+    src = np.ascontiguousarray(src)
+    ij = np.ascontiguousarray(ij, dtype=np.float64)
+    nb, h, w = src.shape
+    _, dh, dw = ij.shape
+    out_i = np.empty((nb, dh, dw), dtype=src.dtype)
+    out_n = np.empty((nb, dh, dw), dtype=src.dtype)
+    stats = np.zeros(2, dtype=np.int64)
+    base, bstride, pitch, i0, j0, ww, wh = _k2_window(src, window)
+    c_d, c_l, c_i, c_p = ctypes.c_double, ctypes.c_long, ctypes.c_int, ctypes.c_void_p
+    lib.xrsh_k2_gather_dual.restype = c_i
+    lib.xrsh_k2_gather_dual.argtypes = [c_p, c_i, c_l, c_i, c_l, c_l, c_l, c_l, c_l, c_l, c_l, c_p, c_p, c_p, c_l, c_l, c_i, c_d,
+                                        c_d, c_p]
+    rc = lib.xrsh_k2_gather_dual(base, dt[src.dtype], bstride, nb, h, w, pitch, i0, j0, ww, wh, ij.ctypes.data,
+                                 out_i.ctypes.data, out_n.ctypes.data, dh, dw, me[method], float(fill_interp), float(fill_near),
+                                 stats.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"xrsh_k2_gather_dual failed ({rc})")
+    return out_i, out_n, (int(stats[0]), int(stats[1]))
