@@ -1627,6 +1627,59 @@ extern "C" int xrsh_k2_gather_dual(const void *src, int dtype, long band_stride,
 """
 
 
+K2_EXPORT_FUSED = r"""
+// xrs_rectify_gather's second half: the staged gather in FUSED mode -- the fractional source index of a target
+// pixel comes from K1's claim words through resolve_pixel, in registers, instead of the ij image
+namespace {
+template <typename T, int METHOD>
+void xrsh_fused_tm(const T *src, int n_bands, const xrs::IjGeom &geom, T *dst, double fill) {
+    using namespace xrs;
+    const int64_t dst_h = geom.row_end - geom.row_begin, dst_w = geom.dst_w;
+    IjSource ijs = {};
+    ijs.ij = nullptr;
+    ijs.geom = geom;
+    StagedParams<T> sp;
+    std::memset(static_cast<void *>(&sp), 0, sizeof(sp));
+    for (int b = 0; b < n_bands; ++b) {
+        sp.src[b] = src + b * geom.src_h * geom.src_w;
+        sp.dst[b] = dst + b * dst_h * dst_w;
+        sp.maps[b] = xrsh_map(sp.src[b], sizeof(T), geom.src_w, geom.src_h, geom.src_w);
+    }
+    const T fill_t = cast_fill<T>(fill);
+    xrsh_launch(static_cast<unsigned>(ceil_div(dst_w, K2S_TW)), static_cast<unsigned>(ceil_div(dst_h, K2S_TH)), K2S_THREADS, false,
+                [&] { k2_gather_staged<T, METHOD, true>(sp, n_bands, geom.src_h, geom.src_w, geom.src_w, 0, 0, ijs, dst_h, dst_w, fill_t); });
+}
+}
+extern "C" int xrsh_k2_gather_fused(const float *src, int n_bands, const double *x, const double *y, long src_h, long src_w,
+                                    const int64_t *tile_boxes, const uint32_t *claims, long dst_h, long dst_w, int tile_h,
+                                    int tile_w, double x_min, double y_min, double y_max, double x_res, double y_res, int j_up,
+                                    long row_begin, long row_end, int method, double fill, float *dst) {
+    using namespace xrs;
+    if (n_bands > K2_MAX_BANDS) return 3;
+    IjGeom g = {};
+    g.x = x; g.y = y; g.src_h = src_h; g.src_w = src_w; g.src_pitch = src_w;
+    g.tile_boxes = tile_boxes; g.claims = const_cast<uint32_t *>(claims);
+    g.dst_h = dst_h; g.dst_w = dst_w;
+    g.tile_h = tile_h < dst_h ? tile_h : static_cast<int>(dst_h);
+    g.tile_w = tile_w < dst_w ? tile_w : static_cast<int>(dst_w);
+    g.ntx = static_cast<int>((dst_w + g.tile_w - 1) / g.tile_w);
+    g.nty = static_cast<int>((dst_h + g.tile_h - 1) / g.tile_h);
+    g.x_min = x_min; g.y_min = y_min; g.y_max = y_max; g.x_res = x_res; g.y_res = y_res;
+    g.j_up = j_up ? 1 : 0;
+    g.row_begin = row_begin; g.row_end = row_end;
+    g.magic_nqi = div_magic_of(static_cast<uint64_t>(src_w - 1));
+    g.magic_tw = div_magic_of(static_cast<uint64_t>(g.tile_w));
+    g.magic_th = div_magic_of(static_cast<uint64_t>(g.tile_h));
+    switch (method) {
+    case XRS_NEAREST: xrsh_fused_tm<float, XRS_NEAREST>(src, n_bands, g, dst, fill); return 0;
+    case XRS_BILINEAR: xrsh_fused_tm<float, XRS_BILINEAR>(src, n_bands, g, dst, fill); return 0;
+    case XRS_TRIANGULAR: xrsh_fused_tm<float, XRS_TRIANGULAR>(src, n_bands, g, dst, fill); return 0;
+    }
+    return 1;
+}
+"""
+
+
 def _kernel_text(name: str, cut_marker: str, drop_includes) -> str:
     text = open(os.path.join(CSRC, name)).read()
     for inc in drop_includes:
@@ -1654,7 +1707,7 @@ def build_k2(out_dir: str) -> str:
     ]
     src = os.path.join(out_dir, "k2_host.cpp")
     with open(src, "w") as fh:
-        fh.write(K2_SHIM + "".join(parts) + K2_EXPORT)
+        fh.write(K2_SHIM + "".join(parts) + K2_EXPORT + K2_EXPORT_FUSED)
     so = os.path.join(out_dir, "libxrs_k2host.so")
     cmd = [gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-ffp-contract=off",
            f"-I{os.path.join(ROOT, 'include')}", src, "-o", so]
@@ -1729,3 +1782,29 @@ def k2_gather_dual(so_path: str, src, ij, method: str, fill_interp, fill_near, w
     if rc != 0:
         raise RuntimeError(f"xrsh_k2_gather_dual failed ({rc})")
     return out_i, out_n, (int(stats[0]), int(stats[1]))
+
+
+def k2_gather_fused(so_path: str, src, x, y, tile_boxes, claims, g, method: str, fill, rows=None) -> np.ndarray:
+    """The gather half of ``xrs_rectify_gather`` (``k2_gather_staged<float, METHOD, FUSED = true>``): float32 bands
+    through K1's claim words (``claims``: (rows, W) uint32 of the row range ``rows``); ``g``: oracle RegularGrid."""
+    lib = ctypes.CDLL(so_path)
+    _, me = _k2_codes()
+    src = np.ascontiguousarray(src, dtype=np.float32)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    boxes = np.ascontiguousarray(tile_boxes, dtype=np.int64)
+    claims = np.ascontiguousarray(claims, dtype=np.uint32)
+    r0, r1 = rows if rows is not None else (0, g.height)
+    nb, h, w = src.shape
+    out = np.empty((nb, r1 - r0, g.width), dtype=np.float32)
+    c_d, c_l, c_i, c_p = ctypes.c_double, ctypes.c_long, ctypes.c_int, ctypes.c_void_p
+    lib.xrsh_k2_gather_fused.restype = c_i
+    lib.xrsh_k2_gather_fused.argtypes = [c_p, c_i, c_p, c_p, c_l, c_l, c_p, c_p, c_l, c_l, c_i, c_i, c_d, c_d, c_d, c_d, c_d, c_i,
+                                         c_l, c_l, c_i, c_d, c_p]
+    rc = lib.xrsh_k2_gather_fused(src.ctypes.data, nb, x.ctypes.data, y.ctypes.data, h, w, boxes.ctypes.data, claims.ctypes.data,
+                                  g.height, g.width, g.tile_h, g.tile_w, float(g.x_min), float(g.y_min), float(g.y_max),
+                                  float(g.x_res), float(g.y_res), int(g.is_j_axis_up), r0, r1, me[method], float(fill),
+                                  out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"xrsh_k2_gather_fused failed ({rc})")
+    return out

@@ -34,6 +34,18 @@ def k2_so(tmp_path_factory):
 
 
 @pytest.fixture(scope="module")
+def k1_so(tmp_path_factory):
+    from . import hostmath
+
+    try:
+        return hostmath.build_k1(str(tmp_path_factory.mktemp("k1host_for_k2")))
+    except RuntimeError as e:
+        if "g++ not available" in str(e):
+            pytest.skip(str(e))
+        raise
+
+
+@pytest.fixture(scope="module")
 def scene():
     w, h = 120, 90
     x, y = swath(w, h, theta=20.0, seed=3)
@@ -140,3 +152,25 @@ def test_resident_window_only(k2_so, scene):
     out_i, out_n, _ = hostmath.k2_gather_dual(k2_so, poisoned, band_ij, "bilinear", nan, nan, window=(i0, j0, i1, j1))
     assert_same(out_i, orect.gather(src, band_ij, "bilinear", nan), "dual, window")
     assert_same(out_n, orect.gather(src, band_ij, "nearest", nan), "dual nearest, window")
+
+
+@pytest.mark.parametrize("tile,j_up,rows", [(48, False, None), ((40, 24), True, None), (64, False, (32, 96))])
+def test_fused_resolve_and_gather(k2_so, k1_so, tile, j_up, rows):
+    """xrs_rectify_gather end to end on the host: K1's claim stage (host build of rectify_ij.cu), then the staged
+    gather in FUSED mode, which resolves the claim words in registers (rectify_common.cuh resolve_pixel) instead of
+    reading an ij image -- equal to the oracle's rectification of the same bands."""
+    from . import hostmath
+
+    w, h = 110, 100
+    x, y = swath(w, h, theta=-25.0, seed=31)
+    x[60, 20:30] = nan
+    size, xy_min = covering_grid_args(x, y, 0.0027)
+    g = ogrid.regular_grid(size, xy_min, 0.0027, tile_size=tile, is_j_axis_up=j_up)
+    windows = orect.source_windows(x, y, g)
+    r0, r1 = rows if rows is not None else (0, g.height)
+    _, claims, _ = hostmath.k1(k1_so, x, y, windows, g, rows=rows)
+    src = _source(np.float32, 5, h, w, seed=6)
+    for method in ("nearest", "bilinear", "triangular"):
+        want, _ = orect.rectify(x, y, src, g, method, nan)
+        got = hostmath.k2_gather_fused(k2_so, src, x, y, windows, claims, g, method, nan, rows=rows)
+        assert_same(got, want[:, r0:r1], f"fused {method}, rows {rows}")
