@@ -38,7 +38,7 @@ def _k0(k0_so, x, y, boxes, xy_border, ij_border, form=0, slab=0):
     return hostmath.k0(k0_so, x, y, x_lo, x_hi, y_lo, y_hi, ij_border, form, slab)
 
 
-@pytest.mark.parametrize("form,slab", [(0, 0), (1, 0), (2, 4), (3, 3)])
+@pytest.mark.parametrize("form,slab", [(0, 0), (2, 6)])  # (all four forms: the two tests below)
 def test_reference_goldens(k0_so, form, slab):
     z = load_golden("ij_bboxes.npz")  # outputs of the reference's own numba kernel (tests/golden/make_golden.py)
     for k in range(int(z["n_cases"])):

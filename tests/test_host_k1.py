@@ -128,13 +128,13 @@ def test_row_bands_with_and_without_a_footprint(k1_so):
     (xrs_band_quad_footprints, restated in tests/helpers.py) only removes quads that cannot reach the band."""
     from . import hostmath
 
-    x, y = swath(100, 140, theta=30.0, seed=23)
+    x, y = swath(80, 110, theta=30.0, seed=23)
     res = 0.0027
     size, xy_min = covering_grid_args(x, y, res)
     g = ogrid.regular_grid(size, xy_min, res, tile_size=48)
     windows = orect.source_windows(x, y, g)
     want = orect.rectify_ij(x, y, g, windows=windows)
-    edges = [0, 40, 88, g.height]
+    edges = [0, 32, 72, g.height]
     fp = quad_footprints_np(x, y, g, edges, group=32)
     for b in range(3):
         rows = (edges[b], edges[b + 1])
