@@ -1808,3 +1808,251 @@ def k2_gather_fused(so_path: str, src, x, y, tile_boxes, claims, g, method: str,
     if rc != 0:
         raise RuntimeError(f"xrsh_k2_gather_fused failed ({rc})")
     return out
+
+
+# ---------------------------------------------------------------------------
+# K3 as kernels (csrc/reproject.cu: k3_lattice_nodes, k3_reproject<T, OUT, METHOD, SEP>) on top of proj.cuh
+# ---------------------------------------------------------------------------
+# Compiled with XRS_K3_LD256=0 (the tap loads are plain loads instead of the 256-byte L2 hint) and with the one
+# `prefetch.global.L2` instruction replaced by a no-op -- memory hints, no arithmetic.  make_proj_consts, the
+# lattice pre-kernel, the tile logic, the separable / row-block / lattice / exact forms and the per-pixel blend
+# are the product's text.  Differences to the device build: libm instead of CUDA's math library and no FMA
+# contraction in proj.cuh (~1e-9 m in the source coordinates).
+K3_SHIM = "#define _GNU_SOURCE 1\n#define XRS_K3_LD256 0\n" + K0_SHIM.replace("#define __shared__\n", "#define __shared__ static\n") + r"""
+#include <string>
+#include <type_traits>
+#include <math.h>
+#define __grid_constant__
+#define __noinline__
+#define __constant__ const
+using std::fabs; using std::sqrt; using std::sin; using std::cos; using std::tan; using std::atan; using std::atan2;
+using std::asin; using std::sinh; using std::asinh; using std::exp; using std::log; using std::rint; using std::fmin;
+using std::fmax; using std::floor; using std::ceil;
+struct double2 { double x, y; };
+namespace xrs {
+static inline int fail(const std::string &) { return 1; }
+static inline double dadd(double a, double b) { return a + b; }
+static inline double dsub(double a, double b) { return a - b; }
+static inline double dmul(double a, double b) { return a * b; }
+static inline double ddiv(double a, double b) { return a / b; }
+template <typename T> static inline void st_stream(T *p, T v) { *p = v; }
+template <typename T> static inline T cast_from_f64(double v) {
+    if constexpr (std::is_floating_point<T>::value) return static_cast<T>(v);
+    else return static_cast<T>(static_cast<long long>(v));
+}
+}
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+template <typename T> static inline T __ldcs(const T *p) { return *p; }
+static inline int __double2int_rd(double d) { return static_cast<int>(std::floor(d)); }
+static inline int __double2int_ru(double d) { return static_cast<int>(std::ceil(d)); }
+static inline int __double2int_rn(double d) { return static_cast<int>(std::nearbyint(d)); }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+// lanes of the warp that have not left the kernel: every lane is either here or gone (see xrsh_lane_state)
+static int xrsh_lane_state[XRSH_MAX_WARPS][32];  // 0 running, 1 returned, 2 at __activemask
+static inline unsigned __activemask() {
+    const int w = static_cast<int>(threadIdx.x >> 5), l = xrsh_l();
+    __atomic_store_n(&xrsh_lane_state[w][l], 2, __ATOMIC_RELEASE);
+    unsigned m = 0;
+    for (int k = 0; k < 32; ++k) {
+        int s;
+        while ((s = __atomic_load_n(&xrsh_lane_state[w][k], __ATOMIC_ACQUIRE)) == 0) sched_yield();
+        if (s == 2) m |= 1u << k;
+    }
+    return m;
+}
+static int xrsh_and_acc[2] = {1, 1};
+static thread_local unsigned xrsh_and_n = 0;
+static inline int __syncthreads_and(int p) {
+    const unsigned k = xrsh_and_n++ & 1u;
+    if (!p) __atomic_store_n(&xrsh_and_acc[k], 0, __ATOMIC_RELEASE);
+    __syncthreads();
+    const int r = __atomic_load_n(&xrsh_and_acc[k], __ATOMIC_ACQUIRE);
+    __syncthreads();
+    if (threadIdx.x == 0) __atomic_store_n(&xrsh_and_acc[k], 1, __ATOMIC_RELEASE);
+    return r;
+}
+"""
+
+K3_EXPORT = r"""
+namespace {
+struct XrshK3Launch { unsigned gx, gy; const std::function<void()> *body; };
+struct XrshK3Thread { unsigned tid; const XrshK3Launch *l; };
+void *xrsh_k3_thread(void *p) {
+    const XrshK3Thread *a = static_cast<const XrshK3Thread *>(p);
+    const XrshK3Launch &l = *a->l;
+    threadIdx.x = a->tid; blockDim.x = xrs::K3T_THREADS; gridDim.x = l.gx; gridDim.y = l.gy;
+    const int w = static_cast<int>(a->tid >> 5), lane = static_cast<int>(a->tid & 31);
+    for (unsigned by = 0; by < l.gy; ++by)
+        for (unsigned bx = 0; bx < l.gx; ++bx) {
+            blockIdx.x = bx; blockIdx.y = by;
+            __atomic_store_n(&xrsh_lane_state[w][lane], 0, __ATOMIC_RELEASE);
+            __atomic_store_n(&xrsh_warps[w].gen[lane], 0u, __ATOMIC_RELEASE);
+            xrsh_gen = 0;
+            __syncthreads();   // every lane is "running" and at generation 0 before any collective of this CTA
+            (*l.body)();
+            __atomic_store_n(&xrsh_lane_state[w][lane], 1, __ATOMIC_RELEASE);
+            __syncthreads();   // the next CTA reuses the shared arrays
+        }
+    return nullptr;
+}
+void xrsh_k3_launch(unsigned gx, unsigned gy, const std::function<void()> &body) {
+    XrshK3Launch l{gx, gy, &body};
+    const int threads = xrs::K3T_THREADS;
+    pthread_barrier_init(&xrsh_block_bar, nullptr, threads);
+    for (int k = 0; k < threads / 32; ++k) pthread_barrier_init(&xrsh_warps[k].bar, nullptr, 32);
+    std::vector<pthread_t> th(threads);
+    std::vector<XrshK3Thread> args(threads);
+    for (int t = 0; t < threads; ++t) {
+        args[t] = XrshK3Thread{static_cast<unsigned>(t), &l};
+        pthread_create(&th[t], nullptr, xrsh_k3_thread, &args[t]);
+    }
+    for (int t = 0; t < threads; ++t) pthread_join(th[t], nullptr);
+    pthread_barrier_destroy(&xrsh_block_bar);
+    for (int k = 0; k < threads / 32; ++k) pthread_barrier_destroy(&xrsh_warps[k].bar);
+}
+
+// launch_reproject of reproject.cu: plan, lattice pre-kernel, band chunks, separable or general kernel
+template <typename T, typename OUT, int METHOD>
+int xrsh_launch_reproject(const xrs::K3Geom &g_in, const T *src, int64_t band_stride, OUT *dst, int n_bands, double fill,
+                          int exact_only, int use_nodes, long *stats) {
+    using namespace xrs;
+    K3Geom g = g_in;
+    g.lat_nodes = nullptr;
+    const int64_t rows = g.row_end - g.row_begin;
+    const unsigned gx = static_cast<unsigned>(ceil_div(g.dst_w, K3T_COLS)), gy = static_cast<unsigned>(ceil_div(g.row_end - g.row_tile0, K3T_ROWS));
+    T fill_t;
+    if constexpr (std::is_floating_point<T>::value) fill_t = static_cast<T>(fill);
+    else fill_t = static_cast<T>(static_cast<long long>(fill));
+    const int plan = choose_plan(g.from, g.to) | (exact_only ? K3_PLAN_EXACT_ONLY : 0);
+    const bool axis_only = (g.from.kind == XRS_PROJ_GEOGRAPHIC || g.from.kind == XRS_PROJ_WEBMERC) &&
+                           (g.to.kind == XRS_PROJ_GEOGRAPHIC || g.to.kind == XRS_PROJ_WEBMERC);
+    std::vector<double> nodes;
+    if (use_nodes && XRS_K3_LATTICE && !axis_only && !(plan & K3_PLAN_EXACT_ONLY) && g.dst_w > 1 && g.dst_h > 1) {
+        const int n_tiles = static_cast<int>(gx * gy);
+        nodes.assign(static_cast<size_t>(n_tiles) * 34, 0.0);
+        blockDim.x = 256; gridDim.x = static_cast<unsigned>(ceil_div(static_cast<int64_t>(n_tiles) * 32, 256));
+        for (unsigned b = 0; b < gridDim.x; ++b)
+            for (unsigned t = 0; t < 256; ++t) { blockIdx.x = b; threadIdx.x = t; k3_lattice_nodes(g, nodes.data(), static_cast<int>(gx), n_tiles); }
+        g.lat_nodes = nodes.data();
+    }
+    stats[0] = plan; stats[1] = axis_only; stats[2] = g.lat_nodes != nullptr;
+    for (int b0 = 0; b0 < n_bands; b0 += K3_MAX_BANDS) {
+        const int nb = std::min(K3_MAX_BANDS, n_bands - b0);
+        K3Planes<T, OUT> planes = {};
+        for (int b = 0; b < nb; ++b) {
+            planes.src[b] = src + (b0 + b) * band_stride;
+            planes.dst[b] = dst + (b0 + b) * rows * g.dst_w;
+        }
+        if (axis_only) xrsh_k3_launch(gx, gy, [&] { k3_reproject<T, OUT, METHOD, true>(g, planes, nb, fill_t, plan); });
+        else xrsh_k3_launch(gx, gy, [&] { k3_reproject<T, OUT, METHOD, false>(g, planes, nb, fill_t, plan); });
+    }
+    return 0;
+}
+}
+
+// xrs_reproject for float32 sources: out_f64 = 1 writes float64 (bilinear as the reference returns it).  src points at
+// the resident window's origin (win_i0, win_j0).
+extern "C" int xrsh_reproject(const float *src, long band_stride, int n_bands, int out_f64, long src_h, long src_w, long src_pitch,
+                              long win_i0, long win_j0, long win_w, long win_h, const xrs_proj *src_crs, const xrs_proj *dst_crs,
+                              const double *dst_x, const double *dst_y, long dst_h, long dst_w, int tile_h, int tile_w,
+                              const double *tile_x0, const double *tile_y0, const int32_t *tile_i0, const int32_t *tile_j0,
+                              int tile_win_w, int tile_win_h, double src_x_res, double src_y_res, int method, double fill,
+                              long row_begin, long row_end, int exact_only, int use_nodes, void *dst, long *stats) {
+    using namespace xrs;
+    K3Geom g;
+    g.lat_nodes = nullptr;
+    if (int rc = make_proj_consts(dst_crs, &g.from)) return rc;
+    if (int rc = make_proj_consts(src_crs, &g.to)) return rc;
+    g.dst_x = dst_x; g.dst_y = dst_y; g.dst_h = dst_h; g.dst_w = dst_w;
+    g.row_begin = row_begin; g.row_end = row_end;
+    g.row_tile0 = row_begin - row_begin % K3T_ROWS;
+    g.tile_h = static_cast<int>(std::min<int64_t>(tile_h, dst_h));
+    g.tile_w = static_cast<int>(std::min<int64_t>(tile_w, dst_w));
+    g.ntx = static_cast<int>(ceil_div(dst_w, g.tile_w));
+    g.tile_x0 = tile_x0; g.tile_y0 = tile_y0; g.tile_i0 = tile_i0; g.tile_j0 = tile_j0;
+    g.tile_win_w = tile_win_w; g.tile_win_h = tile_win_h;
+    g.x_res = src_x_res; g.y_res = src_y_res;
+    g.inv_x_res = 1.0 / src_x_res; g.inv_y_res = 1.0 / src_y_res;
+    g.src_h = src_h; g.src_w = src_w; g.src_pitch = src_pitch;
+    g.win_i0 = win_i0; g.win_j0 = win_j0; g.win_w = win_w; g.win_h = win_h;
+    switch (method) {
+    case XRS_NEAREST:
+        return xrsh_launch_reproject<float, float, XRS_NEAREST>(g, src, band_stride, static_cast<float *>(dst), n_bands, fill, exact_only, use_nodes, stats);
+    case XRS_TRIANGULAR:
+        return xrsh_launch_reproject<float, float, XRS_TRIANGULAR>(g, src, band_stride, static_cast<float *>(dst), n_bands, fill, exact_only, use_nodes, stats);
+    case XRS_BILINEAR:
+        if (out_f64) return xrsh_launch_reproject<float, double, XRS_BILINEAR>(g, src, band_stride, static_cast<double *>(dst), n_bands, fill, exact_only, use_nodes, stats);
+        return xrsh_launch_reproject<float, float, XRS_BILINEAR>(g, src, band_stride, static_cast<float *>(dst), n_bands, fill, exact_only, use_nodes, stats);
+    }
+    return 2;
+}
+"""
+
+
+def build_k3(out_dir: str) -> str:
+    """Host build of proj.cuh + reproject.cu up to (and including) choose_plan."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not available")
+    proj = open(os.path.join(CSRC, "proj.cuh")).read()
+    proj, n = re.subn(r'#include "common.cuh"\n', "", proj)
+    assert n == 1, "proj.cuh no longer includes common.cuh exactly once"
+    proj = proj.replace("#pragma once\n", "")
+    text = open(os.path.join(CSRC, "reproject.cu")).read()
+    for inc in ('"proj.cuh"', '"tma.cuh"'):
+        text, n = re.subn(r"#include " + re.escape(inc) + r"\n", "", text)
+        assert n == 1, f"reproject.cu no longer includes {inc} exactly once"
+    text, n = re.subn(r'asm volatile\("prefetch\.global\.L2 \[%0\];" ::"l"\(planes\.src\[b\] \+ off\)\);',
+                      "(void)(planes.src[b] + off);", text)
+    assert n == 1, "the L2 prefetch instruction of k3_prefetch_box moved"
+    cut = text.find("// The scratch of k3_lattice_nodes comes from")
+    assert cut > 0 and "<<<" not in text[:cut] and "static int choose_plan" in text[:cut], "layout of reproject.cu changed"
+    src = os.path.join(out_dir, "k3_host.cpp")
+    with open(src, "w") as fh:
+        fh.write(K3_SHIM + "#include <functional>\n" + proj + text[:cut] + "\n}  // namespace xrs\n" + K3_EXPORT)
+    so = os.path.join(out_dir, "libxrs_k3host.so")
+    cmd = [gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-ffp-contract=off",
+           f"-I{os.path.join(ROOT, 'include')}", src, "-o", so]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("host build of reproject.cu failed:\n" + res.stderr[-6000:])
+    return so
+
+
+def k3_reproject(so_path: str, src, src_gm, tgt_gm, windows, method: str, fill, out_f64=None, rows=None, window=None,
+                 exact_only: bool = False, use_nodes: bool = True):
+    """``xrs_reproject`` (float32 sources) through the host build: ``(out, (plan, separable kernel, lattice nodes))``.
+    ``src_gm`` / ``tgt_gm``: the product's GridMappings; ``windows``: ``reproject.SourceWindows``; ``window`` =
+    (i0, j0, i1, j1) resident part of the source; arguments are prepared as ``ReprojectPlan`` does."""
+    from xcube_resampling_b200._lib import XrsProj
+
+    lib = ctypes.CDLL(so_path)
+    _, me = _k2_codes()
+    src = np.ascontiguousarray(src, dtype=np.float32)
+    nb, h, w = src.shape
+    if out_f64 is None:
+        out_f64 = method == "bilinear"
+    r0, r1 = rows if rows is not None else (0, tgt_gm.height)
+    out = np.empty((nb, r1 - r0, tgt_gm.width), dtype=np.float64 if out_f64 else np.float32)
+    base, bstride, pitch, i0, j0, ww, wh = _k2_window(src, window)
+    sp, dp = XrsProj.from_crs(src_gm.crs), XrsProj.from_crs(tgt_gm.crs)
+    dst_x = np.ascontiguousarray(tgt_gm.x_values, dtype=np.float64)
+    dst_y = np.ascontiguousarray(tgt_gm.y_values, dtype=np.float64)
+    x0 = np.ascontiguousarray(windows.x0.astype(np.float64).ravel())
+    y0 = np.ascontiguousarray(windows.y0.astype(np.float64).ravel())
+    ti0 = np.ascontiguousarray(windows.i0.astype(np.int32).ravel())
+    tj0 = np.ascontiguousarray(windows.j0.astype(np.int32).ravel())
+    stats = np.zeros(3, dtype=np.int64)
+    c_d, c_l, c_i, c_p = ctypes.c_double, ctypes.c_long, ctypes.c_int, ctypes.c_void_p
+    lib.xrsh_reproject.restype = c_i
+    lib.xrsh_reproject.argtypes = [c_p, c_l, c_i, c_i, c_l, c_l, c_l, c_l, c_l, c_l, c_l, c_p, c_p, c_p, c_p, c_l, c_l, c_i, c_i,
+                                   c_p, c_p, c_p, c_p, c_i, c_i, c_d, c_d, c_i, c_d, c_l, c_l, c_i, c_i, c_p, c_p]
+    rc = lib.xrsh_reproject(base, bstride, nb, int(out_f64), src_gm.height, src_gm.width, pitch, i0, j0, ww, wh,
+                            ctypes.addressof(sp), ctypes.addressof(dp), dst_x.ctypes.data, dst_y.ctypes.data, tgt_gm.height,
+                            tgt_gm.width, tgt_gm.tile_height, tgt_gm.tile_width, x0.ctypes.data, y0.ctypes.data,
+                            ti0.ctypes.data, tj0.ctypes.data, int(windows.win_w), int(windows.win_h), float(src_gm.x_res),
+                            float(src_gm.y_res), me[method], float(fill), r0, r1, int(exact_only), int(use_nodes),
+                            out.ctypes.data, stats.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"xrsh_reproject failed ({rc})")
+    return out, (int(stats[0]), bool(stats[1]), bool(stats[2]))
