@@ -1818,7 +1818,7 @@ def k2_gather_fused(so_path: str, src, x, y, tile_boxes, claims, g, method: str,
 # lattice pre-kernel, the tile logic, the separable / row-block / lattice / exact forms and the per-pixel blend
 # are the product's text.  Differences to the device build: libm instead of CUDA's math library and no FMA
 # contraction in proj.cuh (~1e-9 m in the source coordinates).
-K3_SHIM = "#define _GNU_SOURCE 1\n#define XRS_K3_LD256 0\n" + K0_SHIM.replace("#define __shared__\n", "#define __shared__ static\n") + r"""
+K3K_SHIM = "#define _GNU_SOURCE 1\n#define XRS_K3_LD256 0\n" + K0_SHIM.replace("#define __shared__\n", "#define __shared__ static\n") + r"""
 #include <string>
 #include <type_traits>
 #include <math.h>
@@ -1873,7 +1873,7 @@ static inline int __syncthreads_and(int p) {
 }
 """
 
-K3_EXPORT = r"""
+K3K_EXPORT = r"""
 namespace {
 struct XrshK3Launch { unsigned gx, gy; const std::function<void()> *body; };
 struct XrshK3Thread { unsigned tid; const XrshK3Launch *l; };
@@ -2009,7 +2009,7 @@ def build_k3(out_dir: str) -> str:
     assert cut > 0 and "<<<" not in text[:cut] and "static int choose_plan" in text[:cut], "layout of reproject.cu changed"
     src = os.path.join(out_dir, "k3_host.cpp")
     with open(src, "w") as fh:
-        fh.write(K3_SHIM + "#include <functional>\n" + proj + text[:cut] + "\n}  // namespace xrs\n" + K3_EXPORT)
+        fh.write(K3K_SHIM + "#include <functional>\n" + proj + text[:cut] + "\n}  // namespace xrs\n" + K3K_EXPORT)
     so = os.path.join(out_dir, "libxrs_k3host.so")
     cmd = [gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-ffp-contract=off",
            f"-I{os.path.join(ROOT, 'include')}", src, "-o", so]
