@@ -39,9 +39,13 @@ def test_compressed_store_is_refused(tmp_path):
 
     write_zarr_array(str(tmp_path / "a"), np.zeros((4, 4), dtype=np.float32), (2, 2), ("y", "x"))
     meta = json.load(open(tmp_path / "a" / ".zarray"))
-    meta["compressor"] = {"id": "blosc"}
+    meta["compressor"] = {"id": "jpeg2k"}
     json.dump(meta, open(tmp_path / "a" / ".zarray", "w"))
     with pytest.raises(NotImplementedError, match="zarr package"):
+        ZarrV2Source(str(tmp_path / "a"))
+    meta["compressor"], meta["filters"] = None, [{"id": "delta", "dtype": "<f4"}]
+    json.dump(meta, open(tmp_path / "a" / ".zarray", "w"))
+    with pytest.raises(NotImplementedError, match="filtered"):
         ZarrV2Source(str(tmp_path / "a"))
 
 
@@ -130,4 +134,100 @@ def test_codec_known_answers():
     assert chunk_decoder({"id": "lz4"})(lz4_chunk) == b"abc"
     assert chunk_decoder(None) is None
     with pytest.raises(NotImplementedError, match="zarr package"):
-        chunk_decoder({"id": "blosc", "cname": "lz4"})
+        chunk_decoder({"id": "jpeg2k"})
+
+
+def _blosc_frame(raw: bytes, typesize: int, blocksize: int, shuffle: bool, cname: str, dont_split: bool = False,
+                 store_streams: bool = False) -> bytes:
+    """A Blosc-1 frame assembled from the container description in ``io.blosc_decompress`` (16-byte header,
+    block offsets, per-block streams each prefixed by its int32 size); inner streams from zlib / pyarrow."""
+    import zlib
+
+    import pyarrow as pa
+
+    fmt, enc = {"lz4": (1, lambda r: pa.Codec("lz4_raw").compress(r).to_pybytes()),
+                "snappy": (2, lambda r: pa.Codec("snappy").compress(r).to_pybytes()),
+                "zlib": (3, lambda r: zlib.compress(r, 1)),
+                "zstd": (4, lambda r: pa.Codec("zstd").compress(r).to_pybytes())}[cname]
+    flags = (fmt << 5) | (0x10 if dont_split else 0) | (0x1 if shuffle else 0)
+    nblocks = -(-len(raw) // blocksize)
+    body, starts = b"", []
+    for b in range(nblocks):
+        block = np.frombuffer(raw[b * blocksize:(b + 1) * blocksize], dtype=np.uint8)
+        if shuffle and typesize > 1:
+            n = len(block) // typesize
+            block = np.concatenate([block[:n * typesize].reshape(n, typesize).T.reshape(-1), block[n * typesize:]])
+        split = (not dont_split and typesize <= 16 and blocksize // typesize >= 128 and len(block) == blocksize)
+        nstreams = typesize if split else 1
+        ne = len(block) // nstreams
+        starts.append(16 + 4 * nblocks + len(body))
+        for k in range(nstreams):
+            part = block[k * ne:(k + 1) * ne].tobytes()
+            comp = enc(part)
+            if store_streams or len(comp) >= ne:  # stored verbatim: size field == decoded size
+                comp = part
+            assert len(comp) != ne or comp == part
+            body += len(comp).to_bytes(4, "little") + comp
+    head = bytes([2, 1, flags, typesize]) + len(raw).to_bytes(4, "little") + blocksize.to_bytes(4, "little")
+    total = 16 + 4 * nblocks + len(body)
+    return head + total.to_bytes(4, "little") + b"".join(s.to_bytes(4, "little") for s in starts) + body
+
+
+def test_blosc_known_answers():
+    """Frames written out byte by byte from c-blosc's published container layout."""
+    from xcube_resampling_b200.io import blosc_decompress, chunk_decoder
+
+    assert chunk_decoder({"id": "blosc", "cname": "lz4", "clevel": 5, "shuffle": 1, "blocksize": 0}) is blosc_decompress
+    # flag bit 1: the payload is a plain copy, no block offsets
+    stored = bytes.fromhex("02" "01" "02" "01" "03000000" "03000000" "13000000") + b"abc"
+    assert blosc_decompress(stored) == b"abc"
+    # LZ4 (format 1 in bits 5-7), one block, one stream of 4 bytes: token 0x30 = 3 literals, no match
+    lz4 = bytes.fromhex("02" "01" "20" "01" "03000000" "03000000" "1c000000" "14000000" "04000000" "30") + b"abc"
+    assert blosc_decompress(lz4) == b"abc"
+    # byte shuffle (bit 0), typesize 2, two elements 0x0102, 0x0304: the block holds the low bytes, then the high
+    # bytes; the stream's size field equals its decoded size, so it is stored verbatim
+    shuf = bytes.fromhex("02" "01" "21" "02" "04000000" "04000000" "1c000000" "14000000" "04000000" "02040103")
+    assert np.array_equal(np.frombuffer(blosc_decompress(shuf), dtype="<u2"), [0x0102, 0x0304])
+    # a trailing byte beyond the last whole element is not shuffled
+    shuf5 = bytes.fromhex("02" "01" "21" "02" "05000000" "05000000" "1d000000" "14000000" "05000000" "02040103" "ff")
+    assert blosc_decompress(shuf5) == bytes.fromhex("02010403ff")
+    assert blosc_decompress(bytes.fromhex("02" "01" "21" "04" "00000000" "00000000" "10000000")) == b""
+    with pytest.raises(NotImplementedError, match="bit-shuffled"):
+        blosc_decompress(bytes.fromhex("02" "01" "24" "01" "03000000" "03000000" "1c000000" "14000000" "04000000" "30")
+                         + b"abc")
+    with pytest.raises(NotImplementedError, match="BloscLZ"):
+        blosc_decompress(bytes.fromhex("02" "01" "00" "01" "03000000" "03000000" "1c000000" "14000000" "04000000" "30")
+                         + b"abc")
+    with pytest.raises(ValueError):
+        blosc_decompress(b"\x02\x01")
+    with pytest.raises(ValueError, match="outside"):
+        blosc_decompress(bytes.fromhex("02" "01" "20" "01" "03000000" "03000000" "1c000000" "14000000" "40000000" "30")
+                         + b"abc")
+
+
+@pytest.mark.parametrize("cname", ["lz4", "snappy", "zlib", "zstd"])
+@pytest.mark.parametrize("layout", ["split", "dont_split", "no_shuffle", "stored_streams"])
+def test_blosc_frames_round_trip(cname, layout):
+    """Several blocks, a partial last block, typesize streams per block when splitting applies."""
+    from xcube_resampling_b200.io import blosc_decompress
+
+    rng = np.random.default_rng(11)
+    raw = (rng.integers(0, 40, 1500) / 8).astype(np.float32).tobytes() + b"\x07\x09\x0b"  # 6003 bytes
+    frame = _blosc_frame(raw, 4, 2048, shuffle=layout != "no_shuffle", cname=cname, dont_split=layout == "dont_split",
+                         store_streams=layout == "stored_streams")
+    assert blosc_decompress(frame) == raw
+    assert blosc_decompress(frame + b"padding") == raw  # cbytes, not the buffer length, bounds the frame
+
+
+def test_blosc_compressed_store(tmp_path):
+    """A store as xarray's ``to_zarr`` writes it by default (Blosc, LZ4, byte shuffle), ragged chunks included."""
+    rng = np.random.default_rng(5)
+    a = (rng.integers(0, 50, (3, 40, 70)) / 7).astype(np.float32)
+    write_zarr_array(str(tmp_path / "a"), a, (2, 16, 32), ("band", "y", "x"))
+    _compress_store(str(tmp_path / "a"), lambda r: _blosc_frame(r, 4, 1024, True, "lz4"),
+                    {"id": "blosc", "cname": "lz4", "clevel": 5, "shuffle": 1, "blocksize": 0})
+    src = ZarrV2Source(str(tmp_path / "a"))
+    assert np.array_equal(src.read_all(), a)
+    out = np.empty((2, 40, 70), dtype=np.float32)
+    src.read_bands(1, 2, out)
+    assert np.array_equal(out, a[1:3])

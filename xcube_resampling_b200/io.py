@@ -13,9 +13,10 @@ Stores understood without third-party packages:
   ``add_spatial_ref`` (``cfconv.py``) and the reference's Zarr helpers operate on.  Chunks may be
   uncompressed (``"compressor": null``: read straight into the staging buffer) or compressed with a
   codec whose stream format the standard library or pyarrow decodes (numcodecs ids ``zlib``, ``gzip``,
-  ``bz2``, ``lzma``, ``zstd``, ``lz4``), decoded on the reader thread.  Blosc frames and filters need
-  the ``zarr`` / ``numcodecs`` packages, which this build does not have; open such stores with xarray
-  and pass the arrays instead.
+  ``bz2``, ``lzma``, ``zstd``, ``lz4``, and ``blosc`` -- zarr's default -- with an LZ4 / LZ4HC / Snappy /
+  Zlib / Zstd inner codec, byte shuffle or none: :func:`blosc_decompress`), decoded on the reader thread.
+  BloscLZ or bit-shuffled Blosc frames and Zarr filters need the ``zarr`` / ``numcodecs`` packages, which
+  this build does not have; open such stores with xarray and pass the arrays instead.
 * :class:`NpySource` -- a ``.npy`` file, memory-mapped.
 
 :func:`open_zarr_dataset` assembles a :class:`~xcube_resampling_b200.dataset.Dataset` from a
@@ -82,8 +83,103 @@ def chunk_decoder(compressor: dict | None):
             return codec.decompress(raw[4:], decompressed_size=size).to_pybytes()
 
         return lz4
+    if cid == "blosc":
+        return blosc_decompress
     raise NotImplementedError(f"Zarr chunks compressed with {cid!r} need the zarr package, which this build does not "
                               "have; open the store with xarray and pass the arrays instead")
+
+
+_BLOSC_MAX_SPLITS, _BLOSC_MIN_BUFFERSIZE = 16, 128
+
+
+def _blosc_stream_decoder(fmt: int):
+    """``(bytes, decoded size) -> bytes`` of the inner codec a Blosc-1 frame names in bits 5-7 of its flags."""
+    if fmt == 1:  # LZ4 / LZ4HC: one raw LZ4 block per stream
+        codec = _pyarrow_codec("lz4_raw")
+        return lambda raw, n: codec.decompress(raw, decompressed_size=n).to_pybytes()
+    if fmt == 2:
+        codec = _pyarrow_codec("snappy")
+        return lambda raw, n: codec.decompress(raw, decompressed_size=n).to_pybytes()
+    if fmt == 3:
+        import zlib
+
+        return lambda raw, n: zlib.decompress(raw)
+    if fmt == 4:
+        codec = _pyarrow_codec("zstd")
+        return lambda raw, n: codec.decompress(raw, decompressed_size=n).to_pybytes()
+    raise NotImplementedError("Blosc frames compressed with BloscLZ need the zarr / blosc packages, which this build "
+                              "does not have (lz4, lz4hc, snappy, zlib and zstd frames are decoded)")
+
+
+def blosc_decompress(frame: bytes) -> bytes:
+    """Decode one Blosc-1 frame (what numcodecs' ``Blosc`` -- zarr-v2's default compressor -- writes per chunk),
+    following the container layout c-blosc publishes (README_HEADER.rst, ``blosc_d`` in blosc.c):
+
+    * 16-byte header: version, versionlz, flags, typesize, then little-endian uint32 ``nbytes`` (decoded size),
+      ``blocksize``, ``cbytes`` (size of the whole frame).  Flags: bit 0 byte shuffle, bit 1 the payload is a
+      plain copy, bit 2 bit shuffle, bit 4 blocks are not split, bits 5-7 the inner codec
+      (0 BloscLZ, 1 LZ4 / LZ4HC, 2 Snappy, 3 Zlib, 4 Zstd).
+    * ``ceil(nbytes / blocksize)`` int32 block offsets (from the start of the frame), then the blocks.  A block
+      is ``typesize`` streams (one per byte position of the shuffled block) when splitting applies -- not the
+      last, partial block; ``typesize <= 16``; at least 128 bytes per stream -- else one stream.  A stream is an
+      int32 compressed size followed by the data, stored verbatim when that size equals the decoded size.
+    * byte shuffle within a block of ``n`` elements: byte ``j`` of element ``i`` sits at ``j * n + i``; the
+      ``blocksize % typesize`` trailing bytes are not shuffled.
+
+    The inner codecs come from the standard library / pyarrow; there is no Blosc library in this image, so
+    the tests assemble their frames by hand from this description.  Bit-shuffled frames and BloscLZ raise
+    ``NotImplementedError``."""
+    if len(frame) < 16:
+        raise ValueError("not a Blosc frame: shorter than its 16-byte header")
+    version, _, flags, typesize = frame[0], frame[1], frame[2], frame[3]
+    nbytes, blocksize, cbytes = (int.from_bytes(frame[k:k + 4], "little") for k in (4, 8, 12))
+    if version != 2 or cbytes > len(frame) or (nbytes and blocksize == 0):
+        raise ValueError(f"not a Blosc-1 frame (version {version}, cbytes {cbytes} of {len(frame)} bytes)")
+    if nbytes == 0:
+        return b""
+    if flags & 0x2:  # stored
+        if 16 + nbytes > len(frame):
+            raise ValueError("truncated Blosc frame")
+        return bytes(frame[16:16 + nbytes])
+    if flags & 0x4:
+        raise NotImplementedError("bit-shuffled Blosc frames need the zarr / blosc packages, which this build does "
+                                  "not have")
+    decode = _blosc_stream_decoder(flags >> 5)
+    typesize = max(typesize, 1)
+    shuffled = bool(flags & 0x1) and typesize > 1
+    nblocks = -(-nbytes // blocksize)
+    starts = np.frombuffer(frame, dtype="<i4", count=nblocks, offset=16)
+    out = np.empty(nbytes, dtype=np.uint8)
+    for b in range(nblocks):
+        bsize = min(blocksize, nbytes - b * blocksize)
+        leftover = bsize != blocksize
+        split = (not flags & 0x10 and typesize <= _BLOSC_MAX_SPLITS
+                 and blocksize // typesize >= _BLOSC_MIN_BUFFERSIZE and not leftover)
+        nstreams = typesize if split else 1
+        neblock = bsize // nstreams
+        pos, parts = int(starts[b]), []
+        for _ in range(nstreams):
+            if pos < 16 or pos + 4 > len(frame):
+                raise ValueError("corrupt Blosc frame: stream outside the frame")
+            csize = int.from_bytes(frame[pos:pos + 4], "little", signed=True)
+            pos += 4
+            if csize < 0 or pos + csize > len(frame):
+                raise ValueError("corrupt Blosc frame: stream outside the frame")
+            raw = frame[pos:pos + csize]
+            pos += csize
+            part = bytes(raw) if csize == neblock else decode(raw, neblock)
+            if len(part) != neblock:
+                raise ValueError("corrupt Blosc frame: stream decodes to the wrong size")
+            parts.append(part)
+        block = np.frombuffer(b"".join(parts), dtype=np.uint8)
+        dst = out[b * blocksize:b * blocksize + bsize]
+        if shuffled:
+            n = bsize // typesize
+            dst[:n * typesize] = block[:n * typesize].reshape(typesize, n).T.reshape(-1)
+            dst[n * typesize:] = block[n * typesize:]
+        else:
+            dst[:] = block
+    return out.tobytes()
 
 
 def _zstd_content_size(raw: bytes) -> int | None:
