@@ -231,3 +231,34 @@ def test_blosc_compressed_store(tmp_path):
     out = np.empty((2, 40, 70), dtype=np.float32)
     src.read_bands(1, 2, out)
     assert np.array_equal(out, a[1:3])
+
+
+def test_open_zarr_dataset_on_a_blosc_store(tmp_path):
+    """Every array of the store is compressed, the 1-D axis coordinates and the 0-D ``spatial_ref`` included."""
+    import json
+
+    from xcube_resampling_b200.synthetic import swath
+
+    lon, lat = swath(40, 30, seed=2)
+    data = np.random.default_rng(2).random((3, 30, 40)).astype(np.float32)
+    store = tmp_path / "scene.zarr"
+    write_zarr_array(str(store / "lon"), lon, (16, 16), ("y", "x"))
+    write_zarr_array(str(store / "lat"), lat, (16, 16), ("y", "x"))
+    write_zarr_array(str(store / "rad"), data, (1, 16, 40), ("band", "y", "x"))
+    write_zarr_array(str(store / "band"), np.arange(7, dtype=np.int64), (4,), ("band7",))
+    write_zarr_array(str(store / "spatial_ref"), np.asarray(5, dtype=np.int64), (), ())
+    meta = {"id": "blosc", "cname": "zstd", "clevel": 3, "shuffle": 1, "blocksize": 0}
+    for name, typesize in (("lon", 8), ("lat", 8), ("rad", 4), ("band", 8), ("spatial_ref", 8)):
+        _compress_store(str(store / name), lambda r, t=typesize: _blosc_frame(r, t, 4096, True, "zstd"), meta)
+    ds = open_zarr_dataset(str(store))
+    assert np.array_equal(ds["band"].values, np.arange(7)) and ds["spatial_ref"].values == 5
+    assert np.array_equal(ds["lon"].values, lon) and np.array_equal(ds["lat"].values, lat)
+    assert isinstance(ds["rad"], LazyDataArray) and np.array_equal(ds["rad"].values, data)
+    # a missing chunk of a 1-D array is fill value; "NaN" is JSON's spelling of the float special
+    write_zarr_array(str(store / "t"), np.arange(6, dtype=np.float64), (4,), ("t",))
+    (store / "t" / "1").unlink()
+    m = json.load(open(store / "t" / ".zarray"))
+    m["fill_value"] = "NaN"
+    json.dump(m, open(store / "t" / ".zarray", "w"))
+    t = open_zarr_dataset(str(store))["t"].values
+    assert np.array_equal(t[:4], np.arange(4)) and np.isnan(t[4:]).all() and t.shape == (6,)

@@ -266,8 +266,7 @@ class ZarrV2Source(LazySource):
     def _chunk(self, idx):
         p = os.path.join(self.path, self.sep.join(str(i) for i in idx))
         if not os.path.isfile(p):  # a missing chunk is all fill value
-            fill = self.fill if self.fill not in (None, "NaN") else (np.nan if self.dtype.kind == "f" else 0)
-            return np.full(self.chunks, fill, dtype=self.dtype)
+            return np.full(self.chunks, _fill_value(self.fill, self.dtype), dtype=self.dtype)
         if self._decode is None:
             return np.fromfile(p, dtype=self.dtype).reshape(self.chunks)
         with open(p, "rb") as fh:
@@ -308,10 +307,47 @@ class LazyDataArray(DataArray):
     data = values
 
 
+def _fill_value(fill, dtype: np.dtype):
+    """The value of a missing chunk: ``fill_value`` of ``.zarray`` (``"NaN"`` / ``"Infinity"`` /
+    ``"-Infinity"`` are the JSON spellings of the float specials; ``null`` leaves it undefined -- zero here)."""
+    if isinstance(fill, str) or fill is None:
+        return {"NaN": np.nan, "Infinity": np.inf, "-Infinity": -np.inf}.get(fill, 0) if dtype.kind == "f" else 0
+    return fill
+
+
+def _read_small_array(arr_dir: str, meta: dict) -> np.ndarray:
+    """A 0-D or 1-D Zarr-v2 array (``spatial_ref``, axis coordinates), chunks decoded like those of
+    :class:`ZarrV2Source`; missing chunks hold the fill value."""
+    if meta.get("filters"):
+        raise NotImplementedError(f"{arr_dir}: filtered Zarr arrays need the zarr package, which this build does not "
+                                  "have; open the store with xarray and pass the arrays instead")
+    try:
+        decode = chunk_decoder(meta.get("compressor"))
+    except NotImplementedError as e:
+        raise NotImplementedError(f"{arr_dir}: {e}") from None
+    dt = np.dtype(meta["dtype"])
+    fill = _fill_value(meta.get("fill_value"), dt)
+
+    def chunk(name, count):
+        p = os.path.join(arr_dir, name)
+        if not os.path.isfile(p):
+            return np.full(count, fill, dtype=dt)
+        raw = open(p, "rb").read()
+        return np.frombuffer(raw if decode is None else decode(raw), dtype=dt)[:count]
+
+    shape = tuple(int(n) for n in meta["shape"])
+    if not shape:
+        return chunk("0", 1)[0].copy()
+    n, c = shape[0], int(meta["chunks"][0])
+    return np.concatenate([chunk(str(k), c)[:min(c, n - k * c)] for k in range(-(-n // c))]) if n else np.empty(0, dt)
+
+
 def open_zarr_dataset(path: str, coord_names=("lon", "lat", "x", "y", "longitude", "latitude",
                                               "transformed_x", "transformed_y")) -> Dataset:
-    """An uncompressed Zarr-v2 directory store as a :class:`Dataset`: scalar, 1-D and coordinate-named
-    arrays are read now, every other 2-D / 3-D array becomes a :class:`LazyDataArray`."""
+    """A Zarr-v2 directory store as a :class:`Dataset`: scalar, 1-D and coordinate-named arrays are read
+    now, every other 2-D / 3-D array becomes a :class:`LazyDataArray`.  Values are delivered as stored
+    (what ``xarray.open_zarr(..., mask_and_scale=False)`` gives): ``scale_factor`` / ``add_offset`` /
+    ``_FillValue`` attributes are passed through, not applied."""
     data_vars, coords = {}, {}
     for item in sorted(os.listdir(path)):
         arr_dir = os.path.join(path, item)
@@ -322,15 +358,8 @@ def open_zarr_dataset(path: str, coord_names=("lon", "lat", "x", "y", "longitude
         attrs = json.load(open(attrs_path)) if os.path.isfile(attrs_path) else {}
         dims = attrs.pop("_ARRAY_DIMENSIONS", None) or [f"dim_{k}" for k in range(len(meta["shape"]))]
         shape = tuple(meta["shape"])
-        if len(shape) == 0:
-            chunk = os.path.join(arr_dir, "0")
-            value = np.fromfile(chunk, dtype=np.dtype(meta["dtype"]))[0] if os.path.isfile(chunk) else 0
-            coords[item] = DataArray(np.asarray(value), dims=(), attrs=attrs, name=item)
-        elif len(shape) == 1:
-            dt = np.dtype(meta["dtype"])
-            n, c = shape[0], int(meta["chunks"][0])
-            parts = [np.fromfile(os.path.join(arr_dir, str(k)), dtype=dt)[:min(c, n - k * c)] for k in range(-(-n // c))]
-            coords[item] = DataArray(np.concatenate(parts), dims=dims, attrs=attrs, name=item)
+        if len(shape) <= 1:
+            coords[item] = DataArray(_read_small_array(arr_dir, meta), dims=dims if shape else (), attrs=attrs, name=item)
         else:
             src = ZarrV2Source(arr_dir)
             if item in coord_names:
