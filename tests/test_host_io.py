@@ -6,6 +6,8 @@ import pytest
 
 from xcube_resampling_b200 import GridMapping
 from xcube_resampling_b200.io import (
+    NetCDF3Source,
+    open_netcdf_dataset,
     LazyDataArray,
     NpySource,
     ZarrV2Source,
@@ -262,3 +264,42 @@ def test_open_zarr_dataset_on_a_blosc_store(tmp_path):
     json.dump(m, open(store / "t" / ".zarray", "w"))
     t = open_zarr_dataset(str(store))["t"].values
     assert np.array_equal(t[:4], np.arange(4)) and np.isnan(t[4:]).all() and t.shape == (6,)
+
+
+def test_open_netcdf_classic_dataset(tmp_path):
+    """A NetCDF classic (64-bit offset) file written by scipy: big-endian on disk, lazy 3-D variable over the
+    memory map, coordinates / scalar grid-mapping variable / attributes as a Dataset the CF discovery accepts."""
+    from scipy.io import netcdf_file
+
+    from xcube_resampling_b200.synthetic import swath
+
+    lon, lat = swath(40, 30, seed=3)
+    rad = np.random.default_rng(3).random((3, 30, 40)).astype(np.float32)
+    cls = np.random.default_rng(4).integers(0, 200, (30, 40)).astype(np.int16)
+    path = str(tmp_path / "scene.nc")
+    f = netcdf_file(path, "w", version=2)
+    for name, n in (("band", 3), ("y", 30), ("x", 40)):
+        f.createDimension(name, n)
+    f.title = "scene"
+    for name, typ, dims, values in (("rad", "f4", ("band", "y", "x"), rad), ("cls", "i2", ("y", "x"), cls),
+                                    ("lon", "f8", ("y", "x"), lon), ("lat", "f8", ("y", "x"), lat),
+                                    ("band", "i4", ("band",), np.arange(3))):
+        v = f.createVariable(name, typ, dims)
+        v[:] = values
+    f.variables["rad"].units = "mW.m-2.sr-1.nm-1"
+    f.close()
+    ds = open_netcdf_dataset(path)
+    assert ds.attrs == {"title": "scene"} and ds["rad"].attrs == {"units": "mW.m-2.sr-1.nm-1"}
+    assert isinstance(ds["rad"], LazyDataArray) and isinstance(ds["rad"].source, NetCDF3Source)
+    assert ds["rad"].dims == ("band", "y", "x") and ds["rad"].dtype == np.float32 and ds["rad"].dtype.isnative
+    assert np.array_equal(ds["rad"].values, rad) and np.array_equal(ds["cls"].values, cls)
+    out = np.empty((2, 30, 40), dtype=np.float32)
+    ds["rad"].source.read_bands(1, 2, out)
+    assert np.array_equal(out, rad[1:])
+    assert "lon" in ds.coords and ds["lon"].dtype.isnative and np.array_equal(ds["lon"].values, lon)
+    assert np.array_equal(ds["band"].values, np.arange(3))
+    gm = GridMapping.from_dataset(ds)
+    assert gm.size == (40, 30) and not gm.is_regular
+    (tmp_path / "x.nc").write_bytes(b"\x89HDF\r\n\x1a\n" + bytes(64))
+    with pytest.raises(NotImplementedError, match="NetCDF-4"):
+        open_netcdf_dataset(str(tmp_path / "x.nc"))

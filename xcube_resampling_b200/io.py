@@ -18,8 +18,12 @@ Stores understood without third-party packages:
   BloscLZ or bit-shuffled Blosc frames and Zarr filters need the ``zarr`` / ``numcodecs`` packages, which
   this build does not have; open such stores with xarray and pass the arrays instead.
 * :class:`NpySource` -- a ``.npy`` file, memory-mapped.
+* :class:`NetCDF3Source` -- a variable of a NetCDF classic / 64-bit-offset file (CDF-1 / CDF-2), memory-mapped
+  through ``scipy.io.netcdf_file``; its big-endian values are byte-swapped by the copy into the staging
+  buffer.  NetCDF-4 files are HDF5 containers and need ``netCDF4`` / ``h5py``, which this build does not
+  have; open them with xarray and pass the arrays instead.
 
-:func:`open_zarr_dataset` assembles a :class:`~xcube_resampling_b200.dataset.Dataset` from a
+:func:`open_zarr_dataset` / :func:`open_netcdf_dataset` assemble a :class:`~xcube_resampling_b200.dataset.Dataset` from a
 directory store: coordinate arrays (1-D, or 2-D named like coordinates) are read eagerly, every
 other array becomes a lazy variable.
 """
@@ -235,6 +239,23 @@ class NpySource(LazySource):
         out[:nb] = src[b0:b0 + nb]
 
 
+class NetCDF3Source(LazySource):
+    """One 2-D or 3-D variable of an open ``scipy.io.netcdf_file`` (``mmap=True``).  The file object is kept
+    alive by the source; values are delivered as stored, in native byte order."""
+
+    def __init__(self, nc_file, name: str):
+        self._file = nc_file  # owns the memory map the variable's data points into
+        self._var = nc_file.variables[name]
+        if len(self._var.shape) not in (2, 3):
+            raise ValueError(f"{name}: expected a 2-D or 3-D variable, got shape {self._var.shape}")
+        self.shape = tuple(int(n) for n in self._var.shape)
+        self.dtype = self._var.data.dtype.newbyteorder("=")
+
+    def read_bands(self, b0, nb, out):
+        data = self._var.data
+        out[:nb] = (data[None] if data.ndim == 2 else data)[b0:b0 + nb]
+
+
 class ZarrV2Source(LazySource):
     """One Zarr-v2 array of a directory store (2-D or 3-D, C order; uncompressed or with a codec of
     :func:`chunk_decoder`)."""
@@ -368,6 +389,51 @@ def open_zarr_dataset(path: str, coord_names=("lon", "lat", "x", "y", "longitude
                 data_vars[item] = LazyDataArray(src, dims=dims, attrs=attrs, name=item)
     group_attrs = os.path.join(path, ".zattrs")
     return Dataset(data_vars=data_vars, coords=coords, attrs=json.load(open(group_attrs)) if os.path.isfile(group_attrs) else {})
+
+
+def open_netcdf_dataset(path: str, coord_names=("lon", "lat", "x", "y", "longitude", "latitude",
+                                                "transformed_x", "transformed_y")) -> Dataset:
+    """A NetCDF classic file as a :class:`Dataset`, with the rules of :func:`open_zarr_dataset`: scalar, 1-D
+    and coordinate-named variables are read now, every other 2-D / 3-D variable becomes a
+    :class:`LazyDataArray` over the file's memory map.  Values as stored (no CF mask-and-scale); ``bytes``
+    attributes are decoded to ``str`` as xarray does."""
+    from scipy.io import netcdf_file
+
+    with open(path, "rb") as fh:
+        magic = fh.read(4)
+    if magic[:3] != b"CDF":
+        kind = "a NetCDF-4 / HDF5 file, which needs the netCDF4 or h5py package (not in this build); open it with " \
+               "xarray and pass the arrays instead" if magic == b"\x89HDF" else "not a NetCDF classic file"
+        raise NotImplementedError(f"{path}: {kind}")
+
+    class MappedFile(netcdf_file):
+        """Lazy variables keep views of the memory map for as long as they live, so the map is released by
+        the garbage collector, not by close(): scipy's warning about exactly that is not news here."""
+
+        def close(self):
+            import warnings
+
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", RuntimeWarning)
+                super().close()
+
+        __del__ = close
+
+    nc = MappedFile(path, "r", mmap=True, maskandscale=False)
+
+    def text(v):
+        return v.decode("utf-8", "replace") if isinstance(v, bytes) else v
+
+    data_vars, coords = {}, {}
+    for name, var in nc.variables.items():
+        attrs = {k: text(v) for k, v in var._attributes.items()}
+        dims = tuple(var.dimensions)
+        if len(var.shape) in (2, 3) and name not in coord_names:
+            data_vars[name] = LazyDataArray(NetCDF3Source(nc, name), dims=dims, attrs=attrs, name=name)
+            continue
+        values = np.array(var.data, dtype=var.data.dtype.newbyteorder("="))  # a copy: independent of the map
+        (coords if len(var.shape) <= 2 else data_vars)[name] = DataArray(values, dims=dims, attrs=attrs, name=name)
+    return Dataset(data_vars=data_vars, coords=coords, attrs={k: text(v) for k, v in nc._attributes.items()})
 
 
 def write_zarr_array(path: str, array: np.ndarray, chunks, dims) -> None:
