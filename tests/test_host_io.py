@@ -303,3 +303,45 @@ def test_open_netcdf_classic_dataset(tmp_path):
     (tmp_path / "x.nc").write_bytes(b"\x89HDF\r\n\x1a\n" + bytes(64))
     with pytest.raises(NotImplementedError, match="NetCDF-4"):
         open_netcdf_dataset(str(tmp_path / "x.nc"))
+
+
+def test_mask_and_scale_decoding_of_lazy_variables(tmp_path):
+    """CF packing (Sentinel-3 radiances: uint16 + scale_factor + _FillValue) decoded on the reader thread:
+    fill -> NaN, then raw * scale_factor + add_offset in float32; int32 data decode to float64; variables
+    without coding attributes and the default (mask_and_scale=False) are untouched."""
+    import json
+
+    from xcube_resampling_b200.io import DecodedSource, cf_decoded_dtype
+
+    rng = np.random.default_rng(9)
+    rad = rng.integers(0, 65535, (3, 20, 30)).astype(np.uint16)
+    rad[0, 0, :5] = 65535
+    cnt = rng.integers(-1000, 1000, (20, 30)).astype(np.int32)
+    cnt[3, 4] = -999
+    plain = rng.random((20, 30)).astype(np.float32)
+    store = tmp_path / "s.zarr"
+    write_zarr_array(str(store / "rad"), rad, (1, 8, 16), ("band", "y", "x"))
+    write_zarr_array(str(store / "cnt"), cnt, (8, 16), ("y", "x"))
+    write_zarr_array(str(store / "plain"), plain, (8, 16), ("y", "x"))
+    for name, extra in (("rad", dict(scale_factor=0.01, add_offset=1.5, _FillValue=65535, units="W")),
+                        ("cnt", dict(scale_factor=0.5, missing_value=-999))):
+        attrs = json.load(open(store / name / ".zattrs"))
+        json.dump({**attrs, **extra}, open(store / name / ".zattrs", "w"))
+    ds = open_zarr_dataset(str(store), mask_and_scale=True)
+    got = ds["rad"].values
+    assert ds["rad"].dtype == np.float32 and ds["rad"].attrs == {"units": "W"} and isinstance(ds["rad"].source, DecodedSource)
+    assert np.isnan(got[0, 0, :5]).all() and np.isnan(got).sum() == (rad == 65535).sum()
+    ok = rad != 65535
+    assert np.array_equal(got[ok], rad[ok].astype(np.float32) * np.float32(0.01) + np.float32(1.5))
+    assert np.allclose(got[ok], rad[ok] * 0.01 + 1.5, rtol=1e-6)
+    part = np.empty((2, 20, 30), dtype=np.float32)
+    ds["rad"].source.read_bands(1, 2, part)
+    assert np.array_equal(part, got[1:], equal_nan=True)
+    c = ds["cnt"].values
+    assert c.dtype == np.float64 and np.isnan(c[3, 4]) and np.array_equal(np.delete(c.ravel(), 3 * 30 + 4),
+                                                                          np.delete(cnt.ravel(), 3 * 30 + 4) * 0.5)
+    assert ds["plain"].dtype == np.float32 and not isinstance(ds["plain"].source, DecodedSource)
+    raw = open_zarr_dataset(str(store))
+    assert raw["rad"].dtype == np.uint16 and raw["rad"].attrs["scale_factor"] == 0.01 and np.array_equal(raw["rad"].values, rad)
+    assert cf_decoded_dtype(np.dtype("f4"), {"_FillValue": -1.0}) == np.float32
+    assert cf_decoded_dtype(np.dtype("i8"), {"add_offset": 1}) == np.float64 and cf_decoded_dtype(np.dtype("u1"), {}) is None

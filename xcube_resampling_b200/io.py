@@ -32,6 +32,7 @@ from __future__ import annotations
 
 import json
 import os
+from collections.abc import Mapping
 
 import numpy as np
 
@@ -310,6 +311,55 @@ class ZarrV2Source(LazySource):
                     out[lo - b0:hi - b0, j0:j1, i0:i1] = block[lo - kb * cb:hi - kb * cb, :j1 - j0, :i1 - i0]
 
 
+def cf_decoded_dtype(dtype: np.dtype, attrs: Mapping) -> np.dtype | None:
+    """The float type CF mask-and-scale decoding gives a variable, ``None`` when its attributes ask for none:
+    float32 for integers of up to 16 bits and floats of up to 32 bits (float32 holds them exactly), float64
+    otherwise -- xarray's ``open_dataset(mask_and_scale=True)`` rule for variables without ``add_offset``
+    (with one, xarray's choice has varied between releases; this build keeps the same rule)."""
+    if not any(k in attrs for k in ("scale_factor", "add_offset", "_FillValue", "missing_value")):
+        return None
+    dtype = np.dtype(dtype)
+    small = (dtype.kind in "iu" and dtype.itemsize <= 2) or (dtype.kind == "f" and dtype.itemsize <= 4)
+    return np.dtype(np.float32 if small else np.float64)
+
+
+class DecodedSource(LazySource):
+    """CF mask-and-scale decoding of another source on the reader thread: ``_FillValue`` / ``missing_value``
+    become NaN, then ``raw * scale_factor + add_offset`` in the decoded float type (:func:`cf_decoded_dtype`)."""
+
+    def __init__(self, source: LazySource, attrs: Mapping):
+        self.source, self.shape = source, tuple(source.shape)
+        self.dtype = cf_decoded_dtype(source.dtype, attrs)
+        if self.dtype is None:
+            raise ValueError("the variable's attributes ask for no decoding")
+        fills = [np.asarray(attrs[k]).ravel() for k in ("_FillValue", "missing_value") if k in attrs]
+        self._fills = np.concatenate(fills) if fills else np.empty(0)
+        self._scale, self._offset = attrs.get("scale_factor"), attrs.get("add_offset")
+
+    def read_bands(self, b0, nb, out):
+        raw = np.empty((nb,) + self.shape[-2:], dtype=self.source.dtype)
+        self.source.read_bands(b0, nb, raw)
+        res = out[:nb]
+        np.copyto(res, raw, casting="unsafe")
+        for f in self._fills:
+            if f == f:  # a NaN fill value of float data is NaN already
+                res[raw == raw.dtype.type(f)] = np.nan
+        if self._scale is not None:
+            np.multiply(res, self.dtype.type(self._scale), out=res)
+        if self._offset is not None:
+            np.add(res, self.dtype.type(self._offset), out=res)
+
+
+_CF_CODING_ATTRS = ("scale_factor", "add_offset", "_FillValue", "missing_value")
+
+
+def _lazy_variable(source: LazySource, dims, attrs, name, mask_and_scale: bool) -> "LazyDataArray":
+    if mask_and_scale and cf_decoded_dtype(source.dtype, attrs) is not None:
+        source = DecodedSource(source, attrs)
+        attrs = {k: v for k, v in attrs.items() if k not in _CF_CODING_ATTRS}  # moved to the encoding, as in xarray
+    return LazyDataArray(source, dims=dims, attrs=attrs, name=name)
+
+
 class LazyDataArray(DataArray):
     """A dataset variable whose values stay in a chunked store until a pipeline streams them (``source``);
     ``values`` materialises the whole array for anything that is not a streaming consumer."""
@@ -364,11 +414,12 @@ def _read_small_array(arr_dir: str, meta: dict) -> np.ndarray:
 
 
 def open_zarr_dataset(path: str, coord_names=("lon", "lat", "x", "y", "longitude", "latitude",
-                                              "transformed_x", "transformed_y")) -> Dataset:
+                                              "transformed_x", "transformed_y"), mask_and_scale: bool = False) -> Dataset:
     """A Zarr-v2 directory store as a :class:`Dataset`: scalar, 1-D and coordinate-named arrays are read
-    now, every other 2-D / 3-D array becomes a :class:`LazyDataArray`.  Values are delivered as stored
-    (what ``xarray.open_zarr(..., mask_and_scale=False)`` gives): ``scale_factor`` / ``add_offset`` /
-    ``_FillValue`` attributes are passed through, not applied."""
+    now, every other 2-D / 3-D array becomes a :class:`LazyDataArray`.  By default values are delivered
+    as stored (what ``xarray.open_zarr(..., mask_and_scale=False)`` gives): ``scale_factor`` /
+    ``add_offset`` / ``_FillValue`` attributes are passed through, not applied.  ``mask_and_scale=True``
+    decodes the lazy variables that carry such attributes on the reader thread (:class:`DecodedSource`)."""
     data_vars, coords = {}, {}
     for item in sorted(os.listdir(path)):
         arr_dir = os.path.join(path, item)
@@ -386,17 +437,17 @@ def open_zarr_dataset(path: str, coord_names=("lon", "lat", "x", "y", "longitude
             if item in coord_names:
                 coords[item] = DataArray(src.read_all(), dims=dims, attrs=attrs, name=item)
             else:
-                data_vars[item] = LazyDataArray(src, dims=dims, attrs=attrs, name=item)
+                data_vars[item] = _lazy_variable(src, dims, attrs, item, mask_and_scale)
     group_attrs = os.path.join(path, ".zattrs")
     return Dataset(data_vars=data_vars, coords=coords, attrs=json.load(open(group_attrs)) if os.path.isfile(group_attrs) else {})
 
 
 def open_netcdf_dataset(path: str, coord_names=("lon", "lat", "x", "y", "longitude", "latitude",
-                                                "transformed_x", "transformed_y")) -> Dataset:
+                                                "transformed_x", "transformed_y"), mask_and_scale: bool = False) -> Dataset:
     """A NetCDF classic file as a :class:`Dataset`, with the rules of :func:`open_zarr_dataset`: scalar, 1-D
     and coordinate-named variables are read now, every other 2-D / 3-D variable becomes a
-    :class:`LazyDataArray` over the file's memory map.  Values as stored (no CF mask-and-scale); ``bytes``
-    attributes are decoded to ``str`` as xarray does."""
+    :class:`LazyDataArray` over the file's memory map.  Values as stored unless ``mask_and_scale=True``
+    (then as in :func:`open_zarr_dataset`); ``bytes`` attributes are decoded to ``str`` as xarray does."""
     from scipy.io import netcdf_file
 
     with open(path, "rb") as fh:
@@ -429,7 +480,7 @@ def open_netcdf_dataset(path: str, coord_names=("lon", "lat", "x", "y", "longitu
         attrs = {k: text(v) for k, v in var._attributes.items()}
         dims = tuple(var.dimensions)
         if len(var.shape) in (2, 3) and name not in coord_names:
-            data_vars[name] = LazyDataArray(NetCDF3Source(nc, name), dims=dims, attrs=attrs, name=name)
+            data_vars[name] = _lazy_variable(NetCDF3Source(nc, name), dims, attrs, name, mask_and_scale)
             continue
         values = np.array(var.data, dtype=var.data.dtype.newbyteorder("="))  # a copy: independent of the map
         (coords if len(var.shape) <= 2 else data_vars)[name] = DataArray(values, dims=dims, attrs=attrs, name=name)
