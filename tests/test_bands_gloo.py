@@ -203,3 +203,21 @@ def test_two_rank_row_bands_gloo(worker, tmp_path):
     world = 2
     mp.spawn(worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
+
+
+def test_band_partitions_cover_the_image_for_any_band_count():
+    """Seeded sweep over heights, band counts (1..11, more bands than aligned blocks included), alignments and
+    row weights (zero rows, all-zero images): the bands are contiguous, ordered and cover [0, height)."""
+    import numpy as np
+
+    from xcube_resampling_b200.bands import row_bands, weighted_row_bands
+
+    rng = np.random.default_rng(0)
+    for _ in range(1500):
+        h, n, align = int(rng.integers(1, 400)), int(rng.integers(1, 12)), int(rng.choice([1, 8, 32]))
+        w = rng.random(h) * (rng.random(h) > 0.3)
+        if rng.random() < 0.1:
+            w[:] = 0
+        for bands in (weighted_row_bands(w, n, align=align), row_bands(h, n, align=align)):
+            assert len(bands) == n and bands[0][0] == 0 and bands[-1][1] == h
+            assert all(a <= b for a, b in bands) and all(bands[k][1] == bands[k + 1][0] for k in range(n - 1))
