@@ -345,3 +345,27 @@ def test_mask_and_scale_decoding_of_lazy_variables(tmp_path):
     assert raw["rad"].dtype == np.uint16 and raw["rad"].attrs["scale_factor"] == 0.01 and np.array_equal(raw["rad"].values, rad)
     assert cf_decoded_dtype(np.dtype("f4"), {"_FillValue": -1.0}) == np.float32
     assert cf_decoded_dtype(np.dtype("i8"), {"add_offset": 1}) == np.float64 and cf_decoded_dtype(np.dtype("u1"), {}) is None
+
+
+def test_mask_and_scale_fill_value_spellings():
+    """Fill values as lists, numpy scalars, out-of-range numbers and JSON's "NaN" string."""
+    from xcube_resampling_b200.io import DecodedSource, LazySource
+
+    class Mem(LazySource):
+        def __init__(self, a):
+            self.a, self.shape, self.dtype = a, a.shape, a.dtype
+
+        def read_bands(self, b0, nb, out):
+            out[:nb] = self.a[b0:b0 + nb]
+
+    a = np.array([[[1, 2], [65535, 4]]], dtype=np.uint16)
+    nan = np.nan
+    for attrs, want in (({"_FillValue": 65535}, [1, 2, nan, 4]), ({"_FillValue": np.uint16(65535)}, [1, 2, nan, 4]),
+                        ({"_FillValue": [65535, 2]}, [1, nan, nan, 4]),
+                        ({"_FillValue": "NaN", "scale_factor": 2.0}, [2, 4, 131070, 8]),
+                        ({"missing_value": 70000.0, "_FillValue": -1}, [1, 2, 65535, 4])):
+        got = DecodedSource(Mem(a), attrs).read_all()
+        assert got.dtype == np.float32 and np.array_equal(got.ravel(), np.float32(want), equal_nan=True), attrs
+    f = np.array([[[1.5, nan], [-999.0, 4]]], dtype=np.float64)
+    got = DecodedSource(Mem(f), {"_FillValue": nan, "missing_value": -999.0}).read_all()
+    assert got.dtype == np.float64 and np.array_equal(got.ravel(), [1.5, nan, nan, 4], equal_nan=True)

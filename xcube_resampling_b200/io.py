@@ -332,8 +332,15 @@ class DecodedSource(LazySource):
         self.dtype = cf_decoded_dtype(source.dtype, attrs)
         if self.dtype is None:
             raise ValueError("the variable's attributes ask for no decoding")
-        fills = [np.asarray(attrs[k]).ravel() for k in ("_FillValue", "missing_value") if k in attrs]
-        self._fills = np.concatenate(fills) if fills else np.empty(0)
+        self._fills = []
+        for key in ("_FillValue", "missing_value"):
+            for f in np.asarray(attrs.get(key, [])).ravel().tolist():
+                try:  # JSON attributes may spell the float specials as strings ("NaN"); those mask nothing new
+                    f = float(f) if not isinstance(f, (int, np.integer)) else int(f)
+                except (TypeError, ValueError):
+                    continue
+                if f == f and (source.dtype.kind == "f" or float(f).is_integer()):
+                    self._fills.append(f)
         self._scale, self._offset = attrs.get("scale_factor"), attrs.get("add_offset")
 
     def read_bands(self, b0, nb, out):
@@ -341,8 +348,8 @@ class DecodedSource(LazySource):
         self.source.read_bands(b0, nb, raw)
         res = out[:nb]
         np.copyto(res, raw, casting="unsafe")
-        for f in self._fills:
-            if f == f:  # a NaN fill value of float data is NaN already
+        for f in self._fills:  # a NaN fill value of float data is NaN already and is not in the list
+            if raw.dtype.kind == "f" or np.iinfo(raw.dtype).min <= f <= np.iinfo(raw.dtype).max:
                 res[raw == raw.dtype.type(f)] = np.nan
         if self._scale is not None:
             np.multiply(res, self.dtype.type(self._scale), out=res)
